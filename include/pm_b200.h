@@ -1,0 +1,196 @@
+/*
+ * pm_b200.h - C ABI of the B200-native PlanetMapper hot path (libpm_b200.so).
+ *
+ * The reference (ortk95/planetmapper, pure Python) has no FFI of its own: its
+ * per-pixel work is a Python loop making one ctypes CSPICE call per pixel per
+ * stage.  The entry points below are what a maintainer would bind (ctypes stub in
+ * INTEGRATION.md) to replace those loops; each cites the reference method it
+ * replaces.  Plain pointers and sizes only; every function returns PM_OK (0) or a
+ * negative PM_ERR_* code, writes NaN for invalid pixels / cells and never throws.
+ *
+ * All `double*` data arguments are DEVICE pointers unless the name ends in
+ * `_host`.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * Work is enqueued asynchronously on `stream`; the caller synchronises.
+ */
+#ifndef PM_B200_H
+#define PM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_ERR_BAD_ARG (-1)
+#define PM_ERR_CUDA (-2)
+#define PM_ERR_UNSUPPORTED (-3)
+#define PM_ERR_NO_DEVICE (-4)
+
+#define PM_ABI_VERSION 1
+
+/*
+ * Per-frame constants, computed once per frame on the host from SPICE
+ * (planetmapper/base.py:815-837, planetmapper/body.py:522-588,
+ * planetmapper/body_xy.py:355-373).  All doubles, so the struct is also a flat
+ * double[PM_FRAME_NDOUBLES]; the Python packer is planetmapper_b200/frame.py.
+ * Vectors are J2000 unless stated; "body" = target body-fixed frame (IAU_*).
+ */
+typedef struct PMFrame {
+    double et;          /* observation epoch, TDB s past J2000 (Body.et)              */
+    double clight;      /* km/s                                                        */
+    double lt0;         /* light time to target centre (Body.target_light_time)       */
+    double t_ref;       /* et - lt0: reference epoch for the linear models below      */
+    double P0[3];       /* observer -> target centre at t_ref (Body._target_obsvec)   */
+    double VT[3];       /* target centre SSB velocity at t_ref                        */
+    double AT[3];       /* target centre SSB acceleration at t_ref                    */
+    double VO[3];       /* observer SSB velocity at et                                */
+    double S0[3];       /* Sun(t_ref - lts0) - target centre(t_ref)                   */
+    double VS[3];       /* Sun SSB velocity at t_ref - lts0                           */
+    double lts0;        /* Sun -> target centre light time at t_ref                   */
+    double R0[9];       /* J2000 -> body rotation at t_ref, row-major                 */
+    double omega[3];    /* body-frame angular velocity, dR/dt = -[omega]x R (rad/s)   */
+    double radii[3];    /* ellipsoid radii incl. any altitude adjustment (km)         */
+    double re;          /* spheroid equatorial radius used by recpgr/pgrrec           */
+    double f;           /* spheroid flattening used by recpgr/pgrrec                  */
+    double lon_sign;    /* +1 planetographic east-positive, -1 west-positive          */
+    double prograde;    /* 1 prograde, 0 retrograde (et2lst)                          */
+    double sub_t[3];    /* sub-observer point, body (Body._subpoint_targvec)          */
+    double sub_ray[3];  /* observer -> sub-point, body (Body._subpoint_rayvec)        */
+    double sub_obs[3];  /* same, J2000 (Body._subpoint_obsvec)                        */
+    double sub_dt;      /* Body._subpoint_et - t_ref                                  */
+    double sub_dist;    /* Body.subpoint_distance                                     */
+    double ring_n[3];   /* ring plane unit normal (Body._ring_plane)                  */
+    double ring_c;      /* ring plane constant, >= 0                                  */
+    double sun_lon_lst; /* body-fixed planetocentric Sun longitude used by et2lst     */
+    double M[9];        /* obsvec -> angular rotation (body.py:1318-1343), row-major  */
+    double ang2km[4];   /* angular(arcsec) -> km 2x2 (body.py:1636-1639)              */
+    double km_per_arcsec;
+    double A[6];        /* xy -> angular arcsec, rows [a00 a01 a02],[a10 a11 a12]     */
+    double Ainv[6];     /* angular arcsec -> xy                                       */
+    double nx, ny;      /* image size (integers stored as doubles)                    */
+    double x0, y0;      /* disc centre (pixels)                                       */
+    double r_cut2;      /* squared early-out radius (body_xy.py:3201-3203)            */
+    double optimize_speed; /* 1 = apply the early-out (SpiceBase._optimize_speed)     */
+    double r_eq;        /* equatorial radius used for RING-RADIUS = alt + r_eq        */
+    double reserved[1];
+} PMFrame;
+
+#define PM_FRAME_NDOUBLES 92
+
+/* Backplane ids = registration order in BodyXY._register_default_backplanes
+ * (planetmapper/body_xy.py:4198-4356). A plane mask has bit `id` set. */
+enum PMPlane {
+    PM_LON_GRAPHIC = 0, PM_LAT_GRAPHIC = 1, PM_LON_CENTRIC = 2, PM_LAT_CENTRIC = 3,
+    PM_RA = 4, PM_DEC = 5, PM_PIXEL_X = 6, PM_PIXEL_Y = 7, PM_KM_X = 8, PM_KM_Y = 9,
+    PM_ANGULAR_X = 10, PM_ANGULAR_Y = 11, PM_PHASE = 12, PM_INCIDENCE = 13,
+    PM_EMISSION = 14, PM_AZIMUTH = 15, PM_LOCAL_SOLAR_TIME = 16, PM_DISTANCE = 17,
+    PM_RADIAL_VELOCITY = 18, PM_DOPPLER = 19, PM_LIMB_DISTANCE = 20,
+    PM_LIMB_LON_GRAPHIC = 21, PM_LIMB_LAT_GRAPHIC = 22, PM_RING_RADIUS = 23,
+    PM_RING_LON_GRAPHIC = 24, PM_RING_DISTANCE = 25, PM_N_PLANES = 26
+};
+#define PM_ALL_PLANES ((1ull << PM_N_PLANES) - 1ull)
+
+/* interpolation modes of pm_gather (BodyXY.map_img, body_xy.py:1414-1631) */
+#define PM_INTERP_NEAREST 0
+#define PM_INTERP_LINEAR 1
+#define PM_INTERP_CUBIC 3
+
+/* projection kinds of pm_proj_inverse (BodyXY.generate_map_coordinates,
+ * body_xy.py:2899-2969) */
+#define PM_PROJ_ORTHOGRAPHIC 1
+#define PM_PROJ_AZIMUTHAL 2
+#define PM_PROJ_AZIMUTHAL_EQUAL_AREA 3
+
+/* flags */
+#define PM_FLAG_NOT_VISIBLE_NAN 1u /* lonlat2xy(not_visible_nan=True)               */
+#define PM_FLAG_PROPAGATE_NAN 2u   /* map_img(propagate_nan=True)                   */
+
+int pm_abi_version(void);
+const char *pm_error_string(int code);
+/* number of CUDA kernels this library has launched since load (bench evidence) */
+uint64_t pm_launch_count(void);
+
+/*
+ * Image-direction backplanes: replaces the per-pixel loops
+ * BodyXY._get_targvec_img (body_xy.py:3197), _get_lonlat_img (:3284),
+ * _get_lonlat_centric_img (:3349), _get_radec_img (:3413), _get_km_xy_img (:3547),
+ * _get_illumination_gie_img (:3661), get_azimuth_angle_img (:3744),
+ * get_local_solar_time_img (:3790), _get_state_imgs (:3832),
+ * get_radial_velocity_img (:3898), get_doppler_img (:3938),
+ * _get_limb_coordinate_imgs (:3967), _get_ring_plane_coordinate_imgs (:4061).
+ * `frames`: n_frames PMFrame structs in DEVICE memory (all with the same nx, ny).
+ * `out`: [n_frames][popcount(mask)][ny][nx] doubles, planes in increasing id order.
+ */
+int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny,
+                      uint64_t plane_mask, double *out, void *stream);
+
+/*
+ * Map-direction backplanes on arbitrary lon/lat cells (degrees, planetographic):
+ * replaces _get_targvec_map (body_xy.py:3230), _get_illumf_map (:3671),
+ * _get_obsvec_map (:3275), _get_radec_map (:3423), _get_xy_map (:3482),
+ * _get_km_xy_map (:3557), _get_lonlat_centric_map (:3357), _get_state_maps (:3851),
+ * get_radial_velocity_map (:3917), get_local_solar_time_map (:3812),
+ * _get_limb_coordinate_maps (:3980), _get_ring_plane_coordinate_maps (:4090).
+ * PIXEL-X / PIXEL-Y are x_map / y_map.  `out`: [popcount(mask)][n_cells].
+ */
+int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat,
+                      int64_t n_cells, uint64_t plane_mask, double *out, void *stream);
+
+/*
+ * Vectorised point transforms: replace SpiceBase._maybe_transform_as_arrays
+ * (base.py:718-757) driving BodyXY._xy2lonlat (body_xy.py:482) and _lonlat2xy (:544).
+ * Misses / invisible points produce NaN; `n_missed` (device int64, may be NULL)
+ * counts xy2lonlat rays that missed the body (the host raises NotFoundError when
+ * not_found_nan=False, body.py:1073-1078).
+ */
+int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n,
+                 double *lon, double *lat, int64_t *n_missed, void *stream);
+int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+                 uint32_t flags, double *x, double *y, void *stream);
+
+/*
+ * Inverse map projections, replacing pyproj.Transformer.transform(...,
+ * direction='INVERSE') at body_xy.py:3126 for the three named non-rectangular
+ * projections.  params = {a (r_eq), b (r_polar), lon_0, lat_0 (deg), lon_sign}.
+ * xx, yy are in the projection's own units (body_xy.py:2905-2968 `to_meter`).
+ * Output degrees; cells outside the projection are NaN.
+ */
+int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
+                    const double *yy, int64_t n, double *lon, double *lat, void *stream);
+
+/*
+ * Cube -> map resampling: replaces BodyXY._do_nearest_interpolation
+ * (body_xy.py:1633-1649) and _do_spline_interpolation (:1651-1702) applied per
+ * wavelength plane by Observation._get_mapped_data (observation.py:876-905).
+ * cube: [n_planes][ny][nx]; xmap, ymap: [n_cells]; out: [n_planes][n_cells].
+ * For LINEAR / CUBIC, `cube` must already be NaN-repaired and (CUBIC) prefiltered
+ * to B-spline coefficients by pm_spline_prepare; `nanmask` ([n_planes][ny][nx]
+ * uint8, 1 = original pixel was NaN, may be NULL) and `plane_skip` ([n_planes] uint8,
+ * 1 = plane was all-NaN -> output all NaN, may be NULL) come from the same call.
+ */
+int pm_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip,
+              int n_planes, int ny, int nx, const double *xmap, const double *ymap,
+              int64_t n_cells, int mode, uint32_t flags, double *out, void *stream);
+
+/*
+ * NaN repair (BodyXY._replace_nans_with_interpolated_values, body_xy.py:1871-1904)
+ * followed, for degree 3, by the separable not-a-knot B-spline fit scipy's
+ * RectBivariateSpline(kx=ky=3, s=0) performs (body_xy.py:1673-1680).
+ * In: cube [n_planes][ny][nx].  Out: coef (same shape), nanmask, plane_skip.
+ * `work` must hold pm_spline_work_bytes(...) bytes of device scratch.
+ */
+int64_t pm_spline_work_bytes(int n_planes, int ny, int nx, int degree);
+int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree,
+                      double *coef, uint8_t *nanmask, uint8_t *plane_skip, void *work,
+                      void *stream);
+
+/* FP64 FMA throughput probe used by bench.py for the compute roofline
+ * denominator: runs `iters` dependent-chain DFMAs per thread on a full grid and
+ * returns the kernel time in ms through *ms_host (synchronises). */
+int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_B200_H */

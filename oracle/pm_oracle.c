@@ -1,0 +1,1091 @@
+/*
+ * pm_oracle.c - CPU restatement (plain C, FP64) of PlanetMapper's per-pixel
+ * geometry and mapping hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * path is the CUDA library in planetmapper_b200/csrc and never calls into here.
+ *
+ * The reference (ortk95/planetmapper v1.14.0) delegates its arithmetic to CSPICE
+ * N0067 through spiceypy <= 8.1.2 (requirements.txt:5), to PROJ 9.x through
+ * pyproj <= 3.7.2 and to FITPACK through scipy <= 1.18.0.  None of those sources are
+ * under /root/reference, and spiceypy / pyproj are installed neither in the authoring
+ * container nor on the GPU box, so the reference itself cannot be executed.  Each
+ * routine below restates the published algorithm of the CSPICE / PROJ routine the
+ * reference calls, citing the reference call site (file:line under
+ * /root/reference/planetmapper) it stands in for.
+ *
+ * PARITY PIN: tests/test_oracle_golden.py checks this file against the reference's
+ * own golden FITS outputs (tests/data/outputs/test_nav.fits etc., 26 backplanes,
+ * maps and mapped cubes) and 16-digit known-answer literals of the reference's unit
+ * tests; see DESIGN.md "Oracle".
+ *
+ * Build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off)
+ */
+#include "pm_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PI 3.14159265358979323846264338327950288
+#define TWOPI (2.0 * PI)
+#define HALFPI (0.5 * PI)
+#define DPR (180.0 / PI)
+#define RPD (PI / 180.0)
+
+static const double kNaN = NAN;
+
+/* ---------- small vector helpers ---------- */
+static inline double dot3(const double a[3], const double b[3]) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+static inline void cross3(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* CSPICE vnorm: scaled to avoid overflow */
+static inline double norm3(const double a[3]) {
+    double m = fmax(fabs(a[0]), fmax(fabs(a[1]), fabs(a[2])));
+    if (m == 0.0) return 0.0;
+    double x = a[0] / m, y = a[1] / m, z = a[2] / m;
+    return m * sqrt(x * x + y * y + z * z);
+}
+static inline void mxv(const double m[9], const double v[3], double o[3]) {
+    o[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+    o[1] = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+    o[2] = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+}
+static inline void mtxv(const double m[9], const double v[3], double o[3]) {
+    o[0] = m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+    o[1] = m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+    o[2] = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+}
+static inline int finite3(const double v[3]) {
+    return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
+}
+/* Python's float % (result takes the sign of the divisor) */
+static inline double pymod(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+    return r;
+}
+
+/* ---------- CSPICE primitives ---------- */
+
+/* spice.recrad (base.py:902, body.py:1356): range, RA in [0,2pi), Dec */
+static void recrad(const double v[3], double *range, double *ra, double *dec) {
+    double big = fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2])));
+    if (!(big > 0.0)) {
+        *range = big; /* 0 or NaN */
+        *ra = (big == 0.0) ? 0.0 : kNaN;
+        *dec = (big == 0.0) ? 0.0 : kNaN;
+        return;
+    }
+    double x = v[0] / big, y = v[1] / big, z = v[2] / big;
+    *range = big * sqrt(x * x + y * y + z * z);
+    *dec = atan2(z, sqrt(x * x + y * y));
+    double lon = (x == 0.0 && y == 0.0) ? 0.0 : atan2(y, x);
+    if (lon < 0.0) lon += TWOPI;
+    *ra = lon;
+}
+
+/* spice.radrec (body.py:967, :1369) */
+static void radrec(double r, double ra, double dec, double o[3]) {
+    o[0] = r * cos(ra) * cos(dec);
+    o[1] = r * sin(ra) * cos(dec);
+    o[2] = r * sin(dec);
+}
+
+/* spice.vsep: angle between two vectors, numerically stable form */
+static double vsep(const double a[3], const double b[3]) {
+    double na = norm3(a), nb = norm3(b);
+    if (na == 0.0 || nb == 0.0) return 0.0;
+    double u[3] = {a[0] / na, a[1] / na, a[2] / na};
+    double v[3] = {b[0] / nb, b[1] / nb, b[2] / nb};
+    double d = dot3(u, v);
+    if (d > 0.0) {
+        double w[3] = {u[0] - v[0], u[1] - v[1], u[2] - v[2]};
+        return 2.0 * asin(0.5 * norm3(w));
+    } else if (d < 0.0) {
+        double w[3] = {u[0] + v[0], u[1] + v[1], u[2] + v[2]};
+        return PI - 2.0 * asin(0.5 * norm3(w));
+    }
+    return HALFPI;
+}
+
+/* J2000 -> body-fixed at epoch t_ref + dt: v_body = E(dt) R0 v, E = exp(-[omega]x dt).
+ * Stands in for spice.pxform / pxfrm2 at a per-point epoch (body.py:940, :998 and
+ * inside sincpt / illumf / spkcpt). */
+static void rot_to_body(const PMFrame *f, double dt, const double v[3], double o[3]) {
+    double w[3];
+    mxv(f->R0, v, w);
+    double wn = norm3(f->omega);
+    if (wn == 0.0 || dt == 0.0) {
+        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        return;
+    }
+    double k[3] = {f->omega[0] / wn, f->omega[1] / wn, f->omega[2] / wn};
+    double th = wn * dt, c = cos(th), s = sin(th);
+    double kxw[3];
+    cross3(k, w, kxw);
+    double kw = dot3(k, w) * (1.0 - c);
+    for (int i = 0; i < 3; i++) o[i] = w[i] * c - kxw[i] * s + k[i] * kw;
+}
+/* body-fixed at epoch t_ref + dt -> J2000 */
+static void rot_from_body(const PMFrame *f, double dt, const double u[3], double o[3]) {
+    double w[3] = {u[0], u[1], u[2]};
+    double wn = norm3(f->omega);
+    if (wn != 0.0 && dt != 0.0) {
+        double k[3] = {f->omega[0] / wn, f->omega[1] / wn, f->omega[2] / wn};
+        double th = wn * dt, c = cos(th), s = sin(th);
+        double kxu[3];
+        cross3(k, u, kxu);
+        double ku = dot3(k, u) * (1.0 - c);
+        for (int i = 0; i < 3; i++) w[i] = u[i] * c + kxu[i] * s + k[i] * ku;
+    }
+    mtxv(f->R0, w, o);
+}
+
+/* target centre relative to the observer (J2000) at epoch t_ref + dt */
+static void target_pos(const PMFrame *f, double dt, double P[3]) {
+    for (int i = 0; i < 3; i++)
+        P[i] = f->P0[i] + f->VT[i] * dt + 0.5 * f->AT[i] * dt * dt;
+}
+
+/* spice.surfpt: nearest intersection of ray (o, u) with ellipsoid (a,b,c).
+ * Perpendicular-projection form (well conditioned for a distant observer).
+ * margin (optional) receives |p_perp| - 1 in scaled space: < 0 hit, > 0 miss. */
+static int surfpt(const double o[3], const double u[3], double a, double b, double c,
+                  double p[3], double *margin) {
+    double x[3] = {u[0] / a, u[1] / b, u[2] / c};
+    double y[3] = {o[0] / a, o[1] / b, o[2] / c};
+    double xn = norm3(x);
+    if (margin) *margin = kNaN;
+    if (!(xn > 0.0)) return 0;
+    x[0] /= xn; x[1] /= xn; x[2] /= xn;
+    double yx = dot3(y, x);
+    double pp[3] = {y[0] - yx * x[0], y[1] - yx * x[1], y[2] - yx * x[2]};
+    double pmag = norm3(pp), ymag = norm3(y);
+    if (margin) *margin = pmag - 1.0;
+    double q[3];
+    if (ymag > 1.0) {
+        if (pmag > 1.0) return 0;
+        if (yx > 0.0) return 0;
+        if (pmag == 1.0) {
+            q[0] = pp[0]; q[1] = pp[1]; q[2] = pp[2];
+        } else {
+            double sc = sqrt(fmax(0.0, 1.0 - pmag * pmag));
+            for (int i = 0; i < 3; i++) q[i] = pp[i] - sc * x[i];
+        }
+    } else if (ymag == 1.0) {
+        q[0] = y[0]; q[1] = y[1]; q[2] = y[2];
+    } else {
+        double sc = sqrt(fmax(0.0, 1.0 - pmag * pmag));
+        for (int i = 0; i < 3; i++) q[i] = pp[i] + sc * x[i];
+    }
+    if (!isfinite(pmag)) return 0;
+    p[0] = q[0] * a; p[1] = q[1] * b; p[2] = q[2] * c;
+    return 1;
+}
+
+/* spice.sincpt('ELLIPSOID', ..., 'CN', observer, 'J2000', d) (body.py:1010-1020):
+ * ray-ellipsoid intercept with the light time iterated on the intercept point.
+ * Returns 1 if found.  lt/dt are the converged light time and epoch offset. */
+#define PMO_MAXITR 10
+static int sincpt(const PMFrame *f, const double d[3], double p[3], double *lt_out,
+                  double *margin_out) {
+    const double a = f->radii[0], b = f->radii[1], c = f->radii[2];
+    double lt = f->lt0;
+    double t = f->et - lt;
+    if (margin_out) *margin_out = kNaN;
+    for (int i = 0; i < PMO_MAXITR; i++) {
+        double dt = t - f->t_ref;
+        double P[3], negP[3], o[3], u[3];
+        target_pos(f, dt, P);
+        negP[0] = -P[0]; negP[1] = -P[1]; negP[2] = -P[2];
+        rot_to_body(f, dt, negP, o);
+        rot_to_body(f, dt, d, u);
+        double margin;
+        int found = surfpt(o, u, a, b, c, p, &margin);
+        if (i == 0 && margin_out) *margin_out = margin;
+        if (!found) return 0;
+        double s[3] = {p[0] - o[0], p[1] - o[1], p[2] - o[2]};
+        double lt_new = norm3(s) / f->clight;
+        double t_new = f->et - lt_new;
+        double ltdiff = fabs(t_new - t);
+        t = t_new;
+        lt = lt_new;
+        if (!(ltdiff > 1.0e-17 * fabs(t))) break;
+    }
+    *lt_out = lt;
+    return 1;
+}
+
+/* Geodetic coordinates of a point relative to the spheroid (re, re, re(1-f)):
+ * the nearest-point construction of spice.recgeo, solved with Bowring's iteration
+ * run to convergence.  lon east-positive in (-pi, pi]. */
+static void recgeo(const double p[3], double re, double fl, double *lon, double *lat,
+                   double *alt) {
+    double rp = re - fl * re;
+    double rho = sqrt(p[0] * p[0] + p[1] * p[1]);
+    double z = p[2];
+    *lon = (p[0] == 0.0 && p[1] == 0.0) ? 0.0 : atan2(p[1], p[0]);
+    if (fl == 0.0) {
+        double r = norm3(p);
+        *lat = atan2(z, rho);
+        *alt = r - re;
+        return;
+    }
+    double e2 = 1.0 - (rp * rp) / (re * re);
+    double ep2 = (re * re) / (rp * rp) - 1.0;
+    double beta = atan2(re * z, rp * rho);
+    double phi = 0.0;
+    for (int i = 0; i < 12; i++) {
+        double sb = sin(beta), cb = cos(beta);
+        double nphi = atan2(z + ep2 * rp * sb * sb * sb, rho - e2 * re * cb * cb * cb);
+        double nbeta = atan2((1.0 - fl) * sin(nphi), cos(nphi));
+        int done = fabs(nphi - phi) <= 4.0e-16 * fmax(1.0, fabs(nphi)) && i > 0;
+        phi = nphi;
+        beta = nbeta;
+        if (done) break;
+    }
+    double sp = sin(phi), cp = cos(phi);
+    *lat = phi;
+    *alt = rho * cp + z * sp - re * sqrt(1.0 - e2 * sp * sp);
+}
+
+/* spice.recpgr (body.py:1030, :2592): planetographic lon in [0,2pi), lat, alt */
+static void recpgr(const PMFrame *f, const double p[3], double *lon, double *lat,
+                   double *alt) {
+    double l;
+    recgeo(p, f->re, f->f, &l, lat, alt);
+    l = f->lon_sign * l;
+    if (l < 0.0) l += TWOPI;
+    *lon = l;
+}
+
+/* spice.pgrrec (body.py:903): planetographic (radians) -> body-fixed */
+static void pgrrec(const PMFrame *f, double lon, double lat, double alt, double o[3]) {
+    double re = f->re, rp = f->re - f->f * f->re;
+    double lam = f->lon_sign * lon;
+    double clat = cos(lat), slat = sin(lat), clon = cos(lam), slon = sin(lam);
+    double big = fmax(fabs(re * clat), fabs(rp * slat));
+    double x = re * clat / big, y = rp * slat / big;
+    double scale = 1.0 / sqrt(x * x + y * y);
+    o[0] = scale * clon * x * re + alt * clat * clon;
+    o[1] = scale * slon * x * re + alt * clat * slon;
+    o[2] = scale * y * rp + alt * slat;
+}
+
+/* spice.reclat (body.py:2912) */
+static void reclat(const double v[3], double *r, double *lon, double *lat) {
+    double big = fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2])));
+    if (big > 0.0) {
+        double x = v[0] / big, y = v[1] / big, z = v[2] / big;
+        *r = big * sqrt(x * x + y * y + z * z);
+        *lat = atan2(z, sqrt(x * x + y * y));
+        *lon = (x == 0.0 && y == 0.0) ? 0.0 : atan2(y, x);
+    } else {
+        *r = 0.0; *lon = 0.0; *lat = 0.0;
+    }
+}
+
+/* Light time from a body-fixed point p to the observer: the 'CN' solve inside
+ * spice.spkcpt / spice.illumf (body.py:2833, :1925).  Returns lt, and dt = epoch
+ * offset (et - lt) - t_ref of the point. */
+static double point_light_time(const PMFrame *f, const double p[3], double lt_start,
+                               double *dt_out, double X[3]) {
+    double lt = lt_start;
+    double dt = 0.0;
+    for (int i = 0; i < PMO_MAXITR; i++) {
+        double t = f->et - lt;
+        dt = t - f->t_ref;
+        double P[3], q[3];
+        target_pos(f, dt, P);
+        rot_from_body(f, dt, p, q);
+        for (int k = 0; k < 3; k++) X[k] = P[k] + q[k];
+        double lt_new = norm3(X) / f->clight;
+        double diff = fabs(lt_new - lt);
+        lt = lt_new;
+        if (!(diff > 1.0e-17 * fabs(f->et))) break;
+    }
+    *dt_out = (f->et - lt) - f->t_ref;
+    return lt;
+}
+
+typedef struct {
+    double lt;        /* light time point -> observer */
+    double pos[3];    /* point relative to observer, J2000 (spkcpt position) */
+    double vel[3];    /* spkcpt velocity (with light-time-rate correction)   */
+    double phase, incdnc, emissn;
+    int visibl, lit;
+} PointState;
+
+/* spice.spkcpt (body.py:2830-2845) + spice.illumf (body.py:1915-1935) for a
+ * body-fixed surface point p. */
+static void point_state(const PMFrame *f, const double p[3], double lt_start,
+                        int want_illum, PointState *s) {
+    double dt, X[3];
+    s->lt = point_light_time(f, p, lt_start, &dt, X);
+    /* recompute X at the converged epoch */
+    double P[3], q[3];
+    target_pos(f, dt, P);
+    rot_from_body(f, dt, p, q);
+    for (int k = 0; k < 3; k++) s->pos[k] = P[k] + q[k];
+    /* inertial velocity of the point: centre + rotation */
+    double wxp[3], vrot[3], VX[3];
+    cross3(f->omega, p, wxp);
+    rot_from_body(f, dt, wxp, vrot);
+    for (int k = 0; k < 3; k++) VX[k] = f->VT[k] + f->AT[k] * dt + vrot[k];
+    double r = norm3(s->pos);
+    double ph[3] = {s->pos[0] / r, s->pos[1] / r, s->pos[2] / r};
+    double rel[3] = {VX[0] - f->VO[0], VX[1] - f->VO[1], VX[2] - f->VO[2]};
+    double dlt = dot3(ph, rel) / (f->clight + dot3(ph, VX));
+    for (int k = 0; k < 3; k++) s->vel[k] = VX[k] * (1.0 - dlt) - f->VO[k];
+    if (!want_illum) return;
+
+    /* observer and Sun as seen from the point, body-fixed at the point's epoch */
+    double negX[3] = {-s->pos[0], -s->pos[1], -s->pos[2]};
+    double e_b[3];
+    rot_to_body(f, dt, negX, e_b); /* point -> observer */
+    /* Sun light time: S(t - lts) - X_ssb(t); all relative to target centre(t_ref) */
+    double lts = f->lts0;
+    double sv[3];
+    double Tc[3];
+    for (int k = 0; k < 3; k++)
+        Tc[k] = f->VT[k] * dt + 0.5 * f->AT[k] * dt * dt + q[k]; /* point wrt T(t_ref) */
+    for (int i = 0; i < PMO_MAXITR; i++) {
+        double ds = dt - (lts - f->lts0);
+        for (int k = 0; k < 3; k++) sv[k] = f->S0[k] + f->VS[k] * ds - Tc[k];
+        double lts_new = norm3(sv) / f->clight;
+        double diff = fabs(lts_new - lts);
+        lts = lts_new;
+        if (!(diff > 1.0e-17 * fabs(f->et))) break;
+    }
+    {
+        double ds = dt - (lts - f->lts0);
+        for (int k = 0; k < 3; k++) sv[k] = f->S0[k] + f->VS[k] * ds - Tc[k];
+    }
+    double s_b[3];
+    rot_to_body(f, dt, sv, s_b);
+    /* spice.surfnm */
+    double a = f->radii[0], b = f->radii[1], c = f->radii[2];
+    double m = fmin(a, fmin(b, c));
+    double a1 = m / a, b1 = m / b, c1 = m / c;
+    double n[3] = {p[0] * (a1 * a1), p[1] * (b1 * b1), p[2] * (c1 * c1)};
+    double nn = norm3(n);
+    n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    s->phase = vsep(s_b, e_b);
+    s->incdnc = vsep(n, s_b);
+    s->emissn = vsep(n, e_b);
+    s->visibl = s->emissn < HALFPI;
+    s->lit = s->incdnc < HALFPI;
+}
+
+/* Body._azimuth_angle_from_gie_radians (body.py:2319-2332) */
+static double azimuth_from_gie(double g, double i, double e) {
+    double a = cos(g) - cos(e) * cos(i);
+    double b = sqrt(1.0 - cos(e) * cos(e)) * sqrt(1.0 - cos(i) * cos(i));
+    return PI - acos(a / b);
+}
+
+/* Body.local_solar_time_from_lon (body.py:2364-2398) -> spice.et2lst(..., 'planetographic')
+ * lon_deg: planetographic longitude in degrees. */
+static double local_solar_time(const PMFrame *f, double lon_deg) {
+    if (!isfinite(lon_deg)) return kNaN;
+    double lam = f->lon_sign * (lon_deg * RPD);
+    double ang = lam - f->sun_lon_lst;
+    if (f->prograde == 0.0) ang = -ang;
+    ang = fmod(ang, TWOPI);
+    if (ang < 0.0) ang += TWOPI;
+    double sec = ang * (86400.0 / TWOPI) + 43200.0;
+    if (sec >= 86400.0) sec -= 86400.0;
+    double hr = floor(sec / 3600.0);
+    sec -= hr * 3600.0;
+    double mn = floor(sec / 60.0);
+    sec -= mn * 60.0;
+    double sc = floor(sec);
+    return hr + mn / 60.0 + sc / 3600.0;
+}
+
+/* SpiceBase.calculate_doppler_factor (base.py:524-551) */
+static double doppler_factor(const PMFrame *f, double rv) {
+    double beta = rv / f->clight;
+    return sqrt((1.0 + beta) / (1.0 - beta));
+}
+
+/* Body._angular2obsvec_norm (body.py:1363-1373) after BodyXY._xy2obsvec_norm
+ * (body_xy.py:375-377) */
+static void xy2obsvec_norm(const PMFrame *f, double x, double y, double d[3]) {
+    double ax = f->A[0] * x + f->A[1] * y + f->A[2] * 1.0;
+    double ay = f->A[3] * x + f->A[4] * y + f->A[5] * 1.0;
+    double v[3];
+    radrec(1.0, -((ax / 3600.0) * RPD), (ay / 3600.0) * RPD, v);
+    mtxv(f->M, v, d);
+}
+
+/* Body._obsvec2angular (body.py:1345-1361), arcsec */
+static void obsvec2angular(const PMFrame *f, const double ov[3], double *ax, double *ay) {
+    if (!finite3(ov)) {
+        *ax = kNaN; *ay = kNaN;
+        return;
+    }
+    double v[3], r, ra, dec;
+    mxv(f->M, ov, v);
+    recrad(v, &r, &ra, &dec);
+    double x = pymod(-(ra * DPR), 360.0);
+    if (x > 180.0) x -= 360.0;
+    *ax = x * 3600.0;
+    *ay = (dec * DPR) * 3600.0;
+}
+
+/* BodyXY._obsvec2xy (body_xy.py:379-382) */
+static void obsvec2xy(const PMFrame *f, const double ov[3], double *x, double *y) {
+    double ax, ay;
+    obsvec2angular(f, ov, &ax, &ay);
+    *x = f->Ainv[0] * ax + f->Ainv[1] * ay + f->Ainv[2] * 1.0;
+    *y = f->Ainv[3] * ax + f->Ainv[4] * ay + f->Ainv[5] * 1.0;
+}
+
+/* Body._radec2obsvec_norm (body.py:964-970), degrees in */
+static void radec_deg2obsvec_norm(double ra_deg, double dec_deg, double d[3]) {
+    if (!(isfinite(ra_deg) && isfinite(dec_deg))) {
+        d[0] = d[1] = d[2] = kNaN;
+        return;
+    }
+    radrec(1.0, ra_deg * RPD, dec_deg * RPD, d);
+}
+
+/* Body._obsvec2km (body.py:1645-1650) */
+static void obsvec2km(const PMFrame *f, const double ov[3], double *kx, double *ky) {
+    double ax, ay;
+    obsvec2angular(f, ov, &ax, &ay);
+    *kx = f->ang2km[0] * ax + f->ang2km[1] * ay;
+    *ky = f->ang2km[2] * ax + f->ang2km[3] * ay;
+}
+
+/* Body._targvec2obsvec (body.py:917-948) */
+static void targvec2obsvec(const PMFrame *f, const double tv[3], double ov[3]) {
+    double off[3] = {tv[0] - f->sub_t[0], tv[1] - f->sub_t[1], tv[2] - f->sub_t[2]};
+    double w[3] = {f->sub_ray[0] + off[0], f->sub_ray[1] + off[1], f->sub_ray[2] + off[2]};
+    double dist_offset = norm3(w) - f->sub_dist;
+    double sub_et = f->t_ref + f->sub_dt;
+    double tt = sub_et - dist_offset / f->clight;
+    double q[3];
+    rot_from_body(f, tt - f->t_ref, off, q);
+    for (int k = 0; k < 3; k++) ov[k] = f->sub_obs[k] + q[k];
+}
+
+/* Body._obsvec2targvec (body.py:972-1006), including its frame-mixing norm */
+static void obsvec2targvec(const PMFrame *f, const double ov[3], double tv[3]) {
+    double off[3] = {ov[0] - f->sub_obs[0], ov[1] - f->sub_obs[1], ov[2] - f->sub_obs[2]};
+    double w[3] = {-f->sub_ray[0] + off[0], -f->sub_ray[1] + off[1], -f->sub_ray[2] + off[2]};
+    double dist_offset = norm3(w) - f->sub_dist;
+    double sub_et = f->t_ref + f->sub_dt;
+    double tt = sub_et - dist_offset / f->clight;
+    double q[3];
+    rot_to_body(f, tt - f->t_ref, off, q);
+    for (int k = 0; k < 3; k++) tv[k] = f->sub_t[k] + q[k];
+}
+
+/* Body._ring_coordinates_from_obsvec(only_visible=False) (body.py:2577-2615) */
+static void ring_coordinates(const PMFrame *f, const double ov[3], double *radius,
+                             double *lon_deg, double *dist) {
+    *radius = *lon_deg = *dist = kNaN;
+    if (!finite3(ov)) return;
+    /* spice.inrypl with vertex at the origin */
+    double nd = dot3(f->ring_n, ov);
+    if (nd == 0.0) return;
+    double s = f->ring_c / nd;
+    if (!(s > 0.0) || !isfinite(s)) return;
+    double X[3] = {s * ov[0], s * ov[1], s * ov[2]};
+    double tv[3], lon, lat, alt;
+    obsvec2targvec(f, X, tv);
+    recpgr(f, tv, &lon, &lat, &alt);
+    *radius = alt + f->r_eq;
+    *lon_deg = lon * DPR;
+    *dist = norm3(X);
+}
+
+/* Body._limb_coordinates_from_obsvec (body.py:2081-2110) */
+static void limb_coordinates(const PMFrame *f, const double ov[3], double *lon_deg,
+                             double *lat_deg, double *dist) {
+    *lon_deg = *lat_deg = *dist = kNaN;
+    if (!finite3(ov)) return;
+    /* spice.nplnpt(origin, ov, target centre) */
+    double n = norm3(ov);
+    if (!(n > 0.0)) return;
+    double u[3] = {ov[0] / n, ov[1] / n, ov[2] / n};
+    double t = dot3(f->P0, u);
+    double pn[3] = {t * u[0], t * u[1], t * u[2]};
+    double dv[3] = {f->P0[0] - pn[0], f->P0[1] - pn[1], f->P0[2] - pn[2]};
+    double near_dist = norm3(dv);
+    double tv[3];
+    obsvec2targvec(f, pn, tv);
+    /* spice.surfpt(origin, tv, a, b, c): radial surface point */
+    double a = f->radii[0], b = f->radii[1], c = f->radii[2];
+    double x[3] = {tv[0] / a, tv[1] / b, tv[2] / c};
+    double xn = norm3(x);
+    if (!(xn > 0.0)) return;
+    double sp[3] = {tv[0] / xn, tv[1] / xn, tv[2] / xn};
+    double lon, lat, alt;
+    recpgr(f, sp, &lon, &lat, &alt);
+    *lon_deg = lon * DPR;
+    *lat_deg = lat * DPR;
+    *dist = near_dist - norm3(sp);
+}
+
+/* ---------- per-pixel image direction ---------- */
+typedef struct { double v[PM_N_PLANES]; double margin; } PixelOut;
+
+static void pixel_backplanes(const PMFrame *f, double x, double y, uint64_t mask,
+                             PixelOut *o) {
+    for (int k = 0; k < PM_N_PLANES; k++) o->v[k] = kNaN;
+    o->margin = kNaN;
+    o->v[PM_PIXEL_X] = x; /* BodyXY.get_x_img / get_y_img (body_xy.py:3494-3531) */
+    o->v[PM_PIXEL_Y] = y;
+
+    /* BodyXY._get_radec_img (body_xy.py:3413-3418) */
+    double d[3], r, ra, dec;
+    xy2obsvec_norm(f, x, y, d);
+    recrad(d, &r, &ra, &dec);
+    double ra_deg = ra * DPR, dec_deg = dec * DPR;
+    o->v[PM_RA] = ra_deg;
+    o->v[PM_DEC] = dec_deg;
+
+    /* BodyXY._get_km_xy_img (body_xy.py:3547-3553), angular (:3611-3656) */
+    double d2[3];
+    radec_deg2obsvec_norm(ra_deg, dec_deg, d2);
+    if (mask & ((1ull << PM_KM_X) | (1ull << PM_KM_Y) | (1ull << PM_ANGULAR_X) |
+                (1ull << PM_ANGULAR_Y))) {
+        double kx, ky;
+        obsvec2km(f, d2, &kx, &ky);
+        o->v[PM_KM_X] = kx;
+        o->v[PM_KM_Y] = ky;
+        o->v[PM_ANGULAR_X] = kx / f->km_per_arcsec;
+        o->v[PM_ANGULAR_Y] = ky / f->km_per_arcsec;
+    }
+
+    /* BodyXY._get_targvec_img (body_xy.py:3197-3225) */
+    int on_disc = 0;
+    double p[3], lt = 0.0;
+    double dx = x - f->x0, dy = y - f->y0;
+    if (!(f->optimize_speed != 0.0 && (dx * dx + dy * dy) > f->r_cut2)) {
+        on_disc = sincpt(f, d, p, &lt, &o->margin);
+    }
+    const uint64_t surf_mask =
+        (1ull << PM_LON_GRAPHIC) | (1ull << PM_LAT_GRAPHIC) | (1ull << PM_LON_CENTRIC) |
+        (1ull << PM_LAT_CENTRIC) | (1ull << PM_PHASE) | (1ull << PM_INCIDENCE) |
+        (1ull << PM_EMISSION) | (1ull << PM_AZIMUTH) | (1ull << PM_LOCAL_SOLAR_TIME) |
+        (1ull << PM_DISTANCE) | (1ull << PM_RADIAL_VELOCITY) | (1ull << PM_DOPPLER) |
+        (1ull << PM_RING_RADIUS) | (1ull << PM_RING_LON_GRAPHIC) | (1ull << PM_RING_DISTANCE);
+    double distance = kNaN;
+    if (on_disc && (mask & surf_mask)) {
+        double lon, lat, alt;
+        recpgr(f, p, &lon, &lat, &alt); /* _get_lonlat_img (body_xy.py:3284-3288) */
+        o->v[PM_LON_GRAPHIC] = lon * DPR;
+        o->v[PM_LAT_GRAPHIC] = lat * DPR;
+        double rr, clon, clat;
+        reclat(p, &rr, &clon, &clat); /* _get_lonlat_centric_img (body_xy.py:3349) */
+        o->v[PM_LON_CENTRIC] = clon * DPR;
+        o->v[PM_LAT_CENTRIC] = clat * DPR;
+        PointState s;
+        point_state(f, p, lt, 1, &s);
+        /* _get_illumination_gie_img (body_xy.py:3661-3665) */
+        double g = s.phase * DPR, i = s.incdnc * DPR, e = s.emissn * DPR;
+        o->v[PM_PHASE] = g;
+        o->v[PM_INCIDENCE] = i;
+        o->v[PM_EMISSION] = e;
+        /* get_azimuth_angle_img (body_xy.py:3744-3762): deg -> rad -> formula -> deg */
+        o->v[PM_AZIMUTH] = azimuth_from_gie(g * RPD, i * RPD, e * RPD) * DPR;
+        o->v[PM_LOCAL_SOLAR_TIME] = local_solar_time(f, o->v[PM_LON_GRAPHIC]);
+        distance = s.lt * f->clight; /* get_distance_img (body_xy.py:3870-3880) */
+        o->v[PM_DISTANCE] = distance;
+        /* get_radial_velocity_img (body_xy.py:3898-3913), body.py:2847-2853 */
+        double rn = sqrt(s.pos[0] * s.pos[0] + s.pos[1] * s.pos[1] + s.pos[2] * s.pos[2]);
+        double rv = s.vel[0] * (s.pos[0] / rn) + s.vel[1] * (s.pos[1] / rn) +
+                    s.vel[2] * (s.pos[2] / rn);
+        o->v[PM_RADIAL_VELOCITY] = rv;
+        o->v[PM_DOPPLER] = doppler_factor(f, rv);
+    }
+    /* _get_limb_coordinate_imgs (body_xy.py:3967-3975); uses _get_obsvec_norm_img,
+     * i.e. the RA/Dec degree round trip (body_xy.py:3263-3272) */
+    if (mask & ((1ull << PM_LIMB_DISTANCE) | (1ull << PM_LIMB_LON_GRAPHIC) |
+                (1ull << PM_LIMB_LAT_GRAPHIC))) {
+        limb_coordinates(f, d2, &o->v[PM_LIMB_LON_GRAPHIC], &o->v[PM_LIMB_LAT_GRAPHIC],
+                         &o->v[PM_LIMB_DISTANCE]);
+    }
+    /* _get_ring_plane_coordinate_imgs (body_xy.py:4061-4085) */
+    if (mask & ((1ull << PM_RING_RADIUS) | (1ull << PM_RING_LON_GRAPHIC) |
+                (1ull << PM_RING_DISTANCE))) {
+        double rad, rl, rd;
+        ring_coordinates(f, d2, &rad, &rl, &rd);
+        if (rd > distance) { /* NaN distance compares False: off-disc keeps values */
+            rad = rl = rd = kNaN;
+        }
+        o->v[PM_RING_RADIUS] = rad;
+        o->v[PM_RING_LON_GRAPHIC] = rl;
+        o->v[PM_RING_DISTANCE] = rd;
+    }
+}
+
+static int popcount64(uint64_t m) {
+    int n = 0;
+    while (m) { n += (int)(m & 1ull); m >>= 1; }
+    return n;
+}
+
+int pmo_backplanes_img(const PMFrame *f, int nx, int ny, uint64_t mask, double *out,
+                       double *margin) {
+    if (!f || !out || nx <= 0 || ny <= 0) return PM_ERR_BAD_ARG;
+    mask &= PM_ALL_PLANES;
+    const long npx = (long)nx * ny;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < npx; i++) {
+        int y = (int)(i / nx), x = (int)(i % nx);
+        PixelOut o;
+        pixel_backplanes(f, (double)x, (double)y, mask, &o);
+        int slot = 0;
+        for (int k = 0; k < PM_N_PLANES; k++) {
+            if (mask & (1ull << k)) {
+                out[(long)slot * npx + i] = o.v[k];
+                slot++;
+            }
+        }
+        if (margin) margin[i] = o.margin;
+    }
+    (void)popcount64;
+    return PM_OK;
+}
+
+/* ---------- map direction ---------- */
+static void cell_backplanes(const PMFrame *f, double lon_deg, double lat_deg,
+                            uint64_t mask, PixelOut *o) {
+    for (int k = 0; k < PM_N_PLANES; k++) o->v[k] = kNaN;
+    o->margin = kNaN;
+    /* BodyXY._get_lonlat_map (body_xy.py:3293-3300): lons % 360, non-finite -> NaN */
+    double lonm = isfinite(lon_deg) ? pymod(lon_deg, 360.0) : kNaN;
+    double latm = isfinite(lat_deg) ? lat_deg : kNaN;
+    o->v[PM_LON_GRAPHIC] = lonm;
+    o->v[PM_LAT_GRAPHIC] = latm;
+    /* _get_targvec_map (body_xy.py:3230-3238): skipped when lon is NaN; a NaN lat
+     * gives a NaN targvec through lonlat2targvec (body.py:901-902) */
+    if (isnan(lonm)) return;
+    /* get_local_solar_time_map (body_xy.py:3812-3828) */
+    o->v[PM_LOCAL_SOLAR_TIME] = local_solar_time(f, lonm);
+    if (!isfinite(latm)) return;
+    double tv[3];
+    pgrrec(f, lonm * RPD, latm * RPD, 0.0, tv);
+    if (isnan(tv[0])) return;
+    double rr, clon, clat;
+    reclat(tv, &rr, &clon, &clat); /* _get_lonlat_centric_map (body_xy.py:3357-3364) */
+    o->v[PM_LON_CENTRIC] = clon * DPR;
+    o->v[PM_LAT_CENTRIC] = clat * DPR;
+    PointState s;
+    point_state(f, tv, f->lt0, 1, &s);
+    o->margin = s.emissn - HALFPI;
+    /* _get_illumf_map (body_xy.py:3671-3675) */
+    double g = s.phase * DPR, i = s.incdnc * DPR, e = s.emissn * DPR;
+    o->v[PM_PHASE] = g;
+    o->v[PM_INCIDENCE] = i;
+    o->v[PM_EMISSION] = e;
+    o->v[PM_AZIMUTH] = azimuth_from_gie(g * RPD, i * RPD, e * RPD) * DPR;
+    double distance = s.lt * f->clight; /* get_distance_map (body_xy.py:3883-3893) */
+    o->v[PM_DISTANCE] = distance;
+    double rn = sqrt(s.pos[0] * s.pos[0] + s.pos[1] * s.pos[1] + s.pos[2] * s.pos[2]);
+    double rv = s.vel[0] * (s.pos[0] / rn) + s.vel[1] * (s.pos[1] / rn) +
+                s.vel[2] * (s.pos[2] / rn);
+    o->v[PM_RADIAL_VELOCITY] = rv; /* get_radial_velocity_map (body_xy.py:3917-3936) */
+    o->v[PM_DOPPLER] = doppler_factor(f, rv);
+
+    double ov[3];
+    targvec2obsvec(f, tv, ov); /* _get_obsvec_map (body_xy.py:3275-3280) */
+    if (s.visibl) {
+        /* _get_radec_map (body_xy.py:3423-3432) */
+        double r, ra, dec;
+        recrad(ov, &r, &ra, &dec);
+        double ra_deg = ra * DPR, dec_deg = dec * DPR;
+        o->v[PM_RA] = ra_deg;
+        o->v[PM_DEC] = dec_deg;
+        double d2[3];
+        radec_deg2obsvec_norm(ra_deg, dec_deg, d2);
+        /* _get_xy_map (body_xy.py:3482-3491) */
+        double x, y;
+        obsvec2xy(f, d2, &x, &y);
+        if ((-0.5 < x && x < f->nx - 0.5) && (-0.5 < y && y < f->ny - 0.5)) {
+            o->v[PM_PIXEL_X] = x;
+            o->v[PM_PIXEL_Y] = y;
+        }
+        /* _get_km_xy_map (body_xy.py:3557-3565) */
+        double kx, ky;
+        obsvec2km(f, d2, &kx, &ky);
+        o->v[PM_KM_X] = kx;
+        o->v[PM_KM_Y] = ky;
+        o->v[PM_ANGULAR_X] = kx / f->km_per_arcsec;
+        o->v[PM_ANGULAR_Y] = ky / f->km_per_arcsec;
+    }
+    /* the reference tests `lit` (illumf index 4) here, not `visibl`
+     * (body_xy.py:3981-3986, :4097-4106); reproduced as is */
+    if (s.lit) {
+        if (mask & ((1ull << PM_LIMB_DISTANCE) | (1ull << PM_LIMB_LON_GRAPHIC) |
+                    (1ull << PM_LIMB_LAT_GRAPHIC))) {
+            limb_coordinates(f, ov, &o->v[PM_LIMB_LON_GRAPHIC],
+                             &o->v[PM_LIMB_LAT_GRAPHIC], &o->v[PM_LIMB_DISTANCE]);
+        }
+        if (mask & ((1ull << PM_RING_RADIUS) | (1ull << PM_RING_LON_GRAPHIC) |
+                    (1ull << PM_RING_DISTANCE))) {
+            double rad, rl, rd;
+            ring_coordinates(f, ov, &rad, &rl, &rd);
+            if (rd > distance) rad = rl = rd = kNaN;
+            o->v[PM_RING_RADIUS] = rad;
+            o->v[PM_RING_LON_GRAPHIC] = rl;
+            o->v[PM_RING_DISTANCE] = rd;
+        }
+    }
+}
+
+int pmo_backplanes_map(const PMFrame *f, const double *lon, const double *lat,
+                       int64_t n, uint64_t mask, double *out, double *margin) {
+    if (!f || !out || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    mask &= PM_ALL_PLANES;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        PixelOut o;
+        cell_backplanes(f, lon[i], lat[i], mask, &o);
+        int slot = 0;
+        for (int k = 0; k < PM_N_PLANES; k++) {
+            if (mask & (1ull << k)) {
+                out[(int64_t)slot * n + i] = o.v[k];
+                slot++;
+            }
+        }
+        if (margin) margin[i] = o.margin;
+    }
+    return PM_OK;
+}
+
+/* BodyXY._xy2lonlat (body_xy.py:482-496) -> Body._obsvec_norm2lonlat
+ * (body.py:1058-1081), planetographic degrees; miss -> NaN and counted */
+int pmo_xy2lonlat(const PMFrame *f, const double *x, const double *y, int64_t n,
+                  double *lon, double *lat, int64_t *n_missed) {
+    if (!f || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    int64_t missed = 0;
+#pragma omp parallel for reduction(+ : missed)
+    for (int64_t i = 0; i < n; i++) {
+        double d[3], p[3], lt;
+        lon[i] = lat[i] = kNaN;
+        if (!(isfinite(x[i]) && isfinite(y[i]))) continue;
+        xy2obsvec_norm(f, x[i], y[i], d);
+        if (!sincpt(f, d, p, &lt, NULL)) {
+            missed++;
+            continue;
+        }
+        double lo, la, al;
+        recpgr(f, p, &lo, &la, &al);
+        lon[i] = lo * DPR;
+        lat[i] = la * DPR;
+    }
+    if (n_missed) *n_missed = missed;
+    return PM_OK;
+}
+
+/* BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056)
+ * with alt == 0 visibility through illumf.visibl (body.py:2124-2130) */
+int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_t n,
+                  uint32_t flags, double *x, double *y) {
+    if (!f || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; i++) {
+        x[i] = y[i] = kNaN;
+        if (!(isfinite(lon[i]) && isfinite(lat[i]))) continue;
+        double tv[3];
+        pgrrec(f, lon[i] * RPD, lat[i] * RPD, 0.0, tv);
+        if (flags & PM_FLAG_NOT_VISIBLE_NAN) {
+            PointState s;
+            point_state(f, tv, f->lt0, 1, &s);
+            if (!s.visibl) continue;
+        }
+        double ov[3];
+        targvec2obsvec(f, tv, ov);
+        obsvec2xy(f, ov, &x[i], &y[i]);
+    }
+    return PM_OK;
+}
+
+/* ---------- projections: PROJ inverse for the three named projections
+ * (body_xy.py:2899-2969, :3105-3127).  PROJ works in metres on an ellipsoid with
+ * semi-axes a, b; the reference passes +to_meter so that grid units are body radii
+ * etc.  +axis=wnu flips the sign of the projected x for west-positive bodies. ---------- */
+static void proj_inverse_one(int kind, double a, double b, double lon0_deg,
+                             double lat0_deg, double lon_sign, double xx, double yy,
+                             double *lon_out, double *lat_out) {
+    *lon_out = *lat_out = kNaN;
+    if (!(isfinite(xx) && isfinite(yy))) return;
+    double phi0 = lat0_deg * RPD;
+    /* lon_0 is a planetographic longitude; PROJ's internal lambda is the axis-wnu
+     * swapped easting, so work in "projection east" = lon_sign-free coordinates:
+     * x_internal = lon_sign_axis * x where axis w => -1 */
+    double x = (lon_sign < 0.0 ? -xx : xx);
+    double y = yy;
+    double lam, phi;
+    if (kind == PM_PROJ_ORTHOGRAPHIC) {
+        /* +proj=ortho +a +b +to_meter=a +y_0=a(b/a-1)sin(2 lat0): ellipsoidal
+         * orthographic (PROJ >= 7.2, EPSG method 9840) */
+        double to_meter = a;
+        double y0 = a * (b / a - 1.0) * sin(2.0 * lat0_deg * RPD);
+        double xm = x * to_meter, ym = y * to_meter - y0;
+        double es = 1.0 - (b * b) / (a * a);
+        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
+        if (es == 0.0) {
+            double xs = xm / a, ys = ym / a;
+            double rh = hypot(xs, ys), sinc = rh;
+            if (sinc > 1.0) {
+                if (sinc - 1.0 > 1e-10) return;
+                sinc = 1.0;
+            }
+            double cosc = sqrt(1.0 - sinc * sinc);
+            if (fabs(rh) <= 1e-10) {
+                phi = phi0;
+                lam = 0.0;
+            } else {
+                phi = cosc * sinphi0 + ys * sinc * cosphi0 / rh;
+                double yy2 = (cosc - sinphi0 * phi) * rh;
+                double xx2 = xs * sinc * cosphi0;
+                phi = (fabs(phi) >= 1.0) ? (phi < 0.0 ? -HALFPI : HALFPI) : asin(phi);
+                lam = (yy2 == 0.0 && xx2 == 0.0) ? 0.0 : atan2(xx2, yy2);
+            }
+        } else {
+            /* PROJ ortho_e_inverse: work in units of a */
+            double xs = xm / a, ys = ym / a;
+            double nu0 = 1.0 / sqrt(1.0 - es * sinphi0 * sinphi0);
+            double y_shift = es * nu0 * sinphi0 * cosphi0; /* PROJ's y_shift */
+            if (fabs(cosphi0) < 1e-10) {
+                /* polar */
+                double rh2 = xs * xs + ys * ys;
+                if (rh2 >= 1.0 - 1e-15) {
+                    if (rh2 - 1.0 > 1e-10) return;
+                    phi = 0.0;
+                } else {
+                    phi = acos(sqrt(rh2 * (1.0 - es) / (1.0 - es * rh2))) *
+                          (phi0 > 0.0 ? 1.0 : -1.0);
+                }
+                lam = atan2(xs, ys * (phi0 > 0.0 ? -1.0 : 1.0));
+            } else if (fabs(phi0) < 1e-10) {
+                /* equatorial */
+                double one_es = 1.0 - es;
+                double t = ys * ys / one_es + xs * xs;
+                if (t > 1.0 + 1e-11) return;
+                double sp = ys * sqrt(1.0 - es * (1.0 - xs * xs)) / one_es; /* approx */
+                /* exact: y = (1-es) nu sin(phi), x = nu cos(phi) sin(lam) */
+                /* solve (1-es) sin(phi)/sqrt(1-es sin^2 phi) = ys */
+                double s2 = ys * ys / (one_es * one_es + es * ys * ys);
+                (void)sp;
+                double sphi = (ys < 0.0 ? -1.0 : 1.0) * sqrt(s2);
+                if (fabs(sphi) > 1.0) return;
+                phi = asin(sphi);
+                double nu = 1.0 / sqrt(1.0 - es * sphi * sphi);
+                double sl = xs / (nu * cos(phi));
+                if (fabs(sl) > 1.0) {
+                    if (fabs(sl) - 1.0 > 1e-10) return;
+                    sl = sl < 0.0 ? -1.0 : 1.0;
+                }
+                lam = asin(sl);
+            } else {
+                /* oblique: PROJ checks the point lies inside the projected ellipse of
+                 * the limb, starts from the spherical inverse and runs Newton on
+                 * (x, y) = F(phi, lam) */
+                double yr = ys + y_shift; /* PROJ: xy.y recentred */
+                {
+                    /* limb ellipse test (PROJ ortho_e_inverse):
+                     * x^2 + (y_recentered / sqrt(1 - es cos^2 phi0))^2 <= 1 */
+                    double sc = sqrt(1.0 - es * cosphi0 * cosphi0);
+                    double yt = ys / sc;
+                    (void)yr;
+                    /* PROJ recentres with y_shift/scale: */
+                    double ysr = (ys - 0.0) / sc;
+                    (void)ysr;
+                    double yc = (ys + y_shift - y_shift) / sc;
+                    (void)yc;
+                    (void)yt;
+                }
+                /* initial guess: spherical inverse */
+                double rh = hypot(xs, ys), sinc = rh > 1.0 ? 1.0 : rh;
+                double cosc = sqrt(1.0 - sinc * sinc);
+                if (rh <= 1e-10) {
+                    phi = phi0;
+                    lam = 0.0;
+                } else {
+                    double sp = cosc * sinphi0 + ys * sinc * cosphi0 / rh;
+                    double yy2 = (cosc - sinphi0 * sp) * rh;
+                    double xx2 = xs * sinc * cosphi0;
+                    sp = fmax(-1.0, fmin(1.0, sp));
+                    phi = asin(sp);
+                    lam = atan2(xx2, yy2);
+                }
+                int ok = 0;
+                for (int it = 0; it < 20; it++) {
+                    double cp = cos(phi), sphi = sin(phi), cl = cos(lam), sl = sin(lam);
+                    double w = 1.0 - es * sphi * sphi;
+                    double nu = 1.0 / sqrt(w);
+                    /* forward (EPSG 9840), units of a, relative to the false origin */
+                    double fx = nu * cp * sl;
+                    double fy = nu * (sphi * cosphi0 - cp * sinphi0 * cl) +
+                                es * (nu0 * sinphi0 - nu * sphi) * cosphi0;
+                    double rho = (1.0 - es) * nu / w;
+                    double J11 = -rho * sphi * sl;
+                    double J12 = nu * cp * cl;
+                    double J21 = rho * (cp * cosphi0 + sphi * sinphi0 * cl);
+                    double J22 = nu * sinphi0 * cp * sl;
+                    double D = J11 * J22 - J12 * J21;
+                    double dxr = fx - xs, dyr = fy - ys;
+                    double dphi = (J12 * dyr - J22 * dxr) / D;
+                    double dlam = (-J11 * dyr + J21 * dxr) / D;
+                    phi += dphi;
+                    lam += dlam;
+                    if (phi > HALFPI) phi = HALFPI - (phi - HALFPI);
+                    if (phi < -HALFPI) phi = -HALFPI + (-HALFPI - phi);
+                    if (fabs(dphi) < 1e-12 && fabs(dlam) < 1e-12) {
+                        ok = 1;
+                        break;
+                    }
+                }
+                if (!ok) return;
+                /* reject the far side and points outside the limb */
+                {
+                    double cp = cos(phi), sphi = sin(phi);
+                    double cosc2 = sinphi0 * sphi + cosphi0 * cp * cos(lam);
+                    double w = 1.0 - es * sphi * sphi;
+                    double nu = 1.0 / sqrt(w);
+                    double fx = nu * cp * sin(lam);
+                    double fy = nu * (sphi * cosphi0 - cp * sinphi0 * cos(lam)) +
+                                es * (nu0 * sinphi0 - nu * sphi) * cosphi0;
+                    if (cosc2 < -1e-10) return;
+                    if (fabs(fx - xs) > 1e-9 || fabs(fy - ys) > 1e-9) return;
+                }
+            }
+        }
+    } else if (kind == PM_PROJ_AZIMUTHAL) {
+        /* +proj=aeqd on a sphere of radius a, +to_meter = a*pi: spherical aeqd inverse */
+        double xs = x * PI, ys = y * PI; /* units of the sphere radius */
+        double c_rh = hypot(xs, ys);
+        if (c_rh > PI) {
+            if (c_rh - 1e-10 > PI) return;
+            c_rh = PI;
+        } else if (c_rh < 1e-10) {
+            *lon_out = pymod(lon0_deg, 360.0);
+            *lat_out = lat0_deg;
+            return;
+        }
+        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
+        if (fabs(fabs(phi0) - HALFPI) < 1e-10) { /* polar */
+            if (phi0 > 0.0) {
+                phi = HALFPI - c_rh;
+                lam = atan2(xs, -ys);
+            } else {
+                phi = c_rh - HALFPI;
+                lam = atan2(xs, ys);
+            }
+        } else {
+            double sinc = sin(c_rh), cosc = cos(c_rh);
+            if (fabs(phi0) < 1e-10) { /* equatorial */
+                double sp = ys * sinc / c_rh;
+                sp = fmax(-1.0, fmin(1.0, sp));
+                phi = asin(sp);
+                double xn = xs * sinc, yn = cosc * c_rh;
+                lam = (yn == 0.0) ? 0.0 : atan2(xn, yn);
+            } else {
+                double sp = cosc * sinphi0 + ys * sinc * cosphi0 / c_rh;
+                sp = fmax(-1.0, fmin(1.0, sp));
+                phi = asin(sp);
+                double yn = (cosc - sinphi0 * sin(phi)) * c_rh;
+                double xn = xs * sinc * cosphi0;
+                lam = (yn == 0.0) ? 0.0 : atan2(xn, yn);
+            }
+        }
+    } else if (kind == PM_PROJ_AZIMUTHAL_EQUAL_AREA) {
+        /* +proj=laea on a sphere of radius a, +to_meter = 2a: spherical laea inverse */
+        double xs = x * 2.0, ys = y * 2.0;
+        double rh = hypot(xs, ys);
+        double half = rh * 0.5;
+        if (half > 1.0) return;
+        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
+        double c2 = 2.0 * asin(half);
+        double sinz = sin(c2), cosz = cos(c2);
+        double xn = xs, yn;
+        if (fabs(fabs(phi0) - HALFPI) < 1e-10) { /* polar */
+            if (phi0 > 0.0) {
+                yn = -ys;
+                phi = HALFPI - c2;
+            } else {
+                yn = ys;
+                phi = c2 - HALFPI;
+            }
+            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
+        } else if (fabs(phi0) < 1e-10) { /* equatorial */
+            phi = (fabs(rh) <= 1e-10) ? 0.0 : asin(ys * sinz / rh);
+            xn = xs * sinz;
+            yn = cosz * rh;
+            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
+        } else {
+            double ab = cosz * sinphi0 + ((fabs(rh) <= 1e-10) ? 0.0 : ys * sinz * cosphi0 / rh);
+            phi = (fabs(rh) <= 1e-10) ? phi0 : asin(ab);
+            xn = xs * sinz * cosphi0;
+            yn = (cosz - sin(phi) * sinphi0) * rh;
+            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
+        }
+    } else {
+        return;
+    }
+    /* PROJ internal easting -> planetographic longitude (+axis) and wrap like
+     * pyproj's degree output: lon in [-180, 180] about lon_0 */
+    double lon = lam * DPR;
+    lon = (lon_sign < 0.0 ? -lon : lon) + lon0_deg;
+    /* pyproj returns longitudes normalised to [-180, 180] */
+    while (lon > 180.0) lon -= 360.0;
+    while (lon < -180.0) lon += 360.0;
+    *lon_out = lon;
+    *lat_out = phi * DPR;
+}
+
+int pmo_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
+                     int64_t n, double *lon, double *lat) {
+    if (!params5 || !xx || !yy || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (kind < PM_PROJ_ORTHOGRAPHIC || kind > PM_PROJ_AZIMUTHAL_EQUAL_AREA)
+        return PM_ERR_UNSUPPORTED;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; i++) {
+        proj_inverse_one(kind, params5[0], params5[1], params5[2], params5[3], params5[4],
+                         xx[i], yy[i], &lon[i], &lat[i]);
+    }
+    return PM_OK;
+}
+
+/* ---------- gather ---------- */
+/* BodyXY._do_nearest_interpolation (body_xy.py:1633-1649) over a cube
+ * (Observation._get_mapped_data, observation.py:892-905) */
+int pmo_gather_nearest(const double *cube, int n_planes, int ny, int nx,
+                       const double *xmap, const double *ymap, int64_t n_cells,
+                       double *out) {
+    if (!cube || !xmap || !ymap || !out) return PM_ERR_BAD_ARG;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n_cells; i++) {
+        double x = xmap[i], y = ymap[i];
+        long xi = -999, yi = -999;
+        if (!isnan(x)) xi = (long)nearbyint(x);
+        if (!isnan(y)) yi = (long)nearbyint(y);
+        for (int l = 0; l < n_planes; l++) {
+            double v = kNaN;
+            if (xi != -999) {
+                /* numpy negative indices wrap; cannot occur for x_map/y_map built by
+                 * _get_xy_map, handled for manual maps */
+                long xx = xi < 0 ? xi + nx : xi, yy2 = yi < 0 ? yi + ny : yi;
+                if (xx >= 0 && xx < nx && yy2 >= 0 && yy2 < ny)
+                    v = cube[((int64_t)l * ny + yy2) * nx + xx];
+            }
+            out[(int64_t)l * n_cells + i] = v;
+        }
+    }
+    return PM_OK;
+}
