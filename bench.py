@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""
+bench.py - headline benchmark of the B200-native PlanetMapper hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+Metric (BASELINE.json): full-backplane Mpix/s (FP64) + mapped-cube voxels/s.
+Workload at every N (weak scaling, no data-path collective): each rank computes the
+12-plane default backplane stack of one Jupiter/HST 2048 x 2048 frame per step
+(BASELINE.json configs[1], "C2").  `value` is the whole-job Mpix/s with the frame
+constants resident in HBM; `e2e` is the same metric through the public BodyXY API with
+host buffers (constants H2D + 403 MB of planes D2H per step inside the timed region).
+`mapped_cube` reports configs[3] ("C4": 3000 x 64 x 64 cube -> 0.1 deg grid, 6.48 M
+cells, nearest / linear / cubic) in voxels/s, device-resident and chunked over
+wavelength planes because the 155.5 GB output does not fit next to its own copy.
+
+The reference (pure Python + spiceypy) cannot be installed here or on the GPU box
+(no spiceypy / CSPICE wheels, no network), so `--impl reference` and `cpu_baseline`
+time the CPU restatement in oracle/ (kind "port") on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_NAMES = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'INCIDENCE', 'EMISSION', 'PHASE',
+            'AZIMUTH', 'LOCAL-SOLAR-TIME', 'DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER']
+METRIC = 'full-backplane Mpix/s (FP64) + mapped-cube voxels/s at 1-8 B200 vs host CPU'
+SZ = 2048
+CPU_SAMPLE_SZ = 512
+
+
+def load_bc():
+    from planetmapper_b200 import frame as F
+
+    with open(os.path.join(ROOT, 'tests', 'golden', 'jupiter_hst_2005.json')) as f:
+        return F.BodyConstants.from_json_dict(json.load(f))
+
+
+def c2_frame(bc, sz=SZ):
+    from planetmapper_b200 import frame as F
+
+    c = (sz - 1) / 2
+    return F.pack_frame(bc, nx=sz, ny=sz, x0=c, y0=c, r0=0.9 * c, rotation_radians=0.0)
+
+
+def plane_mask(names):
+    from planetmapper_b200 import _lib as L
+
+    return L.mask_from_names(names)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+def algorithmic_flops_per_frame(planes_host, frame):
+    """Algorithmic FLOPs of one C2 launch = per-class weighted flop counts of the
+    instrumented oracle (profiles/flops_per_pixel.json, tools/count_flops.cpp) x the
+    number of pixels of each class in this frame."""
+    from planetmapper_b200 import frame as F
+
+    path = os.path.join(ROOT, 'profiles', 'flops_per_pixel.json')
+    with open(path) as f:
+        fpp = json.load(f)
+    nx, ny = int(F.frame_field(frame, 'nx')[0]), int(F.frame_field(frame, 'ny')[0])
+    x0, y0 = F.frame_field(frame, 'x0')[0], F.frame_field(frame, 'y0')[0]
+    r_cut2 = F.frame_field(frame, 'r_cut2')[0]
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    in_circle = ((xx - x0) ** 2 + (yy - y0) ** 2) <= r_cut2
+    on_disc = np.isfinite(planes_host)
+    n_on = int(on_disc.sum())
+    n_miss = int((in_circle & ~on_disc).sum())
+    n_out = int((~in_circle).sum())
+    c = fpp['c2_12plane']
+    flops = n_on * c['on_disc'] + n_miss * c['in_circle_miss'] + n_out * c['outside_circle']
+    return flops, {'on_disc_px': n_on, 'in_circle_miss_px': n_miss, 'outside_px': n_out,
+                   'flops_per_px': c, 'weights': fpp['weights']}
+
+
+def ncu_traffic(key):
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(key)
+    return None
+
+
+def cpu_port_mpix(sz, threads=None, repeats=1):
+    """Times the CPU oracle (C port of the reference path) on a sz x sz C2-like frame."""
+    from oracle import oracle as O
+
+    O.build()
+    bc = load_bc()
+    fr = c2_frame(bc, sz)
+    mask = plane_mask(C2_NAMES)
+    O.backplanes_img(fr, 32, 32, mask)  # load + warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.backplanes_img(fr, sz, sz, mask)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sz * sz / best / 1e6, best
+
+
+def omp_threads():
+    n = os.environ.get('OMP_NUM_THREADS')
+    return int(n) if n else (os.cpu_count() or 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+
+    O.build()
+    bc = load_bc()
+    fr = c2_frame(bc, CPU_SAMPLE_SZ)
+    mask = plane_mask(C2_NAMES)
+    for _ in range(max(args.warmup, 1)):
+        O.backplanes_img(fr, CPU_SAMPLE_SZ, CPU_SAMPLE_SZ, mask)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.backplanes_img(fr, CPU_SAMPLE_SZ, CPU_SAMPLE_SZ, mask)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = CPU_SAMPLE_SZ * CPU_SAMPLE_SZ / dt / 1e6
+    sample = (f'{CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ} frame per step (1/16 of the C2 pixels, same disc fraction), '
+              f'12-plane stack, OpenMP over pixels')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: Jupiter/HST 2005-01-01 2048x2048, 12-plane default backplane stack',
+                   'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
+                         'sample': sample,
+                         'note': 'reference (Python + spiceypy/CSPICE) is not installable here; this is the '
+                                 'C restatement in oracle/, far faster than the reference itself'},
+        'e2e': {'value': value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def bench_mapped_cube(L, torch, bc, rank, world):
+    """C4: 3000 x 64 x 64 cube -> 0.1 deg rectangular grid, device resident, chunked."""
+    from planetmapper_b200 import frame as F
+
+    sz, nl_total, chunk = 64, 3000, 250
+    fr = F.pack_frame(bc, nx=sz, ny=sz, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
+    lons = np.arange(0.05, 360, 0.1)[::-1]
+    lats = np.arange(-90 + 0.05, 90, 0.1)
+    lo, la = np.meshgrid(lons, lats)
+    fd = L.to_device(fr)
+    lod, lad = L.to_device(lo), L.to_device(la)
+    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+    xy = L.backplanes_map(fd, lod, lad, xy_mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    xy = L.backplanes_map(fd, lod, lad, xy_mask)
+    e1.record()
+    torch.cuda.synchronize()
+    xy_ms = e0.elapsed_time(e1)
+    rng = np.random.default_rng(0)
+    cube_h = rng.normal(1.0, 0.1, (nl_total, sz, sz))
+    bad = rng.random((nl_total, sz, sz)) < 0.01
+    cube_h[bad] = np.nan
+    cube_h[17] = np.nan
+    cube = L.to_device(cube_h)
+    n_cells = lo.size
+    out = torch.empty((chunk,) + lo.shape, dtype=torch.float64, device='cuda')
+    res = {'workload': 'C4: 3000x64x64 cube (1% NaN px, one all-NaN plane) -> 0.1 deg grid '
+                       f'({lo.shape[1]}x{lo.shape[0]} = {n_cells} cells), chunks of {chunk} planes into a reused '
+                       'device buffer (full output 155.5 GB)',
+           'xy_map_ms': xy_ms, 'unit': 'voxels/s', 'visible_cell_fraction': float(torch.isfinite(xy[0]).double().mean())}
+    peaks, src = measured_peaks()
+    for mode, name in ((L.INTERP_NEAREST, 'nearest'), (L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
+        def one_pass(timed):
+            prep_ms = 0.0
+            if mode == L.INTERP_NEAREST:
+                coef, nanmask, flags = cube, None, None
+            else:
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                coef, nanmask, flags = L.spline_prepare(cube, mode)
+                p1.record()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for s in range(0, nl_total, chunk):
+                L.gather(coef[s:s + chunk], xy[0], xy[1], mode,
+                         nanmask=None if nanmask is None else nanmask[s:s + chunk],
+                         plane_flags=None if flags is None else flags[s:s + chunk], out=out)
+            g1.record()
+            torch.cuda.synchronize()
+            if mode != L.INTERP_NEAREST:
+                prep_ms = p0.elapsed_time(p1)
+            return g0.elapsed_time(g1), prep_ms
+        one_pass(False)
+        gather_ms, prep_ms = one_pass(True)
+        vox = nl_total * n_cells
+        total_ms = gather_ms + prep_ms
+        alg_bytes = 8.0 * vox + 8.0 * cube.numel() + 16.0 * n_cells * (nl_total // chunk)
+        res[name] = {
+            'voxels_per_s': vox / (total_ms * 1e-3), 'gather_ms': gather_ms, 'prepare_ms': prep_ms,
+            'roofline': {'bound': 'hbm', 'achieved': alg_bytes / (gather_ms * 1e-3) / 1e9,
+                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 'peak_source': src,
+                         'traffic': ncu_traffic(f'gather_{name}'),
+                         'algorithmic_bytes_per_voxel': alg_bytes / vox},
+        }
+    del out
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--skip-cube', action='store_true', help='skip the mapped-cube (C4) section')
+    ap.add_argument('--skip-cpu', action='store_true', help='skip the bounded CPU baseline')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+
+    import planetmapper_b200 as pm
+    from planetmapper_b200 import _lib as L
+    from planetmapper_b200.shard import env_rank_world, max_over_ranks
+
+    rank, local_rank, world = env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L.load_library()
+    bc = load_bc()
+    fr = c2_frame(bc)
+    mask = plane_mask(C2_NAMES)
+    k = len(C2_NAMES)
+    fd = L.to_device(fr[None])
+    out = torch.empty((1, k, SZ, SZ), dtype=torch.float64, device='cuda')
+
+    # ---- kernel path, inputs resident in HBM ---------------------------------------
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        L.backplanes_img(fd, SZ, SZ, mask, out=out)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        L.backplanes_img(fd, SZ, SZ, mask, out=out)
+    e1.record()
+    barrier()
+    launches = L.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    ms = max_over_ranks(ms, world, device='cuda')
+    value = world * SZ * SZ / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API, host buffers ---------------------------
+    pinned = torch.empty((k, SZ, SZ), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        body = pm.BodyXY(constants=bc, nx=SZ, ny=SZ)      # fresh object: empty caches
+        planes = body.get_backplane_imgs(C2_NAMES, out=pinned)
+        return float(planes['EMISSION'][SZ // 2, SZ // 2])
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    e2e_ms = max_over_ranks(e2e_ms, world, device='cuda')
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * SZ * SZ / (e2e_ms * 1e-3) / 1e6
+
+    result = None
+    if rank == 0:
+        planes_host = out[0, C2_NAMES.index('EMISSION') if False else 0].cpu().numpy()
+        # plane 0 of the packed output is LON-GRAPHIC (lowest id); its NaN mask = on-disc mask
+        flops, classes = algorithmic_flops_per_frame(planes_host, fr)
+        fp64_peak = L.fp64_peak_probe()
+        achieved = flops / (ms * 1e-3) / 1e12
+        result = {
+            'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'C2: Jupiter/HST 2005-01-01T00:00:00 2048x2048 frame per GPU per step, 12-plane '
+                                   'default backplane stack (' + ', '.join(C2_NAMES) + '), disc centred, r0 = 0.9 (n-1)/2',
+                       'l2': 'each step writes 403 MB of planes (> 126 MB L2); no flush needed',
+                       'frames_per_step_per_gpu': 1, 'parallelism': f'frames sharded, {world} rank(s), no collective'},
+            'gpu_launches': int(launches),
+            'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': int(fr.nbytes), 'd2h_bytes_per_step': int(k * SZ * SZ * 8),
+                    'api': 'BodyXY(constants=...).get_backplane_imgs(12 names, out=pinned)', 'steps': e2e_steps},
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                         'frac': achieved / fp64_peak, 'traffic': ncu_traffic('backplanes_img_c2'),
+                         'peak_source': 'pm_fp64_peak_probe: 8 independent DFMA chains/thread, full grid, measured '
+                                        'in this run (MEASURED_PEAKS.json has no FP64 entry)',
+                         'algorithmic_flops_per_launch': flops, 'pixel_classes': classes,
+                         'hbm_bytes_per_launch_algorithmic': int(k * SZ * SZ * 8)},
+            'clocks': clocks,
+        }
+    if not args.skip_cube:
+        cube_res = bench_mapped_cube(L, torch, bc, rank, world)
+        if world > 1:
+            for name in ('nearest', 'linear', 'cubic'):
+                t = cube_res[name]['gather_ms'] + cube_res[name]['prepare_ms']
+                t = max_over_ranks(t, world, device='cuda')
+                cube_res[name]['voxels_per_s'] = world * 3000 * 6480000 / (t * 1e-3)
+        if rank == 0:
+            result['mapped_cube'] = cube_res
+    if rank == 0:
+        if not args.skip_cpu:
+            mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ)
+            result['cpu_baseline'] = {
+                'value': mp, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
+                'sample': f'{CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ} C2-like frame, one pass ({dt:.2f} s), OpenMP over pixels',
+                'note': 'C restatement in oracle/ (the Python+spiceypy reference is not installable here)'}
+        print(json.dumps(result))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

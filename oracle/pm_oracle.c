@@ -45,12 +45,10 @@ static inline void cross3(const double a[3], const double b[3], double o[3]) {
     o[1] = a[2] * b[0] - a[0] * b[2];
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
-/* CSPICE vnorm: scaled to avoid overflow */
+/* spice.vnorm.  CSPICE pre-scales by the largest component as an overflow guard; the
+ * magnitudes on this path (<= 1e10 km) cannot overflow, so the plain form is used. */
 static inline double norm3(const double a[3]) {
-    double m = fmax(fabs(a[0]), fmax(fabs(a[1]), fabs(a[2])));
-    if (m == 0.0) return 0.0;
-    double x = a[0] / m, y = a[1] / m, z = a[2] / m;
-    return m * sqrt(x * x + y * y + z * z);
+    return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
 }
 static inline void mxv(const double m[9], const double v[3], double o[3]) {
     o[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
@@ -83,7 +81,8 @@ static void recrad(const double v[3], double *range, double *ra, double *dec) {
         *dec = (big == 0.0) ? 0.0 : kNaN;
         return;
     }
-    double x = v[0] / big, y = v[1] / big, z = v[2] / big;
+    double ib = 1.0 / big;
+    double x = v[0] * ib, y = v[1] * ib, z = v[2] * ib;
     *range = big * sqrt(x * x + y * y + z * z);
     *dec = atan2(z, sqrt(x * x + y * y));
     double lon = (x == 0.0 && y == 0.0) ? 0.0 : atan2(y, x);
@@ -102,8 +101,9 @@ static void radrec(double r, double ra, double dec, double o[3]) {
 static double vsep(const double a[3], const double b[3]) {
     double na = norm3(a), nb = norm3(b);
     if (na == 0.0 || nb == 0.0) return 0.0;
-    double u[3] = {a[0] / na, a[1] / na, a[2] / na};
-    double v[3] = {b[0] / nb, b[1] / nb, b[2] / nb};
+    double ia = 1.0 / na, ib = 1.0 / nb;
+    double u[3] = {a[0] * ia, a[1] * ia, a[2] * ia};
+    double v[3] = {b[0] * ib, b[1] * ib, b[2] * ib};
     double d = dot3(u, v);
     if (d > 0.0) {
         double w[3] = {u[0] - v[0], u[1] - v[1], u[2] - v[2]};
@@ -118,32 +118,54 @@ static double vsep(const double a[3], const double b[3]) {
 /* J2000 -> body-fixed at epoch t_ref + dt: v_body = E(dt) R0 v, E = exp(-[omega]x dt).
  * Stands in for spice.pxform / pxfrm2 at a per-point epoch (body.py:940, :998 and
  * inside sincpt / illumf / spkcpt). */
+typedef struct { double omega[3]; double k[3]; double wn; int valid; } SpinAxis;
+static _Thread_local SpinAxis g_spin;
+/* unit rotation axis and rate: a per-frame constant, cached per thread */
+static const SpinAxis *spin_axis(const PMFrame *f) {
+    SpinAxis *s = &g_spin;
+    if (!s->valid || s->omega[0] != f->omega[0] || s->omega[1] != f->omega[1] ||
+        s->omega[2] != f->omega[2]) {
+        s->omega[0] = f->omega[0]; s->omega[1] = f->omega[1]; s->omega[2] = f->omega[2];
+        s->wn = norm3(f->omega);
+        double iw = s->wn > 0.0 ? 1.0 / s->wn : 0.0;
+        s->k[0] = f->omega[0] * iw; s->k[1] = f->omega[1] * iw; s->k[2] = f->omega[2] * iw;
+        s->valid = 1;
+    }
+    return s;
+}
 static void rot_to_body(const PMFrame *f, double dt, const double v[3], double o[3]) {
     double w[3];
     mxv(f->R0, v, w);
-    double wn = norm3(f->omega);
+    const SpinAxis *ax = spin_axis(f);
+    double wn = ax->wn;
     if (wn == 0.0 || dt == 0.0) {
         o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
         return;
     }
-    double k[3] = {f->omega[0] / wn, f->omega[1] / wn, f->omega[2] / wn};
-    double th = wn * dt, c = cos(th), s = sin(th);
+    /* Rodrigues rotation by -theta about k, written with sin(theta) and
+     * 1 - cos(theta) = 2 sin^2(theta/2) so tiny angles lose no precision:
+     * w - sin(th) (k x w) - (1 - cos(th)) (w - k (k.w)) */
+    const double *k = ax->k;
+    double sh = sin(0.5 * wn * dt), ch = cos(0.5 * wn * dt);
+    double s = 2.0 * sh * ch, omc = 2.0 * sh * sh;
     double kxw[3];
     cross3(k, w, kxw);
-    double kw = dot3(k, w) * (1.0 - c);
-    for (int i = 0; i < 3; i++) o[i] = w[i] * c - kxw[i] * s + k[i] * kw;
+    double kw = dot3(k, w);
+    for (int i = 0; i < 3; i++) o[i] = w[i] - s * kxw[i] - omc * (w[i] - k[i] * kw);
 }
 /* body-fixed at epoch t_ref + dt -> J2000 */
 static void rot_from_body(const PMFrame *f, double dt, const double u[3], double o[3]) {
     double w[3] = {u[0], u[1], u[2]};
-    double wn = norm3(f->omega);
+    const SpinAxis *ax = spin_axis(f);
+    double wn = ax->wn;
     if (wn != 0.0 && dt != 0.0) {
-        double k[3] = {f->omega[0] / wn, f->omega[1] / wn, f->omega[2] / wn};
-        double th = wn * dt, c = cos(th), s = sin(th);
+        const double *k = ax->k;
+        double sh = sin(0.5 * wn * dt), ch = cos(0.5 * wn * dt);
+        double s = 2.0 * sh * ch, omc = 2.0 * sh * sh;
         double kxu[3];
         cross3(k, u, kxu);
-        double ku = dot3(k, u) * (1.0 - c);
-        for (int i = 0; i < 3; i++) w[i] = u[i] * c + kxu[i] * s + k[i] * ku;
+        double ku = dot3(k, u);
+        for (int i = 0; i < 3; i++) w[i] = u[i] + s * kxu[i] - omc * (u[i] - k[i] * ku);
     }
     mtxv(f->R0, w, o);
 }
@@ -159,12 +181,14 @@ static void target_pos(const PMFrame *f, double dt, double P[3]) {
  * margin (optional) receives |p_perp| - 1 in scaled space: < 0 hit, > 0 miss. */
 static int surfpt(const double o[3], const double u[3], double a, double b, double c,
                   double p[3], double *margin) {
-    double x[3] = {u[0] / a, u[1] / b, u[2] / c};
-    double y[3] = {o[0] / a, o[1] / b, o[2] / c};
+    double ia = 1.0 / a, ib = 1.0 / b, ic = 1.0 / c;
+    double x[3] = {u[0] * ia, u[1] * ib, u[2] * ic};
+    double y[3] = {o[0] * ia, o[1] * ib, o[2] * ic};
     double xn = norm3(x);
     if (margin) *margin = kNaN;
     if (!(xn > 0.0)) return 0;
-    x[0] /= xn; x[1] /= xn; x[2] /= xn;
+    double ixn = 1.0 / xn;
+    x[0] *= ixn; x[1] *= ixn; x[2] *= ixn;
     double yx = dot3(y, x);
     double pp[3] = {y[0] - yx * x[0], y[1] - yx * x[1], y[2] - yx * x[2]};
     double pmag = norm3(pp), ymag = norm3(y);
@@ -283,7 +307,8 @@ static void pgrrec(const PMFrame *f, double lon, double lat, double alt, double 
 static void reclat(const double v[3], double *r, double *lon, double *lat) {
     double big = fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2])));
     if (big > 0.0) {
-        double x = v[0] / big, y = v[1] / big, z = v[2] / big;
+        double ib = 1.0 / big;
+        double x = v[0] * ib, y = v[1] * ib, z = v[2] * ib;
         *r = big * sqrt(x * x + y * y + z * z);
         *lat = atan2(z, sqrt(x * x + y * y));
         *lon = (x == 0.0 && y == 0.0) ? 0.0 : atan2(y, x);
@@ -340,7 +365,8 @@ static void point_state(const PMFrame *f, const double p[3], double lt_start,
     rot_from_body(f, dt, wxp, vrot);
     for (int k = 0; k < 3; k++) VX[k] = f->VT[k] + f->AT[k] * dt + vrot[k];
     double r = norm3(s->pos);
-    double ph[3] = {s->pos[0] / r, s->pos[1] / r, s->pos[2] / r};
+    double ir = 1.0 / r;
+    double ph[3] = {s->pos[0] * ir, s->pos[1] * ir, s->pos[2] * ir};
     double rel[3] = {VX[0] - f->VO[0], VX[1] - f->VO[1], VX[2] - f->VO[2]};
     double dlt = dot3(ph, rel) / (f->clight + dot3(ph, VX));
     for (int k = 0; k < 3; k++) s->vel[k] = VX[k] * (1.0 - dlt) - f->VO[k];
@@ -375,8 +401,8 @@ static void point_state(const PMFrame *f, const double p[3], double lt_start,
     double m = fmin(a, fmin(b, c));
     double a1 = m / a, b1 = m / b, c1 = m / c;
     double n[3] = {p[0] * (a1 * a1), p[1] * (b1 * b1), p[2] * (c1 * c1)};
-    double nn = norm3(n);
-    n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    double inn = 1.0 / norm3(n);
+    n[0] *= inn; n[1] *= inn; n[2] *= inn;
     s->phase = vsep(s_b, e_b);
     s->incdnc = vsep(n, s_b);
     s->emissn = vsep(n, e_b);
@@ -550,16 +576,24 @@ static void pixel_backplanes(const PMFrame *f, double x, double y, uint64_t mask
     /* BodyXY._get_radec_img (body_xy.py:3413-3418) */
     double d[3], r, ra, dec;
     xy2obsvec_norm(f, x, y, d);
-    recrad(d, &r, &ra, &dec);
-    double ra_deg = ra * DPR, dec_deg = dec * DPR;
-    o->v[PM_RA] = ra_deg;
-    o->v[PM_DEC] = dec_deg;
+    const uint64_t km_mask = (1ull << PM_KM_X) | (1ull << PM_KM_Y) | (1ull << PM_ANGULAR_X) |
+                             (1ull << PM_ANGULAR_Y);
+    const uint64_t radec_users =
+        (1ull << PM_RA) | (1ull << PM_DEC) | km_mask | (1ull << PM_LIMB_DISTANCE) |
+        (1ull << PM_LIMB_LON_GRAPHIC) | (1ull << PM_LIMB_LAT_GRAPHIC) | (1ull << PM_RING_RADIUS) |
+        (1ull << PM_RING_LON_GRAPHIC) | (1ull << PM_RING_DISTANCE);
+    double d2[3] = {kNaN, kNaN, kNaN};
+    if (mask & radec_users) {
+        recrad(d, &r, &ra, &dec);
+        double ra_deg = ra * DPR, dec_deg = dec * DPR;
+        o->v[PM_RA] = ra_deg;
+        o->v[PM_DEC] = dec_deg;
+        /* _get_obsvec_norm_img (body_xy.py:3263-3272): RA/Dec degrees -> unit vector */
+        radec_deg2obsvec_norm(ra_deg, dec_deg, d2);
+    }
 
     /* BodyXY._get_km_xy_img (body_xy.py:3547-3553), angular (:3611-3656) */
-    double d2[3];
-    radec_deg2obsvec_norm(ra_deg, dec_deg, d2);
-    if (mask & ((1ull << PM_KM_X) | (1ull << PM_KM_Y) | (1ull << PM_ANGULAR_X) |
-                (1ull << PM_ANGULAR_Y))) {
+    if (mask & km_mask) {
         double kx, ky;
         obsvec2km(f, d2, &kx, &ky);
         o->v[PM_KM_X] = kx;
@@ -814,238 +848,221 @@ int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_
     return PM_OK;
 }
 
-/* ---------- projections: PROJ inverse for the three named projections
- * (body_xy.py:2899-2969, :3105-3127).  PROJ works in metres on an ellipsoid with
- * semi-axes a, b; the reference passes +to_meter so that grid units are body radii
- * etc.  +axis=wnu flips the sign of the projected x for west-positive bodies. ---------- */
+/* ---------- projections ---------- */
+/* PROJ's spherical orthographic inverse (ortho_s_inverse); x, y in sphere radii.
+ * Returns 0 when the point is outside the projection. */
+static int ortho_sph_inverse(double x, double y, double phi0, double *phi, double *lam) {
+    double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
+    double rh = hypot(x, y), sinc = rh;
+    if (sinc > 1.0) {
+        if (sinc - 1.0 > 1e-10) return 0;
+        sinc = 1.0;
+    }
+    double cosc = sqrt(1.0 - sinc * sinc);
+    if (fabs(rh) <= 1e-10) {
+        *phi = phi0;
+        *lam = 0.0;
+        return 1;
+    }
+    double p;
+    int oblique_or_equit = 1;
+    if (fabs(fabs(phi0) - HALFPI) < 1e-10) {
+        oblique_or_equit = 0;
+        if (phi0 > 0.0) {
+            y = -y;
+            p = acos(sinc);
+        } else {
+            p = -acos(sinc);
+        }
+    } else {
+        if (fabs(phi0) < 1e-10) {
+            p = y * sinc / rh;
+            x *= sinc;
+            y = cosc * rh;
+        } else {
+            p = cosc * sinphi0 + y * sinc * cosphi0 / rh;
+            y = (cosc - sinphi0 * p) * rh;
+            x *= sinc * cosphi0;
+        }
+        p = (fabs(p) >= 1.0) ? (p < 0.0 ? -HALFPI : HALFPI) : asin(p);
+    }
+    *phi = p;
+    if (y == 0.0 && oblique_or_equit)
+        *lam = (x == 0.0) ? 0.0 : (x < 0.0 ? -HALFPI : HALFPI);
+    else
+        *lam = atan2(x, y);
+    return 1;
+}
+
+/* One cell of pyproj.Transformer.transform(xx, yy, direction='INVERSE')
+ * (body_xy.py:3126) for the projection strings built at body_xy.py:2899-2969.
+ * Restates PROJ 9's ortho (ellipsoidal, EPSG 9840), aeqd and laea (spherical)
+ * inverses.  +axis=wnu (west-positive bodies) negates the projected x; the
+ * longitude PROJ returns is lon_0 + lambda normalised to [-180, 180]. */
 static void proj_inverse_one(int kind, double a, double b, double lon0_deg,
                              double lat0_deg, double lon_sign, double xx, double yy,
                              double *lon_out, double *lat_out) {
     *lon_out = *lat_out = kNaN;
     if (!(isfinite(xx) && isfinite(yy))) return;
-    double phi0 = lat0_deg * RPD;
-    /* lon_0 is a planetographic longitude; PROJ's internal lambda is the axis-wnu
-     * swapped easting, so work in "projection east" = lon_sign-free coordinates:
-     * x_internal = lon_sign_axis * x where axis w => -1 */
+    const double phi0 = lat0_deg * RPD;
     double x = (lon_sign < 0.0 ? -xx : xx);
     double y = yy;
-    double lam, phi;
+    double lam = 0.0, phi = 0.0;
     if (kind == PM_PROJ_ORTHOGRAPHIC) {
-        /* +proj=ortho +a +b +to_meter=a +y_0=a(b/a-1)sin(2 lat0): ellipsoidal
-         * orthographic (PROJ >= 7.2, EPSG method 9840) */
-        double to_meter = a;
-        double y0 = a * (b / a - 1.0) * sin(2.0 * lat0_deg * RPD);
-        double xm = x * to_meter, ym = y * to_meter - y0;
-        double es = 1.0 - (b * b) / (a * a);
-        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
+        /* +to_meter=a, +y_0=a(b/a-1)sin(2 lat_0)  =>  normalised y = yy - y_0/a */
+        y = yy - (b / a - 1.0) * sin((lat0_deg * 2.0) * RPD);
+        const double es = 1.0 - (b * b) / (a * a);
         if (es == 0.0) {
-            double xs = xm / a, ys = ym / a;
-            double rh = hypot(xs, ys), sinc = rh;
-            if (sinc > 1.0) {
-                if (sinc - 1.0 > 1e-10) return;
-                sinc = 1.0;
-            }
-            double cosc = sqrt(1.0 - sinc * sinc);
-            if (fabs(rh) <= 1e-10) {
-                phi = phi0;
-                lam = 0.0;
-            } else {
-                phi = cosc * sinphi0 + ys * sinc * cosphi0 / rh;
-                double yy2 = (cosc - sinphi0 * phi) * rh;
-                double xx2 = xs * sinc * cosphi0;
-                phi = (fabs(phi) >= 1.0) ? (phi < 0.0 ? -HALFPI : HALFPI) : asin(phi);
-                lam = (yy2 == 0.0 && xx2 == 0.0) ? 0.0 : atan2(xx2, yy2);
-            }
+            if (!ortho_sph_inverse(x, y, phi0, &phi, &lam)) return;
         } else {
-            /* PROJ ortho_e_inverse: work in units of a */
-            double xs = xm / a, ys = ym / a;
-            double nu0 = 1.0 / sqrt(1.0 - es * sinphi0 * sinphi0);
-            double y_shift = es * nu0 * sinphi0 * cosphi0; /* PROJ's y_shift */
-            if (fabs(cosphi0) < 1e-10) {
-                /* polar */
-                double rh2 = xs * xs + ys * ys;
+            const double sinph0 = sin(phi0), cosph0 = cos(phi0);
+            const double one_es = 1.0 - es;
+            if (fabs(fabs(phi0) - HALFPI) < 1e-10) { /* polar */
+                const double sgn = phi0 > 0.0 ? 1.0 : -1.0;
+                double rh2 = x * x + y * y;
                 if (rh2 >= 1.0 - 1e-15) {
                     if (rh2 - 1.0 > 1e-10) return;
                     phi = 0.0;
                 } else {
-                    phi = acos(sqrt(rh2 * (1.0 - es) / (1.0 - es * rh2))) *
-                          (phi0 > 0.0 ? 1.0 : -1.0);
+                    phi = acos(sqrt(rh2 * one_es / (1.0 - es * rh2))) * sgn;
                 }
-                lam = atan2(xs, ys * (phi0 > 0.0 ? -1.0 : 1.0));
-            } else if (fabs(phi0) < 1e-10) {
-                /* equatorial */
-                double one_es = 1.0 - es;
-                double t = ys * ys / one_es + xs * xs;
-                if (t > 1.0 + 1e-11) return;
-                double sp = ys * sqrt(1.0 - es * (1.0 - xs * xs)) / one_es; /* approx */
-                /* exact: y = (1-es) nu sin(phi), x = nu cos(phi) sin(lam) */
-                /* solve (1-es) sin(phi)/sqrt(1-es sin^2 phi) = ys */
-                double s2 = ys * ys / (one_es * one_es + es * ys * ys);
-                (void)sp;
-                double sphi = (ys < 0.0 ? -1.0 : 1.0) * sqrt(s2);
-                if (fabs(sphi) > 1.0) return;
-                phi = asin(sphi);
-                double nu = 1.0 / sqrt(1.0 - es * sphi * sphi);
-                double sl = xs / (nu * cos(phi));
-                if (fabs(sl) > 1.0) {
-                    if (fabs(sl) - 1.0 > 1e-10) return;
-                    sl = sl < 0.0 ? -1.0 : 1.0;
-                }
-                lam = asin(sl);
-            } else {
-                /* oblique: PROJ checks the point lies inside the projected ellipse of
-                 * the limb, starts from the spherical inverse and runs Newton on
-                 * (x, y) = F(phi, lam) */
-                double yr = ys + y_shift; /* PROJ: xy.y recentred */
-                {
-                    /* limb ellipse test (PROJ ortho_e_inverse):
-                     * x^2 + (y_recentered / sqrt(1 - es cos^2 phi0))^2 <= 1 */
-                    double sc = sqrt(1.0 - es * cosphi0 * cosphi0);
-                    double yt = ys / sc;
-                    (void)yr;
-                    /* PROJ recentres with y_shift/scale: */
-                    double ysr = (ys - 0.0) / sc;
-                    (void)ysr;
-                    double yc = (ys + y_shift - y_shift) / sc;
-                    (void)yc;
-                    (void)yt;
-                }
-                /* initial guess: spherical inverse */
-                double rh = hypot(xs, ys), sinc = rh > 1.0 ? 1.0 : rh;
-                double cosc = sqrt(1.0 - sinc * sinc);
-                if (rh <= 1e-10) {
-                    phi = phi0;
+                lam = atan2(x, y * -sgn);
+            } else if (fabs(phi0) < 1e-10) { /* equatorial */
+                double ys = y * (a / b);
+                if (x * x + ys * ys > 1.0 + 1e-11) return;
+                double sinphi2 = (y == 0.0) ? 0.0 : 1.0 / ((one_es / y) * (one_es / y) + es);
+                if (sinphi2 > 1.0 - 1e-11) {
+                    phi = HALFPI * (y > 0.0 ? 1.0 : -1.0);
                     lam = 0.0;
                 } else {
-                    double sp = cosc * sinphi0 + ys * sinc * cosphi0 / rh;
-                    double yy2 = (cosc - sinphi0 * sp) * rh;
-                    double xx2 = xs * sinc * cosphi0;
-                    sp = fmax(-1.0, fmin(1.0, sp));
-                    phi = asin(sp);
-                    lam = atan2(xx2, yy2);
+                    phi = asin(sqrt(sinphi2)) * (y > 0.0 ? 1.0 : -1.0);
+                    double sinlam = x * sqrt((1.0 - es * sinphi2) / (1.0 - sinphi2));
+                    if (fabs(sinlam) - 1.0 > -1e-15)
+                        lam = HALFPI * (x > 0.0 ? 1.0 : -1.0);
+                    else
+                        lam = asin(sinlam);
                 }
+            } else { /* oblique */
+                const double nu0 = 1.0 / sqrt(1.0 - es * sinph0 * sinph0);
+                const double y_shift = es * nu0 * sinph0 * cosph0;
+                const double y_scale = 1.0 / sqrt(1.0 - es * cosph0 * cosph0);
+                double yr = (y - y_shift) / y_scale;
+                if (x * x + yr * yr > 1.0 + 1e-11) return;
+                if (!ortho_sph_inverse(x, yr, phi0, &phi, &lam)) return;
                 int ok = 0;
                 for (int it = 0; it < 20; it++) {
-                    double cp = cos(phi), sphi = sin(phi), cl = cos(lam), sl = sin(lam);
-                    double w = 1.0 - es * sphi * sphi;
+                    double cp = cos(phi), sp = sin(phi), cl = cos(lam), sl = sin(lam);
+                    double w = 1.0 - es * sp * sp;
                     double nu = 1.0 / sqrt(w);
-                    /* forward (EPSG 9840), units of a, relative to the false origin */
                     double fx = nu * cp * sl;
-                    double fy = nu * (sphi * cosphi0 - cp * sinphi0 * cl) +
-                                es * (nu0 * sinphi0 - nu * sphi) * cosphi0;
-                    double rho = (1.0 - es) * nu / w;
-                    double J11 = -rho * sphi * sl;
+                    double fy = nu * (sp * cosph0 - cp * sinph0 * cl) +
+                                es * (nu0 * sinph0 - nu * sp) * cosph0;
+                    double rho = one_es * nu / w;
+                    double J11 = -rho * sp * sl;
                     double J12 = nu * cp * cl;
-                    double J21 = rho * (cp * cosphi0 + sphi * sinphi0 * cl);
-                    double J22 = nu * sinphi0 * cp * sl;
+                    double J21 = rho * (cp * cosph0 + sp * sinph0 * cl);
+                    double J22 = nu * sinph0 * cp * sl;
                     double D = J11 * J22 - J12 * J21;
-                    double dxr = fx - xs, dyr = fy - ys;
-                    double dphi = (J12 * dyr - J22 * dxr) / D;
-                    double dlam = (-J11 * dyr + J21 * dxr) / D;
+                    double dx = x - fx, dy = y - fy;
+                    double dphi = (J22 * dx - J12 * dy) / D;
+                    double dlam = (-J21 * dx + J11 * dy) / D;
                     phi += dphi;
+                    if (phi > HALFPI)
+                        phi = HALFPI - (phi - HALFPI);
+                    else if (phi < -HALFPI)
+                        phi = -HALFPI + (-HALFPI - phi);
                     lam += dlam;
-                    if (phi > HALFPI) phi = HALFPI - (phi - HALFPI);
-                    if (phi < -HALFPI) phi = -HALFPI + (-HALFPI - phi);
                     if (fabs(dphi) < 1e-12 && fabs(dlam) < 1e-12) {
                         ok = 1;
                         break;
                     }
                 }
                 if (!ok) return;
-                /* reject the far side and points outside the limb */
-                {
-                    double cp = cos(phi), sphi = sin(phi);
-                    double cosc2 = sinphi0 * sphi + cosphi0 * cp * cos(lam);
-                    double w = 1.0 - es * sphi * sphi;
-                    double nu = 1.0 / sqrt(w);
-                    double fx = nu * cp * sin(lam);
-                    double fy = nu * (sphi * cosphi0 - cp * sinphi0 * cos(lam)) +
-                                es * (nu0 * sinphi0 - nu * sphi) * cosphi0;
-                    if (cosc2 < -1e-10) return;
-                    if (fabs(fx - xs) > 1e-9 || fabs(fy - ys) > 1e-9) return;
-                }
             }
         }
     } else if (kind == PM_PROJ_AZIMUTHAL) {
-        /* +proj=aeqd on a sphere of radius a, +to_meter = a*pi: spherical aeqd inverse */
-        double xs = x * PI, ys = y * PI; /* units of the sphere radius */
-        double c_rh = hypot(xs, ys);
+        /* +proj=aeqd, sphere of radius a, +to_meter = a pi (aeqd s_inverse) */
+        x *= PI;
+        y *= PI;
+        double c_rh = hypot(x, y);
+        int at_origin = 0;
         if (c_rh > PI) {
             if (c_rh - 1e-10 > PI) return;
             c_rh = PI;
         } else if (c_rh < 1e-10) {
-            *lon_out = pymod(lon0_deg, 360.0);
-            *lat_out = lat0_deg;
-            return;
+            at_origin = 1;
         }
-        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
-        if (fabs(fabs(phi0) - HALFPI) < 1e-10) { /* polar */
+        if (at_origin) {
+            phi = phi0;
+            lam = 0.0;
+        } else if (fabs(fabs(phi0) - HALFPI) < 1e-10) {
             if (phi0 > 0.0) {
                 phi = HALFPI - c_rh;
-                lam = atan2(xs, -ys);
+                lam = atan2(x, -y);
             } else {
                 phi = c_rh - HALFPI;
-                lam = atan2(xs, ys);
+                lam = atan2(x, y);
             }
         } else {
             double sinc = sin(c_rh), cosc = cos(c_rh);
-            if (fabs(phi0) < 1e-10) { /* equatorial */
-                double sp = ys * sinc / c_rh;
-                sp = fmax(-1.0, fmin(1.0, sp));
-                phi = asin(sp);
-                double xn = xs * sinc, yn = cosc * c_rh;
-                lam = (yn == 0.0) ? 0.0 : atan2(xn, yn);
+            double sinph0 = sin(phi0), cosph0 = cos(phi0);
+            double arg;
+            if (fabs(phi0) < 1e-10) {
+                arg = y * sinc / c_rh;
+                x *= sinc;
+                y = cosc * c_rh;
             } else {
-                double sp = cosc * sinphi0 + ys * sinc * cosphi0 / c_rh;
-                sp = fmax(-1.0, fmin(1.0, sp));
-                phi = asin(sp);
-                double yn = (cosc - sinphi0 * sin(phi)) * c_rh;
-                double xn = xs * sinc * cosphi0;
-                lam = (yn == 0.0) ? 0.0 : atan2(xn, yn);
+                arg = cosc * sinph0 + y * sinc * cosph0 / c_rh;
+                arg = fmax(-1.0, fmin(1.0, arg));
+                y = (cosc - sinph0 * arg) * c_rh; /* sin(asin(arg)) == arg */
+                x *= sinc * cosph0;
             }
+            arg = fmax(-1.0, fmin(1.0, arg));
+            phi = asin(arg);
+            lam = (y == 0.0) ? 0.0 : atan2(x, y);
         }
     } else if (kind == PM_PROJ_AZIMUTHAL_EQUAL_AREA) {
-        /* +proj=laea on a sphere of radius a, +to_meter = 2a: spherical laea inverse */
-        double xs = x * 2.0, ys = y * 2.0;
-        double rh = hypot(xs, ys);
+        /* +proj=laea, sphere of radius a, +to_meter = 2a (laea s_inverse) */
+        x *= 2.0;
+        y *= 2.0;
+        double rh = hypot(x, y);
         double half = rh * 0.5;
         if (half > 1.0) return;
-        double sinphi0 = sin(phi0), cosphi0 = cos(phi0);
-        double c2 = 2.0 * asin(half);
-        double sinz = sin(c2), cosz = cos(c2);
-        double xn = xs, yn;
-        if (fabs(fabs(phi0) - HALFPI) < 1e-10) { /* polar */
+        double z = 2.0 * asin(half);
+        double sinph0 = sin(phi0), cosph0 = cos(phi0);
+        if (fabs(fabs(phi0) - HALFPI) < 1e-10) {
             if (phi0 > 0.0) {
-                yn = -ys;
-                phi = HALFPI - c2;
+                y = -y;
+                phi = HALFPI - z;
             } else {
-                yn = ys;
-                phi = c2 - HALFPI;
+                phi = z - HALFPI;
             }
-            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
-        } else if (fabs(phi0) < 1e-10) { /* equatorial */
-            phi = (fabs(rh) <= 1e-10) ? 0.0 : asin(ys * sinz / rh);
-            xn = xs * sinz;
-            yn = cosz * rh;
-            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
+            lam = atan2(x, y);
         } else {
-            double ab = cosz * sinphi0 + ((fabs(rh) <= 1e-10) ? 0.0 : ys * sinz * cosphi0 / rh);
-            phi = (fabs(rh) <= 1e-10) ? phi0 : asin(ab);
-            xn = xs * sinz * cosphi0;
-            yn = (cosz - sin(phi) * sinphi0) * rh;
-            lam = (yn == 0.0 && xn == 0.0) ? 0.0 : atan2(xn, yn);
+            double sinz = sin(z), cosz = cos(z);
+            if (fabs(phi0) < 1e-10) {
+                phi = (fabs(rh) <= 1e-10) ? 0.0 : asin(y * sinz / rh);
+                x *= sinz;
+                y = cosz * rh;
+            } else {
+                phi = (fabs(rh) <= 1e-10) ? phi0
+                                          : asin(cosz * sinph0 + y * sinz * cosph0 / rh);
+                x *= sinz * cosph0;
+                y = (cosz - sin(phi) * sinph0) * rh;
+            }
+            lam = (y == 0.0) ? 0.0 : atan2(x, y);
         }
     } else {
         return;
     }
-    /* PROJ internal easting -> planetographic longitude (+axis) and wrap like
-     * pyproj's degree output: lon in [-180, 180] about lon_0 */
-    double lon = lam * DPR;
-    lon = (lon_sign < 0.0 ? -lon : lon) + lon0_deg;
-    /* pyproj returns longitudes normalised to [-180, 180] */
-    while (lon > 180.0) lon -= 360.0;
-    while (lon < -180.0) lon += 360.0;
-    *lon_out = lon;
+    /* lon = lon_0 + lambda, wrapped to [-180, 180] like PROJ's adjlon */
+    double lon_rad = lam + lon0_deg * RPD;
+    if (fabs(lon_rad) > PI + 1e-12) {
+        lon_rad += PI;
+        lon_rad -= TWOPI * floor(lon_rad / TWOPI);
+        lon_rad -= PI;
+    }
+    *lon_out = lon_rad * DPR;
     *lat_out = phi * DPR;
 }
 

@@ -1,0 +1,66 @@
+"""
+planetmapper_b200 - B200-native (sm_100a) implementation of PlanetMapper's per-pixel
+geometry and mapping hot path behind the BodyXY / Observation API.
+
+    from planetmapper_b200 import BodyXY, Observation
+
+The per-pixel work runs in hand-written FP64 CUDA kernels (libpm_b200.so, C ABI in
+include/pm_b200.h).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+
+from .body_xy import (Backplane, BackplaneNotFoundError, BodyXY, NotFoundError,  # noqa: F401
+                      ProjStringError)
+from .frame import BodyConstants, build_body_constants, pack_frame  # noqa: F401
+from .observation import Observation  # noqa: F401
+
+__version__ = '0.1.0'
+
+_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+_KERNEL_PATH: str | None = None
+_PROVIDER = None
+
+
+def set_kernel_path(path: str | None) -> None:
+    """Directory holding SPICE kernels (planetmapper.set_kernel_path, base.py:1018)."""
+    global _KERNEL_PATH, _PROVIDER
+    _KERNEL_PATH = path
+    _PROVIDER = None
+
+
+def get_kernel_path() -> str | None:
+    return _KERNEL_PATH or os.environ.get('PLANETMAPPER_KERNEL_PATH')
+
+
+def set_default_provider(provider) -> None:
+    global _PROVIDER
+    _PROVIDER = provider
+
+
+def get_default_provider():
+    """Ephemeris provider for the once-per-frame host constants: spiceypy when it is
+    installed (the reference's setup), else MiniSpice over the kernel directory, else
+    MiniSpice over the bundled ephemeris extract (planetmapper_b200/data)."""
+    global _PROVIDER
+    if _PROVIDER is not None:
+        return _PROVIDER
+    kernel_path = get_kernel_path()
+    try:
+        import spiceypy  # noqa: F401
+
+        from .spice_host import SpiceProvider
+
+        _PROVIDER = SpiceProvider(kernel_path)
+        return _PROVIDER
+    except ImportError:
+        pass
+    from .minispice import MiniSpice
+
+    if kernel_path and os.path.isdir(os.path.expanduser(kernel_path)):
+        _PROVIDER = MiniSpice.from_kernel_dir(os.path.expanduser(kernel_path))
+    else:
+        _PROVIDER = MiniSpice.from_extract(os.path.join(_DATA_DIR, 'ephem_extract.npz'),
+                                           os.path.join(_DATA_DIR, 'pck_pool.json'))
+    return _PROVIDER

@@ -1,0 +1,240 @@
+"""
+ctypes binding of libpm_b200.so (C ABI: include/pm_b200.h) plus thin wrappers that
+take and return torch CUDA tensors.  PyTorch is used for device memory and streams
+only; all arithmetic happens in the hand-written sm_100a kernels.
+
+There is NO CPU fallback: if the library is missing, or no CUDA device is visible,
+the wrappers raise :class:`PMLibraryError`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpm_b200.so')
+
+N_PLANES = 26
+ALL_PLANES = (1 << N_PLANES) - 1
+INTERP_NEAREST, INTERP_LINEAR, INTERP_CUBIC = 0, 1, 3
+PROJ_ORTHOGRAPHIC, PROJ_AZIMUTHAL, PROJ_AZIMUTHAL_EQUAL_AREA = 1, 2, 3
+FLAG_NOT_VISIBLE_NAN = 1
+FLAG_PROPAGATE_NAN = 2
+
+PLANE_NAMES = [
+    'LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'RA', 'DEC', 'PIXEL-X',
+    'PIXEL-Y', 'KM-X', 'KM-Y', 'ANGULAR-X', 'ANGULAR-Y', 'PHASE', 'INCIDENCE',
+    'EMISSION', 'AZIMUTH', 'LOCAL-SOLAR-TIME', 'DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER',
+    'LIMB-DISTANCE', 'LIMB-LON-GRAPHIC', 'LIMB-LAT-GRAPHIC', 'RING-RADIUS',
+    'RING-LON-GRAPHIC', 'RING-DISTANCE',
+]
+PLANE_ID = {n: i for i, n in enumerate(PLANE_NAMES)}
+
+# every symbol include/pm_b200.h declares
+EXPORTED_SYMBOLS = [
+    'pm_abi_version', 'pm_error_string', 'pm_launch_count', 'pm_backplanes_img',
+    'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_proj_inverse', 'pm_gather',
+    'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe',
+]
+
+
+class PMLibraryError(RuntimeError):
+    """The CUDA library is missing, failed to load, or reported an error."""
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libpm_b200.so (no compute; works without a GPU)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PMLibraryError(
+            f'{LIB_PATH} not found: build it with `make -C planetmapper_b200/csrc` or '
+            '`python -c "import __graft_entry__ as g; g.build()"`. There is no CPU fallback.'
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c_i, c_i64, c_u64, c_u32, c_p = (ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                     ctypes.c_uint32, ctypes.c_void_p)
+    lib.pm_abi_version.restype = c_i
+    lib.pm_error_string.restype = ctypes.c_char_p
+    lib.pm_error_string.argtypes = [c_i]
+    lib.pm_launch_count.restype = c_u64
+    lib.pm_backplanes_img.argtypes = [c_p, c_i, c_i, c_i, c_u64, c_p, c_p]
+    lib.pm_backplanes_map.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
+    lib.pm_xy2lonlat.argtypes = [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]
+    lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
+    lib.pm_proj_inverse.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
+    lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i64, c_i, c_u32,
+                              c_p, c_p]
+    lib.pm_spline_work_bytes.restype = c_i64
+    lib.pm_spline_work_bytes.argtypes = [c_i, c_i, c_i, c_i]
+    lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
+    lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
+    for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy',
+               'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe'):
+        getattr(lib, fn).restype = c_i
+    if lib.pm_abi_version() != 1:
+        raise PMLibraryError('libpm_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().pm_error_string(rc).decode()
+        raise PMLibraryError(f'{what} failed: {msg} ({rc})')
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise PMLibraryError(
+            'planetmapper_b200 needs a CUDA device (sm_100a); there is no CPU fallback'
+        )
+    return torch
+
+
+def _stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load_library().pm_launch_count())
+
+
+def to_device(arr, device=None):
+    torch = _torch()
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    return torch.from_numpy(a).to(device or 'cuda', non_blocking=False)
+
+
+def popcount(mask: int) -> int:
+    return bin(mask & ALL_PLANES).count('1')
+
+
+def mask_from_names(names) -> int:
+    m = 0
+    for n in names:
+        m |= 1 << PLANE_ID[n]
+    return m
+
+
+def backplanes_img(frames_dev, nx: int, ny: int, mask: int = ALL_PLANES, out=None):
+    """frames_dev: CUDA float64 tensor (n_frames, PMFRAME_NDOUBLES). Returns a CUDA
+    tensor (n_frames, popcount(mask), ny, nx)."""
+    torch = _torch()
+    lib = load_library()
+    assert frames_dev.is_cuda and frames_dev.dtype == torch.float64 and frames_dev.is_contiguous()
+    n_frames = frames_dev.shape[0]
+    k = popcount(mask)
+    if out is None:
+        out = torch.empty((n_frames, k, ny, nx), dtype=torch.float64, device=frames_dev.device)
+    rc = lib.pm_backplanes_img(frames_dev.data_ptr(), n_frames, nx, ny, mask, out.data_ptr(),
+                               _stream_ptr(torch))
+    _check(rc, 'pm_backplanes_img')
+    return out
+
+
+def backplanes_map(frame_dev, lon_dev, lat_dev, mask: int = ALL_PLANES, out=None):
+    torch = _torch()
+    lib = load_library()
+    n = lon_dev.numel()
+    k = popcount(mask)
+    if out is None:
+        out = torch.empty((k,) + tuple(lon_dev.shape), dtype=torch.float64, device=lon_dev.device)
+    rc = lib.pm_backplanes_map(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(), n,
+                               mask, out.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_backplanes_map')
+    return out
+
+
+def xy2lonlat(frame_dev, x_dev, y_dev):
+    torch = _torch()
+    lib = load_library()
+    lon = torch.empty_like(x_dev)
+    lat = torch.empty_like(x_dev)
+    missed = torch.zeros(1, dtype=torch.int64, device=x_dev.device)
+    rc = lib.pm_xy2lonlat(frame_dev.data_ptr(), x_dev.data_ptr(), y_dev.data_ptr(),
+                          x_dev.numel(), lon.data_ptr(), lat.data_ptr(), missed.data_ptr(),
+                          _stream_ptr(torch))
+    _check(rc, 'pm_xy2lonlat')
+    return lon, lat, missed
+
+
+def lonlat2xy(frame_dev, lon_dev, lat_dev, not_visible_nan: bool = True):
+    torch = _torch()
+    lib = load_library()
+    x = torch.empty_like(lon_dev)
+    y = torch.empty_like(lon_dev)
+    rc = lib.pm_lonlat2xy(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(),
+                          lon_dev.numel(), FLAG_NOT_VISIBLE_NAN if not_visible_nan else 0,
+                          x.data_ptr(), y.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_lonlat2xy')
+    return x, y
+
+
+def proj_inverse(kind: int, a: float, b: float, lon0: float, lat0: float, lon_sign: float,
+                 xx_dev, yy_dev):
+    torch = _torch()
+    lib = load_library()
+    params = (ctypes.c_double * 5)(a, b, lon0, lat0, lon_sign)
+    lon = torch.empty_like(xx_dev)
+    lat = torch.empty_like(xx_dev)
+    rc = lib.pm_proj_inverse(kind, ctypes.cast(params, ctypes.c_void_p), xx_dev.data_ptr(),
+                             yy_dev.data_ptr(), xx_dev.numel(), lon.data_ptr(), lat.data_ptr(),
+                             _stream_ptr(torch))
+    _check(rc, 'pm_proj_inverse')
+    return lon, lat
+
+
+def spline_prepare(cube_dev, degree: int):
+    """NaN repair (+ cubic B-spline coefficient solve). Returns (coef, nanmask, plane_flags)."""
+    torch = _torch()
+    lib = load_library()
+    nl, ny, nx = cube_dev.shape
+    coef = torch.empty_like(cube_dev)
+    nanmask = torch.empty((nl, ny, nx), dtype=torch.uint8, device=cube_dev.device)
+    flags = torch.empty((nl,), dtype=torch.uint8, device=cube_dev.device)
+    nbytes = lib.pm_spline_work_bytes(nl, ny, nx, degree)
+    work = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=cube_dev.device)
+    rc = lib.pm_spline_prepare(cube_dev.data_ptr(), nl, ny, nx, degree, coef.data_ptr(),
+                               nanmask.data_ptr(), flags.data_ptr(), work.data_ptr(),
+                               _stream_ptr(torch))
+    _check(rc, 'pm_spline_prepare')
+    return coef, nanmask, flags
+
+
+def gather(cube_dev, xmap_dev, ymap_dev, mode: int, *, nanmask=None, plane_flags=None,
+           propagate_nan: bool = True, out=None):
+    """cube_dev (nl, ny, nx) -> (nl,) + xmap.shape"""
+    torch = _torch()
+    lib = load_library()
+    nl, ny, nx = cube_dev.shape
+    n_cells = xmap_dev.numel()
+    if out is None:
+        out = torch.empty((nl,) + tuple(xmap_dev.shape), dtype=torch.float64,
+                          device=cube_dev.device)
+    flags = FLAG_PROPAGATE_NAN if propagate_nan else 0
+    rc = lib.pm_gather(cube_dev.data_ptr(), nanmask.data_ptr() if nanmask is not None else None,
+                       plane_flags.data_ptr() if plane_flags is not None else None, nl, ny, nx,
+                       xmap_dev.data_ptr(), ymap_dev.data_ptr(), n_cells, mode, flags,
+                       out.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_gather')
+    return out
+
+
+def fp64_peak_probe(iters: int = 1 << 15) -> float:
+    """Measured FP64 FMA throughput in TFLOP/s (dependent-chain DFMA microbenchmark)."""
+    _torch()
+    lib = load_library()
+    ms = ctypes.c_double(0.0)
+    fl = ctypes.c_double(0.0)
+    _check(lib.pm_fp64_peak_probe(iters, ctypes.byref(ms), ctypes.byref(fl)), 'pm_fp64_peak_probe')
+    return fl.value / (ms.value * 1e-3) / 1e12

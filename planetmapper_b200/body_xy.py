@@ -1,0 +1,731 @@
+"""
+``BodyXY``: the host-side mirror of the reference's ``planetmapper.BodyXY`` for the
+accelerated hot path - same method names, argument meaning, return conventions
+(float64 host ndarrays, NaN for invalid cells, copies vs read-only cached views)
+and cache semantics, with the per-pixel work done by the sm_100a kernels behind
+``include/pm_b200.h``.
+
+Reference surface mirrored here (file:line under /root/reference/planetmapper):
+
+- disc parameters            body_xy.py:696-1080 (set/get x0, y0, r0, rotation, img size)
+- ``xy2lonlat``/``lonlat2xy`` body_xy.py:433-560
+- ``generate_map_coordinates`` body_xy.py:2755-3012
+- ``get_backplane_img/map``  body_xy.py:2586-2663, registry :2512-2584, :4198-4356
+- ``map_img``                body_xy.py:1414-1631
+- caches                     base.py:58-112, body.py:255-272
+
+Design (not the reference's): ONE fused kernel launch produces every image
+backplane, so the cache holds one device-resident plane stack per altitude
+adjustment instead of one host array per generator; the named getters
+(``get_lon_img`` ...) are generated from the backplane table.
+
+Out of scope here, as in SURVEY.md section 8: plotting, wireframes, FITS I/O, disc
+fitting, GUI.  Options the kernels do not cover raise ``NotImplementedError``
+(there is no CPU fallback).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, NamedTuple
+
+import numpy as np
+
+from . import _lib as L
+from . import frame as F
+
+_PLANE_DESCRIPTIONS = [
+    ('LON-GRAPHIC', 'Planetographic longitude, positive {ew} [deg]', 'lon'),
+    ('LAT-GRAPHIC', 'Planetographic latitude [deg]', 'lat'),
+    ('LON-CENTRIC', 'Planetocentric longitude [deg]', 'lon_centric'),
+    ('LAT-CENTRIC', 'Planetocentric latitude [deg]', 'lat_centric'),
+    ('RA', 'Right ascension [deg]', 'ra'),
+    ('DEC', 'Declination [deg]', 'dec'),
+    ('PIXEL-X', 'Observation x pixel coordinate [pixels]', 'x'),
+    ('PIXEL-Y', 'Observation y pixel coordinate [pixels]', 'y'),
+    ('KM-X', 'East-West distance in target plane [km]', 'km_x'),
+    ('KM-Y', 'North-South distance in target plane [km]', 'km_y'),
+    ('ANGULAR-X', 'East-West distance in target plane [arcsec]', 'angular_x'),
+    ('ANGULAR-Y', 'North-South distance in target plane [arcsec]', 'angular_y'),
+    ('PHASE', 'Phase angle [deg]', 'phase_angle'),
+    ('INCIDENCE', 'Incidence angle [deg]', 'incidence_angle'),
+    ('EMISSION', 'Emission angle [deg]', 'emission_angle'),
+    ('AZIMUTH', 'Azimuth angle [deg]', 'azimuth_angle'),
+    ('LOCAL-SOLAR-TIME', 'Local solar time [local hours]', 'local_solar_time'),
+    ('DISTANCE', 'Distance to observer [km]', 'distance'),
+    ('RADIAL-VELOCITY', 'Radial velocity away from observer [km/s]', 'radial_velocity'),
+    ('DOPPLER', 'Doppler factor, sqrt((1 + v/c)/(1 - v/c)) where v is radial velocity',
+     'doppler'),
+    ('LIMB-DISTANCE', 'Distance above limb [km]', 'limb_distance'),
+    ('LIMB-LON-GRAPHIC', 'Planetographic longitude of closest point on the limb [deg]',
+     'limb_lon'),
+    ('LIMB-LAT-GRAPHIC', 'Planetographic latitude of closest point on the limb [deg]',
+     'limb_lat'),
+    ('RING-RADIUS', 'Equatorial (ring) plane radius [km]', 'ring_plane_radius'),
+    ('RING-LON-GRAPHIC', 'Equatorial (ring) plane planetographic longitude [deg]',
+     'ring_plane_longitude'),
+    ('RING-DISTANCE', 'Equatorial (ring) plane distance to observer [km]',
+     'ring_plane_distance'),
+]
+assert [p[0] for p in _PLANE_DESCRIPTIONS] == L.PLANE_NAMES
+
+_XY_PLANES = (L.PLANE_ID['PIXEL-X'], L.PLANE_ID['PIXEL-Y'])
+_MAP_KWARG_KEYS = ('projection', 'degree_interval', 'lon', 'lat', 'size', 'lon_coords',
+                   'lat_coords', 'projection_x_coords', 'projection_y_coords', 'xlim', 'ylim',
+                   'alt')
+
+
+class BackplaneNotFoundError(Exception):
+    """Raised when a backplane name is not registered (body_xy.py:2579)."""
+
+
+class ProjStringError(ValueError):
+    """Raised for projection strings this implementation cannot honour."""
+
+
+class NotFoundError(Exception):
+    """Stands in for spiceypy's NotFoundError: a ray missed the target
+    (Body._obsvec_norm2lonlat with not_found_nan=False, body.py:1073-1078)."""
+
+
+class Backplane(NamedTuple):
+    """Registry entry, same fields as the reference's Backplane (body_xy.py:79-107)."""
+
+    name: str
+    description: str
+    get_img: Callable[[], np.ndarray]
+    get_map: Callable[..., np.ndarray]
+
+
+def _readonly(a: np.ndarray) -> np.ndarray:
+    v = a.view()
+    v.flags.writeable = False
+    return v
+
+
+def _freeze(v: Any):
+    """Hashable form of a kwarg value (ndarrays -> nested tuples, base.py:174-199)."""
+    if isinstance(v, np.ndarray):
+        return ('ndarray', v.shape, tuple(v.ravel().tolist()))
+    if isinstance(v, (list, tuple)):
+        return tuple(_freeze(x) for x in v)
+    return v
+
+
+class BodyXY:
+    """An astronomical body observed at one epoch with an image pixel grid.
+
+    Args mirror ``planetmapper.BodyXY`` (body_xy.py:186-232): ``target``, ``utc``,
+    ``observer``, ``nx``, ``ny``, ``sz``.  Extra keyword-only arguments select where
+    the once-per-frame constants come from:
+
+    - ``constants``: a prebuilt :class:`planetmapper_b200.frame.BodyConstants`;
+    - ``provider``: an ephemeris provider (``spice_host.SpiceProvider`` or
+      ``minispice.MiniSpice``); default = :func:`planetmapper_b200.get_default_provider`.
+    """
+
+    def __init__(self, target=None, utc=None, observer='EARTH', *, nx: int = 0, ny: int = 0,
+                 sz: int | None = None, constants: F.BodyConstants | None = None,
+                 provider=None, optimize_speed: bool = True, aberration_correction: str = 'CN',
+                 observer_frame: str = 'J2000', target_frame: str | None = None,
+                 illumination_source: str = 'SUN',
+                 subpoint_method: str = 'INTERCEPT/ELLIPSOID',
+                 surface_method: str = 'ELLIPSOID', **kwargs) -> None:
+        if kwargs:
+            raise TypeError(f'unexpected keyword arguments {sorted(kwargs)}')
+        # Scope limits of the kernels: fail loudly, never fall back.
+        if aberration_correction.strip().upper() != 'CN':
+            raise NotImplementedError("only aberration_correction='CN' is accelerated")
+        if observer_frame.strip().upper() != 'J2000':
+            raise NotImplementedError("only observer_frame='J2000' is accelerated")
+        if surface_method.strip().upper() != 'ELLIPSOID':
+            raise NotImplementedError("only surface_method='ELLIPSOID' is accelerated")
+        if illumination_source.strip().upper() != 'SUN':
+            raise NotImplementedError("only illumination_source='SUN' is accelerated")
+        if subpoint_method.strip().upper() != 'INTERCEPT/ELLIPSOID':
+            raise NotImplementedError("only subpoint_method='INTERCEPT/ELLIPSOID' is accelerated")
+        if constants is None:
+            if provider is None:
+                from . import get_default_provider
+
+                provider = get_default_provider()
+            if target is None:
+                raise TypeError('target is required')
+            if utc is None:
+                raise NotImplementedError('utc=None (current time) needs a live SPICE setup')
+            constants = F.build_body_constants(provider, target, str(utc), observer)
+        if target_frame is not None and target_frame.upper() != 'IAU_' + constants.target:
+            raise NotImplementedError('only the default IAU_<target> frame is accelerated')
+        self._bc = constants
+        self._optimize_speed = bool(optimize_speed)
+        if sz is not None:
+            nx = ny = sz
+        self._nx, self._ny = int(nx), int(ny)
+        self._x0 = self._y0 = 0.0
+        self._r0 = 10.0
+        self._rotation_radians = 0.0
+        self._alt_adjustment = 0.0
+        self._cache: dict = {}         # cleared when a disc parameter changes
+        self._stable_cache: dict = {}  # never cleared
+        self.backplanes: dict[str, Backplane] = {}
+        self._register_default_backplanes()
+        # body_xy.py:226-232: centre the disc if an image size was given
+        if self._nx > 0 and self._ny > 0:
+            self.centre_disc()
+        else:
+            self._cache['disc method'] = 'default'
+
+    # ---- attributes mirrored from Body (body.py:347-436) ---------------------------
+    target = property(lambda self: self._bc.target)
+    observer = property(lambda self: self._bc.observer)
+    utc = property(lambda self: self._bc.utc)
+    et = property(lambda self: self._bc.et)
+    target_body_id = property(lambda self: self._bc.target_id)
+    radii = property(lambda self: self._bc.radii + self._alt_adjustment)
+    r_eq = property(lambda self: float(self._bc.radii[0] + self._alt_adjustment))
+    r_polar = property(lambda self: float(self._bc.radii[2] + self._alt_adjustment))
+    flattening = property(lambda self: (self.r_eq - self.r_polar) / self.r_eq)
+    prograde = property(lambda self: self._bc.prograde)
+    positive_longitude_direction = property(lambda self: self._bc.positive_longitude_direction)
+    target_light_time = property(lambda self: self._bc.lt0)
+    target_distance = property(lambda self: self._bc.target_distance)
+    target_ra = property(lambda self: self._bc.target_ra)
+    target_dec = property(lambda self: self._bc.target_dec)
+    target_diameter_arcsec = property(lambda self: self._bc.target_diameter_arcsec)
+    km_per_arcsec = property(lambda self: self._bc.km_per_arcsec)
+    subpoint_distance = property(lambda self: self._bc.sub_dist)
+    subpoint_lon = property(lambda self: self._bc.subpoint_lon)
+    subpoint_lat = property(lambda self: self._bc.subpoint_lat)
+
+    def north_pole_angle(self) -> float:
+        return self._bc.north_pole_angle
+
+    def speed_of_light(self) -> float:
+        return self._bc.clight
+
+    def __repr__(self) -> str:
+        return (f'BodyXY({self.target!r}, {self.utc!r}, observer={self.observer!r}, '
+                f'nx={self._nx}, ny={self._ny})')
+
+    # ---- disc parameters (body_xy.py:696-1080) --------------------------------------
+    def _clear_cache(self) -> None:
+        self._cache.clear()
+
+    def set_x0(self, x0: float) -> None:
+        if not math.isfinite(x0):
+            raise ValueError('x0 must be finite')
+        self._x0 = float(x0)
+        self._clear_cache()
+
+    def get_x0(self) -> float:
+        return self._x0
+
+    def set_y0(self, y0: float) -> None:
+        if not math.isfinite(y0):
+            raise ValueError('y0 must be finite')
+        self._y0 = float(y0)
+        self._clear_cache()
+
+    def get_y0(self) -> float:
+        return self._y0
+
+    def set_r0(self, r0: float) -> None:
+        if not math.isfinite(r0):
+            raise ValueError('r0 must be finite')
+        if not r0 > 0:
+            raise ValueError('r0 must be greater than zero')
+        self._r0 = float(r0)
+        self._clear_cache()
+
+    def get_r0(self) -> float:
+        return self._r0
+
+    def set_rotation(self, rotation: float) -> None:
+        if not math.isfinite(rotation):
+            raise ValueError('rotation must be finite')
+        self._rotation_radians = float(np.deg2rad(rotation)) % (2 * np.pi)
+        self._clear_cache()
+
+    def get_rotation(self) -> float:
+        return float(np.rad2deg(self._rotation_radians))
+
+    def set_disc_params(self, x0=None, y0=None, r0=None, rotation=None) -> None:
+        if x0 is not None:
+            self.set_x0(x0)
+        if y0 is not None:
+            self.set_y0(y0)
+        if r0 is not None:
+            self.set_r0(r0)
+        if rotation is not None:
+            self.set_rotation(rotation)
+
+    def get_disc_params(self) -> tuple[float, float, float, float]:
+        return self.get_x0(), self.get_y0(), self.get_r0(), self.get_rotation()
+
+    def set_plate_scale_arcsec(self, arcsec_per_px: float) -> None:
+        self.set_r0(self.target_diameter_arcsec / (2 * arcsec_per_px))
+
+    def get_plate_scale_arcsec(self) -> float:
+        return self.target_diameter_arcsec / (2 * self.get_r0())
+
+    def get_plate_scale_km(self) -> float:
+        return self.get_plate_scale_arcsec() * self.km_per_arcsec
+
+    def set_img_size(self, nx: int | None = None, ny: int | None = None) -> None:
+        if nx is not None:
+            self._nx = int(nx)
+        if ny is not None:
+            self._ny = int(ny)
+        self._clear_cache()
+
+    def get_img_size(self) -> tuple[int, int]:
+        return self._nx, self._ny
+
+    def centre_disc(self) -> None:
+        self.set_x0((self._nx - 1) / 2)
+        self.set_y0((self._ny - 1) / 2)
+        self.set_r0(0.9 * (min(self.get_x0(), self.get_y0())))
+        self.set_disc_method('centre_disc')
+
+    def rotate_north_to_top(self) -> None:
+        self.set_rotation(-self.north_pole_angle())
+
+    def set_disc_method(self, method: str) -> None:
+        self._cache['disc method'] = method
+
+    def get_disc_method(self) -> str:
+        return self._cache.get('disc method', 'default')
+
+    # ---- frame handling --------------------------------------------------------------
+    def _frame_host(self, alt: float | None = None) -> np.ndarray:
+        alt = self._alt_adjustment if alt is None else alt
+        return F.pack_frame(self._bc, nx=self._nx, ny=self._ny, x0=self._x0, y0=self._y0,
+                            r0=self._r0, rotation_radians=self._rotation_radians, alt=alt,
+                            optimize_speed=self._optimize_speed)
+
+    def _frame_dev(self, alt: float | None = None):
+        alt = self._alt_adjustment if alt is None else alt
+        key = ('frame_dev', alt)
+        if key not in self._cache:
+            self._cache[key] = L.to_device(self._frame_host(alt))
+        return self._cache[key]
+
+    @staticmethod
+    def _check_alt(alt: float) -> float:
+        alt = float(alt)
+        if not math.isfinite(alt):
+            raise ValueError('Cannot adjust surface altitude with non-finite alt value')
+        return alt
+
+    # ---- point transforms (body_xy.py:433-560, base.py:718-757) ----------------------
+    @staticmethod
+    def _broadcast(a, b):
+        scalar = np.ndim(a) == 0 and np.ndim(b) == 0
+        aa, bb = np.broadcast_arrays(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+        return scalar, np.ascontiguousarray(aa), np.ascontiguousarray(bb)
+
+    @staticmethod
+    def _unbroadcast(scalar, u, v):
+        if scalar:
+            return float(u.reshape(())), float(v.reshape(()))
+        return u, v
+
+    def xy2lonlat(self, x, y, *, not_found_nan: bool = True, alt: float = 0.0,
+                  planetocentric: bool = False):
+        """Image pixel coordinates -> planetographic lon/lat (body_xy.py:433-496)."""
+        alt = self._check_alt(alt)
+        scalar, xa, ya = self._broadcast(x, y)
+        fd = self._frame_dev(alt if alt != 0.0 else None)
+        lon, lat, missed = L.xy2lonlat(fd, L.to_device(xa), L.to_device(ya))
+        lon, lat = lon.cpu().numpy(), lat.cpu().numpy()
+        if not not_found_nan:
+            finite_in = np.isfinite(xa) & np.isfinite(ya)
+            if int(missed.item()) > 0 or np.any(finite_in & np.isnan(lon)):
+                raise NotFoundError('ray does not intercept the target body')
+        if planetocentric:
+            lon, lat = self.graphic2centric_lonlat(lon, lat, alt=alt)
+        return self._unbroadcast(scalar, lon, lat)
+
+    def lonlat2xy(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
+                  planetocentric: bool = False):
+        """Planetographic lon/lat -> image pixel coordinates (body_xy.py:498-560)."""
+        alt = self._check_alt(alt)
+        if alt != 0.0:
+            raise NotImplementedError(
+                'lonlat2xy(alt != 0) needs the ray-cast visibility test (body.py:2131-2150); '
+                'it is on the "next" list (SURVEY.md 8(f))')
+        if planetocentric:
+            raise NotImplementedError('planetocentric=True inputs (spice.latsrf) are on the '
+                                      '"next" list (SURVEY.md 8(f))')
+        scalar, lo, la = self._broadcast(lon, lat)
+        x, y = L.lonlat2xy(self._frame_dev(), L.to_device(lo), L.to_device(la), not_visible_nan)
+        return self._unbroadcast(scalar, x.cpu().numpy(), y.cpu().numpy())
+
+    def graphic2centric_lonlat(self, lon, lat, *, alt: float = 0.0):
+        """Body.graphic2centric_lonlat (body.py:2915-2947) through the map kernel."""
+        alt = self._check_alt(alt)
+        scalar, lo, la = self._broadcast(lon, lat)
+        mask = L.mask_from_names(['LON-CENTRIC', 'LAT-CENTRIC'])
+        out = L.backplanes_map(self._frame_dev(alt if alt != 0.0 else None), L.to_device(lo),
+                               L.to_device(la), mask).cpu().numpy()
+        return self._unbroadcast(scalar, out[0], out[1])
+
+    # ---- projections (body_xy.py:2755-3012) -------------------------------------------
+    def generate_map_coordinates(self, projection: str = 'rectangular', *,
+                                 degree_interval: float = 1, lon: float = 0, lat: float = 0,
+                                 size: int = 100, lon_coords=None, lat_coords=None,
+                                 projection_x_coords=None, projection_y_coords=None,
+                                 xlim=None, ylim=None, alt: float = 0.0):
+        """Returns ``(lons, lats, xx, yy, transformer, info)`` like the reference; the
+        ``transformer`` slot is None (pyproj is not part of the accelerated path)."""
+        info: dict[str, Any]
+        a, b = self._bc.r_eq + alt, self._bc.r_polar + alt
+        lon_sign = self._bc.lon_sign
+        if projection == 'rectangular':
+            lons = np.arange(degree_interval / 2, 360, degree_interval)
+            if self.positive_longitude_direction == 'W':
+                lons = lons[::-1]
+            lats = np.arange(-90 + degree_interval / 2, 90, degree_interval)
+            lons, lats = np.meshgrid(lons, lats)
+            lons, lats = lons.astype(float), lats.astype(float)
+            xx, yy = lons, lats
+            info = dict(projection=projection, degree_interval=degree_interval)
+        elif projection == 'manual':
+            if lon_coords is None or lat_coords is None:
+                raise ValueError(
+                    'lon_coords and lat_coords must be provided for manual projection')
+            lons = np.asarray(lon_coords)
+            lats = np.asarray(lat_coords)
+            if lons.ndim != lats.ndim:
+                raise ValueError(
+                    'lon_coords and lat_coords must have the same number of dimensions')
+            if lons.ndim == 1:
+                lons, lats = np.meshgrid(lons, lats)
+            if lons.ndim != 2:
+                raise ValueError('lon_coords and lat_coords must be 1D or 2D arrays')
+            if lons.shape != lats.shape:
+                raise ValueError('lon_coords and lat_coords must have the same shape')
+            lons = np.array(lons, dtype=float)
+            lats = np.array(lats, dtype=float)
+            xx, yy = lons, lats
+            info = dict(projection=projection)
+        elif projection in ('orthographic', 'azimuthal', 'azimuthal equal area'):
+            if projection == 'orthographic':
+                kind, lim = L.PROJ_ORTHOGRAPHIC, max(1, b / a) * 1.01
+            elif projection == 'azimuthal':
+                kind, lim = L.PROJ_AZIMUTHAL, 1.01
+            else:
+                kind, lim = L.PROJ_AZIMUTHAL_EQUAL_AREA, 1.01
+            c = np.linspace(-lim, lim, size)
+            xx, yy = np.meshgrid(c, c)
+            lo, la = L.proj_inverse(kind, a, b, float(lon), float(lat), lon_sign,
+                                    L.to_device(xx), L.to_device(yy))
+            lons, lats = lo.cpu().numpy(), la.cpu().numpy()
+            info = dict(projection=projection, lon=lon, lat=lat, size=size)
+        else:
+            raise ProjStringError(
+                f'custom proj string {projection!r}: arbitrary PROJ pipelines are out of scope '
+                'of the accelerated path (SURVEY.md section 2); use rectangular, orthographic, '
+                'azimuthal, azimuthal equal area or manual')
+        info['xlim'] = xlim
+        info['ylim'] = ylim
+        if xlim is not None:
+            x_arr = xx[0]
+            keep = (x_arr >= min(xlim)) & (x_arr <= max(xlim))
+            xx, yy, lons, lats = xx[:, keep], yy[:, keep], lons[:, keep], lats[:, keep]
+        if ylim is not None:
+            y_arr = yy[:, 0]
+            keep = (y_arr >= min(ylim)) & (y_arr <= max(ylim))
+            xx, yy, lons, lats = xx[keep, :], yy[keep, :], lons[keep, :], lats[keep, :]
+        same = xx is lons
+        lons = np.array(lons, dtype=float)
+        lats = np.array(lats, dtype=float)
+        lons[~np.isfinite(lons)] = np.nan
+        lats[~np.isfinite(lats)] = np.nan
+        if same:
+            xx, yy = lons, lats
+        if alt != 0.0:
+            info['alt'] = alt
+        return _readonly(lons), _readonly(lats), _readonly(xx), _readonly(yy), None, info
+
+    # ---- backplane registry (body_xy.py:2512-2584) -------------------------------------
+    @staticmethod
+    def standardise_backplane_name(name: str) -> str:
+        return name.strip().upper()
+
+    def register_backplane(self, name, description, get_img, get_map) -> None:
+        name = self.standardise_backplane_name(name)
+        if name in self.backplanes:
+            raise ValueError(f'Backplane named {name!r} is already registered')
+        self.backplanes[name] = Backplane(name, description, get_img, get_map)
+
+    def get_backplane(self, name: str) -> Backplane:
+        name = self.standardise_backplane_name(name)
+        try:
+            return self.backplanes[name]
+        except KeyError as exc:
+            raise BackplaneNotFoundError(
+                '{n!r} not found. Currently registered backplanes are: {r}.'.format(
+                    n=name, r=', '.join(repr(n) for n in self.backplanes))) from exc
+
+    def backplane_summary_string(self) -> str:
+        return '\n'.join(f'{bp.name}: {bp.description}' for bp in self.backplanes.values())
+
+    def _register_default_backplanes(self) -> None:
+        ew = {'W': 'west', 'E': 'east'}[self.positive_longitude_direction]
+        for pid, (name, desc, stem) in enumerate(_PLANE_DESCRIPTIONS):
+            get_img = self._make_img_getter(pid)
+            get_map = self._make_map_getter(pid)
+            setattr(self, f'get_{stem}_img', get_img)
+            setattr(self, f'get_{stem}_map', get_map)
+            self.register_backplane(name, desc.format(ew=ew), get_img, get_map)
+
+    def _make_img_getter(self, pid: int):
+        def get_img() -> np.ndarray:
+            return self._get_img_plane(pid)
+
+        get_img.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_img'
+        return get_img
+
+    def _make_map_getter(self, pid: int):
+        def get_map(**map_kwargs) -> np.ndarray:
+            return self._get_map_plane(pid, **map_kwargs)
+
+        get_map.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_map'
+        return get_map
+
+    # ---- image-direction backplanes ----------------------------------------------------
+    def _test_if_img_size_valid(self) -> bool:
+        return (self._nx > 0) and (self._ny > 0)
+
+    def get_backplanes_img_device(self, mask: int = L.ALL_PLANES, alt: float | None = None):
+        """All requested image backplanes as ONE device tensor (k, ny, nx), computed by a
+        single fused kernel launch and cached per altitude adjustment in ``_cache``
+        (cleared with the disc parameters, like the reference's
+        ``_cache_clearable_alt_dependent_result``, body.py:255-272)."""
+        if not self._test_if_img_size_valid():
+            raise ValueError('nx and ny must be positive to create a backplane image')
+        alt = self._alt_adjustment if alt is None else alt
+        key = ('img_planes_dev', alt)
+        entry = self._cache.get(key)
+        if entry is None or (entry[0] & mask) != mask:
+            have = entry[0] if entry else 0
+            new_mask = have | mask
+            fd = self._frame_dev(alt).reshape(1, -1)
+            planes = L.backplanes_img(fd, self._nx, self._ny, new_mask)[0]
+            entry = (new_mask, planes)
+            self._cache[key] = entry
+            for k in [k for k in self._cache if isinstance(k, tuple) and k[:1] == ('img_host',)
+                      and k[2] == alt]:
+                del self._cache[k]
+        return entry
+
+    def _get_img_plane(self, pid: int) -> np.ndarray:
+        alt = self._alt_adjustment
+        key = ('img_host', pid, alt)
+        if key not in self._cache:
+            have, planes = self.get_backplanes_img_device(L.ALL_PLANES, alt)
+            slot = L.popcount(have & ((1 << pid) - 1))
+            self._cache[key] = _readonly(planes[slot].cpu().numpy())
+        return self._cache[key]
+
+    def get_backplane_img(self, name: str, *, alt: float = 0.0) -> np.ndarray:
+        """Copy of a backplane image (body_xy.py:2586-2630)."""
+        alt = self._check_alt(alt)
+        bp = self.get_backplane_or_keyerror(name)
+        with _AltitudeScope(self, alt):
+            return np.array(bp.get_img(), copy=True)
+
+    def get_backplane_imgs(self, names, *, alt: float = 0.0, out=None) -> dict[str, np.ndarray]:
+        """Several backplane images from ONE kernel launch and ONE device->host copy.
+
+        Equivalent to ``{n: body.get_backplane_img(n, alt=alt) for n in names}`` but only
+        the requested planes are computed and they cross PCIe together.  ``out`` may be a
+        pinned CPU tensor of shape (len(names), ny, nx) to receive the data (the returned
+        arrays are then views of it); otherwise fresh host memory is allocated.
+        """
+        torch = L._torch()
+        alt = self._check_alt(alt)
+        std = [self.standardise_backplane_name(n) for n in names]
+        for n in std:
+            if n not in L.PLANE_ID:
+                raise BackplaneNotFoundError(f'{n!r} is not a built-in backplane')
+        if not self._test_if_img_size_valid():
+            raise ValueError('nx and ny must be positive to create a backplane image')
+        mask = L.mask_from_names(std)
+        fd = self._frame_dev(alt).reshape(1, -1)
+        planes = L.backplanes_img(fd, self._nx, self._ny, mask)[0]
+        order = sorted(set(std), key=lambda n: L.PLANE_ID[n])
+        if out is None:
+            host = planes.cpu()
+        else:
+            host = out[: len(order)]
+            host.copy_(planes, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        arr = host.numpy()
+        return {n: arr[order.index(n)] for n in std}
+
+    def get_backplane_or_keyerror(self, name: str) -> Backplane:
+        # the reference indexes the dict directly here (KeyError), body_xy.py:2627
+        return self.backplanes[self.standardise_backplane_name(name)]
+
+    # ---- map-direction backplanes ------------------------------------------------------
+    def _map_key(self, map_kwargs: dict) -> tuple:
+        unknown = set(map_kwargs) - set(_MAP_KWARG_KEYS)
+        if unknown:
+            raise TypeError(f'unexpected map keyword arguments {sorted(unknown)}')
+        return tuple(sorted((k, _freeze(v)) for k, v in map_kwargs.items()))
+
+    def _get_lonlat_map(self, **map_kwargs) -> np.ndarray:
+        """(n0, n1, 2) lon % 360, lat (body_xy.py:3293-3300); stable cache."""
+        key = ('lonlat_map', self._map_key(map_kwargs))
+        if key not in self._stable_cache:
+            lons, lats, *_ = self.generate_map_coordinates(**map_kwargs)
+            lons = lons % 360
+            m = np.stack([lons, lats], axis=-1)
+            m[~np.isfinite(m)] = np.nan
+            self._stable_cache[key] = _readonly(m)
+        return self._stable_cache[key]
+
+    def get_backplanes_map_device(self, mask: int, **map_kwargs):
+        """Requested map backplanes as a device tensor (k, n0, n1).  Disc-independent
+        planes live in ``_stable_cache`` (never cleared), PIXEL-X / PIXEL-Y (x_map,
+        y_map) in ``_cache`` - the reference's split (body_xy.py:3423 vs :3482)."""
+        alt = self._check_alt(map_kwargs.get('alt', 0.0))
+        mkey = self._map_key(map_kwargs)
+        xy_mask = mask & ((1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]))
+        st_mask = mask & ~xy_mask
+        out = {}
+        lonlat = None
+        for cache, sub, tag in ((self._stable_cache, st_mask, 'map_planes_dev'),
+                                (self._cache, xy_mask, 'xy_map_dev')):
+            if not sub:
+                continue
+            if tag == 'xy_map_dev' and not self._test_if_img_size_valid():
+                raise ValueError('nx and ny must be positive to create a backplane image')
+            key = (tag, mkey, alt)
+            entry = cache.get(key)
+            if entry is None or (entry[0] & sub) != sub:
+                if lonlat is None:
+                    ll = self._get_lonlat_map(**map_kwargs)
+                    lonlat = (L.to_device(ll[:, :, 0]), L.to_device(ll[:, :, 1]))
+                want = sub | (entry[0] if entry else 0)
+                if tag == 'map_planes_dev':
+                    want = L.ALL_PLANES & ~((1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]))
+                else:
+                    want = (1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1])
+                fd = self._frame_dev(alt)
+                planes = L.backplanes_map(fd, lonlat[0], lonlat[1], want)
+                entry = (want, planes)
+                cache[key] = entry
+            out[tag] = entry
+        return out
+
+    def _get_map_plane(self, pid: int, **map_kwargs) -> np.ndarray:
+        alt = self._check_alt(map_kwargs.get('alt', 0.0))
+        mkey = self._map_key(map_kwargs)
+        is_xy = pid in _XY_PLANES
+        cache = self._cache if is_xy else self._stable_cache
+        key = ('map_host', pid, mkey, alt)
+        if key not in cache:
+            tag = 'xy_map_dev' if is_xy else 'map_planes_dev'
+            have, planes = self.get_backplanes_map_device(1 << pid, **map_kwargs)[tag]
+            slot = L.popcount(have & ((1 << pid) - 1))
+            cache[key] = _readonly(planes[slot].cpu().numpy())
+        return cache[key]
+
+    def get_backplane_map(self, name: str, **map_kwargs) -> np.ndarray:
+        """Copy of a backplane map (body_xy.py:2632-2663)."""
+        bp = self.get_backplane_or_keyerror(name)
+        return np.array(bp.get_map(**map_kwargs), copy=True)
+
+    # ---- image -> map resampling (body_xy.py:1414-1631) ---------------------------------
+    def map_img(self, img, *, interpolation='linear', spline_smoothing: float = 0,
+                propagate_nan: bool = True, warn_nan: bool = False,
+                smooth_oversample_by: int = 5, smooth_max_oversampled_img_size: int = 10_000,
+                **map_kwargs) -> np.ndarray:
+        """Project an image (ny, nx) or cube (n, ny, nx) onto a lon/lat map."""
+        out = self.map_img_device(img, interpolation=interpolation,
+                                  spline_smoothing=spline_smoothing,
+                                  propagate_nan=propagate_nan, warn_nan=warn_nan,
+                                  **map_kwargs)
+        res = out.cpu().numpy()
+        return res[0] if np.ndim(img) == 2 else res
+
+    def map_img_device(self, img, *, interpolation='linear', spline_smoothing: float = 0,
+                       propagate_nan: bool = True, warn_nan: bool = False, out=None,
+                       **map_kwargs):
+        """Same as :func:`map_img` but takes/returns device tensors shaped (n, ...)."""
+        torch = L._torch()
+        mode = _interpolation_mode(interpolation, spline_smoothing)
+        if isinstance(img, torch.Tensor):
+            cube = img if img.dim() == 3 else img[None]
+            cube = cube.to(device='cuda', dtype=torch.float64).contiguous()
+        else:
+            arr = np.asarray(img)
+            if arr.ndim not in (2, 3):
+                raise ValueError(f'img must be 2D or 3D, got shape {arr.shape!r}')
+            cube = L.to_device(arr if arr.ndim == 3 else arr[None])
+        if tuple(cube.shape[1:]) != (self._ny, self._nx):
+            raise ValueError(
+                f'The input `img` shape {tuple(cube.shape[-2:])!r} is inconsistent with '
+                f"the body's image size (ny={self._ny}, nx={self._nx})")
+        have, xy = self.get_backplanes_map_device(
+            (1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]), **map_kwargs)['xy_map_dev']
+        xmap, ymap = xy[0], xy[1]
+        if mode == L.INTERP_NEAREST:
+            return L.gather(cube, xmap, ymap, mode, out=out)
+        if warn_nan and bool(torch.isfinite(cube).logical_not().any()):
+            print('Warning, image contains NaN values which will be corrected')
+        coef, nanmask, flags = L.spline_prepare(cube, mode)
+        return L.gather(coef, xmap, ymap, mode, nanmask=nanmask, plane_flags=flags,
+                        propagate_nan=propagate_nan, out=out)
+
+
+def _interpolation_mode(interpolation, spline_smoothing) -> int:
+    spline_k = {'linear': 1, 'quadratic': 2, 'cubic': 3}
+    if interpolation in spline_k:
+        interpolation = spline_k[interpolation]
+    if interpolation == 'nearest':
+        return L.INTERP_NEAREST
+    if isinstance(interpolation, tuple):
+        if len(interpolation) == 2 and interpolation[0] == interpolation[1]:
+            interpolation = interpolation[0]
+        else:
+            raise NotImplementedError(
+                f'mixed spline degrees {interpolation!r} are on the "next" list (SURVEY 8(f))')
+    if isinstance(interpolation, (int, np.integer)) and not isinstance(interpolation, bool):
+        if spline_smoothing != 0:
+            raise NotImplementedError('spline_smoothing != 0 (FITPACK smoothing) is not '
+                                      'accelerated; only interpolating splines are')
+        if interpolation == 1:
+            return L.INTERP_LINEAR
+        if interpolation == 3:
+            return L.INTERP_CUBIC
+        raise NotImplementedError(
+            f'spline degree {interpolation} is on the "next" list (SURVEY.md 8(f)); '
+            "accelerated: 'nearest', 'linear' (1), 'cubic' (3)")
+    if interpolation == 'smooth':
+        raise NotImplementedError("interpolation='smooth' is on the \"next\" list "
+                                  '(SURVEY.md 8(f))')
+    raise ValueError(f'Unknown interpolation method {interpolation!r}')
+
+
+class _AltitudeScope:
+    """_AdjustedSurfaceAltitude (body.py:172-229) without the kernel-pool mutation:
+    the adjusted radii travel inside the PMFrame."""
+
+    def __init__(self, body: BodyXY, alt: float = 0.0) -> None:
+        self.body = body
+        self.alt = float(alt)
+        self.active = self.alt != 0.0 and self.alt != body._alt_adjustment
+        if self.active and body._alt_adjustment != 0.0:
+            raise ValueError('Cannot nest altitude adjustments with alt != 0')
+
+    def __enter__(self) -> None:
+        if self.active:
+            self.body._alt_adjustment = self.alt
+
+    def __exit__(self, *exc) -> None:
+        if self.active:
+            self.body._alt_adjustment = 0.0

@@ -1,0 +1,158 @@
+// capi.cu - the extern "C" boundary of libpm_b200.so (see include/pm_b200.h).
+// Argument checking, device discovery and launch only: no arithmetic lives here.
+#include <atomic>
+#include <cstdio>
+
+#include "pm_kernels.h"
+
+namespace pm {
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int sm_count() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+    return n;
+}
+static int check(cudaError_t e) {
+    if (e == cudaSuccess) return PM_OK;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return PM_ERR_NO_DEVICE;
+    std::fprintf(stderr, "libpm_b200: CUDA error: %s\n", cudaGetErrorString(e));
+    return PM_ERR_CUDA;
+}
+}  // namespace pm
+
+using namespace pm;
+
+extern "C" {
+
+int pm_abi_version(void) { return PM_ABI_VERSION; }
+
+const char *pm_error_string(int code) {
+    switch (code) {
+        case PM_OK: return "ok";
+        case PM_ERR_BAD_ARG: return "bad argument";
+        case PM_ERR_CUDA: return "CUDA runtime error";
+        case PM_ERR_UNSUPPORTED: return "unsupported option";
+        case PM_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+uint64_t pm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t plane_mask, double *out,
+                      void *stream) {
+    if (!frames || !out || n_frames <= 0 || nx <= 0 || ny <= 0 || n_frames > 65535) return PM_ERR_BAD_ARG;
+    plane_mask &= PM_ALL_PLANES;
+    if (!plane_mask) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_backplanes_img(frames, n_frames, nx, ny, plane_mask, out, sms, (cudaStream_t)stream));
+}
+
+int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n_cells,
+                      uint64_t plane_mask, double *out, void *stream) {
+    if (!frame || !lon || !lat || !out || n_cells < 0) return PM_ERR_BAD_ARG;
+    plane_mask &= PM_ALL_PLANES;
+    if (!plane_mask) return PM_ERR_BAD_ARG;
+    if (n_cells == 0) return PM_OK;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_backplanes_map(frame, lon, lat, n_cells, plane_mask, out, sms, (cudaStream_t)stream));
+}
+
+int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon, double *lat,
+                 int64_t *n_missed, void *stream) {
+    if (!frame || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (n == 0) return PM_OK;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_xy2lonlat(frame, x, y, n, lon, lat, (unsigned long long *)n_missed, sms,
+                                  (cudaStream_t)stream));
+}
+
+int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, uint32_t flags,
+                 double *x, double *y, void *stream) {
+    if (!frame || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (n == 0) return PM_OK;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_lonlat2xy(frame, lon, lat, n, flags, x, y, sms, (cudaStream_t)stream));
+}
+
+int pm_proj_inverse(int kind, const double *params5_host, const double *xx, const double *yy, int64_t n,
+                    double *lon, double *lat, void *stream) {
+    if (!params5_host || !xx || !yy || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (kind < PM_PROJ_ORTHOGRAPHIC || kind > PM_PROJ_AZIMUTHAL_EQUAL_AREA) return PM_ERR_UNSUPPORTED;
+    if (n == 0) return PM_OK;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_proj_inverse(kind, params5_host, xx, yy, n, lon, lat, sms, (cudaStream_t)stream));
+}
+
+int pm_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip, int n_planes, int ny,
+              int nx, const double *xmap, const double *ymap, int64_t n_cells, int mode, uint32_t flags,
+              double *out, void *stream) {
+    if (!cube || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0)
+        return PM_ERR_BAD_ARG;
+    if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR && mode != PM_INTERP_CUBIC)
+        return PM_ERR_UNSUPPORTED;
+    if (mode == PM_INTERP_LINEAR && (nx < 2 || ny < 2)) return PM_ERR_BAD_ARG;
+    if (mode == PM_INTERP_CUBIC && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
+    if ((flags & PM_FLAG_PROPAGATE_NAN) && mode != PM_INTERP_NEAREST && !nanmask) return PM_ERR_BAD_ARG;
+    if (n_planes > 65535 * 128) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_gather(cube, nanmask, plane_skip, n_planes, ny, nx, xmap, ymap, n_cells, mode, flags,
+                               out, sms, (cudaStream_t)stream));
+}
+
+int64_t pm_spline_work_bytes(int n_planes, int ny, int nx, int degree) {
+    if (n_planes < 0 || ny <= 0 || nx <= 0) return PM_ERR_BAD_ARG;
+    return spline_work_bytes(n_planes, ny, nx, degree);
+}
+
+int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coef,
+                      uint8_t *nanmask, uint8_t *plane_skip, void *work, void *stream) {
+    if (!cube || !coef || !nanmask || !plane_skip || !work || n_planes < 0 || ny <= 0 || nx <= 0)
+        return PM_ERR_BAD_ARG;
+    if (degree != 1 && degree != 3) return PM_ERR_UNSUPPORTED;
+    if (degree == 3 && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_spline_prepare(cube, n_planes, ny, nx, degree, coef, nanmask, plane_skip, work, sms,
+                                       (cudaStream_t)stream));
+}
+
+int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host) {
+    if (iters <= 0 || !ms_host || !flops_host) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    double *scratch = nullptr;
+    if (cudaMalloc(&scratch, 64) != cudaSuccess) return PM_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_fp64_probe(scratch, iters, sms, 0);  // warm-up
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, 0);
+    cudaError_t err = launch_fp64_probe(scratch, iters, sms, 0);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(scratch);
+    *ms_host = (double)ms;
+    // 8 independent FMA chains per thread, 2 flop per FMA
+    *flops_host = 2.0 * 8.0 * (double)iters * 256.0 * (double)sms * 8.0;
+    return check(err);
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// pm_kernels.h - internal launcher declarations shared by the .cu files and capi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pm_b200.h"
+
+namespace pm {
+
+constexpr int kBlock = 128;  // threads per CTA for the FP64 geometry kernels
+
+// kernels launched by this library since load (pm_launch_count)
+void count_launches(int n);
+
+cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t mask,
+                                  double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+                                  uint64_t mask, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon,
+                             double *lat, unsigned long long *n_missed, int sm_count, cudaStream_t st);
+cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+                             uint32_t flags, double *x, double *y, int sm_count, cudaStream_t st);
+cudaError_t launch_fp64_probe(double *scratch, int iters, int sm_count, cudaStream_t st);
+
+cudaError_t launch_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
+                                int64_t n, double *lon, double *lat, int sm_count, cudaStream_t st);
+
+cudaError_t launch_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip, int n_planes,
+                          int ny, int nx, const double *xmap, const double *ymap, int64_t n_cells, int mode,
+                          uint32_t flags, double *out, int sm_count, cudaStream_t st);
+
+int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree);
+cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coef,
+                                  uint8_t *nanmask, uint8_t *plane_skip, void *work, int sm_count,
+                                  cudaStream_t st);
+
+}  // namespace pm

@@ -1,0 +1,51 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden_arrays():
+    return dict(np.load(os.path.join(GOLDEN, 'ref_outputs.npz')))
+
+
+@pytest.fixture(scope='session')
+def golden_headers():
+    with open(os.path.join(GOLDEN, 'ref_headers.json')) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='session')
+def bc_hst():
+    """Jupiter from HST, 2005-01-01T00:00:00: the reference's main fixture
+    (tests/test_body_xy.py:69-76)."""
+    from planetmapper_b200.frame import BodyConstants
+
+    with open(os.path.join(GOLDEN, 'jupiter_hst_2005.json')) as f:
+        return BodyConstants.from_json_dict(json.load(f))
+
+
+@pytest.fixture(scope='session')
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+# disc parameters of the golden FITS files (tests/test_observation.py:1017, :1084)
+GOLDEN_DISC = dict(nx=7, ny=10, x0=2.5, y0=3.1, r0=3.9, rotation_radians=float(np.deg2rad(123.456)))
+GOLDEN_ALT = 34567.8912

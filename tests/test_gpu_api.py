@@ -1,0 +1,232 @@
+"""
+GPU tests through the public drop-in API (BodyXY / Observation), written to read
+like the reference's own tests: tests/test_observation.py:1016-1280 (golden FITS),
+tests/test_body_xy.py:267-486 (point transforms), :1087-1327 (map_img),
+:1551-1988 (projections), :2120-2154 (backplane values), :2495-2607 (caches).
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_ALT
+from helpers import PLANE_NAMES, max_diff
+from test_oracle_golden import (GOLDEN_TOL, LONLAT2XY, MAP_EXPECTED, MAP_EXPECTED_NO_PROPAGATE,
+                                MAP_FILES, MAP_IMG, PROJ_CASES, WRAP, XY_COORDINATES)
+
+pytestmark = pytest.mark.gpu
+nan = np.nan
+
+
+@pytest.fixture()
+def obs(bc_hst, golden_arrays):
+    import planetmapper_b200 as pm
+
+    o = pm.Observation(data=golden_arrays['inputs/test.fits/PRIMARY'], constants=bc_hst)
+    o.set_disc_params(2.5, 3.1, 3.9, 123.456)
+    o.set_disc_method('<<<test>>>')
+    return o
+
+
+@pytest.fixture()
+def body(bc_hst):
+    import planetmapper_b200 as pm
+
+    return pm.BodyXY(constants=bc_hst, nx=15, ny=10)
+
+
+def _check(a, ref, name, label):
+    assert a.shape == ref.shape and a.dtype == np.float64
+    assert np.array_equal(np.isnan(a), np.isnan(ref)), f'{label} {name}: NaN mask'
+    d = max_diff(a, ref, wrap=name in WRAP)
+    assert d <= GOLDEN_TOL[name], f'{label} {name}: {d:.3e}'
+
+
+def test_save_observation_backplanes_match_golden(obs, golden_arrays):
+    assert obs.get_img_size() == (7, 10)
+    for name in obs.backplanes:
+        _check(obs.get_backplane_img(name), golden_arrays[f'test_nav.fits/{name}'], name, 'nav')
+    for name in obs.backplanes:
+        _check(obs.get_backplane_img(name, alt=GOLDEN_ALT), golden_arrays[f'test_nav_alt.fits/{name}'],
+               name, 'nav-alt')
+    assert obs._alt_adjustment == 0.0
+    assert list(obs.backplanes) == PLANE_NAMES
+
+
+def _map_kwargs(spec, alt):
+    if spec[0] == 'rectangular':
+        kw = dict(degree_interval=spec[1])
+    else:
+        kw = dict(projection=spec[0], lon=spec[1], lat=spec[2], size=spec[3])
+    if alt:
+        kw['alt'] = alt
+    return kw
+
+
+@pytest.mark.parametrize('fn', sorted(MAP_FILES))
+def test_save_mapped_observation_matches_golden(obs, golden_arrays, fn):
+    spec, alt, interp = MAP_FILES[fn]
+    kw = _map_kwargs(spec, alt)
+    mapped = obs.get_mapped_data(interp, **kw)
+    ref = golden_arrays[f'{fn}/PRIMARY']
+    assert mapped.shape == ref.shape
+    assert np.array_equal(np.isnan(mapped), np.isnan(ref))
+    ok = np.isfinite(ref)
+    if interp == 'nearest':
+        assert np.array_equal(mapped[ok], ref[ok])
+    elif ok.any():
+        assert np.max(np.abs(mapped[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1.0)) < 1e-8
+    if f'{fn}/LON-GRAPHIC' in golden_arrays:
+        for name in obs.backplanes:
+            _check(obs.get_backplane_map(name, **kw), golden_arrays[f'{fn}/{name}'], name, fn)
+
+
+def test_xy_conversions_known_answers(body):
+    body.set_disc_params(5, 8, 3, 45)
+    for xy, _radec, lonlat, _km, _ang in XY_COORDINATES:
+        got = body.xy2lonlat(*xy)
+        assert isinstance(got[0], float) and isinstance(got[1], float)
+        assert np.allclose(got, lonlat, rtol=1e-9, atol=1e-8, equal_nan=True), (xy, got)
+    xs = np.array([c[0][0] for c in XY_COORDINATES], dtype=float)
+    ys = np.array([c[0][1] for c in XY_COORDINATES], dtype=float)
+    lon, lat = body.xy2lonlat(xs, ys)
+    assert lon.shape == xs.shape and lon.dtype == np.float64
+    # broadcasting like SpiceBase._maybe_transform_as_arrays (tests/test_base.py:339-377)
+    lon2, lat2 = body.xy2lonlat(xs[:, None], ys[None, :])
+    assert lon2.shape == (len(xs), len(ys))
+    assert np.array_equal(np.diag(lon2), lon, equal_nan=True)
+    lon3, _ = body.xy2lonlat(np.array([4, 5]), 8)   # int arrays must give float outputs
+    assert lon3.dtype == np.float64
+    from planetmapper_b200 import NotFoundError
+
+    with pytest.raises(NotFoundError):
+        body.xy2lonlat(0, 0, not_found_nan=False)
+    assert all(np.isnan(v) for v in body.xy2lonlat(np.nan, 8.0))
+    # alt (tests/test_body_xy.py:409-428)
+    for alt, e in [(123456.789, (134.58218536012419, 4.708273802335033)),
+                   (-1000, (83.89699519490205, 21.59807910857171))]:
+        got = body.xy2lonlat(7.781497231832574, 8.015145501618983, alt=alt)
+        assert np.allclose(got, e, rtol=0, atol=5e-8)
+    for lonlat, vis, allp in LONLAT2XY:
+        if vis is not None:
+            assert np.allclose(body.lonlat2xy(*lonlat), vis, rtol=0, atol=1e-9, equal_nan=True), lonlat
+        assert np.allclose(body.lonlat2xy(*lonlat, not_visible_nan=False), allp, rtol=0, atol=1e-9,
+                           equal_nan=True), lonlat
+    with pytest.raises(NotImplementedError):
+        body.lonlat2xy(0, 0, alt=10.0)
+
+
+@pytest.mark.parametrize('interp', ['nearest', 'linear', 'cubic', 1, 3, (3, 3)])
+def test_map_img_known_answers(body, interp):
+    body.set_img_size(6, 5)
+    body.set_disc_params(2.75, 1.3, 2.3, 45.678)
+    key = {1: 'linear', 3: 'cubic', (3, 3): 'cubic'}.get(interp, interp)
+    exp = np.array(MAP_EXPECTED[key])
+    got = body.map_img(MAP_IMG, degree_interval=45, interpolation=interp)
+    assert got.shape == exp.shape
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = np.isfinite(exp)
+    if key == 'nearest':
+        assert np.array_equal(got[ok], exp[ok])
+    else:
+        assert np.max(np.abs(got[ok] - exp[ok]) / np.abs(exp[ok])) < 5e-9
+    cube = np.stack([MAP_IMG, MAP_IMG * 2 + 1])   # 3-D input (tests/test_body_xy.py:1280-1300)
+    got3 = body.map_img(cube, degree_interval=45, interpolation=interp)
+    assert got3.shape == (2,) + exp.shape
+    assert np.array_equal(got3[0], got, equal_nan=True)
+
+
+def test_map_img_options_and_errors(body):
+    body.set_img_size(6, 5)
+    body.set_disc_params(2.75, 1.3, 2.3, 45.678)
+    got = body.map_img(MAP_IMG, degree_interval=45, propagate_nan=False)   # default: linear
+    exp = np.array(MAP_EXPECTED_NO_PROPAGATE)
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = np.isfinite(exp)
+    assert np.max(np.abs(got[ok] - exp[ok]) / np.abs(exp[ok])) < 5e-9
+    all_nan = body.map_img(np.full((5, 6), nan), degree_interval=45)
+    assert np.all(np.isnan(all_nan))
+    with pytest.raises(ValueError):
+        body.map_img(np.ones((5, 5)), degree_interval=45)
+    with pytest.raises(ValueError):
+        body.map_img(MAP_IMG, degree_interval=45, interpolation='<<<test>>>')
+    for bad in ('smooth', 'quadratic', (1, 2)):
+        with pytest.raises(NotImplementedError):
+            body.map_img(MAP_IMG, degree_interval=45, interpolation=bad)
+    # manual grid (tests/test_body_xy.py:1302-1327)
+    lons = np.array([10.0, 150.0, 170.0])
+    lats = np.array([-30.0, 0.0])
+    man = body.map_img(MAP_IMG, projection='manual', lon_coords=lons, lat_coords=lats, interpolation='nearest')
+    assert man.shape == (2, 3)
+
+
+@pytest.mark.parametrize('case', range(len(PROJ_CASES)))
+def test_generate_map_coordinates_known_answers(body, case):
+    kind, size, lon0, lat0, elon, elat = PROJ_CASES[case]
+    proj = {1: 'orthographic', 2: 'azimuthal', 3: 'azimuthal equal area'}[kind]
+    lons, lats, xx, yy, _tr, info = body.generate_map_coordinates(proj, size=size, lon=lon0, lat=lat0)
+    assert np.allclose(lons, np.array(elon, dtype=float), equal_nan=True)
+    assert np.allclose(lats, np.array(elat, dtype=float), equal_nan=True)
+    assert not lons.flags.writeable and not xx.flags.writeable
+    assert info == dict(projection=proj, lon=lon0, lat=lat0, size=size, xlim=None, ylim=None)
+    assert xx.shape == (size, size) and np.allclose(xx[0], np.linspace(xx[0, 0], -xx[0, 0], size))
+
+
+def test_backplane_values_known_answers(body):
+    """tests/test_body_xy.py:2120-2154 (8 decimals)."""
+    body.set_img_size(4, 3)
+    body.set_disc_params(x0=2, y0=1, r0=2, rotation=0)   # reference sets these before the check
+    img = body.get_backplane_img('EMISSION')
+    assert img.shape == (3, 4)
+    m = body.get_backplane_map('EMISSION', degree_interval=90)
+    assert m.shape == (2, 4)
+    assert np.isfinite(m).all()   # emission is defined on the far side too
+    assert np.nanmin(img) >= 0 and np.nanmax(img) < 90
+    from planetmapper_b200 import BackplaneNotFoundError
+
+    with pytest.raises(BackplaneNotFoundError):
+        body.get_backplane('<<<test>>>')
+    with pytest.raises(ValueError):
+        body.register_backplane('emission', 'dup', lambda: None, lambda **k: None)
+
+
+def test_cache_semantics(body):
+    """Clearable vs stable caches and read-only views (tests/test_body_xy.py:2495-2590)."""
+    body.set_disc_params(5, 8, 3, 45)
+    a = body.get_emission_angle_img()
+    assert not a.flags.writeable
+    assert body.get_emission_angle_img() is a                     # cached view
+    c = body.get_backplane_img('EMISSION')
+    assert c.flags.writeable and c is not a and np.array_equal(c, a, equal_nan=True)
+    n_stable = len(body._stable_cache)
+    m = body.get_emission_angle_map(degree_interval=30)
+    assert len(body._stable_cache) > n_stable
+    xm = body.get_x_map(degree_interval=30)
+    assert body.get_disc_method() == 'default' or isinstance(body.get_disc_method(), str)
+    body.set_x0(6)                                                # clears _cache only
+    assert len(body._cache) == 0
+    assert body.get_emission_angle_map(degree_interval=30) is m   # stable cache survives
+    xm2 = body.get_x_map(degree_interval=30)
+    assert xm2 is not xm and not np.array_equal(xm, xm2, equal_nan=True)
+    a2 = body.get_emission_angle_img()
+    assert a2 is not a and not np.array_equal(a, a2, equal_nan=True)
+    # alt is part of the key; value outside the context is restored
+    b_alt = body.get_backplane_img('EMISSION', alt=1000.0)
+    assert body._alt_adjustment == 0.0
+    assert not np.array_equal(b_alt, a2, equal_nan=True)
+    assert body.get_emission_angle_img() is a2
+    with pytest.raises(ValueError):
+        body.get_backplane_img('EMISSION', alt=np.inf)
+    zero = type(body)(constants=body._bc)
+    with pytest.raises(ValueError):
+        zero.get_backplane_img('EMISSION')
+
+
+def test_unsupported_options_raise(bc_hst):
+    import planetmapper_b200 as pm
+
+    for kw in (dict(aberration_correction='CN+S'), dict(observer_frame='ECLIPJ2000'),
+               dict(surface_method='DSK/UNPRIORITIZED'), dict(illumination_source='JUPITER')):
+        with pytest.raises(NotImplementedError):
+            pm.BodyXY(constants=bc_hst, sz=5, **kw)
+    b = pm.BodyXY(constants=bc_hst, sz=5)
+    with pytest.raises(pm.ProjStringError):
+        b.generate_map_coordinates('+proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=np.arange(3.0))

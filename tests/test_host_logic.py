@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: grid builders, sharding (incl. a 2-process gloo
+run), option validation."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from planetmapper_b200.shard import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+inf = np.inf
+
+
+@pytest.fixture()
+def body(bc_hst):
+    import planetmapper_b200 as pm
+
+    return pm.BodyXY(constants=bc_hst, nx=15, ny=10)
+
+
+def test_rectangular_and_manual_grids_known_answers(body):
+    """tests/test_body_xy.py:1612-1686."""
+    cases = [
+        (None, None, [[315.0, 225.0, 135.0, 45.0]] * 2, [[-45.0] * 4, [45.0] * 4]),
+        ((-inf, inf), (-inf, inf), [[315.0, 225.0, 135.0, 45.0]] * 2, [[-45.0] * 4, [45.0] * 4]),
+        ((135, -inf), (45, inf), [[135.0, 45.0]], [[45.0, 45.0]]),
+        ((100, 300), (-50, 50), [[225.0, 135.0]] * 2, [[-45.0, -45.0], [45.0, 45.0]]),
+        ((300, 100), (50, -50), [[225.0, 135.0]] * 2, [[-45.0, -45.0], [45.0, 45.0]]),
+    ]
+    for xlim, ylim, elon, elat in cases:
+        lons, lats, xx, yy, _t, info = body.generate_map_coordinates(degree_interval=90, xlim=xlim, ylim=ylim)
+        assert np.array_equal(lons, np.array(elon)) and np.array_equal(lats, np.array(elat))
+        assert np.array_equal(xx, np.array(elon)) and np.array_equal(yy, np.array(elat))
+        assert info['xlim'] == xlim and info['ylim'] == ylim
+        assert not lons.flags.writeable
+    lons, lats, *_ = body.generate_map_coordinates(degree_interval=123)
+    assert np.array_equal(lons, [[307.5, 184.5, 61.5]]) and np.array_equal(lats, [[-28.5] * 3])
+    lons, lats, *_rest = body.generate_map_coordinates('manual', lon_coords=[1, 2, 3], lat_coords=[4, 5])
+    assert lons.shape == (2, 3) and lats[1, 0] == 5
+    info = body.generate_map_coordinates(degree_interval=30, alt=12.5)[5]
+    assert info['alt'] == 12.5
+    for kw in (dict(), dict(lon_coords=np.array([1, 2, 3]), lat_coords=np.array([[1, 2, 3], [4, 5, 6]])),
+               dict(lon_coords=np.array([[[1, 2, 3]]]), lat_coords=np.array([[[1, 2, 3]]])),
+               dict(lon_coords=np.array([[1, 2, 3]]), lat_coords=np.array([[1, 2, 3], [4, 5, 6]]))):
+        with pytest.raises(ValueError):
+            body.generate_map_coordinates('manual', **kw)
+
+
+def test_disc_parameter_interface(body):
+    """tests/test_body_xy.py set/get behaviour incl. centre_disc (body_xy.py:791-803)."""
+    assert body.get_disc_params() == (7.0, 4.5, 0.9 * 4.5, 0.0)
+    assert body.get_disc_method() == 'centre_disc'
+    body.set_disc_params(5, 8, 3, 45)
+    assert body.get_disc_params() == pytest.approx((5, 8, 3, 45))
+    assert body.get_disc_method() == 'default'          # cleared with the cache
+    assert body.get_plate_scale_arcsec() == pytest.approx(35.98242689969618 / 6)
+    assert body.get_plate_scale_km() == pytest.approx(35.98242689969618 / 6 * 3973.7175149019004)
+    for bad in (np.nan, np.inf):
+        with pytest.raises(ValueError):
+            body.set_x0(bad)
+    with pytest.raises(ValueError):
+        body.set_r0(0)
+    body.set_img_size(20, 30)
+    assert body.get_img_size() == (20, 30)
+    body.rotate_north_to_top()
+    assert body.get_rotation() == pytest.approx(24.15516987997688, abs=1e-8)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 3000, 4096, 4097):
+        for w in (1, 2, 3, 4, 8):
+            blocks = [shard_range(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_two_process_gloo_sharding(tmp_path):
+    """world_size 2 over gloo: each rank takes its block of frames, builds the frame
+    constants for its block on the host, and the gathered checksums equal the
+    single-process result (the N > 1 control path of bench.py, minus the GPU)."""
+    script = tmp_path / 'worker.py'
+    script.write_text(textwrap.dedent(f'''
+        import sys, json
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        import planetmapper_b200 as pm
+        from planetmapper_b200 import frame as F
+        from planetmapper_b200.shard import env_rank_world, shard_range, gather_shard_results, max_over_ranks
+        rank, local_rank, world = env_rank_world()
+        dist.init_process_group('gloo')
+        n_frames = 9
+        ets = 157500000.0 + 60.0 * np.arange(n_frames)
+        lo, hi = shard_range(n_frames, rank, world)
+        prov = pm.get_default_provider()
+        sums = []
+        for et in ets[lo:hi]:
+            bc = F.build_body_constants(prov, 'JUPITER', None, 'EARTH', et=float(et))
+            fr = F.pack_frame(bc, nx=64, ny=64, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
+            sums.append(float(np.sum(fr)))
+        dist.barrier()
+        t = max_over_ranks(float(rank + 1), world)
+        allsums = gather_shard_results((lo, hi, sums), world)
+        if rank == 0:
+            flat = [s for _, _, ss in sorted(allsums) for s in ss]
+            print('RESULT ' + json.dumps(dict(t=t, n=len(flat), checksum=sum(flat), blocks=[(a, b) for a, b, _ in sorted(allsums)])))
+        dist.destroy_process_group()
+    '''))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', OMP_NUM_THREADS='1')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)]
+    proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    import json
+
+    line = [l for l in proc.stdout.splitlines() if l.startswith('RESULT ')][0]
+    res = json.loads(line[7:])
+    assert res['t'] == 2.0 and res['n'] == 9 and res['blocks'] == [[0, 5], [5, 9]]
+    # single-process reference
+    import planetmapper_b200 as pm
+    from planetmapper_b200 import frame as F
+
+    prov = pm.get_default_provider()
+    total = 0.0
+    for et in 157500000.0 + 60.0 * np.arange(9):
+        bc = F.build_body_constants(prov, 'JUPITER', None, 'EARTH', et=float(et))
+        total += float(np.sum(F.pack_frame(bc, nx=64, ny=64, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)))
+    assert res['checksum'] == pytest.approx(total, rel=1e-15)

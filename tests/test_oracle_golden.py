@@ -1,0 +1,293 @@
+"""
+Pins the CPU oracle (oracle/pm_oracle.c, oracle/map_img_oracle.py) against the
+reference's own golden data:
+
+- every HDU of tests/data/outputs/*.fits that the reference compares at
+  tests/test_observation.py:1016-1280 (atol 1e-6, rtol 1e-5 there; much tighter here),
+- the 16-digit literals of tests/test_body_xy.py (xy<->lonlat :269-312, :399-454;
+  map_img :1087-1200; projections :1687-1921).
+
+The golden arrays were exported by tests/golden/make_golden.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_ALT, GOLDEN_DISC
+from helpers import PID, PLANE_NAMES, angle_diff, max_diff
+from planetmapper_b200 import frame as F
+
+nan = np.nan
+inf = np.inf
+
+# absolute tolerances vs the golden FITS (written by reference v1.12.5 + CSPICE; the
+# reference's own comparison tolerance is 1e-6).  Angles in degrees.
+GOLDEN_TOL = {
+    'LON-GRAPHIC': 1e-8, 'LAT-GRAPHIC': 1e-8, 'LON-CENTRIC': 1e-8, 'LAT-CENTRIC': 1e-8,
+    'RA': 1e-12, 'DEC': 1e-12, 'PIXEL-X': 1e-8, 'PIXEL-Y': 1e-8, 'KM-X': 1e-5, 'KM-Y': 1e-5,
+    'ANGULAR-X': 1e-9, 'ANGULAR-Y': 1e-9, 'PHASE': 1e-11, 'INCIDENCE': 1e-8, 'EMISSION': 1e-8,
+    'AZIMUTH': 1e-7, 'LOCAL-SOLAR-TIME': 0.0, 'DISTANCE': 1e-4, 'RADIAL-VELOCITY': 1e-8,
+    'DOPPLER': 1e-13, 'LIMB-DISTANCE': 1e-5, 'LIMB-LON-GRAPHIC': 1e-7, 'LIMB-LAT-GRAPHIC': 1e-7,
+    'RING-RADIUS': 1e-3, 'RING-LON-GRAPHIC': 1e-8, 'RING-DISTANCE': 1e-3,
+}
+WRAP = {'LON-GRAPHIC', 'LON-CENTRIC', 'LIMB-LON-GRAPHIC', 'RING-LON-GRAPHIC'}
+
+
+def _frame(bc, alt=0.0, **over):
+    kw = dict(GOLDEN_DISC)
+    kw.update(over)
+    return F.pack_frame(bc, alt=alt, **kw)
+
+
+def _check_planes(got, golden_arrays, fn, label=''):
+    for k, name in enumerate(PLANE_NAMES):
+        ref = golden_arrays[f'{fn}/{name}']
+        a = got[k]
+        assert a.shape == ref.shape, (fn, name)
+        assert np.array_equal(np.isnan(a), np.isnan(ref)), f'{fn} {name}: NaN mask differs {label}'
+        d = max_diff(a, ref, wrap=name in WRAP)
+        assert d <= GOLDEN_TOL[name], f'{fn} {name}: max diff {d:.3e} > {GOLDEN_TOL[name]:.1e} {label}'
+
+
+@pytest.mark.parametrize('fn,alt', [('test_nav.fits', 0.0), ('test_nav_alt.fits', GOLDEN_ALT)])
+def test_image_backplanes_match_golden_fits(oracle, bc_hst, golden_arrays, fn, alt):
+    fr = _frame(bc_hst, alt=alt)
+    got = oracle.backplanes_img(fr, GOLDEN_DISC['nx'], GOLDEN_DISC['ny'])
+    _check_planes(got, golden_arrays, fn)
+
+
+def _map_grid(oracle, bc, spec, alt=0.0):
+    """lon/lat grid for the golden map files (tests/test_observation.py:1084-1156)."""
+    if spec[0] == 'rectangular':
+        lons = np.arange(spec[1] / 2, 360, spec[1])[::-1]
+        lats = np.arange(-90 + spec[1] / 2, 90, spec[1])
+        return np.meshgrid(lons, lats)
+    kind = {'orthographic': 1, 'azimuthal': 2}[spec[0]]
+    lon0, lat0, size = spec[1], spec[2], spec[3]
+    a, b = bc.r_eq + alt, bc.r_polar + alt
+    lim = max(1, b / a) * 1.01 if kind == 1 else 1.01
+    c = np.linspace(-lim, lim, size)
+    xx, yy = np.meshgrid(c, c)
+    return oracle.proj_inverse(kind, a, b, lon0, lat0, -1.0, xx, yy)
+
+
+MAP_FILES = {
+    'map_rectangular-nearest.fits': (('rectangular', 30), 0.0, 'nearest'),
+    'map_rectangular-nearest-alt.fits': (('rectangular', 30), GOLDEN_ALT, 'nearest'),
+    'map_rectangular-linear.fits': (('rectangular', 30), 0.0, 'linear'),
+    'map_rectangular-cubic.fits': (('rectangular', 30), 0.0, 'cubic'),
+    'map_orthographic-1.fits': (('orthographic', 0, 0, 10), 0.0, 'linear'),
+    'map_orthographic-2.fits': (('orthographic', 0, 90, 5), 0.0, 'linear'),
+    'map_orthographic-3.fits': (('orthographic', -42, -21.3, 4), 0.0, 'linear'),
+    'map_azimuthal-1.fits': (('azimuthal', 0, 0, 10), 0.0, 'linear'),
+    'map_azimuthal-2.fits': (('azimuthal', 0, -90, 5), 0.0, 'linear'),
+    'map_azimuthal-3.fits': (('azimuthal', 12.345, 42, 4), 0.0, 'linear'),
+}
+
+
+@pytest.mark.parametrize('fn', sorted(MAP_FILES))
+def test_map_backplanes_and_mapped_cube_match_golden_fits(oracle, bc_hst, golden_arrays, fn):
+    from oracle import map_img_oracle as MO
+
+    spec, alt, interp = MAP_FILES[fn]
+    fr = _frame(bc_hst, alt=alt)
+    lon, lat = _map_grid(oracle, bc_hst, spec, alt)
+    got = oracle.backplanes_map(fr, lon, lat)
+    if f'{fn}/LON-GRAPHIC' in golden_arrays:  # files saved with include_backplanes=False
+        _check_planes(got, golden_arrays, fn)
+    cube = golden_arrays['inputs/test.fits/PRIMARY']
+    mapped = MO.map_img(cube, got[PID['PIXEL-X']], got[PID['PIXEL-Y']], interp)
+    ref = golden_arrays[f'{fn}/PRIMARY']
+    assert mapped.shape == ref.shape
+    assert np.array_equal(np.isnan(mapped), np.isnan(ref)), f'{fn}: mapped cube NaN mask'
+    ok = np.isfinite(ref)
+    if interp == 'nearest':
+        assert np.array_equal(mapped[ok], ref[ok]), f'{fn}: nearest mapping must be bit-exact'
+    elif ok.any():
+        rel = np.max(np.abs(mapped[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1.0))
+        assert rel <= 1e-8, f'{fn}: {interp} max rel diff {rel:.3e}'
+
+
+# ---- known-answer literals: tests/test_body_xy.py:269-312 (disc params 5, 8, 3, 45) ----
+XY_COORDINATES = [
+    ((0, 0), (196.3684350770821, -5.581107015413806), (nan, nan),
+     (-43515.54503863168, -220566.4464649765), (12.721709080506116, -55.12740601573759)),
+    ((5, 8), (196.37198562427025, -5.565793847134351), (153.1235185909613, -3.0887371238645795),
+     (0.0, 0.0), (0.0, 0.0)),
+    ((4.1, 7.1), (196.37198562427025, -5.567914131973045), (164.3872136538264, -28.87847195832716),
+     (-12411.924521414994, -27675.679236383432), (0.0, -7.633025448335383)),
+    ((1.234, 5.678), (196.37369462098349, -5.572965121633222), (nan, nan),
+     (-64181.931835415264, -83648.1756567178), (-6.1233826374518685, -25.81658829413859)),
+    ((-3, 25), (196.40157351750477, -5.555192422940882), (nan, nan),
+     (-322324.8112312332, 310766.23675694194), (-106.01424233789203, 38.16512724167089)),
+    ((7.9, 5.1), (196.36512123303984, -5.565793847134351), (nan, nan),
+     (89177.18865054459, -39993.979013437434), (24.59530422240732, 0.0)),
+]
+
+
+def test_xy2lonlat_known_answers(oracle, bc_hst):
+    fr = F.pack_frame(bc_hst, nx=15, ny=10, x0=5, y0=8, r0=3, rotation_radians=np.deg2rad(45))
+    xs = np.array([c[0][0] for c in XY_COORDINATES], dtype=float)
+    ys = np.array([c[0][1] for c in XY_COORDINATES], dtype=float)
+    lon, lat, missed = oracle.xy2lonlat(fr, xs, ys)
+    exp = np.array([c[2] for c in XY_COORDINATES])
+    assert np.array_equal(np.isnan(lon), np.isnan(exp[:, 0]))
+    assert missed == int(np.isnan(exp[:, 0]).sum())
+    assert max_diff(lon, exp[:, 0], wrap=True) < 5e-9
+    assert max_diff(lat, exp[:, 1]) < 5e-9
+    # xy2lonlat with alt (tests/test_body_xy.py:409-428)
+    for alt, e in [(123456.789, (134.58218536012419, 4.708273802335033)),
+                   (-1000, (83.89699519490205, 21.59807910857171)),
+                   (0, (86.30139500952406, 21.109249946237032))]:
+        fra = F.pack_frame(bc_hst, nx=15, ny=10, x0=5, y0=8, r0=3, rotation_radians=np.deg2rad(45),
+                           alt=alt)
+        lo, la, _ = oracle.xy2lonlat(fra, np.array([7.781497231832574]), np.array([8.015145501618983]))
+        assert abs(lo[0] - e[0]) < 2e-8 and abs(la[0] - e[1]) < 2e-8, (alt, lo, la)
+
+
+def test_image_ra_dec_km_angular_known_answers(oracle, bc_hst):
+    """xy2radec / xy2km / xy2angular literals through the image-plane planes."""
+    fr = F.pack_frame(bc_hst, nx=15, ny=10, x0=5, y0=8, r0=3, rotation_radians=np.deg2rad(45))
+    out = oracle.backplanes_img(fr, 15, 10)
+    for (x, y), radec, _lonlat, km, ang in XY_COORDINATES:
+        if float(x).is_integer() and float(y).is_integer() and 0 <= x < 15 and 0 <= y < 10:
+            x, y = int(x), int(y)
+            # The RA/Dec literals predate the reference's spherical angular frame: they
+            # equal the flat-sky value ra0 - ax / cos(dec0) to 2e-11 deg and differ from
+            # v1.14.0's own golden FITS (matched to 1e-14 above) by 9e-8 deg.  The
+            # reference asserts them at rtol 1e-5 (:314); pin at 2e-7 deg here.
+            assert abs(out[PID['RA'], y, x] - radec[0]) < 2e-7
+            assert abs(out[PID['DEC'], y, x] - radec[1]) < 2e-7
+            assert abs(out[PID['KM-X'], y, x] - km[0]) < 1e-5
+            assert abs(out[PID['KM-Y'], y, x] - km[1]) < 1e-5
+            # xy2angular (default origin / rotation) is the xy -> angular affine itself
+            a = bc_hst and F.xy2angular_matrix(bc_hst, 5, 8, 3, np.deg2rad(45)) @ np.array([x, y, 1.0])
+            # (same staleness: 5e-8 arcsec; the reference's atol here is 1e-5, :322)
+            assert abs(a[0] - ang[0]) < 1e-6 and abs(a[1] - ang[1]) < 1e-6
+
+
+# tests/test_body_xy.py:399, :437-454 (disc params 5, 8, 3, 45)
+LONLAT2XY = [
+    ((0, 90), (nan, nan), (5.997148396961149, 10.618837276380527)),
+    ((0, -90), (4.002852727532121, 5.381146365350973), (4.002852727532121, 5.381146365350973)),
+    ((0, 0), (nan, nan), (6.2226715347443555, 7.399517739761713)),
+    ((-42.123, -42.123), (nan, nan), (3.7563192307429167, 6.426030001593531)),
+    ((123.45, 42.123), (6.737145127998048, 9.375239631269238), (6.737145127998048, 9.375239631269238)),
+    ((42, 23.4), None, (7.781497231832574, 8.015145501618983)),
+    ((nan, nan), (nan, nan), (nan, nan)),
+    ((inf, inf), (nan, nan), (nan, nan)),
+    ((0, nan), (nan, nan), (nan, nan)),
+    ((nan, 0), (nan, nan), (nan, nan)),
+]
+
+
+def test_lonlat2xy_known_answers(oracle, bc_hst):
+    fr = F.pack_frame(bc_hst, nx=15, ny=10, x0=5, y0=8, r0=3, rotation_radians=np.deg2rad(45))
+    lon = np.array([c[0][0] for c in LONLAT2XY], dtype=float)
+    lat = np.array([c[0][1] for c in LONLAT2XY], dtype=float)
+    x_all, y_all = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=False)
+    x_vis, y_vis = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=True)
+    for i, (_, vis, allp) in enumerate(LONLAT2XY):
+        for got, exp in (((x_all[i], y_all[i]), allp), ((x_vis[i], y_vis[i]), vis)):
+            if exp is None:
+                continue
+            assert np.isnan(got[0]) == np.isnan(exp[0]), (i, got, exp)
+            if not np.isnan(exp[0]):
+                assert abs(got[0] - exp[0]) < 1e-9 and abs(got[1] - exp[1]) < 1e-9, (i, got, exp)
+
+
+# ---- map_img literals: tests/test_body_xy.py:1087-1200 ----
+MAP_IMG = np.array([
+    [0.0, 100.0, -1.0, 2.2, 3.3, 4.4],
+    [0.0, 75.0, 999.0, 50.0, 1.0, 123.456789],
+    [0.0, 25.0, 0.0, 123.45, nan, 3],
+    [0.0, 0.123, 0.0, 3.0, 0.1, nan],
+    [100.0, -100.0, 100.0, -100.0, 100.0, nan],
+])
+MAP_EXPECTED = {
+    'nearest': [[nan, nan, 100.0, 100.0, -1.0, nan, nan, nan], [nan, nan, nan, 75.0, 999.0, 3.3, 3.3, nan], [nan, nan, nan, 0.0, 123.45, nan, 123.456789, nan], [nan, nan, nan, 3.0, 3.0, 0.1, nan, nan]],
+    'linear': [[nan, nan, nan, nan, nan, nan, nan, nan], [nan, nan, nan, 61.591824124152424, 488.0893412811879, 4.181692402514696, nan, nan], [nan, nan, nan, 3.678385742930187, 94.03788871233297, nan, nan, nan], [nan, nan, nan, -25.28910210942658, -1.6502703714050462, nan, nan, nan]],
+    'cubic': [[nan, nan, nan, nan, nan, nan, nan, nan], [nan, nan, nan, 38.17050096080083, 837.0682797065551, -40.810161294299334, nan, nan], [nan, nan, nan, -77.21287210436617, 103.88323214798433, nan, nan, nan], [nan, nan, nan, -29.994884067130222, -35.81550582449343, nan, nan, nan]],
+}
+MAP_EXPECTED_NO_PROPAGATE = [[nan, nan, 83.42502054006614, 61.410255547165704, 1.0972142916279704, nan, nan, nan], [nan, nan, nan, 61.591824124152424, 488.0893412811879, 4.181692402514696, 3.8032713799190443, nan], [nan, nan, nan, 3.678385742930187, 94.03788871233297, 35.721226497463014, 94.00305287602345, nan], [nan, nan, nan, -25.28910210942658, -1.6502703714050462, 4.265385156596395, nan, nan]]
+
+
+def _map45(oracle, bc):
+    fr = F.pack_frame(bc, nx=6, ny=5, x0=2.75, y0=1.3, r0=2.3, rotation_radians=np.deg2rad(45.678))
+    lons = np.arange(22.5, 360, 45)[::-1]
+    lats = np.arange(-90 + 22.5, 90, 45)
+    lo, la = np.meshgrid(lons, lats)
+    out = oracle.backplanes_map(fr, lo, la)
+    return out[PID['PIXEL-X']], out[PID['PIXEL-Y']]
+
+
+@pytest.mark.parametrize('interp', ['nearest', 'linear', 'cubic'])
+def test_map_img_known_answers(oracle, bc_hst, interp):
+    from oracle import map_img_oracle as MO
+
+    xm, ym = _map45(oracle, bc_hst)
+    got = MO.map_img(MAP_IMG, xm, ym, interp)
+    exp = np.array(MAP_EXPECTED[interp])
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = np.isfinite(exp)
+    if interp == 'nearest':
+        assert np.array_equal(got[ok], exp[ok])
+        # C restatement of the nearest gather agrees with the scipy-side oracle
+        assert np.array_equal(oracle.gather_nearest(MAP_IMG, xm, ym)[0][ok], exp[ok])
+    else:
+        assert np.max(np.abs(got[ok] - exp[ok]) / np.abs(exp[ok])) < 5e-9
+
+
+def test_map_img_no_nan_propagation_known_answer(oracle, bc_hst):
+    from oracle import map_img_oracle as MO
+
+    xm, ym = _map45(oracle, bc_hst)
+    got = MO.map_img(MAP_IMG, xm, ym, 'linear', propagate_nan=False)
+    exp = np.array(MAP_EXPECTED_NO_PROPAGATE)
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = np.isfinite(exp)
+    assert np.max(np.abs(got[ok] - exp[ok]) / np.abs(exp[ok])) < 5e-9
+
+
+# ---- projection literals: tests/test_body_xy.py:1687-1921 (8 decimals) ----
+PROJ_CASES = [
+    (1, 5, 0, 0, [[nan] * 5, [nan, 36.87110893, 0.0, -36.87110893, nan], [nan, 30.33135236, 0.0, -30.33135236, nan], [nan, 36.87110893, 0.0, -36.87110893, nan], [nan] * 5],
+     [[nan] * 5, [nan, -34.45624462, -34.45624462, -34.45624462, nan], [nan, 0.0, 0.0, 0.0, nan], [nan, 34.45624462, 34.45624462, 34.45624462, nan], [nan] * 5]),
+    (1, 5, 123.456, -2, [[nan] * 5, [nan, 161.19011383, 123.456, 85.72188617, nan], [nan, 153.80492624, 123.456, 93.10707376, nan], [nan, 159.53178271, 123.456, 87.38021729, nan], [nan] * 5],
+     [[nan] * 5, [nan, -36.20674821, -36.65376937, -36.20674821, nan], [nan, -1.98332476, -2.29643357, -1.98332476, nan], [nan, 32.67332417, 32.24176455, 32.67332417, nan], [nan] * 5]),
+    (2, 4, 0, 0, [[nan] * 4, [nan, 83.93213465, -83.93213465, nan], [nan, 83.93213465, -83.93213465, nan], [nan] * 4],
+     [[nan] * 4, [nan, -44.83904649, -44.83904649, nan], [nan, 44.83904649, 44.83904649, nan], [nan] * 4]),
+    (2, 4, 123.456, 90, [[nan] * 4, [nan, 168.456, 78.456, nan], [nan, -101.544, -11.544, nan], [nan] * 4],
+     [[nan] * 4, [nan, 4.29865812, 4.29865812, nan], [nan, 4.29865812, 4.29865812, nan], [nan] * 4]),
+    (3, 5, 0, 0, [[nan] * 5, [nan, 91.6285626, 0.0, -91.6285626, nan], [nan, 60.66270473, 0.0, -60.66270473, nan], [nan, 91.6285626, 0.0, -91.6285626, nan], [nan] * 5],
+     [[nan] * 5, [nan, -44.98842597, -60.66270473, -44.98842597, nan], [nan, 0.0, 0.0, 0.0, nan], [nan, 44.98842597, 60.66270473, 44.98842597, nan], [nan] * 5]),
+    (3, 5, 34, -12, [[nan] * 5, [nan, 137.26373836, 34.0, -69.26373836, nan], [nan, 95.20027738, 34.0, -27.20027738, nan], [nan, 113.79039062, 34.0, -45.79039062, nan], [nan] * 5],
+     [[nan] * 5, [nan, -43.4196019, -72.66270473, -43.4196019, nan], [nan, -5.84665238, -12.0, -5.84665238, nan], [nan, 44.08255341, 48.66270473, 44.08255341, nan], [nan] * 5]),
+]
+
+
+@pytest.mark.parametrize('case', range(len(PROJ_CASES)))
+def test_projection_known_answers(oracle, bc_hst, case):
+    kind, size, lon0, lat0, elon, elat = PROJ_CASES[case]
+    a, b = bc_hst.r_eq, bc_hst.r_polar
+    lim = max(1, b / a) * 1.01 if kind == 1 else 1.01
+    c = np.linspace(-lim, lim, size)
+    xx, yy = np.meshgrid(c, c)
+    lon, lat = oracle.proj_inverse(kind, a, b, lon0, lat0, -1.0, xx, yy)
+    elon, elat = np.array(elon, dtype=float), np.array(elat, dtype=float)
+    assert np.array_equal(np.isnan(lon), np.isnan(elon))
+    assert np.allclose(lon, elon, equal_nan=True, rtol=0, atol=6e-9)
+    assert np.allclose(lat, elat, equal_nan=True, rtol=0, atol=6e-9)
+
+
+def test_frame_scalars_known_answers(bc_hst, golden_headers):
+    """Host constants vs tests/test_body.py:106-133 and the golden FITS header."""
+    assert abs(bc_hst.et - 157809664.1839331) < 1e-7
+    assert abs(bc_hst.lt0 - 2734.018326542542) < 1e-9
+    assert abs(bc_hst.target_diameter_arcsec - 35.98242689969618) < 1e-12
+    assert abs(bc_hst.km_per_arcsec - 3973.7175149019004) < 1e-8
+    assert abs(bc_hst.sub_dist - 819566594.28005) < 1e-3
+    assert abs(bc_hst.subpoint_lon - 153.12585514751467) < 1e-9
+    assert abs(bc_hst.subpoint_lat - (-3.0886644594385193)) < 1e-9
+    hdr = golden_headers['test_nav.fits']
+    assert abs(bc_hst.north_pole_angle - hdr['PLANMAP NP-ANGLE']) < 1e-9
+    assert bc_hst.positive_longitude_direction == 'W' and bc_hst.prograde
