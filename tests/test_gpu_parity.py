@@ -91,8 +91,11 @@ def check_img_planes(got, ref, margin, fr, label):
         elif name in ('RING-DISTANCE', 'RING-RADIUS'):
             assert np.max(d[both]) <= 1e-12 * p0 * 50, f'{label} {name}: {np.max(d[both]):.3e} km'
         elif name == 'RING-LON-GRAPHIC':
+            # ray / ring-plane intercept: a perpendicular ray error is stretched by
+            # 1 / sin(opening angle) = RING-DISTANCE / ring_c along the plane
             rr = np.abs(ref[PID['RING-RADIUS']])
-            t = np.maximum(1e-9, np.rad2deg(8 * np.spacing(p0) / np.maximum(rr, 1.0)))
+            stretch = np.abs(ref[PID['RING-DISTANCE']]) / F.frame_field(fr, 'ring_c')[0]
+            t = np.maximum(1e-9, np.rad2deg(8 * np.spacing(p0) * stretch / np.maximum(rr, 1.0)))
             assert np.all(d[both] <= t[both]), f'{label} {name}: {np.max(d[both]):.3e}'
         elif name.startswith('LIMB'):
             # the limb point is the radial projection of the ray's closest approach to
