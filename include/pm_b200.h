@@ -190,6 +190,15 @@ int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degr
  * returns the kernel time in ms through *ms_host (synchronises). */
 int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
 
+/* Diagnostic: evaluates one of the library's own FP64 primitives (the MUFU-seeded
+ * reciprocal / rsqrt / sqrt / division and the polynomial sin / cos / atan2 / acos
+ * that replace CUDA's libm on the hot path) elementwise, so tests can measure their
+ * ulp error on the device.  kind: 0 rcp(a), 1 rsqrt(a), 2 sqrt(a), 3 sin(a) and
+ * 4 cos(a) for |a| <= pi/4, 5 atan2(a, b), 6 acos(a), 7 a / b, 8 sin(a), 9 cos(a)
+ * for any |a| < 1e5.  `b` may be NULL for the one-argument kinds. */
+int pm_math_probe(int kind, const double *a, const double *b, int64_t n, double *out,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

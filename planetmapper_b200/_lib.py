@@ -37,7 +37,7 @@ PLANE_ID = {n: i for i, n in enumerate(PLANE_NAMES)}
 EXPORTED_SYMBOLS = [
     'pm_abi_version', 'pm_error_string', 'pm_launch_count', 'pm_backplanes_img',
     'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_proj_inverse', 'pm_gather',
-    'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe',
+    'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
 ]
 
 
@@ -76,8 +76,10 @@ def load_library() -> ctypes.CDLL:
     lib.pm_spline_work_bytes.argtypes = [c_i, c_i, c_i, c_i]
     lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
     lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
+    lib.pm_math_probe.argtypes = [c_i, c_p, c_p, c_i64, c_p, c_p]
     for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy',
-               'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe'):
+               'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
+               'pm_math_probe'):
         getattr(lib, fn).restype = c_i
     if lib.pm_abi_version() != 1:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
@@ -238,3 +240,14 @@ def fp64_peak_probe(iters: int = 1 << 15) -> float:
     fl = ctypes.c_double(0.0)
     _check(lib.pm_fp64_peak_probe(iters, ctypes.byref(ms), ctypes.byref(fl)), 'pm_fp64_peak_probe')
     return fl.value / (ms.value * 1e-3) / 1e12
+
+
+def math_probe(kind: int, a_dev, b_dev=None):
+    """Evaluate one of the library's FP64 primitives elementwise (pm_math_probe)."""
+    torch = _torch()
+    lib = load_library()
+    out = torch.empty_like(a_dev)
+    rc = lib.pm_math_probe(kind, a_dev.data_ptr(), b_dev.data_ptr() if b_dev is not None else None,
+                           a_dev.numel(), out.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_math_probe')
+    return out

@@ -21,6 +21,8 @@ cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double
 cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
                              uint32_t flags, double *x, double *y, int sm_count, cudaStream_t st);
 cudaError_t launch_fp64_probe(double *scratch, int iters, int sm_count, cudaStream_t st);
+cudaError_t launch_math_probe(int kind, const double *a, const double *b, int64_t n, double *out,
+                              cudaStream_t st);
 
 cudaError_t launch_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                                 int64_t n, double *lon, double *lat, int sm_count, cudaStream_t st);

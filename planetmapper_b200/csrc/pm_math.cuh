@@ -1,0 +1,229 @@
+// pm_math.cuh - FP64 primitives tuned for the sm_100a FP64 pipe.
+//
+// Why not CUDA's libm here: the first version of the backplane kernel (profiles/
+// r1_summary.md) spent two thirds of its issue slots outside the FP64 pipe - 64-bit
+// polynomial coefficients materialised as UMOV/IMAD pairs, slow-path CALLs for div /
+// sqrt / trig range reduction, 161 KB of straight-line code missing the instruction
+// cache.  The routines below
+//   * seed division and square root with one MUFU (rcp.approx / rsqrt.approx.f64,
+//     ~20 good bits) and finish with a cubically convergent FMA step (no slow path:
+//     every operand on the hot path is a finite, normal, kilometre-scale number),
+//   * keep polynomial coefficients in __constant__ tables so a DFMA reads them as
+//     c[bank][offset] operands instead of moving immediates into registers,
+//   * use argument ranges the geometry guarantees (|angle| <= pi/4 for pixel offsets
+//     and frame spins) and leave everything else to a cold, non-inlined fallback.
+// Accuracy is <= 1-2 ulp for every routine (tests/test_device_math.py measures it on
+// the host build, tests/test_gpu_math.py on the GPU), i.e. five orders of magnitude
+// inside the 1e-9 deg parity bar.
+//
+// The header also compiles for the host (nvcc host pass) so that tests can run the
+// very same per-pixel code against the oracle without a GPU; the MUFU seeds are then
+// emulated by truncating an exact result to 20 mantissa bits.  The product never
+// executes the host instantiation (no CPU fallback): libpm_b200.so only exports
+// launchers of __global__ kernels.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define PM_HD __host__ __device__ __forceinline__
+#define PM_HD_NOINLINE static __host__ __device__ __noinline__
+#define PM_DEV_TABLE(name, n, ...)                        \
+    static __constant__ double name##_dev[n] = {__VA_ARGS__}; \
+    static const double name##_host[n] = {__VA_ARGS__};
+#else
+#define PM_HD inline
+#define PM_HD_NOINLINE static
+#define PM_DEV_TABLE(name, n, ...) static const double name##_host[n] = {__VA_ARGS__};
+#endif
+
+#ifdef __CUDA_ARCH__
+#define PM_T(name) name##_dev
+#else
+#define PM_T(name) name##_host
+#endif
+
+namespace pm {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPi = 2.0 * kPi;
+constexpr double kHalfPi = 0.5 * kPi;
+constexpr double kQuarterPi = 0.25 * kPi;
+constexpr double kDpr = 180.0 / kPi;
+constexpr double kRpd = kPi / 180.0;
+
+// minimax fits (mpmath, Chebyshev nodes, 60 digits; tools/fit_coefficients.py):
+//   atan(q) = q + q z A(z),  z = q^2 <= tan(pi/8)^2      |err| < 6e-18
+//   sin(x)  = x + x z S(z),  z = x^2 <= (pi/4)^2          |err| < 2e-17
+//   cos(x)  = 1 - z/2 + z^2 C(z)                           |err| < 5e-19
+PM_DEV_TABLE(kAtanC, 11, -0.33333333333333330153, 0.19999999999995512409, -0.14285714284664817984,
+             0.11111111015117633147, -0.090909045724876297519, 0.076921830599006634224,
+             -0.066645096033476166205, 0.058581328952289710071, -0.050853659265352889958,
+             0.039229237259412692422, -0.019173922433769131861)
+PM_DEV_TABLE(kSinC, 6, -0.16666666666666664621, 0.008333333333330946103, -0.00019841269836754970194,
+             2.7557316100683122624e-6, -2.5051131455447427132e-8, 1.5918101231677278624e-10)
+PM_DEV_TABLE(kCosC, 6, 0.041666666666666665387, -0.0013888888888887395746, 0.000024801587298763433277,
+             -2.7557317270560382548e-7, 2.0876146024701932874e-9, -1.1382614869434128293e-11)
+// misc constants read as constant-bank operands: tan(pi/8), pi/4, pi/2, pi, 2/pi,
+// pi/2 split (hi, lo), 2 pi, 1/(2 pi)
+PM_DEV_TABLE(kMisc, 9, 0.4142135623730950488016887, 0.78539816339744830961566, 1.5707963267948966192313,
+             3.1415926535897932384626, 0.6366197723675813430755351, 1.570796326794896619231322,
+             6.12323399573676588613033e-17, 6.283185307179586476925287, 0.1591549430918953357688838)
+
+// ---- MUFU seeds ----------------------------------------------------------------
+PM_HD double rcp_seed(double b) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+#else
+    uint64_t u;
+    memcpy(&u, &b, 8);
+    u &= 0xFFFFFFFF00000000ull;
+    double bt;
+    memcpy(&bt, &u, 8);
+    double r = 1.0 / bt;
+    memcpy(&u, &r, 8);
+    u &= 0xFFFFFFFF00000000ull;
+    memcpy(&r, &u, 8);
+    return r;
+#endif
+}
+PM_HD double rsqrt_seed(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    u &= 0xFFFFFFFF00000000ull;
+    double xt;
+    memcpy(&xt, &u, 8);
+    double r = 1.0 / ::sqrt(xt);
+    memcpy(&u, &r, 8);
+    u &= 0xFFFFFFFF00000000ull;
+    memcpy(&r, &u, 8);
+    return r;
+#endif
+}
+
+// 1 / b for finite normal b != 0 (no denormal / inf / zero slow path)
+PM_HD double fast_rcp(double b) {
+    double r = rcp_seed(b);
+    double e = fma(-b, r, 1.0);  // |e| <~ 2^-19
+    e = fma(e, e, e);            // e + e^2: cubic convergence, residual e^3 ~ 2^-57
+    return fma(r, e, r);
+}
+// a / b, correctly rounded in all but a vanishing fraction of cases
+PM_HD double fast_div(double a, double b) {
+    double r = fast_rcp(b);
+    double q = a * r;
+    double rem = fma(-b, q, a);
+    return fma(rem, r, q);
+}
+// 1 / sqrt(x) for finite normal x > 0
+PM_HD double fast_rsqrt(double x) {
+    double y = rsqrt_seed(x);
+    double xy = x * y;
+    double e = fma(-xy, y, 1.0);       // 1 - x y^2
+    double p = fma(0.375, e, 0.5);     // y (1 + e/2 + 3 e^2 / 8): residual 5/16 e^3
+    return fma(y, p * e, y);
+}
+// sqrt(x) for x >= 0 (x == 0 -> 0).  Not for negative x (see fast_sqrt_nan).
+PM_HD double fast_sqrt(double x) {
+    double y = fast_rsqrt(x + 1.0e-300);  // keeps the seed finite at x == 0
+    double s = x * y;
+    double rem = fma(-s, s, x);
+    return fma(rem, 0.5 * y, s);
+}
+// sqrt that keeps IEEE's NaN for negative input
+PM_HD double fast_sqrt_nan(double x) { return (x < 0.0) ? NAN : fast_sqrt(x); }
+
+// ---- trig ----------------------------------------------------------------------
+// sin, cos for |x| <= pi/4 (no range reduction)
+PM_HD void sincos_quarter(double x, double &s, double &c) {
+    const double z = x * x;
+    double ps = PM_T(kSinC)[5];
+    double pc = PM_T(kCosC)[5];
+#pragma unroll
+    for (int i = 4; i >= 0; i--) {
+        ps = fma(ps, z, PM_T(kSinC)[i]);
+        pc = fma(pc, z, PM_T(kCosC)[i]);
+    }
+    s = fma(x * z, ps, x);
+    c = fma(z * z, pc, fma(-0.5, z, 1.0));
+}
+// library fallback, kept out of line so the hot code stays small
+PM_HD_NOINLINE void sincos_lib(double x, double *s, double *c) {
+#ifdef __CUDA_ARCH__
+    ::sincos(x, s, c);
+#else
+    *s = ::sin(x);
+    *c = ::cos(x);
+#endif
+}
+// sin, cos for small arguments with a cold fallback for everything else
+PM_HD void sincos_small(double x, double &s, double &c) {
+    if (fabs(x) <= PM_T(kMisc)[1]) {
+        sincos_quarter(x, s, c);
+    } else {
+        sincos_lib(x, &s, &c);
+    }
+}
+// sin, cos for |x| < ~1e5 (two-term Cody-Waite with FMA), cold fallback beyond
+PM_HD void sincos_full(double x, double &s, double &c) {
+    if (!(fabs(x) < 1.0e5)) {
+        sincos_lib(x, &s, &c);
+        return;
+    }
+    const double k = rint(x * PM_T(kMisc)[4]);
+    double r = fma(-k, PM_T(kMisc)[5], x);
+    r = fma(-k, PM_T(kMisc)[6], r);
+    double sr, cr;
+    sincos_quarter(r, sr, cr);
+    const int n = (int)k;
+    if (n & 1) {
+        double t = sr;
+        sr = cr;
+        cr = -t;
+    }
+    if (n & 2) {
+        sr = -sr;
+        cr = -cr;
+    }
+    s = sr;
+    c = cr;
+}
+
+// atan2(y, x), full quadrant, atan2(0, 0) = 0 (the convention recrad / reclat / recgeo
+// apply explicitly).  One division; the argument is folded into |q| <= tan(pi/8) with
+// atan(a/b) = pi/4 + atan((a - b)/(a + b)).
+PM_HD double fast_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const bool sw = ay > ax;
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+    if (!(mx > 0.0)) return (mx == 0.0) ? 0.0 : NAN;
+    const bool hi = mn > mx * PM_T(kMisc)[0];
+    const double num = hi ? (mn - mx) : mn;
+    const double den = hi ? (mn + mx) : mx;
+    const double q = fast_div(num, den);
+    const double z = q * q;
+    double p = PM_T(kAtanC)[10];
+#pragma unroll
+    for (int i = 9; i >= 0; i--) p = fma(p, z, PM_T(kAtanC)[i]);
+    double r = fma(q * z, p, q);
+    if (hi) r += PM_T(kMisc)[1];
+    if (sw) r = PM_T(kMisc)[2] - r;
+    if (x < 0.0) r = PM_T(kMisc)[3] - r;
+    return (y < 0.0) ? -r : r;
+}
+// acos(x); NaN for |x| > 1 like the libm routine
+PM_HD double fast_acos(double x) {
+    return fast_atan2(fast_sqrt_nan((1.0 - x) * (1.0 + x)), x);
+}
+
+}  // namespace pm

@@ -11,15 +11,11 @@ conditioning number only (tests/helpers.py:surface_tolerances explains why).
 import numpy as np
 import pytest
 
-from helpers import PID, PLANE_NAMES, angle_diff, lst_boundary, masks_equal, surface_tolerances
+from helpers import (IMG_CASES, PID, PLANE_NAMES, WRAP, angle_diff, check_img_planes, check_map_planes,
+                     img_case as _img_case, masks_equal, surface_tolerances)
 from planetmapper_b200 import frame as F
 
 pytestmark = pytest.mark.gpu
-
-WRAP = {'LON-GRAPHIC', 'LON-CENTRIC', 'LIMB-LON-GRAPHIC', 'RING-LON-GRAPHIC'}
-SURFACE = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'PHASE', 'INCIDENCE', 'EMISSION',
-           'AZIMUTH', 'DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER']
-
 
 @pytest.fixture(scope='module')
 def L():
@@ -30,86 +26,6 @@ def L():
     assert torch.cuda.is_available()
     _lib.load_library()
     return _lib
-
-
-def _img_case(bc, nx, ny, x0, y0, r0, rot_deg, alt=0.0):
-    return F.pack_frame(bc, nx=nx, ny=ny, x0=x0, y0=y0, r0=r0, rotation_radians=np.deg2rad(rot_deg), alt=alt)
-
-
-IMG_CASES = {
-    'golden-7x10': (7, 10, 2.5, 3.1, 3.9, 123.456, 0.0),
-    'golden-7x10-alt': (7, 10, 2.5, 3.1, 3.9, 123.456, 34567.8912),
-    'C1-100x100': (100, 100, 49.5, 49.5, 44.55, 0.0, 0.0),
-    'rot-200x160': (200, 160, 99.5, 79.5, 70.0, 30.0, 0.0),
-    'offset-disc-partly-outside': (64, 48, 50.0, 10.0, 40.0, 200.0, 0.0),
-    'ragged-1x37': (1, 37, 0.0, 18.0, 12.0, 0.0, 0.0),
-}
-
-
-def check_img_planes(got, ref, margin, fr, label):
-    """Shared comparison of 26 image-direction planes (GPU `got` vs oracle `ref`)."""
-    grazing = np.abs(margin) < 1e-9
-    grazing = np.where(np.isnan(margin), False, grazing)
-    p0 = float(np.linalg.norm(F.frame_field(fr, 'P0')))
-    r_min = float(np.min(F.frame_field(fr, 'radii')))
-    w = float(np.linalg.norm(F.frame_field(fr, 'omega')))
-    tol, kappa = surface_tolerances(ref, p0, r_min, w)
-    report = {}
-    n_grazing_mismatch = 0
-    for name in PLANE_NAMES:
-        a, b = got[PID[name]], ref[PID[name]]
-        ok, n_bad, n_ex = masks_equal(a, b, exclude=grazing)
-        n_grazing_mismatch = max(n_grazing_mismatch, n_ex)
-        assert ok, f'{label} {name}: {n_bad} NaN-mask mismatches outside grazing pixels'
-        both = np.isfinite(a) & np.isfinite(b) & ~grazing
-        if not both.any():
-            continue
-        d = angle_diff(a, b) if name in WRAP else np.abs(a - b)
-        if name in tol:
-            ratio = np.max(d[both] / tol[name][both])
-            report[name] = ratio
-            assert ratio <= 1.0, f'{label} {name}: diff/tol = {ratio:.3f} (max diff {np.max(d[both]):.3e})'
-        elif name == 'LOCAL-SOLAR-TIME':
-            lon_tol = tol['LON-GRAPHIC']
-            boundary = lst_boundary(ref[PID['LON-GRAPHIC']], F.frame_field(fr, 'lon_sign')[0],
-                                    F.frame_field(fr, 'sun_lon_lst')[0], tol_s=1e-6) | \
-                (240.0 * lon_tol > 1e-6) & lst_boundary(ref[PID['LON-GRAPHIC']], F.frame_field(fr, 'lon_sign')[0],
-                                                        F.frame_field(fr, 'sun_lon_lst')[0], tol_s=1e-4)
-            sel = both & ~boundary
-            assert np.array_equal(a[sel], b[sel]), f'{label} LST differs away from second boundaries'
-            # at a boundary the value may flip by exactly one second
-            flip = both & boundary & (a != b)
-            assert np.all(np.abs(a[flip] - b[flip]) < 1.5 / 3600), label
-        elif name in ('RA', 'DEC'):
-            assert np.max(d[both]) <= 1e-12, f'{label} {name}: {np.max(d[both]):.3e}'
-        elif name in ('PIXEL-X', 'PIXEL-Y'):
-            assert np.array_equal(a[both], b[both])
-        elif name in ('KM-X', 'KM-Y'):
-            assert np.max(d[both]) <= 1e-5, f'{label} {name}: {np.max(d[both]):.3e} km'
-        elif name in ('ANGULAR-X', 'ANGULAR-Y'):
-            assert np.max(d[both]) <= 1e-8, f'{label} {name}: {np.max(d[both]):.3e} arcsec'
-        elif name in ('RING-DISTANCE', 'RING-RADIUS'):
-            assert np.max(d[both]) <= 1e-12 * p0 * 50, f'{label} {name}: {np.max(d[both]):.3e} km'
-        elif name == 'RING-LON-GRAPHIC':
-            # ray / ring-plane intercept: a perpendicular ray error is stretched by
-            # 1 / sin(opening angle) = RING-DISTANCE / ring_c along the plane
-            rr = np.abs(ref[PID['RING-RADIUS']])
-            stretch = np.abs(ref[PID['RING-DISTANCE']]) / F.frame_field(fr, 'ring_c')[0]
-            t = np.maximum(1e-9, np.rad2deg(8 * np.spacing(p0) * stretch / np.maximum(rr, 1.0)))
-            assert np.all(d[both] <= t[both]), f'{label} {name}: {np.max(d[both]):.3e}'
-        elif name.startswith('LIMB'):
-            # the limb point is the radial projection of the ray's closest approach to
-            # the centre: conditioning ~ r / (distance of closest approach)
-            near = np.abs(ref[PID['LIMB-DISTANCE']] + r_min)
-            cond = np.maximum(1.0, r_min * 1.2 / np.maximum(near, 1e-3))
-            if name == 'LIMB-DISTANCE':
-                assert np.max(d[both]) <= 1e-12 * p0 * 50, f'{label} {name}: {np.max(d[both]):.3e} km'
-            else:
-                t = np.maximum(1e-9, np.rad2deg(16 * np.spacing(p0) / r_min) * cond)
-                if name == 'LIMB-LON-GRAPHIC':
-                    t = t / np.maximum(np.cos(np.deg2rad(ref[PID['LIMB-LAT-GRAPHIC']])), 1e-9)
-                assert np.all(d[both] <= t[both]), f'{label} {name}: {np.max(d[both] / t[both]):.3f}'
-    return report, int(grazing.sum()), n_grazing_mismatch
 
 
 @pytest.mark.parametrize('case', sorted(IMG_CASES))
@@ -177,48 +93,7 @@ def test_map_backplanes_vs_oracle(L, oracle, bc_hst, case):
     lo[2, 2] = -725.0      # lon % 360
     ref, margin = oracle.backplanes_map(fr, lo, la, with_margin=True)
     got = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la)).cpu().numpy()
-    grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
-    # also cells grazing the terminator (`lit` drives the LIMB / RING maps)
-    graz_lit = np.where(np.isnan(ref[PID['INCIDENCE']]), False, np.abs(ref[PID['INCIDENCE']] - 90.0) < 1e-7)
-    p0 = float(np.linalg.norm(F.frame_field(fr, 'P0')))
-    for name in PLANE_NAMES:
-        a, b = got[PID[name]], ref[PID[name]]
-        ex = grazing | graz_lit if (name.startswith('LIMB') or name.startswith('RING')) else grazing
-        if name in ('PIXEL-X', 'PIXEL-Y'):
-            # cells within 1e-9 px of the image frame edge may flip (counted, not hidden)
-            x, y = ref[PID['PIXEL-X']], ref[PID['PIXEL-Y']]
-            gx, gy = got[PID['PIXEL-X']], got[PID['PIXEL-Y']]
-            edge = np.zeros(x.shape, dtype=bool)
-            for v, n in ((np.where(np.isnan(x), gx, x), nx), (np.where(np.isnan(y), gy, y), ny)):
-                with np.errstate(invalid='ignore'):
-                    edge |= (np.abs(v + 0.5) < 1e-9) | (np.abs(v - (n - 0.5)) < 1e-9)
-            ex = ex | edge
-        ok, n_bad, _ = masks_equal(a, b, exclude=ex)
-        assert ok, f'{case} map {name}: {n_bad} mask mismatches'
-        both = np.isfinite(a) & np.isfinite(b)
-        if not both.any():
-            continue
-        d = angle_diff(a, b) if name in WRAP else np.abs(a - b)
-        m = float(np.max(d[both]))
-        if name in ('LON-GRAPHIC', 'LAT-GRAPHIC', 'LOCAL-SOLAR-TIME'):
-            assert m == 0.0, (name, m)
-        elif name in ('LON-CENTRIC', 'LAT-CENTRIC', 'PHASE', 'INCIDENCE', 'EMISSION', 'RA', 'DEC'):
-            assert m <= 1e-9, (name, m)
-        elif name == 'AZIMUTH':
-            tol, _ = surface_tolerances(ref, p0, 6e4, 1.8e-4)
-            assert np.all(d[both] <= np.maximum(tol['AZIMUTH'][both], 1e-9)), (name, m)
-        elif name in ('DISTANCE', 'RING-DISTANCE', 'RING-RADIUS', 'LIMB-DISTANCE'):
-            assert m <= 1e-12 * p0 * 50, (name, m)
-        elif name in ('RADIAL-VELOCITY',):
-            assert m <= 1e-12 * 40 + 2e-13, (name, m)
-        elif name == 'DOPPLER':
-            assert m <= 1e-15, (name, m)
-        elif name in ('PIXEL-X', 'PIXEL-Y'):
-            assert m <= 1e-9 * max(nx, ny), (name, m)   # <= 1e-9 deg on the sky
-        elif name in ('KM-X', 'KM-Y'):
-            assert m <= 1e-5, (name, m)
-        elif name in ('ANGULAR-X', 'ANGULAR-Y'):
-            assert m <= 1e-8, (name, m)
+    check_map_planes(got, ref, margin, fr, nx, ny, case)
 
 
 def test_point_transforms_vs_oracle(L, oracle, bc_hst):
@@ -368,8 +243,13 @@ def test_full_size_2048_properties(L, bc_hst):
     lon, lat = g('LON-GRAPHIC')[ys[sel], xs[sel]].contiguous(), g('LAT-GRAPHIC')[ys[sel], xs[sel]].contiguous()
     x2, y2 = L.lonlat2xy(fd[0], lon, lat, True)
     assert torch.isfinite(x2).all()
-    assert (x2 - xs[sel].double()).abs().max().item() < 1e-6
-    assert (y2 - ys[sel].double()).abs().max().item() < 1e-6
+    # The reference's inverse (body.py:917-948) dates the point with the sub-observer
+    # light time plus a line-of-sight offset and ignores the target's translation over
+    # that offset, so its own round trip is only good to ~1e-3 px at this scale (the
+    # reference tests it with atol=1e-3, tests/test_body_xy.py:333-337; the CPU oracle
+    # shows 1.4e-3 px on this frame).  The bar here is that inherent error, not 1e-9.
+    assert (x2 - xs[sel].double()).abs().max().item() < 5e-3
+    assert (y2 - ys[sel].double()).abs().max().item() < 5e-3
     # LST is a multiple of 1/3600 h
     lst = g('LOCAL-SOLAR-TIME')[on] * 3600.0
     assert (lst - torch.round(lst)).abs().max().item() < 1e-6
@@ -386,7 +266,8 @@ def test_full_grid_gather_properties(L, bc_hst):
     fd = L.to_device(fr)
     planes = L.backplanes_map(fd, L.to_device(lo), L.to_device(la),
                               L.mask_from_names(['PIXEL-X', 'PIXEL-Y', 'EMISSION', 'RA']))
-    xm, ym, emi, ra = planes[2], planes[3], planes[1], planes[0]
+    # packed plane order is by plane id: RA (4), PIXEL-X (6), PIXEL-Y (7), EMISSION (14)
+    ra, xm, ym, emi = planes[0], planes[1], planes[2], planes[3]
     # visibility consistency (tests/test_body_xy.py:2592-2607): RA finite <=> emission < 90
     assert torch.equal(torch.isfinite(ra), emi < 90.0)
     vis = torch.isfinite(xm)
