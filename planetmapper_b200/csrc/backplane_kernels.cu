@@ -14,6 +14,8 @@
 #include "pm_device.cuh"
 #include "pm_kernels.h"
 
+#include <cstdlib>
+
 namespace pm {
 
 constexpr int kPerThread = 4;  // elements per thread and CTA (amortises the frame load)
@@ -21,33 +23,49 @@ constexpr int kPerThread = 4;  // elements per thread and CTA (amortises the fra
 // plane slot of id k inside the packed output = number of requested planes below k
 __device__ __forceinline__ int slot(uint64_t mask, int k) { return __popcll(mask & (bit(k) - 1ull)); }
 
+// Element offset of every plane inside the packed plane-major output, computed once per
+// CTA (shared memory) instead of a popcount + 64-bit multiply in front of every store
+struct PlaneTable {
+    int64_t off[PM_N_PLANES];
+};
+__device__ __forceinline__ void fill_plane_table(PlaneTable &t, uint64_t mask, int64_t plane_stride) {
+    // lanes 1..26 of the last warp: they are idle during the derived-constant step
+    const int k = (int)threadIdx.x - ((int)blockDim.x - 31);
+    if (k >= 0 && k < PM_N_PLANES) t.off[k] = (int64_t)slot(mask, k) * plane_stride;
+}
+
 // Receives the planes of one pixel / cell and streams them to the plane-major output
 struct PlaneSink {
     double *base;  // out + element index
-    int64_t plane_stride;
-    uint64_t mask;
-    __device__ __forceinline__ void put(int k, double v) const {
-        __stcs(base + (int64_t)slot(mask, k) * plane_stride, v);
-    }
+    const PlaneTable *tab;
+    __device__ __forceinline__ void put(int k, double v) const { __stcs(base + tab->off[k], v); }
 };
 
 // ---------------------------------------------------------------------------------
 // Image direction: all requested backplanes for every pixel of every frame.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame *__restrict__ frames,
-                                                                   uint32_t nx, uint32_t npx, uint64_t mask,
-                                                                   double *__restrict__ out_all) {
+template <bool kSky, int kMinBlocks, int kPix>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) backplanes_img_kernel(const PMFrame *__restrict__ frames,
+                                                                            uint32_t nx, uint32_t npx,
+                                                                            uint64_t mask,
+                                                                            double *__restrict__ out_all) {
     __shared__ FrameD fs;
-    load_frame(fs, frames + blockIdx.y);
+    __shared__ PlaneTable tab;
+    fill_plane_table(tab, mask, (int64_t)npx);
+    load_frame(fs, frames + blockIdx.y);  // (its barriers also publish the table)
     double *out = out_all + (int64_t)blockIdx.y * __popcll(mask) * npx;
-    const uint32_t first = blockIdx.x * (uint32_t)(kBlock * kPerThread) + threadIdx.x;
+    uint32_t idx = blockIdx.x * (uint32_t)(kBlock * kPix) + threadIdx.x;
+    uint32_t yi = idx / nx, xi = idx - yi * nx;  // one division per thread, then incremental
 #pragma unroll 1
-    for (int r = 0; r < kPerThread; r++) {
-        const uint32_t idx = first + r * kBlock;
-        if (idx >= npx) break;
-        const uint32_t yi = idx / nx, xi = idx - yi * nx;
-        PlaneSink sink{out + idx, (int64_t)npx, mask};
-        image_pixel(fs, (double)xi, (double)yi, mask, sink);
+    for (int r = 0; r < kPix && idx < npx; r++) {
+        PlaneSink sink{out + idx, &tab};
+        image_pixel<kSky>(fs, (double)xi, (double)yi, mask, sink);
+        idx += kBlock;
+        xi += kBlock;
+        while (xi >= nx) {
+            xi -= nx;
+            yi++;
+        }
     }
 }
 
@@ -60,13 +78,15 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_map_kernel(const PMFrame
                                                                    int64_t n, uint64_t mask,
                                                                    double *__restrict__ out) {
     __shared__ FrameD fs;
+    __shared__ PlaneTable tab;
+    fill_plane_table(tab, mask, n);
     load_frame(fs, frame);
     const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
 #pragma unroll 1
     for (int r = 0; r < kPerThread; r++) {
         const int64_t idx = first + r * kBlock;
         if (idx >= n) break;
-        PlaneSink sink{out + idx, n, mask};
+        PlaneSink sink{out + idx, &tab};
         map_cell(fs, __ldg(lon_in + idx), __ldg(lat_in + idx), mask, sink);
     }
 }
@@ -174,8 +194,26 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     (void)sm_count;
     const int64_t npx = (int64_t)nx * ny;
     if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
-    dim3 grid(chunks_for(npx), n_frames);
-    backplanes_img_kernel<<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, out);
+    static const int variant = getenv("PM_IMG_VARIANT") ? atoi(getenv("PM_IMG_VARIANT")) : 0;
+#define PM_LAUNCH_IMG(MB, PIX)                                                                      \
+    do {                                                                                            \
+        const int64_t per = (int64_t)kBlock * PIX;                                                  \
+        dim3 grid((unsigned)((npx + per - 1) / per), n_frames);                                     \
+        if (mask & kSkyMask)                                                                        \
+            backplanes_img_kernel<true, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, out); \
+        else                                                                                        \
+            backplanes_img_kernel<false, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, out); \
+    } while (0)
+    switch (variant) {
+        case 1: PM_LAUNCH_IMG(4, 8); break;
+        case 2: PM_LAUNCH_IMG(5, 4); break;
+        case 3: PM_LAUNCH_IMG(5, 8); break;
+        case 4: PM_LAUNCH_IMG(3, 4); break;
+        case 5: PM_LAUNCH_IMG(3, 8); break;
+        case 6: PM_LAUNCH_IMG(4, 16); break;
+        default: PM_LAUNCH_IMG(4, 4); break;
+    }
+#undef PM_LAUNCH_IMG
     count_launches(1);
     return cudaGetLastError();
 }

@@ -86,42 +86,17 @@ struct FrameD {
 };
 
 constexpr int kDeriveItems = 13;
-// One independent slice of the derived constants (thread `item` of a CTA, or a host loop)
+// One independent slice of the derived constants (one thread of a CTA, or a host loop).
+// Uses the MUFU-seeded primitives: this runs in every CTA's prologue while the other
+// warps wait at a barrier, so its latency matters.
 PM_HD void derive_frame_item(FrameD &s, int item) {
     const PMFrame &f = s.f;
-    if (item == 0) {
-        s.inv_c = 1.0 / f.clight;
-        double wn = ::sqrt(f.omega[0] * f.omega[0] + f.omega[1] * f.omega[1] + f.omega[2] * f.omega[2]);
-        s.wn = wn;
-        double iw = wn > 0.0 ? 1.0 / wn : 0.0;
-        s.k[0] = f.omega[0] * iw;
-        s.k[1] = f.omega[1] * iw;
-        s.k[2] = f.omega[2] * iw;
-        s.inv_kmpa = 1.0 / f.km_per_arcsec;
-    } else if (item == 1) {
-        double a = f.radii[0], b = f.radii[1], c = f.radii[2];
-        s.inv_r[0] = 1.0 / a;
-        s.inv_r[1] = 1.0 / b;
-        s.inv_r[2] = 1.0 / c;
-        double m = fmin(a, fmin(b, c));
-        s.nw[0] = (m / a) * (m / a);
-        s.nw[1] = (m / b) * (m / b);
-        s.nw[2] = (m / c) * (m / c);
-    } else if (item == 2) {
-        double rp = f.re - f.f * f.re;
-        s.rp = rp;
-        s.e2 = 1.0 - (rp * rp) / (f.re * f.re);
-        s.ep2 = (f.re * f.re) / (rp * rp) - 1.0;
-        s.omf = 1.0 - f.f;
-        s.inv_omf2 = 1.0 / ((1.0 - f.f) * (1.0 - f.f));
-        s.biaxial = (f.radii[0] == f.radii[1]) && (f.re == f.radii[0]) && (fabs(rp - f.radii[2]) <= 4e-16 * f.radii[2]);
-        s.pad_ = 0;
-    } else if (item <= 8) {
+    if (item >= 3 && item <= 8) {
         const double *src = item == 3 ? f.P0 : item == 4 ? f.VT : item == 5 ? f.AT : item == 6 ? f.VO : item == 7 ? f.S0 : f.VS;
         double *dst = item == 3 ? s.P0b : item == 4 ? s.VTb : item == 5 ? s.ATb : item == 6 ? s.VOb : item == 7 ? s.S0b : s.VSb;
         for (int r = 0; r < 3; r++)
             dst[r] = f.R0[3 * r] * src[0] + f.R0[3 * r + 1] * src[1] + f.R0[3 * r + 2] * src[2];
-    } else if (item <= 11) {
+    } else if (item >= 9 && item <= 11) {
         const int r = item - 9;  // row r of R0 M^T
         for (int c = 0; c < 3; c++)
             s.G[3 * r + c] = f.R0[3 * r] * f.M[3 * c] + f.R0[3 * r + 1] * f.M[3 * c + 1] + f.R0[3 * r + 2] * f.M[3 * c + 2];
@@ -131,17 +106,59 @@ PM_HD void derive_frame_item(FrameD &s, int item) {
             s.As[c] = -(f.A[c] * sc);
             s.As[3 + c] = f.A[3 + c] * sc;
         }
+        s.inv_kmpa = fast_rcp(f.km_per_arcsec);
+    } else if (item == 0) {
+        s.inv_c = fast_rcp(f.clight);
+        const double w2 = f.omega[0] * f.omega[0] + f.omega[1] * f.omega[1] + f.omega[2] * f.omega[2];
+        const double iw = w2 > 0.0 ? fast_rsqrt(w2) : 0.0;
+        s.wn = w2 * iw;
+        s.k[0] = f.omega[0] * iw;
+        s.k[1] = f.omega[1] * iw;
+        s.k[2] = f.omega[2] * iw;
+    } else if (item == 1) {
+        const double a = f.radii[0], b = f.radii[1], c = f.radii[2];
+        const double ia = fast_rcp(a), ib = fast_rcp(b), ic = fast_rcp(c);
+        s.inv_r[0] = ia;
+        s.inv_r[1] = ib;
+        s.inv_r[2] = ic;
+        const double m = fmin(a, fmin(b, c));
+        s.nw[0] = (m * ia) * (m * ia);
+        s.nw[1] = (m * ib) * (m * ib);
+        s.nw[2] = (m * ic) * (m * ic);
+    } else if (item == 2) {
+        const double rp = f.re - f.f * f.re;
+        s.rp = rp;
+        s.e2 = 1.0 - fast_div(rp * rp, f.re * f.re);
+        s.ep2 = fast_div(f.re * f.re, rp * rp) - 1.0;
+        s.omf = 1.0 - f.f;
+        s.inv_omf2 = fast_rcp((1.0 - f.f) * (1.0 - f.f));
+        s.biaxial = (f.radii[0] == f.radii[1]) && (f.re == f.radii[0]) && (fabs(rp - f.radii[2]) <= 4e-16 * f.radii[2]);
+        s.pad_ = 0;
     }
 }
 
 #ifdef __CUDACC__
-// Cooperative load of one PMFrame into shared memory + derived constants.
+// Cooperative load of one PMFrame into shared memory + derived constants.  The
+// derivation is spread over the four warps of the CTA so that items with different
+// code paths run concurrently instead of serialising inside one warp:
+// warp 0: the six R0 v products, warp 1: R0 M^T rows + pixel affine, warp 2: spin /
+// radii reciprocals, warp 3: spheroid constants.
 __device__ __forceinline__ void load_frame(FrameD &s, const PMFrame *__restrict__ g) {
     const double *src = reinterpret_cast<const double *>(g);
     double *dst = reinterpret_cast<double *>(&s.f);
     for (int i = threadIdx.x; i < PM_FRAME_NDOUBLES; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
-    if (threadIdx.x < kDeriveItems) derive_frame_item(s, threadIdx.x);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    int item = -1;
+    if (blockDim.x >= 128) {
+        if (w == 0 && l < 6) item = 3 + l;
+        else if (w == 1 && l < 4) item = 9 + l;
+        else if (w == 2 && l < 2) item = l;
+        else if (w == 3 && l == 0) item = 2;
+    } else if (threadIdx.x < kDeriveItems) {
+        item = threadIdx.x;
+    }
+    if (item >= 0) derive_frame_item(s, item);
     __syncthreads();
 }
 #endif
@@ -180,14 +197,14 @@ PM_HD V3 spin_fwd(const FrameD &fs, Rot r, V3 w) {
     const V3 t = mk(fma(k.x, kw, -w.x), fma(k.y, kw, -w.y), fma(k.z, kw, -w.z));
     return axpy(r.omc, t, axpy(r.s, c, w));
 }
-// exp(+theta [k]x) u (inverse spin)
-PM_HD V3 spin_bwd(const FrameD &fs, Rot r, V3 u) {
+// exp(+theta [k]x) u (inverse spin); kxu = k x u may be supplied by the caller
+PM_HD V3 spin_bwd_c(const FrameD &fs, Rot r, V3 u, V3 kxu) {
     const V3 k = ld3(fs.k);
-    const V3 c = cross(k, u);
     const double ku = dot(k, u);
     const V3 t = mk(fma(k.x, ku, -u.x), fma(k.y, ku, -u.y), fma(k.z, ku, -u.z));
-    return axpy(r.omc, t, axpy(r.s, c, u));
+    return axpy(r.omc, t, axpy(r.s, kxu, u));
 }
+PM_HD V3 spin_bwd(const FrameD &fs, Rot r, V3 u) { return spin_bwd_c(fs, r, u, cross(ld3(fs.k), u)); }
 // pxform('J2000', body, t_ref + dt) v   (inside sincpt / illumf / spkcpt, body.py:998)
 PM_HD V3 to_body(const FrameD &fs, Rot r, V3 v) { return spin_fwd(fs, r, mxv(fs.f.R0, v)); }
 // pxform(body, 'J2000', t_ref + dt) u   (body.py:940)
@@ -420,8 +437,9 @@ PM_HD void illum_angles(V3 n, V3 s, V3 e, bool want_az, Illum &out) {
 
 // Illumination geometry of body-fixed point p at epoch offset dt (spin r), given the
 // point -> observer vector e (body frame at the epoch).  Solves the Sun -> point light
-// time from the frame's seed lts0: the contraction factor is v_sun / c ~ 4e-5 and the
-// seed is off by <= R / c, so one refinement leaves a direction error < 1e-13 rad.
+// time from the frame's seed lts0.  VS is the Sun's barycentric velocity (~0.013 km/s):
+// the contraction factor of the iteration is VS / c ~ 4e-8 and the seed is off by
+// <= R / c, so ONE refinement leaves a Sun-direction error below 1e-18 rad.
 PM_HD void illum_at(const FrameD &fs, V3 p, V3 p0 /* spin_bwd(p) */, V3 e, Rot r, double dt, bool want_az,
                     Illum &out) {
     const PMFrame &f = fs.f;
@@ -432,9 +450,7 @@ PM_HD void illum_at(const FrameD &fs, V3 p, V3 p0 /* spin_bwd(p) */, V3 e, Rot r
                        fs.S0b[2] - fma(fs.ATb[2], h, fma(fs.VTb[2], dt, p0.z)));
     const V3 VSb = ld3(fs.VSb);
     V3 sv = axpy(dt, VSb, base);
-    double lts = norm(sv) * fs.inv_c;
-    sv = axpy(dt - (lts - f.lts0), VSb, base);
-    lts = norm(sv) * fs.inv_c;
+    const double lts = norm(sv) * fs.inv_c;
     sv = axpy(dt - (lts - f.lts0), VSb, base);
     const V3 s_b = spin_fwd(fs, r, sv);
     const V3 n = mul3(p, fs.nw);  // spice.surfnm direction
@@ -489,8 +505,7 @@ PM_HD V3 xy2ray_local(const FrameD &fs, double x, double y) {
     const double ra = fma(fs.As[0], x, fma(fs.As[1], y, fs.As[2]));
     const double dec = fma(fs.As[3], x, fma(fs.As[4], y, fs.As[5]));
     double sr, cr, sd, cd;
-    sincos_small(ra, sr, cr);
-    sincos_small(dec, sd, cd);
+    sincos_small2(ra, dec, sr, cr, sd, cd);
     return mk(cr * cd, sr * cd, sd);
 }
 
@@ -585,16 +600,20 @@ constexpr uint64_t kSkyMask = bit(PM_RA) | bit(PM_DEC) | kKmMask | kLimbMask | k
 // receives each requested plane exactly once.
 // Replaces the loops listed at pm_backplanes_img in include/pm_b200.h.
 // ---------------------------------------------------------------------------------
-template <class Sink>
-PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask, Sink &out) {
+// kSky = false compiles out RA / DEC / KM / ANGULAR / LIMB / RING planes (the launcher
+// picks it when none is requested): smaller code, fewer registers for the default
+// surface stack.
+template <bool kSky, class Sink>
+PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, Sink &out) {
     const PMFrame &f = fs.f;
     const double nan = NAN;
+    const uint64_t mask = kSky ? mask_in : (mask_in & ~kSkyMask);
     if (mask & bit(PM_PIXEL_X)) out.put(PM_PIXEL_X, x);  // BodyXY.get_x_img / get_y_img (body_xy.py:3494-3531)
     if (mask & bit(PM_PIXEL_Y)) out.put(PM_PIXEL_Y, y);
 
     const V3 v = xy2ray_local(fs, x, y);
     V3 d2 = mk(nan, nan, nan);
-    if (mask & kSkyMask) {
+    if (kSky && (mask & kSkyMask)) {
         // BodyXY._get_radec_img (body_xy.py:3413-3418)
         const V3 d = mtxv(f.M, v);
         double ra, dec;
@@ -651,7 +670,8 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask, Sink
         }
         if (mask & (kIllumMask | kStateMask | kRingMask)) {
             // spkcpt's converged light time is the intercept's own: |X| = |p - o|
-            const V3 p0 = spin_bwd(fs, it.r, p);
+            const V3 kxp = cross(ld3(fs.k), p);  // shared by the inverse spin and omega x p
+            const V3 p0 = spin_bwd_c(fs, it.r, p, kxp);
             if (mask & kIllumMask) {  // _get_illumination_gie_img (body_xy.py:3661-3665)
                 Illum il;
                 illum_at(fs, p, p0, -it.E, it.r, it.dt, (mask & bit(PM_AZIMUTH)) != 0, il);
@@ -667,7 +687,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask, Sink
                 const double iL = fast_rcp(it.L);
                 const V3 vt = axpy(it.dt, ld3(fs.ATb), ld3(fs.VTb));
                 const V3 X0 = it.Pb + p0;
-                const double a = (dot(vt, X0) + dot(cross(ld3(f.omega), p), it.E)) * iL;
+                const double a = fma(fs.wn, dot(kxp, it.E), dot(vt, X0)) * iL;
                 const double b = dot(ld3(fs.VOb), X0) * iL;
                 const double rv = radial_velocity(fs, a, b);
                 if (mask & bit(PM_RADIAL_VELOCITY)) out.put(PM_RADIAL_VELOCITY, rv);
@@ -682,14 +702,14 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask, Sink
                 if (m & bit(k)) out.put(k, nan);
     }
 
-    if (mask & kLimbMask) {  // _get_limb_coordinate_imgs (body_xy.py:3967-3975)
+    if (kSky && (mask & kLimbMask)) {  // _get_limb_coordinate_imgs (body_xy.py:3967-3975)
         double llon, llat, ldist;
         limb_coordinates(fs, d2, llon, llat, ldist);
         if (mask & bit(PM_LIMB_DISTANCE)) out.put(PM_LIMB_DISTANCE, ldist);
         if (mask & bit(PM_LIMB_LON_GRAPHIC)) out.put(PM_LIMB_LON_GRAPHIC, llon);
         if (mask & bit(PM_LIMB_LAT_GRAPHIC)) out.put(PM_LIMB_LAT_GRAPHIC, llat);
     }
-    if (mask & kRingMask) {  // _get_ring_plane_coordinate_imgs (body_xy.py:4061-4085)
+    if (kSky && (mask & kRingMask)) {  // _get_ring_plane_coordinate_imgs (body_xy.py:4061-4085)
         double rad, rl, rd;
         ring_coordinates(fs, d2, rad, rl, rd);
         if (rd > v_dist) rad = rl = rd = nan;  // NaN distance compares false (quirk kept)

@@ -174,6 +174,17 @@ PM_HD void sincos_small(double x, double &s, double &c) {
         sincos_lib(x, &s, &c);
     }
 }
+// sin, cos of two small angles with ONE range test, so that the four polynomial
+// chains share a basic block (cold library fallback for anything above pi/4)
+PM_HD void sincos_small2(double a, double b, double &sa, double &ca, double &sb, double &cb) {
+    if (fmax(fabs(a), fabs(b)) <= PM_T(kMisc)[1]) {
+        sincos_quarter(a, sa, ca);
+        sincos_quarter(b, sb, cb);
+    } else {
+        sincos_lib(a, &sa, &ca);
+        sincos_lib(b, &sb, &cb);
+    }
+}
 // sin, cos for |x| < ~1e5 (two-term Cody-Waite with FMA), cold fallback beyond
 PM_HD void sincos_full(double x, double &s, double &c) {
     if (!(fabs(x) < 1.0e5)) {
@@ -203,14 +214,15 @@ PM_HD void sincos_full(double x, double &s, double &c) {
 // apply explicitly).  One division; the argument is folded into |q| <= tan(pi/8) with
 // atan(a/b) = pi/4 + atan((a - b)/(a + b)).
 PM_HD double fast_atan2(double y, double x) {
+    // branch-free on purpose: independent calls then sit in one basic block and the
+    // scheduler interleaves their dependent FMA chains
     const double ax = fabs(x), ay = fabs(y);
     const bool sw = ay > ax;
     const double mx = sw ? ay : ax, mn = sw ? ax : ay;
-    if (!(mx > 0.0)) return (mx == 0.0) ? 0.0 : NAN;
     const bool hi = mn > mx * PM_T(kMisc)[0];
     const double num = hi ? (mn - mx) : mn;
     const double den = hi ? (mn + mx) : mx;
-    const double q = fast_div(num, den);
+    const double q = fast_div(num, den);  // 0 / 0 -> NaN, replaced below
     const double z = q * q;
     double p = PM_T(kAtanC)[10];
 #pragma unroll
@@ -219,7 +231,8 @@ PM_HD double fast_atan2(double y, double x) {
     if (hi) r += PM_T(kMisc)[1];
     if (sw) r = PM_T(kMisc)[2] - r;
     if (x < 0.0) r = PM_T(kMisc)[3] - r;
-    return (y < 0.0) ? -r : r;
+    r = (y < 0.0) ? -r : r;
+    return (mx == 0.0) ? 0.0 : r;
 }
 // acos(x); NaN for |x| > 1 like the libm routine
 PM_HD double fast_acos(double x) {

@@ -29,7 +29,10 @@ int hc_backplanes_img(const PMFrame *frame, int nx, int ny, uint64_t mask, doubl
         double v[PM_N_PLANES];
         for (int k = 0; k < PM_N_PLANES; k++) v[k] = NAN;
         ArraySink sink{v};
-        pm::image_pixel(fs, (double)(idx % nx), (double)(idx / nx), mask, sink);
+        if (mask & pm::kSkyMask)
+            pm::image_pixel<true>(fs, (double)(idx % nx), (double)(idx / nx), mask, sink);
+        else
+            pm::image_pixel<false>(fs, (double)(idx % nx), (double)(idx / nx), mask, sink);
         for (int k = 0; k < PM_N_PLANES; k++) out[(int64_t)k * n + idx] = v[k];
     }
     return 0;
