@@ -23,22 +23,30 @@ constexpr int kPerThread = 4;  // elements per thread and CTA (amortises the fra
 // plane slot of id k inside the packed output = number of requested planes below k
 __device__ __forceinline__ int slot(uint64_t mask, int k) { return __popcll(mask & (bit(k) - 1ull)); }
 
-// Element offset of every plane inside the packed plane-major output, computed once per
-// CTA (shared memory) instead of a popcount + 64-bit multiply in front of every store
-struct PlaneTable {
-    int64_t off[PM_N_PLANES];
+// Byte offset of every plane inside the packed plane-major output.  Filled on the host
+// and passed BY VALUE as a kernel parameter: parameters live in the constant bank, so a
+// store address is `pixel pointer + c[0][offset]` (two integer adds with a constant
+// operand) instead of a popcount, a 64-bit multiply and a shared-memory load per store.
+struct PlaneOffsets {
+    int64_t byte_off[PM_N_PLANES];
 };
-__device__ __forceinline__ void fill_plane_table(PlaneTable &t, uint64_t mask, int64_t plane_stride) {
-    // lanes 1..26 of the last warp: they are idle during the derived-constant step
-    const int k = (int)threadIdx.x - ((int)blockDim.x - 31);
-    if (k >= 0 && k < PM_N_PLANES) t.off[k] = (int64_t)slot(mask, k) * plane_stride;
+static PlaneOffsets make_plane_offsets(uint64_t mask, int64_t plane_stride) {
+    PlaneOffsets po;
+    int slot = 0;
+    for (int k = 0; k < PM_N_PLANES; k++) {
+        po.byte_off[k] = (int64_t)slot * plane_stride * (int64_t)sizeof(double);
+        if (mask & bit(k)) slot++;
+    }
+    return po;
 }
 
 // Receives the planes of one pixel / cell and streams them to the plane-major output
 struct PlaneSink {
-    double *base;  // out + element index
-    const PlaneTable *tab;
-    __device__ __forceinline__ void put(int k, double v) const { __stcs(base + tab->off[k], v); }
+    char *base;  // byte address of this element in plane slot 0
+    const PlaneOffsets &po;
+    __device__ __forceinline__ void put(int k, double v) const {
+        __stcs(reinterpret_cast<double *>(base + po.byte_off[k]), v);
+    }
 };
 
 // ---------------------------------------------------------------------------------
@@ -48,17 +56,16 @@ template <bool kSky, int kMinBlocks, int kPix>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) backplanes_img_kernel(const PMFrame *__restrict__ frames,
                                                                             uint32_t nx, uint32_t npx,
                                                                             uint64_t mask,
+                                                                            const __grid_constant__ PlaneOffsets po,
                                                                             double *__restrict__ out_all) {
     __shared__ FrameD fs;
-    __shared__ PlaneTable tab;
-    fill_plane_table(tab, mask, (int64_t)npx);
-    load_frame(fs, frames + blockIdx.y);  // (its barriers also publish the table)
+    load_frame(fs, frames + blockIdx.y);
     double *out = out_all + (int64_t)blockIdx.y * __popcll(mask) * npx;
     uint32_t idx = blockIdx.x * (uint32_t)(kBlock * kPix) + threadIdx.x;
     uint32_t yi = idx / nx, xi = idx - yi * nx;  // one division per thread, then incremental
 #pragma unroll 1
     for (int r = 0; r < kPix && idx < npx; r++) {
-        PlaneSink sink{out + idx, &tab};
+        PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
         image_pixel<kSky>(fs, (double)xi, (double)yi, mask, sink);
         idx += kBlock;
         xi += kBlock;
@@ -76,17 +83,16 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_map_kernel(const PMFrame
                                                                    const double *__restrict__ lon_in,
                                                                    const double *__restrict__ lat_in,
                                                                    int64_t n, uint64_t mask,
+                                                                   const __grid_constant__ PlaneOffsets po,
                                                                    double *__restrict__ out) {
     __shared__ FrameD fs;
-    __shared__ PlaneTable tab;
-    fill_plane_table(tab, mask, n);
     load_frame(fs, frame);
     const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
 #pragma unroll 1
     for (int r = 0; r < kPerThread; r++) {
         const int64_t idx = first + r * kBlock;
         if (idx >= n) break;
-        PlaneSink sink{out + idx, &tab};
+        PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
         map_cell(fs, __ldg(lon_in + idx), __ldg(lat_in + idx), mask, sink);
     }
 }
@@ -194,15 +200,16 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     (void)sm_count;
     const int64_t npx = (int64_t)nx * ny;
     if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
+    const PlaneOffsets po = make_plane_offsets(mask, npx);
     static const int variant = getenv("PM_IMG_VARIANT") ? atoi(getenv("PM_IMG_VARIANT")) : 0;
 #define PM_LAUNCH_IMG(MB, PIX)                                                                      \
     do {                                                                                            \
         const int64_t per = (int64_t)kBlock * PIX;                                                  \
         dim3 grid((unsigned)((npx + per - 1) / per), n_frames);                                     \
         if (mask & kSkyMask)                                                                        \
-            backplanes_img_kernel<true, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, out); \
+            backplanes_img_kernel<true, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, po, out); \
         else                                                                                        \
-            backplanes_img_kernel<false, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, out); \
+            backplanes_img_kernel<false, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, po, out); \
     } while (0)
     switch (variant) {
         case 1: PM_LAUNCH_IMG(4, 8); break;
@@ -220,7 +227,7 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
 cudaError_t launch_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
                                   uint64_t mask, double *out, int sm_count, cudaStream_t st) {
     (void)sm_count;
-    backplanes_map_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, mask, out);
+    backplanes_map_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, mask, make_plane_offsets(mask, n), out);
     count_launches(1);
     return cudaGetLastError();
 }
