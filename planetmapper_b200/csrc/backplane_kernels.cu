@@ -52,19 +52,18 @@ struct PlaneSink {
 // ---------------------------------------------------------------------------------
 // Image direction: all requested backplanes for every pixel of every frame.
 // ---------------------------------------------------------------------------------
-template <bool kSky, int kMinBlocks, int kPix>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) backplanes_img_kernel(const PMFrame *__restrict__ frames,
-                                                                            uint32_t nx, uint32_t npx,
-                                                                            uint64_t mask,
-                                                                            const __grid_constant__ PlaneOffsets po,
-                                                                            double *__restrict__ out_all) {
+template <bool kSky>
+__global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame *__restrict__ frames, uint32_t nx,
+                                                                   uint32_t npx, int per_thread, uint64_t mask,
+                                                                   const __grid_constant__ PlaneOffsets po,
+                                                                   double *__restrict__ out_all) {
     __shared__ FrameD fs;
     load_frame(fs, frames + blockIdx.y);
     double *out = out_all + (int64_t)blockIdx.y * __popcll(mask) * npx;
-    uint32_t idx = blockIdx.x * (uint32_t)(kBlock * kPix) + threadIdx.x;
+    uint32_t idx = blockIdx.x * (uint32_t)(kBlock * per_thread) + threadIdx.x;
     uint32_t yi = idx / nx, xi = idx - yi * nx;  // one division per thread, then incremental
 #pragma unroll 1
-    for (int r = 0; r < kPix && idx < npx; r++) {
+    for (int r = 0; r < per_thread && idx < npx; r++) {
         PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
         image_pixel<kSky>(fs, (double)xi, (double)yi, mask, sink);
         idx += kBlock;
@@ -195,32 +194,29 @@ static unsigned chunks_for(int64_t n) {
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// Pixels per thread: as many as possible (amortises the per-CTA frame staging) while the
+// grid still has >= 3 waves of resident CTAs for the hardware scheduler to balance.
+static int pick_per_thread(int64_t n, int64_t n_batches, int sm_count) {
+    const int64_t tiles = ((n + kBlock - 1) / kBlock) * n_batches;
+    const int64_t target = (int64_t)sm_count * 4 * 3;
+    int per = 16;
+    while (per > 1 && tiles / per < target) per >>= 1;
+    return per;
+}
+
 cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t mask,
                                   double *out, int sm_count, cudaStream_t st) {
-    (void)sm_count;
     const int64_t npx = (int64_t)nx * ny;
     if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
     const PlaneOffsets po = make_plane_offsets(mask, npx);
-    static const int variant = getenv("PM_IMG_VARIANT") ? atoi(getenv("PM_IMG_VARIANT")) : 0;
-#define PM_LAUNCH_IMG(MB, PIX)                                                                      \
-    do {                                                                                            \
-        const int64_t per = (int64_t)kBlock * PIX;                                                  \
-        dim3 grid((unsigned)((npx + per - 1) / per), n_frames);                                     \
-        if (mask & kSkyMask)                                                                        \
-            backplanes_img_kernel<true, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, po, out); \
-        else                                                                                        \
-            backplanes_img_kernel<false, MB, PIX><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, mask, po, out); \
-    } while (0)
-    switch (variant) {
-        case 1: PM_LAUNCH_IMG(4, 8); break;
-        case 2: PM_LAUNCH_IMG(5, 4); break;
-        case 3: PM_LAUNCH_IMG(5, 8); break;
-        case 4: PM_LAUNCH_IMG(3, 4); break;
-        case 5: PM_LAUNCH_IMG(3, 8); break;
-        case 6: PM_LAUNCH_IMG(4, 16); break;
-        default: PM_LAUNCH_IMG(4, 4); break;
-    }
-#undef PM_LAUNCH_IMG
+    static const int forced = getenv("PM_IMG_PER_THREAD") ? atoi(getenv("PM_IMG_PER_THREAD")) : 0;  // tuning only
+    const int per = forced > 0 ? forced : pick_per_thread(npx, n_frames, sm_count);
+    const int64_t chunk = (int64_t)kBlock * per;
+    dim3 grid((unsigned)((npx + chunk - 1) / chunk), n_frames);
+    if (mask & kSkyMask)
+        backplanes_img_kernel<true><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
+    else
+        backplanes_img_kernel<false><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -56,22 +56,22 @@ constexpr double kDpr = 180.0 / kPi;
 constexpr double kRpd = kPi / 180.0;
 
 // minimax fits (mpmath, Chebyshev nodes, 60 digits; tools/fit_coefficients.py):
-//   atan(q) = q + q z A(z),  z = q^2 <= tan(pi/8)^2      |err| < 6e-18
+//   atan(q) = q + q z A(z),  z = q^2 <= tan(pi/12)^2     |err| < 2e-17
 //   sin(x)  = x + x z S(z),  z = x^2 <= (pi/4)^2          |err| < 2e-17
 //   cos(x)  = 1 - z/2 + z^2 C(z)                           |err| < 5e-19
-PM_DEV_TABLE(kAtanC, 11, -0.33333333333333330153, 0.19999999999995512409, -0.14285714284664817984,
-             0.11111111015117633147, -0.090909045724876297519, 0.076921830599006634224,
-             -0.066645096033476166205, 0.058581328952289710071, -0.050853659265352889958,
-             0.039229237259412692422, -0.019173922433769131861)
+PM_DEV_TABLE(kAtanC, 8, -0.33333333333333245175, 0.19999999999842781854, -0.14285714239619743943,
+             0.11111105950225735071, -0.090906243717563017737, 0.076837307398386464706,
+             -0.065219990167523964706, 0.04578335659104139954)
 PM_DEV_TABLE(kSinC, 6, -0.16666666666666664621, 0.008333333333330946103, -0.00019841269836754970194,
              2.7557316100683122624e-6, -2.5051131455447427132e-8, 1.5918101231677278624e-10)
 PM_DEV_TABLE(kCosC, 6, 0.041666666666666665387, -0.0013888888888887395746, 0.000024801587298763433277,
              -2.7557317270560382548e-7, 2.0876146024701932874e-9, -1.1382614869434128293e-11)
-// misc constants read as constant-bank operands: tan(pi/8), pi/4, pi/2, pi, 2/pi,
-// pi/2 split (hi, lo), 2 pi, 1/(2 pi)
-PM_DEV_TABLE(kMisc, 9, 0.4142135623730950488016887, 0.78539816339744830961566, 1.5707963267948966192313,
+// misc constants read as constant-bank operands: tan(pi/12), pi/4, pi/2, pi, 2/pi,
+// pi/2 split (hi, lo), 2 pi, 1/(2 pi), sqrt(3), pi/6
+PM_DEV_TABLE(kMisc, 11, 0.2679491924311227064725537, 0.78539816339744830961566, 1.5707963267948966192313,
              3.1415926535897932384626, 0.6366197723675813430755351, 1.570796326794896619231322,
-             6.12323399573676588613033e-17, 6.283185307179586476925287, 0.1591549430918953357688838)
+             6.12323399573676588613033e-17, 6.283185307179586476925287, 0.1591549430918953357688838,
+             1.732050807568877293527446, 0.5235987755982988730771072)
 
 // ---- MUFU seeds ----------------------------------------------------------------
 PM_HD double rcp_seed(double b) {
@@ -211,8 +211,9 @@ PM_HD void sincos_full(double x, double &s, double &c) {
 }
 
 // atan2(y, x), full quadrant, atan2(0, 0) = 0 (the convention recrad / reclat / recgeo
-// apply explicitly).  One division; the argument is folded into |q| <= tan(pi/8) with
-// atan(a/b) = pi/4 + atan((a - b)/(a + b)).
+// apply explicitly).  One division; with a = min(|x|,|y|), b = max(|x|,|y|) the argument
+// is folded into |q| <= tan(pi/12) by
+//   atan(a/b) = pi/6 + atan((sqrt(3) a - b) / (sqrt(3) b + a))      for a/b > tan(pi/12).
 PM_HD double fast_atan2(double y, double x) {
     // branch-free on purpose: independent calls then sit in one basic block and the
     // scheduler interleaves their dependent FMA chains
@@ -220,15 +221,15 @@ PM_HD double fast_atan2(double y, double x) {
     const bool sw = ay > ax;
     const double mx = sw ? ay : ax, mn = sw ? ax : ay;
     const bool hi = mn > mx * PM_T(kMisc)[0];
-    const double num = hi ? (mn - mx) : mn;
-    const double den = hi ? (mn + mx) : mx;
+    const double num = hi ? fma(PM_T(kMisc)[9], mn, -mx) : mn;
+    const double den = hi ? fma(PM_T(kMisc)[9], mx, mn) : mx;
     const double q = fast_div(num, den);  // 0 / 0 -> NaN, replaced below
     const double z = q * q;
-    double p = PM_T(kAtanC)[10];
+    double p = PM_T(kAtanC)[7];
 #pragma unroll
-    for (int i = 9; i >= 0; i--) p = fma(p, z, PM_T(kAtanC)[i]);
+    for (int i = 6; i >= 0; i--) p = fma(p, z, PM_T(kAtanC)[i]);
     double r = fma(q * z, p, q);
-    if (hi) r += PM_T(kMisc)[1];
+    if (hi) r += PM_T(kMisc)[10];
     if (sw) r = PM_T(kMisc)[2] - r;
     if (x < 0.0) r = PM_T(kMisc)[3] - r;
     r = (y < 0.0) ? -r : r;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times the image kernel's tuning variants (PM_IMG_VARIANT, debug only) on C2.
+"""Times the image kernel's tuning variants (PM_IMG_PER_THREAD, debug only) on C2.
    python tools/tune_img.py [variants...]"""
 import os
 import subprocess
@@ -30,6 +30,6 @@ for rep in range(5):
 chk = torch.nan_to_num(out, nan=0.0).sum().item()
 print('variant', %r, 'ms %%.4f' %% best, 'Mpix/s %%.0f' %% (bench.SZ * bench.SZ / best / 1e3), 'checksum %%.17g' %% chk)
 '''
-for v in (sys.argv[1:] or ['0', '1', '2', '3', '4', '5', '6', '7']):
-    env = dict(os.environ, PM_IMG_VARIANT=v)
+for v in (sys.argv[1:] or ['1', '2', '4', '8', '16', '0']):
+    env = dict(os.environ, PM_IMG_PER_THREAD=v)
     subprocess.run([sys.executable, '-c', CHILD % (ROOT, v)], env=env, check=False)
