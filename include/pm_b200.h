@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -163,26 +163,33 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
  * Cube -> map resampling: replaces BodyXY._do_nearest_interpolation
  * (body_xy.py:1633-1649) and _do_spline_interpolation (:1651-1702) applied per
  * wavelength plane by Observation._get_mapped_data (observation.py:876-905).
- * cube: [n_planes][ny][nx]; xmap, ymap: [n_cells]; out: [n_planes][n_cells].
- * For LINEAR / CUBIC, `cube` must already be NaN-repaired and (CUBIC) prefiltered
- * to B-spline coefficients by pm_spline_prepare; `nanmask` ([n_planes][ny][nx]
- * uint8, 1 = original pixel was NaN, may be NULL) and `plane_skip` ([n_planes] uint8,
- * 1 = plane was all-NaN -> output all NaN, may be NULL) come from the same call.
+ * Resamples planes [plane_begin, plane_begin + plane_count) of an n_planes cube:
+ * xmap, ymap: [n_cells]; out: [plane_count][n_cells].
+ *   NEAREST:  `src` is the raw cube [n_planes][ny][nx]; nanbits / plane_bits unused.
+ *   LINEAR / CUBIC: `src`, `nanbits`, `plane_bits` are the three buffers filled by
+ *   pm_spline_prepare for the same (n_planes, ny, nx); plane_begin must be a multiple
+ *   of 4.  Their layout is private to the library (plane-quad interleaved coefficients
+ *   [ceil(n/4)][ny][nx][4], NaN bit planes [ny*nx][ceil(n/32)], per-word plane bits).
  */
-int pm_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip,
-              int n_planes, int ny, int nx, const double *xmap, const double *ymap,
-              int64_t n_cells, int mode, uint32_t flags, double *out, void *stream);
+int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits,
+              int n_planes, int ny, int nx, int plane_begin, int plane_count,
+              const double *xmap, const double *ymap, int64_t n_cells, int mode,
+              uint32_t flags, double *out, void *stream);
 
 /*
  * NaN repair (BodyXY._replace_nans_with_interpolated_values, body_xy.py:1871-1904)
  * followed, for degree 3, by the separable not-a-knot B-spline fit scipy's
- * RectBivariateSpline(kx=ky=3, s=0) performs (body_xy.py:1673-1680).
- * In: cube [n_planes][ny][nx].  Out: coef (same shape), nanmask, plane_skip.
+ * RectBivariateSpline(kx=ky=3, s=0) performs (body_xy.py:1673-1680), packed for
+ * pm_gather.  In: cube [n_planes][ny][nx].  Out: coef (pm_spline_coef_bytes),
+ * nanbits (pm_spline_nanbits_bytes), plane_bits (pm_spline_planebits_bytes).
  * `work` must hold pm_spline_work_bytes(...) bytes of device scratch.
  */
+int64_t pm_spline_coef_bytes(int n_planes, int ny, int nx);
+int64_t pm_spline_nanbits_bytes(int n_planes, int ny, int nx);
+int64_t pm_spline_planebits_bytes(int n_planes);
 int64_t pm_spline_work_bytes(int n_planes, int ny, int nx, int degree);
 int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree,
-                      double *coef, uint8_t *nanmask, uint8_t *plane_skip, void *work,
+                      double *coef, uint32_t *nanbits, uint32_t *plane_bits, void *work,
                       void *stream);
 
 /* FP64 FMA throughput probe used by bench.py for the compute roofline

@@ -37,6 +37,7 @@ PLANE_ID = {n: i for i, n in enumerate(PLANE_NAMES)}
 EXPORTED_SYMBOLS = [
     'pm_abi_version', 'pm_error_string', 'pm_launch_count', 'pm_backplanes_img',
     'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_proj_inverse', 'pm_gather',
+    'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
 ]
 
@@ -70,9 +71,14 @@ def load_library() -> ctypes.CDLL:
     lib.pm_xy2lonlat.argtypes = [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
     lib.pm_proj_inverse.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
-    lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i64, c_i, c_u32,
+    lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i64, c_i, c_u32,
                               c_p, c_p]
-    lib.pm_spline_work_bytes.restype = c_i64
+    for fn in ('pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_work_bytes',
+               'pm_spline_planebits_bytes'):
+        getattr(lib, fn).restype = c_i64
+    lib.pm_spline_coef_bytes.argtypes = [c_i, c_i, c_i]
+    lib.pm_spline_nanbits_bytes.argtypes = [c_i, c_i, c_i]
+    lib.pm_spline_planebits_bytes.argtypes = [c_i]
     lib.pm_spline_work_bytes.argtypes = [c_i, c_i, c_i, c_i]
     lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
     lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
@@ -81,7 +87,7 @@ def load_library() -> ctypes.CDLL:
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 1:
+    if lib.pm_abi_version() != 2:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -196,36 +202,80 @@ def proj_inverse(kind: int, a: float, b: float, lon0: float, lat0: float, lon_si
     return lon, lat
 
 
-def spline_prepare(cube_dev, degree: int):
-    """NaN repair (+ cubic B-spline coefficient solve). Returns (coef, nanmask, plane_flags)."""
+class Spline:
+    """Prepared spline operand of a cube (device buffers filled by pm_spline_prepare;
+    layout private to the library, see include/pm_b200.h)."""
+
+    def __init__(self, coef, nanbits, plane_bits, n_planes, ny, nx, degree):
+        self.coef, self.nanbits, self.plane_bits = coef, nanbits, plane_bits
+        self.n_planes, self.ny, self.nx, self.degree = n_planes, ny, nx, degree
+
+    def planes(self):
+        """Coefficients back in the natural (n_planes, ny, nx) layout (tests / debugging)."""
+        nq = (self.n_planes + 3) // 4
+        c = self.coef.view(nq, self.ny, self.nx, 4).permute(0, 3, 1, 2).reshape(nq * 4, self.ny, self.nx)
+        return c[:self.n_planes].contiguous()
+
+    def nanmask(self):
+        """Original-NaN mask (n_planes, ny, nx) as a bool tensor (tests / debugging)."""
+        import torch
+
+        nw = (self.n_planes + 31) // 32
+        w = self.nanbits.view(self.ny, self.nx, nw).to(torch.int64)
+        bits = (w[..., None] >> torch.arange(32, device=w.device)) & 1
+        return bits.reshape(self.ny, self.nx, nw * 32).permute(2, 0, 1)[:self.n_planes].bool()
+
+    def all_nan_planes(self):
+        import torch
+
+        nw = (self.n_planes + 31) // 32
+        w = self.plane_bits[:nw].to(torch.int64)
+        bits = (w[:, None] >> torch.arange(32, device=w.device)) & 1
+        return bits.reshape(-1)[:self.n_planes].bool()
+
+
+def spline_prepare(cube_dev, degree: int) -> Spline:
+    """NaN repair (+ cubic B-spline coefficient solve) packed for :func:`gather`."""
     torch = _torch()
     lib = load_library()
     nl, ny, nx = cube_dev.shape
-    coef = torch.empty_like(cube_dev)
-    nanmask = torch.empty((nl, ny, nx), dtype=torch.uint8, device=cube_dev.device)
-    flags = torch.empty((nl,), dtype=torch.uint8, device=cube_dev.device)
+    dev = cube_dev.device
+    coef = torch.empty((lib.pm_spline_coef_bytes(nl, ny, nx) // 8,), dtype=torch.float64, device=dev)
+    nanbits = torch.empty((lib.pm_spline_nanbits_bytes(nl, ny, nx) // 4,), dtype=torch.int32, device=dev)
+    plane_bits = torch.empty((lib.pm_spline_planebits_bytes(nl) // 4,), dtype=torch.int32, device=dev)
     nbytes = lib.pm_spline_work_bytes(nl, ny, nx, degree)
-    work = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=cube_dev.device)
+    work = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
     rc = lib.pm_spline_prepare(cube_dev.data_ptr(), nl, ny, nx, degree, coef.data_ptr(),
-                               nanmask.data_ptr(), flags.data_ptr(), work.data_ptr(),
+                               nanbits.data_ptr(), plane_bits.data_ptr(), work.data_ptr(),
                                _stream_ptr(torch))
     _check(rc, 'pm_spline_prepare')
-    return coef, nanmask, flags
+    return Spline(coef, nanbits, plane_bits, nl, ny, nx, degree)
 
 
-def gather(cube_dev, xmap_dev, ymap_dev, mode: int, *, nanmask=None, plane_flags=None,
+def gather(src, xmap_dev, ymap_dev, mode: int, *, plane_begin: int = 0, plane_count=None,
            propagate_nan: bool = True, out=None):
-    """cube_dev (nl, ny, nx) -> (nl,) + xmap.shape"""
+    """Resample planes [plane_begin, plane_begin + plane_count) of a cube onto map cells.
+    `src` is the raw CUDA cube (nl, ny, nx) for NEAREST and a :class:`Spline` for
+    LINEAR / CUBIC.  Returns (plane_count,) + xmap.shape."""
     torch = _torch()
     lib = load_library()
-    nl, ny, nx = cube_dev.shape
+    if mode == INTERP_NEAREST:
+        nl, ny, nx = src.shape
+        assert src.is_contiguous()
+        ptrs = (src.data_ptr(), None, None)
+    else:
+        if not isinstance(src, Spline):
+            raise PMLibraryError('gather(LINEAR / CUBIC) needs the Spline from spline_prepare()')
+        nl, ny, nx = src.n_planes, src.ny, src.nx
+        ptrs = (src.coef.data_ptr(), src.nanbits.data_ptr(), src.plane_bits.data_ptr())
+    if plane_count is None:
+        plane_count = nl - plane_begin
     n_cells = xmap_dev.numel()
     if out is None:
-        out = torch.empty((nl,) + tuple(xmap_dev.shape), dtype=torch.float64,
-                          device=cube_dev.device)
+        out = torch.empty((plane_count,) + tuple(xmap_dev.shape), dtype=torch.float64,
+                          device=xmap_dev.device)
     flags = FLAG_PROPAGATE_NAN if propagate_nan else 0
-    rc = lib.pm_gather(cube_dev.data_ptr(), nanmask.data_ptr() if nanmask is not None else None,
-                       plane_flags.data_ptr() if plane_flags is not None else None, nl, ny, nx,
+    rc = lib.pm_gather(ptrs[0], ptrs[1], ptrs[2], nl, ny, nx, plane_begin, plane_count,
                        xmap_dev.data_ptr(), ymap_dev.data_ptr(), n_cells, mode, flags,
                        out.data_ptr(), _stream_ptr(torch))
     _check(rc, 'pm_gather')

@@ -677,9 +677,8 @@ class BodyXY:
             return L.gather(cube, xmap, ymap, mode, out=out)
         if warn_nan and bool(torch.isfinite(cube).logical_not().any()):
             print('Warning, image contains NaN values which will be corrected')
-        coef, nanmask, flags = L.spline_prepare(cube, mode)
-        return L.gather(coef, xmap, ymap, mode, nanmask=nanmask, plane_flags=flags,
-                        propagate_nan=propagate_nan, out=out)
+        spline = L.spline_prepare(cube, mode)
+        return L.gather(spline, xmap, ymap, mode, propagate_nan=propagate_nan, out=out)
 
 
 def _interpolation_mode(interpolation, spline_smoothing) -> int:

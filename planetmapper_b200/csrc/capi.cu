@@ -95,37 +95,50 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx, cons
     return check(launch_proj_inverse(kind, params5_host, xx, yy, n, lon, lat, sms, (cudaStream_t)stream));
 }
 
-int pm_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip, int n_planes, int ny,
-              int nx, const double *xmap, const double *ymap, int64_t n_cells, int mode, uint32_t flags,
-              double *out, void *stream) {
-    if (!cube || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0)
+int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes, int ny, int nx,
+              int plane_begin, int plane_count, const double *xmap, const double *ymap, int64_t n_cells, int mode,
+              uint32_t flags, double *out, void *stream) {
+    if (!src || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 ||
+        plane_count < 0 || plane_begin + plane_count > n_planes)
         return PM_ERR_BAD_ARG;
     if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR && mode != PM_INTERP_CUBIC)
         return PM_ERR_UNSUPPORTED;
     if (mode == PM_INTERP_LINEAR && (nx < 2 || ny < 2)) return PM_ERR_BAD_ARG;
     if (mode == PM_INTERP_CUBIC && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
-    if ((flags & PM_FLAG_PROPAGATE_NAN) && mode != PM_INTERP_NEAREST && !nanmask) return PM_ERR_BAD_ARG;
-    if (n_planes > 65535 * 128) return PM_ERR_BAD_ARG;
+    if (mode != PM_INTERP_NEAREST && (!nanbits || !plane_bits || (plane_begin & 3))) return PM_ERR_BAD_ARG;
+    if (plane_count > 65535 * 128) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
-    return check(launch_gather(cube, nanmask, plane_skip, n_planes, ny, nx, xmap, ymap, n_cells, mode, flags,
-                               out, sms, (cudaStream_t)stream));
+    return check(launch_gather(src, nanbits, plane_bits, n_planes, ny, nx, plane_begin, plane_count, xmap, ymap,
+                               n_cells, mode, flags, out, sms, (cudaStream_t)stream));
 }
 
+int64_t pm_spline_coef_bytes(int n_planes, int ny, int nx) {
+    if (n_planes < 0 || ny <= 0 || nx <= 0) return PM_ERR_BAD_ARG;
+    return spline_coef_bytes(n_planes, ny, nx);
+}
+int64_t pm_spline_nanbits_bytes(int n_planes, int ny, int nx) {
+    if (n_planes < 0 || ny <= 0 || nx <= 0) return PM_ERR_BAD_ARG;
+    return spline_nanbits_bytes(n_planes, ny, nx);
+}
+int64_t pm_spline_planebits_bytes(int n_planes) {
+    if (n_planes < 0) return PM_ERR_BAD_ARG;
+    return spline_planebits_bytes(n_planes);
+}
 int64_t pm_spline_work_bytes(int n_planes, int ny, int nx, int degree) {
     if (n_planes < 0 || ny <= 0 || nx <= 0) return PM_ERR_BAD_ARG;
     return spline_work_bytes(n_planes, ny, nx, degree);
 }
 
 int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coef,
-                      uint8_t *nanmask, uint8_t *plane_skip, void *work, void *stream) {
-    if (!cube || !coef || !nanmask || !plane_skip || !work || n_planes < 0 || ny <= 0 || nx <= 0)
+                      uint32_t *nanbits, uint32_t *plane_bits, void *work, void *stream) {
+    if (!cube || !coef || !nanbits || !plane_bits || !work || n_planes < 0 || ny <= 0 || nx <= 0)
         return PM_ERR_BAD_ARG;
     if (degree != 1 && degree != 3) return PM_ERR_UNSUPPORTED;
     if (degree == 3 && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
-    return check(launch_spline_prepare(cube, n_planes, ny, nx, degree, coef, nanmask, plane_skip, work, sms,
+    return check(launch_spline_prepare(cube, n_planes, ny, nx, degree, coef, nanbits, plane_bits, work, sms,
                                        (cudaStream_t)stream));
 }
 

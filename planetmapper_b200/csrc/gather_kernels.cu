@@ -62,139 +62,197 @@ __host__ __device__ __forceinline__ int bspline3_weights(double x, int n, double
     return l - 3;
 }
 
-template <int MODE>
+// ---------------------------------------------------------------------------------
+// nearest neighbour: reads the raw cube [n_planes][ny][nx]
+// ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGatherBlock)
-    gather_kernel(const double *__restrict__ cube, const uint8_t *__restrict__ nanmask,
-                  const uint8_t *__restrict__ plane_skip, int n_planes, int ny, int nx,
-                  const double *__restrict__ xmap, const double *__restrict__ ymap, int64_t n_cells,
-                  uint32_t flags, double *__restrict__ out, int planes_per_group) {
+    gather_nearest_kernel(const double *__restrict__ cube, int ny, int nx, int plane_begin, int plane_count,
+                          const double *__restrict__ xmap, const double *__restrict__ ymap, int64_t n_cells,
+                          double *__restrict__ out, int planes_per_group) {
     const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
     const int l0 = blockIdx.y * planes_per_group;
-    const int l1 = min(l0 + planes_per_group, n_planes);
+    const int l1 = min(l0 + planes_per_group, plane_count);
     const int64_t plane_px = (int64_t)ny * nx;
     const double x = __ldg(xmap + cell), y = __ldg(ymap + cell);
     const double nan = NAN;
     bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
-
-    if (MODE == PM_INTERP_NEAREST) {
-        int64_t off = 0;
-        if (valid) {
-            // np.round is round-half-to-even == rint (body_xy.py:1642-1643)
-            long xi = (long)rint(x), yi = isnan(y) ? -999 : (long)rint(y);
-            if (xi < 0) xi += nx;  // numpy negative indices wrap
-            if (yi < 0) yi += ny;
-            valid = xi >= 0 && xi < nx && yi >= 0 && yi < ny;
-            off = (int64_t)yi * nx + xi;
-        }
-        const double *src = cube + (int64_t)l0 * plane_px + off;
-        double *dst = out + (int64_t)l0 * n_cells + cell;
-        int l = l0;
-        for (; l + 4 <= l1; l += 4) {
-            double v0 = nan, v1 = nan, v2 = nan, v3 = nan;
-            if (valid) {
-                v0 = __ldg(src);
-                v1 = __ldg(src + plane_px);
-                v2 = __ldg(src + 2 * plane_px);
-                v3 = __ldg(src + 3 * plane_px);
-            }
-            __stcs(dst, v0);
-            __stcs(dst + n_cells, v1);
-            __stcs(dst + 2 * n_cells, v2);
-            __stcs(dst + 3 * n_cells, v3);
-            src += 4 * plane_px;
-            dst += 4 * n_cells;
-        }
-        for (; l < l1; l++) {
-            __stcs(dst, valid ? __ldg(src) : nan);
-            src += plane_px;
-            dst += n_cells;
-        }
-        return;
+    int64_t off = 0;
+    if (valid) {
+        // np.round is round-half-to-even == rint (body_xy.py:1642-1643)
+        long xi = (long)rint(x), yi = isnan(y) ? -999 : (long)rint(y);
+        if (xi < 0) xi += nx;  // numpy negative indices wrap
+        if (yi < 0) yi += ny;
+        valid = xi >= 0 && xi < nx && yi >= 0 && yi < ny;
+        off = (int64_t)yi * nx + xi;
     }
+    const double *src = cube + (int64_t)(plane_begin + l0) * plane_px + off;
+    double *dst = out + (int64_t)l0 * n_cells + cell;
+    int l = l0;
+    for (; l + 4 <= l1; l += 4) {
+        double v0 = nan, v1 = nan, v2 = nan, v3 = nan;
+        if (valid) {
+            v0 = __ldg(src);
+            v1 = __ldg(src + plane_px);
+            v2 = __ldg(src + 2 * plane_px);
+            v3 = __ldg(src + 3 * plane_px);
+        }
+        __stcs(dst, v0);
+        __stcs(dst + n_cells, v1);
+        __stcs(dst + 2 * n_cells, v2);
+        __stcs(dst + 3 * n_cells, v3);
+        src += 4 * plane_px;
+        dst += 4 * n_cells;
+    }
+    for (; l < l1; l++) {
+        __stcs(dst, valid ? __ldg(src) : nan);
+        src += plane_px;
+        dst += n_cells;
+    }
+}
 
-    // ---- spline modes ----
+// ---------------------------------------------------------------------------------
+// spline modes: read the prepared operand of pm_spline_prepare
+//   coefq   [ceil(n_planes / 4)][ny][nx][4]   four wavelength planes of one pixel are
+//           32 contiguous bytes, so one 256-bit load feeds four FMAs and the K x K
+//           footprint of a cell is K runs of K x 32 contiguous bytes;
+//   nanbits [ny * nx][n_words]                bit (l % 32) of word l / 32 = pixel was NaN
+//           in plane l: the propagate_nan test costs four word loads per 32 planes;
+//   plane_bits [2][n_words]                   row 0: all-NaN planes, row 1: words with any
+//           NaN pixel (nanbits needs consulting).
+// The K x K weight products are formed once per cell; per output voxel the kernel then
+// issues K*K/4 loads, K*K FMAs and one streaming store.
+// ---------------------------------------------------------------------------------
+struct Quad {
+    double v[4];
+};
+__device__ __forceinline__ Quad ldg_quad(const double *p) {
+    Quad q;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(q.v[0]), "=d"(q.v[1]), "=d"(q.v[2]), "=d"(q.v[3])
+                 : "l"(p));
+    return q;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_spline_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
+                         const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int plane_begin,
+                         int plane_count, const double *__restrict__ xmap, const double *__restrict__ ymap,
+                         int64_t n_cells, uint32_t flags, double *__restrict__ out, int planes_per_group) {
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 4
+    const int l1 = min(l0 + planes_per_group, plane_count);
+    const double x = __ldg(xmap + cell), y = __ldg(ymap + cell);
+    const double nan = NAN;
+    bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
     const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
-    int nb_x0 = 0, nb_x1 = 0, nb_y0 = 0, nb_y1 = 0;
+    int64_t nb00 = 0, nb01 = 0, nb10 = 0, nb11 = 0;
     if (valid && propagate) {
         // BodyXY._should_propagate_nan_to_map (body_xy.py:1855-1866)
         if (x < 0.0 || y < 0.0 || x > nx - 1 || y > ny - 1) valid = false;
-        nb_x0 = max((int)floor(x), 0);
-        nb_x1 = min((int)ceil(x), nx - 1);
-        nb_y0 = max((int)floor(y), 0);
-        nb_y1 = min((int)ceil(y), ny - 1);
+        const int x0 = max((int)floor(x), 0), x1 = min((int)ceil(x), nx - 1);
+        const int y0 = max((int)floor(y), 0), y1 = min((int)ceil(y), ny - 1);
+        nb00 = ((int64_t)y0 * nx + x0) * n_words;
+        nb01 = ((int64_t)y0 * nx + x1) * n_words;
+        nb10 = ((int64_t)y1 * nx + x0) * n_words;
+        nb11 = ((int64_t)y1 * nx + x1) * n_words;
     }
-    constexpr int K = (MODE == PM_INTERP_CUBIC) ? 4 : 2;
-    double wx[K], wy[K];
+    double w[K * K];
     int ix = 0, iy = 0;
     if (valid) {
-        if (MODE == PM_INTERP_CUBIC) {
+        double wx[K], wy[K];
+        if (K == 4) {
             ix = bspline3_weights(x, nx, wx);
             iy = bspline3_weights(y, ny, wy);
         } else {
-            double xe = fmin(fmax(x, 0.0), (double)(nx - 1));
-            double ye = fmin(fmax(y, 0.0), (double)(ny - 1));
+            const double xe = fmin(fmax(x, 0.0), (double)(nx - 1));
+            const double ye = fmin(fmax(y, 0.0), (double)(ny - 1));
             ix = min((int)floor(xe), nx - 2);
             iy = min((int)floor(ye), ny - 2);
-            double fx = xe - ix, fy = ye - iy;
+            const double fx = xe - ix, fy = ye - iy;
             wx[0] = 1.0 - fx;
             wx[1] = fx;
             wy[0] = 1.0 - fy;
             wy[1] = fy;
         }
+#pragma unroll
+        for (int a = 0; a < K; a++)
+#pragma unroll
+            for (int b = 0; b < K; b++) w[a * K + b] = wy[a] * wx[b];
     }
-    const int64_t base = (int64_t)iy * nx + ix;
-    for (int l = l0; l < l1; l++) {
-        double v = nan;
-        const uint8_t pflag = plane_skip ? plane_skip[l] : 0;
-        bool ok = valid && !(pflag & kPlaneAllNan);
-        if (ok && propagate && (pflag & kPlaneHasNan)) {
-            const uint8_t *m = nanmask + (int64_t)l * plane_px;
-            ok = !(m[(int64_t)nb_y0 * nx + nb_x0] | m[(int64_t)nb_y0 * nx + nb_x1] |
-                   m[(int64_t)nb_y1 * nx + nb_x0] | m[(int64_t)nb_y1 * nx + nb_x1]);
+    const int64_t quad_stride = (int64_t)ny * nx * 4;  // doubles per plane quad
+    const int64_t row_stride = (int64_t)nx * 4;
+    const double *src = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + ((int64_t)iy * nx + ix) * 4;
+    double *dst = out + (int64_t)l0 * n_cells + cell;
+    uint32_t bad = 0;
+    int cur_word = -1;
+    for (int l = l0; l < l1; l += 4) {
+        const int gl = plane_begin + l;  // global plane index of this quad (multiple of 4)
+        const int word = gl >> 5;
+        if (word != cur_word) {  // uniform: once per 32 planes
+            cur_word = word;
+            bad = __ldg(plane_bits + word);
+            if (valid && propagate && __ldg(plane_bits + n_words + word))
+                bad |= __ldg(nanbits + nb00 + word) | __ldg(nanbits + nb01 + word) | __ldg(nanbits + nb10 + word) |
+                       __ldg(nanbits + nb11 + word);
         }
-        if (ok) {
-            const double *c = cube + (int64_t)l * plane_px + base;
-            // FITPACK fpbisp accumulation order: first axis (rows, y) outer
-            double sp = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (valid) {
+            // FITPACK fpbisp order: rows (y) outer, columns inner
 #pragma unroll
             for (int a = 0; a < K; a++) {
 #pragma unroll
-                for (int b = 0; b < K; b++) sp += __ldg(c + a * nx + b) * wy[a] * wx[b];
+                for (int b = 0; b < K; b++) {
+                    const Quad c = ldg_quad(src + a * row_stride + b * 4);
+                    const double ww = w[a * K + b];
+                    a0 = fma(c.v[0], ww, a0);
+                    a1 = fma(c.v[1], ww, a1);
+                    a2 = fma(c.v[2], ww, a2);
+                    a3 = fma(c.v[3], ww, a3);
+                }
             }
-            v = sp;
         }
-        __stcs(out + (int64_t)l * n_cells + cell, v);
+        const uint32_t nib = valid ? ((bad >> (gl & 31)) & 0xFu) : 0xFu;
+        const int left = l1 - l;
+        __stcs(dst, (nib & 1u) ? nan : a0);
+        if (left > 1) __stcs(dst + n_cells, (nib & 2u) ? nan : a1);
+        if (left > 2) __stcs(dst + 2 * n_cells, (nib & 4u) ? nan : a2);
+        if (left > 3) __stcs(dst + 3 * n_cells, (nib & 8u) ? nan : a3);
+        src += quad_stride;
+        dst += 4 * n_cells;
     }
 }
 
-cudaError_t launch_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip, int n_planes,
-                          int ny, int nx, const double *xmap, const double *ymap, int64_t n_cells, int mode,
-                          uint32_t flags, double *out, int sm_count, cudaStream_t st) {
+cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
+                          int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
+                          int64_t n_cells, int mode, uint32_t flags, double *out, int sm_count, cudaStream_t st) {
     (void)sm_count;
-    if (n_cells == 0 || n_planes == 0) return cudaSuccess;
+    if (n_cells == 0 || plane_count == 0) return cudaSuccess;
     int ppg = 128;  // planes per CTA: amortises the per-cell weights, bounds CTA run time
-    if (n_planes < ppg) ppg = n_planes;
-    dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)((n_planes + ppg - 1) / ppg));
+    if (plane_count < ppg) ppg = (plane_count + 3) / 4 * 4;
+    dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)((plane_count + ppg - 1) / ppg));
+    const int n_words = (n_planes + 31) / 32;
     switch (mode) {
         case PM_INTERP_NEAREST:
-            gather_kernel<PM_INTERP_NEAREST><<<grid, kGatherBlock, 0, st>>>(
-                cube, nanmask, plane_skip, n_planes, ny, nx, xmap, ymap, n_cells, flags, out, ppg);
-                count_launches(1);
+            gather_nearest_kernel<<<grid, kGatherBlock, 0, st>>>(src, ny, nx, plane_begin, plane_count, xmap, ymap,
+                                                                 n_cells, out, ppg);
             break;
         case PM_INTERP_LINEAR:
-            gather_kernel<PM_INTERP_LINEAR><<<grid, kGatherBlock, 0, st>>>(
-                cube, nanmask, plane_skip, n_planes, ny, nx, xmap, ymap, n_cells, flags, out, ppg);
-                count_launches(1);
+            gather_spline_kernel<2><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                   plane_begin, plane_count, xmap, ymap, n_cells,
+                                                                   flags, out, ppg);
             break;
         case PM_INTERP_CUBIC:
-            gather_kernel<PM_INTERP_CUBIC><<<grid, kGatherBlock, 0, st>>>(
-                cube, nanmask, plane_skip, n_planes, ny, nx, xmap, ymap, n_cells, flags, out, ppg);
-                count_launches(1);
+            gather_spline_kernel<4><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                   plane_begin, plane_count, xmap, ymap, n_cells,
+                                                                   flags, out, ppg);
             break;
         default:
             return cudaErrorInvalidValue;
     }
+    count_launches(1);
     return cudaGetLastError();
 }
 
@@ -209,20 +267,17 @@ struct PlaneStats {
 // pass 1: NaN mask, bad-pixel counts, plane flags, copy into the coefficient buffer
 __global__ void __launch_bounds__(256) classify_kernel(const double *__restrict__ cube, int64_t plane_px,
                                                        double *__restrict__ coef,
-                                                       uint8_t *__restrict__ nanmask,
                                                        uint8_t *__restrict__ plane_skip,
                                                        PlaneStats *__restrict__ stats) {
     const int l = blockIdx.x;
     const double *src = cube + (int64_t)l * plane_px;
     double *dst = coef + (int64_t)l * plane_px;
-    uint8_t *m = nanmask + (int64_t)l * plane_px;
     long long n_nan = 0, n_bad = 0;
     for (int64_t i = threadIdx.x; i < plane_px; i += blockDim.x) {
         double v = src[i];
         bool isn = isnan(v);
         n_nan += isn;
         n_bad += !isfinite(v);
-        m[i] = isn ? 1 : 0;
         dst[i] = v;
     }
     __shared__ long long s_nan[256], s_bad[256];
@@ -405,6 +460,52 @@ __global__ void __launch_bounds__(128) prefilter_cols_kernel(double *__restrict_
     }
 }
 
+// pass 6: pack the repaired / prefiltered planes [l][y][x] into plane quads
+// [l / 4][y][x][l % 4] (zero padding up to a multiple of four planes)
+__global__ void __launch_bounds__(256) pack_quads_kernel(const double *__restrict__ planes, int n_planes,
+                                                         int64_t plane_px, double *__restrict__ coefq) {
+    const int64_t n_quads = (n_planes + 3) / 4;
+    const int64_t total = n_quads * plane_px;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = t / plane_px, px = t - q * plane_px;
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t l = 4 * q + j;
+            v[j] = l < n_planes ? planes[l * plane_px + px] : 0.0;
+        }
+        double4 o = make_double4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<double4 *>(coefq + t * 4) = o;
+    }
+}
+// pass 7: NaN bit planes [pixel][word] of the ORIGINAL cube and the per-word plane bits
+__global__ void __launch_bounds__(256) pack_nanbits_kernel(const double *__restrict__ cube, int n_planes,
+                                                           int64_t plane_px, int n_words,
+                                                           uint32_t *__restrict__ nanbits) {
+    const int64_t total = plane_px * n_words;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t wd = t / plane_px, px = t - wd * plane_px;  // consecutive threads -> consecutive pixels
+        uint32_t bits = 0;
+        const int lbeg = (int)wd * 32, lend = min(lbeg + 32, n_planes);
+        for (int l = lbeg; l < lend; l++) bits |= (isnan(cube[(int64_t)l * plane_px + px]) ? 1u : 0u) << (l - lbeg);
+        nanbits[px * n_words + wd] = bits;
+    }
+}
+__global__ void plane_bits_kernel(const uint8_t *__restrict__ plane_skip, int n_planes, int n_words,
+                                  uint32_t *__restrict__ plane_bits) {
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wd >= n_words) return;
+    uint32_t skip = 0, has = 0;
+    for (int l = wd * 32; l < min(wd * 32 + 32, n_planes); l++) {
+        if (plane_skip[l] & kPlaneAllNan) skip |= 1u << (l - wd * 32);
+        if (plane_skip[l] & kPlaneHasNan) has = 1u;
+    }
+    plane_bits[wd] = skip;
+    plane_bits[n_words + wd] = has;
+}
+
 // host: LU factors (no pivoting; the B-spline collocation matrix is totally positive)
 static const std::vector<double> &nak_lu(int n) {
     static std::map<int, std::vector<double>> cache;
@@ -444,14 +545,23 @@ static const std::vector<double> &nak_lu(int n) {
 
 static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
+int64_t spline_coef_bytes(int n_planes, int ny, int nx) {
+    return (int64_t)((n_planes + 3) / 4) * ny * nx * 4 * (int64_t)sizeof(double);
+}
+int64_t spline_nanbits_bytes(int n_planes, int ny, int nx) {
+    return (int64_t)ny * nx * ((n_planes + 31) / 32) * (int64_t)sizeof(uint32_t);
+}
+int64_t spline_planebits_bytes(int n_planes) { return 2 * (int64_t)((n_planes + 31) / 32) * (int64_t)sizeof(uint32_t); }
+
 int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree) {
-    int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double));
+    int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double)) +
+                align256((int64_t)n_planes) + align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
     if (degree == 3) b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
     return b;
 }
 
-cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coef,
-                                  uint8_t *nanmask, uint8_t *plane_skip, void *work, int sm_count,
+cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coefq,
+                                  uint32_t *nanbits, uint32_t *plane_bits, void *work, int sm_count,
                                   cudaStream_t st) {
     if (n_planes == 0) return cudaSuccess;
     char *w = static_cast<char *>(work);
@@ -459,15 +569,18 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     w += align256((int64_t)n_planes * sizeof(PlaneStats));
     double *median = reinterpret_cast<double *>(w);
     w += align256((int64_t)n_planes * sizeof(double));
+    uint8_t *plane_skip = reinterpret_cast<uint8_t *>(w);
+    w += align256((int64_t)n_planes);
+    double *coef = reinterpret_cast<double *>(w);  // natural layout [l][y][x] scratch
+    w += align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
     const int64_t plane_px = (int64_t)ny * nx;
-    classify_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, coef, nanmask, plane_skip, stats);
-    count_launches(1);
+    const int n_words = (n_planes + 31) / 32;
+    classify_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, coef, plane_skip, stats);
     median_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, stats, median);
-    count_launches(1);
     int64_t total = plane_px * n_planes;
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
     repair_kernel<<<blocks, 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
-    count_launches(1);
+    count_launches(3);
     if (degree == 3) {
         double *lu_x = reinterpret_cast<double *>(w);
         w += align256((int64_t)5 * nx * sizeof(double));
@@ -482,10 +595,17 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
         int rb = (int)std::min<int64_t>((rows + 127) / 128, (int64_t)sm_count * 16);
         int cb = (int)std::min<int64_t>((cols + 127) / 128, (int64_t)sm_count * 16);
         prefilter_rows_kernel<<<rb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_x);
-        count_launches(1);
         prefilter_cols_kernel<<<cb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_y);
-        count_launches(1);
+        count_launches(2);
     }
+    const int64_t quads_total = (int64_t)((n_planes + 3) / 4) * plane_px;
+    pack_quads_kernel<<<(int)std::min<int64_t>((quads_total + 255) / 256, (int64_t)sm_count * 32), 256, 0, st>>>(
+        coef, n_planes, plane_px, coefq);
+    const int64_t words_total = plane_px * n_words;
+    pack_nanbits_kernel<<<(int)std::min<int64_t>((words_total + 255) / 256, (int64_t)sm_count * 32), 256, 0, st>>>(
+        cube, n_planes, plane_px, n_words, nanbits);
+    plane_bits_kernel<<<(n_words + 127) / 128, 128, 0, st>>>(plane_skip, n_planes, n_words, plane_bits);
+    count_launches(3);
     return cudaGetLastError();
 }
 

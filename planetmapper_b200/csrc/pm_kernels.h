@@ -27,13 +27,16 @@ cudaError_t launch_math_probe(int kind, const double *a, const double *b, int64_
 cudaError_t launch_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                                 int64_t n, double *lon, double *lat, int sm_count, cudaStream_t st);
 
-cudaError_t launch_gather(const double *cube, const uint8_t *nanmask, const uint8_t *plane_skip, int n_planes,
-                          int ny, int nx, const double *xmap, const double *ymap, int64_t n_cells, int mode,
-                          uint32_t flags, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
+                          int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
+                          int64_t n_cells, int mode, uint32_t flags, double *out, int sm_count, cudaStream_t st);
 
+int64_t spline_coef_bytes(int n_planes, int ny, int nx);
+int64_t spline_nanbits_bytes(int n_planes, int ny, int nx);
+int64_t spline_planebits_bytes(int n_planes);
 int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree);
-cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coef,
-                                  uint8_t *nanmask, uint8_t *plane_skip, void *work, int sm_count,
+cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degree, double *coefq,
+                                  uint32_t *nanbits, uint32_t *plane_bits, void *work, int sm_count,
                                   cudaStream_t st);
 
 }  // namespace pm

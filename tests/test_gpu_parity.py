@@ -180,14 +180,20 @@ def test_gather_vs_scipy_oracle(L, oracle, bc_hst, nx, ny):
     got = L.gather(cd, xy[0], xy[1], L.INTERP_NEAREST).cpu().numpy()
     ref = MO.map_img(cube, xm, ym, 'nearest')
     assert np.array_equal(got, ref, equal_nan=True), 'nearest gather must be bit-exact'
+    sub = L.gather(cd, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=1, plane_count=2).cpu().numpy()
+    assert np.array_equal(sub, ref[1:3], equal_nan=True)
     assert np.array_equal(oracle.gather_nearest(cube, xm, ym), ref, equal_nan=True)
     for mode, name in ((L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
         if name == 'cubic' and min(nx, ny) < 4:
             continue
         for prop in (True, False):
-            coef, nanmask, flags = L.spline_prepare(cd, mode)
-            got = L.gather(coef, xy[0], xy[1], mode, nanmask=nanmask, plane_flags=flags,
-                           propagate_nan=prop).cpu().numpy()
+            spline = L.spline_prepare(cd, mode)
+            got = L.gather(spline, xy[0], xy[1], mode, propagate_nan=prop).cpu().numpy()
+            # a quad-aligned sub-range of planes equals the same planes of the full call
+            if cube.shape[0] > 4:
+                sub = L.gather(spline, xy[0], xy[1], mode, plane_begin=4, plane_count=3,
+                               propagate_nan=prop).cpu().numpy()
+                assert np.array_equal(sub, got[4:7], equal_nan=True)
             ref = MO.map_img(cube, xm, ym, name, propagate_nan=prop)
             assert np.array_equal(np.isnan(got), np.isnan(ref)), (name, prop)
             ok = np.isfinite(ref)
@@ -201,15 +207,18 @@ def test_nan_repair_matches_reference_recipe(L, bc_hst):
 
     rng = np.random.default_rng(3)
     cube = _cube(rng, 9, 20, 17)
-    coef, nanmask, flags = L.spline_prepare(L.to_device(cube), L.INTERP_LINEAR)
-    coef = coef.cpu().numpy()
+    spline = L.spline_prepare(L.to_device(cube), L.INTERP_LINEAR)
+    coef = spline.planes().cpu().numpy()
+    nanmask = spline.nanmask().cpu().numpy()
+    all_nan = spline.all_nan_planes().cpu().numpy()
     for l in range(cube.shape[0]):
+        assert np.array_equal(nanmask[l], np.isnan(cube[l]))
         if np.all(np.isnan(cube[l])):
-            assert flags[l].item() & 1
+            assert all_nan[l]
             continue
+        assert not all_nan[l]
         ref = MO.replace_nans_with_interpolated_values(cube[l])
         assert np.allclose(coef[l], ref, rtol=1e-14, atol=0), l
-        assert np.array_equal(nanmask[l].cpu().numpy().astype(bool), np.isnan(cube[l]))
 
 
 # ---- size-independent properties at BASELINE.json's full sizes ------------------------
@@ -282,8 +291,7 @@ def test_full_grid_gather_properties(L, bc_hst):
     assert torch.equal(near[0][vis], torch.round(xm[vis])) and torch.equal(near[1][vis], torch.round(ym[vis]))
     assert torch.equal(torch.isfinite(near[0]), vis)
     for mode in (L.INTERP_LINEAR, L.INTERP_CUBIC):
-        coef, nanmask, flags = L.spline_prepare(cube, mode)
-        out = L.gather(coef, xm, ym, mode, nanmask=nanmask, plane_flags=flags, propagate_nan=True)
+        out = L.gather(L.spline_prepare(cube, mode), xm, ym, mode, propagate_nan=True)
         inside = vis & (xm >= 0) & (ym >= 0) & (xm <= sz - 1) & (ym <= sz - 1)
         assert torch.equal(torch.isfinite(out[0]), inside)
         # both spline kinds reproduce linear functions: sampling the x / y ramps returns the map

@@ -79,8 +79,8 @@ def main():
         cmp('gather nearest', g, MO.map_img(cube, xm, ym, 'nearest'))
         for mode, name in ((L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
             for prop in (True, False):
-                coef, nanmask, flags = L.spline_prepare(cd, mode)
-                g = L.gather(coef, xd, yd, mode, nanmask=nanmask, plane_flags=flags,
+                coef = L.spline_prepare(cd, mode)
+                g = L.gather(coef, xd, yd, mode,
                              propagate_nan=prop).cpu().numpy()
                 r = MO.map_img(cube, xm, ym, name, propagate_nan=prop)
                 cmp(f'gather {name} p={int(prop)}', g, r)
@@ -131,15 +131,15 @@ def main():
     out = torch.empty((nl,) + tuple(lo.shape), dtype=torch.float64, device='cuda')
     for mode, name in ((0, 'nearest'), (1, 'linear'), (3, 'cubic')):
         if mode:
-            coef, nanmask, flags = L.spline_prepare(cube, mode)
+            coef = L.spline_prepare(cube, mode)
         else:
-            coef, nanmask, flags = cube, None, None
-        L.gather(coef, xy[0], xy[1], mode, nanmask=nanmask, plane_flags=flags, out=out)
+            coef = cube
+        L.gather(coef, xy[0], xy[1], mode, out=out)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            L.gather(coef, xy[0], xy[1], mode, nanmask=nanmask, plane_flags=flags, out=out)
+            L.gather(coef, xy[0], xy[1], mode, out=out)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3

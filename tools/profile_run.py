@@ -40,7 +40,7 @@ else:
         for _ in range(2):
             L.backplanes_map(fd, lod, lad, L.ALL_PLANES)
     else:
-        nl = 250
+        nl = 256
         rng = np.random.default_rng(0)
         cube_h = rng.normal(1.0, 0.1, (nl, sz, sz))
         cube_h[rng.random(cube_h.shape) < 0.01] = np.nan
@@ -48,10 +48,10 @@ else:
         out = torch.empty((nl,) + lo.shape, dtype=torch.float64, device='cuda')
         for mode in (0, 1, 3):
             if mode:
-                coef, nanmask, flags = L.spline_prepare(cube, mode)
+                coef = L.spline_prepare(cube, mode)
             else:
-                coef, nanmask, flags = cube, None, None
+                coef = cube
             for _ in range(2):
-                L.gather(coef, xy[0], xy[1], mode, nanmask=nanmask, plane_flags=flags, out=out)
+                L.gather(coef, xy[0], xy[1], mode, out=out)
 torch.cuda.synchronize()
 print('done', what)
