@@ -215,7 +215,7 @@ def bench_mapped_cube(L, torch, bc, rank, world):
     """C4: 3000 x 64 x 64 cube -> 0.1 deg rectangular grid, device resident, chunked."""
     from planetmapper_b200 import frame as F
 
-    sz, nl_total, chunk = 64, 3000, 256
+    sz, nl_total, chunk = 64, 3000, 512
     fr = F.pack_frame(bc, nx=sz, ny=sz, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
     lons = np.arange(0.05, 360, 0.1)[::-1]
     lats = np.arange(-90 + 0.05, 90, 0.1)

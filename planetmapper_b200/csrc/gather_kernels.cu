@@ -16,6 +16,7 @@
 #include "pm_device.cuh"
 #include "pm_kernels.h"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -53,7 +54,7 @@ __host__ __device__ __forceinline__ int bspline3_weights(double x, int n, double
             if (i < jj) {
                 int li = l + 1 + i, lj = li - jj;
                 double tli = nak_knot(li, n), tlj = nak_knot(lj, n);
-                double f = hh[i] / (tli - tlj);
+                double f = fast_div(hh[i], tli - tlj);  // knot spans are 1, 2 or 3: exact or correctly rounded
                 h[i] = h[i] + f * (tli - xe);
                 h[i + 1] = f * (xe - tlj);
             }
@@ -134,35 +135,34 @@ __device__ __forceinline__ Quad ldg_quad(const double *p) {
     return q;
 }
 
+// Per-cell state of the spline gather (weights, footprint origin, NaN-test pixels)
 template <int K>
-__global__ void __launch_bounds__(kGatherBlock)
-    gather_spline_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
-                         const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int plane_begin,
-                         int plane_count, const double *__restrict__ xmap, const double *__restrict__ ymap,
-                         int64_t n_cells, uint32_t flags, double *__restrict__ out, int planes_per_group) {
-    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 4
-    const int l1 = min(l0 + planes_per_group, plane_count);
-    const double x = __ldg(xmap + cell), y = __ldg(ymap + cell);
-    const double nan = NAN;
-    bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
-    const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
-    int64_t nb00 = 0, nb01 = 0, nb10 = 0, nb11 = 0;
-    if (valid && propagate) {
+struct CellState {
+    double w[K * K];     // wy[a] * wx[b], FITPACK fpbisp order (rows outer)
+    int64_t origin;      // ((iy * nx + ix) * 4): offset of the footprint inside a plane quad
+    uint32_t nb[4];      // pixel indices floor/ceil(x, y) for _should_propagate_nan_to_map
+    uint32_t bad;        // NaN bits of the current 32-plane word
+    bool valid;
+};
+template <int K>
+__device__ __forceinline__ void setup_cell(CellState<K> &c, double x, double y, int ny, int nx, bool propagate) {
+    c.valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
+    c.bad = 0;
+    c.origin = 0;
+    c.nb[0] = c.nb[1] = c.nb[2] = c.nb[3] = 0;
+    if (c.valid && propagate) {
         // BodyXY._should_propagate_nan_to_map (body_xy.py:1855-1866)
-        if (x < 0.0 || y < 0.0 || x > nx - 1 || y > ny - 1) valid = false;
+        if (x < 0.0 || y < 0.0 || x > nx - 1 || y > ny - 1) c.valid = false;
         const int x0 = max((int)floor(x), 0), x1 = min((int)ceil(x), nx - 1);
         const int y0 = max((int)floor(y), 0), y1 = min((int)ceil(y), ny - 1);
-        nb00 = ((int64_t)y0 * nx + x0) * n_words;
-        nb01 = ((int64_t)y0 * nx + x1) * n_words;
-        nb10 = ((int64_t)y1 * nx + x0) * n_words;
-        nb11 = ((int64_t)y1 * nx + x1) * n_words;
+        c.nb[0] = (uint32_t)(y0 * nx + x0);
+        c.nb[1] = (uint32_t)(y0 * nx + x1);
+        c.nb[2] = (uint32_t)(y1 * nx + x0);
+        c.nb[3] = (uint32_t)(y1 * nx + x1);
     }
-    double w[K * K];
-    int ix = 0, iy = 0;
-    if (valid) {
+    if (c.valid) {
         double wx[K], wy[K];
+        int ix, iy;
         if (K == 4) {
             ix = bspline3_weights(x, nx, wx);
             iy = bspline3_weights(y, ny, wy);
@@ -180,48 +180,364 @@ __global__ void __launch_bounds__(kGatherBlock)
 #pragma unroll
         for (int a = 0; a < K; a++)
 #pragma unroll
-            for (int b = 0; b < K; b++) w[a * K + b] = wy[a] * wx[b];
+            for (int b = 0; b < K; b++) c.w[a * K + b] = wy[a] * wx[b];
+        c.origin = ((int64_t)iy * nx + ix) * 4;
+    } else {
+#pragma unroll
+        for (int k = 0; k < K * K; k++) c.w[k] = 0.0;
     }
+}
+
+// C = cells per thread.  With C == 2 a thread owns two adjacent cells: map grids are
+// usually much finer than the image (C4: 0.1 deg cells on ~3 deg pixels), so both cells
+// read the same K x K footprint and every 256-bit coefficient load feeds 8 FMAs.  That
+// matters for the cubic case, where the L1 -> register return path (128 B/clk/SM), not
+// HBM, bounds a one-cell-per-thread kernel: 16 coefficients x 8 B per voxel.
+template <int K, int C, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherBlock / C, kMinBlocks)
+    gather_spline_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
+                         const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int plane_begin,
+                         int plane_count, const double *__restrict__ xmap, const double *__restrict__ ymap,
+                         int64_t n_cells, uint32_t flags, double *__restrict__ out, int planes_per_group) {
+    const int64_t cell0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * C;
+    if (cell0 >= n_cells) return;
+    const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 4
+    const int l1 = min(l0 + planes_per_group, plane_count);
+    const double nan = NAN;
+    const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
+    CellState<K> cs[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const bool in_range = cell0 + c < n_cells;
+        const double x = in_range ? __ldg(xmap + cell0 + c) : nan, y = in_range ? __ldg(ymap + cell0 + c) : nan;
+        setup_cell<K>(cs[c], x, y, ny, nx, propagate);
+    }
+    const bool shared_patch = (C == 2) && cs[0].valid && cs[C - 1].valid && cs[0].origin == cs[C - 1].origin;
     const int64_t quad_stride = (int64_t)ny * nx * 4;  // doubles per plane quad
     const int64_t row_stride = (int64_t)nx * 4;
-    const double *src = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + ((int64_t)iy * nx + ix) * 4;
-    double *dst = out + (int64_t)l0 * n_cells + cell;
-    uint32_t bad = 0;
+    const double *src = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride;
+    double *dst = out + (int64_t)l0 * n_cells + cell0;
+    const bool pair_store = (C == 2) && (cell0 + 1 < n_cells) && ((n_cells & 1) == 0);
     int cur_word = -1;
     for (int l = l0; l < l1; l += 4) {
         const int gl = plane_begin + l;  // global plane index of this quad (multiple of 4)
         const int word = gl >> 5;
         if (word != cur_word) {  // uniform: once per 32 planes
             cur_word = word;
-            bad = __ldg(plane_bits + word);
-            if (valid && propagate && __ldg(plane_bits + n_words + word))
-                bad |= __ldg(nanbits + nb00 + word) | __ldg(nanbits + nb01 + word) | __ldg(nanbits + nb10 + word) |
-                       __ldg(nanbits + nb11 + word);
+            const uint32_t skip = __ldg(plane_bits + word);
+            const bool consult = propagate && __ldg(plane_bits + n_words + word);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                uint32_t bad = skip;
+                if (cs[c].valid && consult) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) bad |= __ldg(nanbits + (int64_t)cs[c].nb[k] * n_words + word);
+                }
+                cs[c].bad = bad;
+            }
         }
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        if (valid) {
-            // FITPACK fpbisp order: rows (y) outer, columns inner
+        double acc[C][4];
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+        if (shared_patch) {
+            const double *p = src + cs[0].origin;
 #pragma unroll
             for (int a = 0; a < K; a++) {
 #pragma unroll
                 for (int b = 0; b < K; b++) {
-                    const Quad c = ldg_quad(src + a * row_stride + b * 4);
-                    const double ww = w[a * K + b];
-                    a0 = fma(c.v[0], ww, a0);
-                    a1 = fma(c.v[1], ww, a1);
-                    a2 = fma(c.v[2], ww, a2);
-                    a3 = fma(c.v[3], ww, a3);
+                    const Quad q = ldg_quad(p + a * row_stride + b * 4);
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const double ww = cs[c].w[a * K + b];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[c][j] = fma(q.v[j], ww, acc[c][j]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (cs[c].valid) {
+                    const double *p = src + cs[c].origin;
+#pragma unroll
+                    for (int a = 0; a < K; a++) {
+#pragma unroll
+                        for (int b = 0; b < K; b++) {
+                            const Quad q = ldg_quad(p + a * row_stride + b * 4);
+                            const double ww = cs[c].w[a * K + b];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[c][j] = fma(q.v[j], ww, acc[c][j]);
+                        }
+                    }
                 }
             }
         }
-        const uint32_t nib = valid ? ((bad >> (gl & 31)) & 0xFu) : 0xFu;
         const int left = l1 - l;
-        __stcs(dst, (nib & 1u) ? nan : a0);
-        if (left > 1) __stcs(dst + n_cells, (nib & 2u) ? nan : a1);
-        if (left > 2) __stcs(dst + 2 * n_cells, (nib & 4u) ? nan : a2);
-        if (left > 3) __stcs(dst + 3 * n_cells, (nib & 8u) ? nan : a3);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t nib = cs[c].valid ? ((cs[c].bad >> (gl & 31)) & 0xFu) : 0xFu;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((nib >> j) & 1u) acc[c][j] = nan;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < left) {
+                double *d = dst + (int64_t)j * n_cells;
+                if (pair_store) {
+                    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(d), "d"(acc[0][j]), "d"(acc[C - 1][j])
+                                 : "memory");
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+                        if (cell0 + c < n_cells) __stcs(d + c, acc[c][j]);
+                }
+            }
+        }
         src += quad_stride;
         dst += 4 * n_cells;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Cubic gather for maps much finer than the image (the C4 case: ~1500 cells per pixel).
+//
+// For cells that share a 4 x 4 footprint the interpolation is a small dense product
+//     out[plane][cell] = sum_k coef[plane][k] * w[k][cell],   k = 0..15,
+// and the one-cell-per-thread kernel above is bound by the L1 -> register return path
+// (every voxel pulls its 16 coefficients = 128 B through a 128 B/clk/SM pipe: ncu shows
+// l1tex__data_pipe_lsu_wavefronts at 82 % while DRAM sits at 45 %).  Sharing loaded
+// coefficients between the cells of one thread (C = 2) only moves the bound to register
+// pressure.  The warp-level FP64 MMA (DMMA.8x8x4) is the register-tiled form of exactly
+// this product: a warp owns 32 consecutive cells and streams planes 8 at a time,
+//     A (8 planes x 4 coefficients)  one coefficient per lane, loaded once per footprint,
+//     B (4 coefficients x 8 cells)   the cell weights, held in registers for all planes,
+//     D (8 planes x 8 cells)         two voxels per lane,
+// so a voxel costs 16 B of L1 traffic instead of 128 B.  Cells of an 8-cell tile that do
+// NOT share the footprint are handled by repeating the product per distinct footprint
+// with the other cells' weights zeroed, so the result is exact for any map; the launcher
+// only selects this kernel when the map is dense enough for sharing to be the rule.
+// The arithmetic is IEEE FP64 FMA like the scalar kernel (accumulation order differs).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kGatherBlock, 2)
+    gather_cubic_mma_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
+                            const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int n_planes_padded,
+                            int plane_begin, int plane_count, const double *__restrict__ xmap,
+                            const double *__restrict__ ymap, int64_t n_cells, uint32_t flags,
+                            double *__restrict__ out, int planes_per_group) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int64_t warp_cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
+    if (warp_cell >= n_cells) return;  // whole warp
+    const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 8
+    const int l1 = min(l0 + planes_per_group, plane_count);
+    const double nan = NAN;
+    const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
+
+    // ---- per-cell setup: the four lanes of group g all describe cell 8 i + g of tile i
+    double bw[4][4];          // B fragments: bw[i][j] = wy[j] * wx[t] of tile i's cell g
+    uint32_t origin[4];       // iy * nx + ix of the footprint (pixel index)
+    uint32_t nbp[4];          // NaN-test pixels, packed: x0 | y0 << 14 | (x1 - x0) << 28 | (y1 - y0) << 29
+    uint32_t cls[4];          // lanes of the tile sharing this lane's footprint
+    uint32_t valid_mask[4];   // ballot of valid cells per tile
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t cell = warp_cell + 8 * i + g;
+        const bool in_range = cell < n_cells;
+        const double x = in_range ? __ldg(xmap + cell) : nan, y = in_range ? __ldg(ymap + cell) : nan;
+        bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
+        nbp[i] = 0;
+        if (valid && propagate) {
+            // BodyXY._should_propagate_nan_to_map (body_xy.py:1855-1866)
+            if (x < 0.0 || y < 0.0 || x > nx - 1 || y > ny - 1) valid = false;
+            const int x0 = max((int)floor(x), 0), x1 = min((int)ceil(x), nx - 1);
+            const int y0 = max((int)floor(y), 0), y1 = min((int)ceil(y), ny - 1);
+            nbp[i] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(x1 > x0) << 28) | ((uint32_t)(y1 > y0) << 29);
+        }
+        origin[i] = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < 4; j++) bw[i][j] = 0.0;
+        if (valid) {
+            double wx[4], wy[4];
+            const int ix = bspline3_weights(x, nx, wx);
+            const int iy = bspline3_weights(y, ny, wy);
+            const double wxt = t == 0 ? wx[0] : (t == 1 ? wx[1] : (t == 2 ? wx[2] : wx[3]));
+#pragma unroll
+            for (int j = 0; j < 4; j++) bw[i][j] = wy[j] * wxt;
+            origin[i] = (uint32_t)(iy * nx + ix);
+        }
+        valid_mask[i] = __ballot_sync(kFull, valid);
+        cls[i] = __match_any_sync(kFull, origin[i]);
+    }
+    if ((valid_mask[0] | valid_mask[1] | valid_mask[2] | valid_mask[3]) == 0) {
+        // nothing visible in these 32 cells: stream NaN, 16 lanes x 16 B per plane row
+        const int64_t cell = warp_cell + 2 * (lane & 15);
+        for (int l = l0 + (lane >> 4); l < l1; l += 2) {
+            double *d = out + (int64_t)l * n_cells + cell;
+            if (((n_cells & 1) == 0) && cell + 1 < n_cells) {
+                asm volatile("st.global.cs.v2.f64 [%0], {%1, %1};" ::"l"(d), "d"(nan) : "memory");
+            } else {
+                if (cell < n_cells) __stcs(d, nan);
+                if (cell + 1 < n_cells) __stcs(d + 1, nan);
+            }
+        }
+        return;
+    }
+
+    const int64_t quad_stride = (int64_t)ny * nx * 4;
+    const int64_t row_stride = (int64_t)nx * 4;
+    // lane's fixed offset inside a footprint: plane (g & 3) of quad (g >> 2), column t
+    const int64_t lane_off = (int64_t)(g >> 2) * quad_stride + t * 4 + (g & 3);
+    const bool pair_ok = (n_cells & 1) == 0;
+
+    // ---- distinct footprints of the warp (plane independent): the usual case is one or
+    // two (32 cells of a fine map straddle at most one pixel boundary)
+    uint32_t org0 = 0xffffffffu, org1 = 0xffffffffu;
+    uint32_t mine01 = 0;   // bit i: this lane's cell of tile i uses footprint 0; bit 4 + i: footprint 1
+    uint32_t tiles = 0;    // (uniform) bit i: tile i has footprint-0 cells; bit 4 + i: footprint-1 cells;
+                           // bit 8 + i: every valid cell of tile i uses footprint 0 (no masking needed)
+    bool simple = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t todo = valid_mask[i];
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const uint32_t members = __shfl_sync(kFull, cls[i], leader);
+            const uint32_t org = __shfl_sync(kFull, origin[i], leader);
+            const uint32_t me = (members >> lane) & 1u;
+            if (org0 == 0xffffffffu || org == org0) {
+                org0 = org;
+                mine01 |= me << i;
+                tiles |= 1u << i;
+                if (members == valid_mask[i]) tiles |= 1u << (8 + i);
+            } else if (org1 == 0xffffffffu || org == org1) {
+                org1 = org;
+                mine01 |= me << (4 + i);
+                tiles |= 1u << (4 + i);
+            } else {
+                simple = false;
+            }
+            todo &= ~members;
+        }
+    }
+
+    uint32_t ok[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // per tile: bit p set = plane p of the word is good, for
+                                                           // this lane's two OUTPUT cells (2t, 2t + 1)
+    int cur_word = -1;
+    double *dst_row = out + (int64_t)(l0 + g) * n_cells + warp_cell + 2 * t;
+    const double *pbase = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + lane_off;
+    const bool has1 = org1 != 0xffffffffu;
+    auto load_a = [&](double (&a)[4], uint32_t org, const double *pb, bool in_coef) {
+        const double *p = pb + (int64_t)org * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = in_coef ? __ldg(p + j * row_stride) : 0.0;
+    };
+    // A fragment of footprint 0 is software-prefetched one plane tile ahead; footprint 1's is
+    // issued at the top of the iteration and first needed after the footprint-0 products
+    double a0[4];
+    if (simple) load_a(a0, org0, pbase, (plane_begin + l0 + g) < n_planes_padded);
+    for (int l = l0; l < l1; l += 8) {
+        const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (multiple of 4)
+        const int word = (gl + g) >> 5;
+        if (word != cur_word) {  // changes at most once per 32 planes (per lane: planes gl + g)
+            cur_word = word;
+            const uint32_t skip = __ldg(plane_bits + word);
+            const bool consult = propagate && __ldg(plane_bits + n_words + word);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                // bits of the cell this lane DESCRIBES (cell g), then exchanged to the lanes that STORE it
+                uint32_t bits = skip;
+                const bool v = (valid_mask[i] >> lane) & 1u;
+                if (consult && v) {
+                    const int x0 = nbp[i] & 0x3fff, y0 = (nbp[i] >> 14) & 0x3fff;
+                    const int dx = (nbp[i] >> 28) & 1, dy = (nbp[i] >> 29) & 1;
+                    const uint32_t *nbw = nanbits + ((int64_t)y0 * nx + x0) * n_words + word;
+                    bits |= __ldg(nbw) | __ldg(nbw + (int64_t)dx * n_words) | __ldg(nbw + (int64_t)dy * nx * n_words) |
+                            __ldg(nbw + ((int64_t)dy * nx + dx) * n_words);
+                }
+                const uint32_t good = v ? ~bits : 0u;
+                ok[i][0] = __shfl_sync(kFull, good, 4 * (2 * t));
+                ok[i][1] = __shfl_sync(kFull, good, 4 * (2 * t + 1));
+            }
+        }
+        double d[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
+        const bool in_coef = (gl + g) < n_planes_padded;
+        if (simple) {
+            double a1[4], n0[4];
+            if (has1) load_a(a1, org1, pbase, in_coef);
+            const bool more = l + 8 < l1;
+            if (more) load_a(n0, org0, pbase + 2 * quad_stride, (gl + 8 + g) < n_planes_padded);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (tiles & (1u << i)) {
+                    const bool keep = (tiles & (1u << (8 + i))) || ((mine01 >> i) & 1u);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a0[j], keep ? bw[i][j] : 0.0);
+                }
+            }
+            if (has1) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (tiles & (1u << (4 + i))) {
+                        const bool keep = (mine01 >> (4 + i)) & 1u;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a1[j], keep ? bw[i][j] : 0.0);
+                    }
+                }
+            }
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) a0[j] = n0[j];
+            }
+        } else {
+            // general case: one pass per distinct footprint among each tile's cells
+            uint32_t a_origin = 0xffffffffu;
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t todo = valid_mask[i];
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    const uint32_t members = __shfl_sync(kFull, cls[i], leader);
+                    const uint32_t org = __shfl_sync(kFull, origin[i], leader);
+                    if (org != a_origin) {
+                        a_origin = org;
+                        load_a(a, org, pbase, in_coef);
+                    }
+                    const bool member = (members >> lane) & 1u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a[j], member ? bw[i][j] : 0.0);
+                    todo &= ~members;
+                }
+            }
+        }
+        // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
+        if (l + g < l1) {
+            const int sh = (gl + g) & 31;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int64_t cell = warp_cell + 8 * i + 2 * t;
+                const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
+                const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
+                double *dst = dst_row + 8 * i;
+                if (pair_ok && cell + 1 < n_cells) {
+                    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
+                } else {
+                    if (cell < n_cells) __stcs(dst, o0);
+                    if (cell + 1 < n_cells) __stcs(dst + 1, o1);
+                }
+            }
+        }
+        pbase += 2 * quad_stride;
+        dst_row += 8 * n_cells;
     }
 }
 
@@ -232,6 +548,7 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
     if (n_cells == 0 || plane_count == 0) return cudaSuccess;
     int ppg = 128;  // planes per CTA: amortises the per-cell weights, bounds CTA run time
     if (plane_count < ppg) ppg = (plane_count + 3) / 4 * 4;
+    // every CTA covers kGatherBlock cells (128 threads x 2 cells for the cubic kernel)
     dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)((plane_count + ppg - 1) / ppg));
     const int n_words = (n_planes + 31) / 32;
     switch (mode) {
@@ -240,14 +557,34 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                                                                  n_cells, out, ppg);
             break;
         case PM_INTERP_LINEAR:
-            gather_spline_kernel<2><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                   plane_begin, plane_count, xmap, ymap, n_cells,
-                                                                   flags, out, ppg);
+            gather_spline_kernel<2, 1, 4><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                      plane_begin, plane_count, xmap, ymap, n_cells,
+                                                                      flags, out, ppg);
             break;
         case PM_INTERP_CUBIC:
-            gather_spline_kernel<4><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                   plane_begin, plane_count, xmap, ymap, n_cells,
-                                                                   flags, out, ppg);
+        {
+            static const int v = getenv("PM_CUBIC_VARIANT") ? atoi(getenv("PM_CUBIC_VARIANT")) : -1;  // tuning only
+            // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel
+            const bool dense = n_cells >= (int64_t)8 * nx * ny && nx < 16384 && ny < 16384;
+            if (v == 0 || (v < 0 && !dense)) {
+                gather_spline_kernel<4, 1, 2><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                             plane_begin, plane_count, xmap, ymap,
+                                                                             n_cells, flags, out, ppg);
+            } else if (v == 3) {
+                gather_spline_kernel<4, 2, 3><<<grid, kGatherBlock / 2, 0, st>>>(src, nanbits, plane_bits, n_words, ny,
+                                                                                 nx, plane_begin, plane_count, xmap,
+                                                                                 ymap, n_cells, flags, out, ppg);
+            } else {
+                // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is
+                // heavier here than in the scalar kernel
+                static const int mma_ppg = getenv("PM_MMA_PPG") ? atoi(getenv("PM_MMA_PPG")) : 512;  // tuning only
+                const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
+                dim3 grid2(grid.x, (unsigned)((plane_count + g2 - 1) / g2));
+                gather_cubic_mma_kernel<<<grid2, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                        (n_planes + 3) / 4 * 4, plane_begin,
+                                                                        plane_count, xmap, ymap, n_cells, flags, out, g2);
+            }
+        }
             break;
         default:
             return cudaErrorInvalidValue;

@@ -1,9 +1,10 @@
 #!/bin/bash
-# Disassembles libpm_b200.so's backplane kernels with inlining line info:
-#   tools/disasm_kernel.sh out.dis
+# Disassembles one translation unit of libpm_b200.so with inlining line info:
+#   tools/disasm_kernel.sh out.dis [backplane_kernels|gather_kernels|proj_kernels]
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+UNIT="${2:-backplane_kernels}"
 TMP=$(mktemp -d)
-(cd "$TMP" && cuobjdump -xelf backplane_kernels "$ROOT/planetmapper_b200/libpm_b200.so" >/dev/null)
-nvdisasm -gi -c "$TMP"/backplane_kernels*.cubin > "$1"
+(cd "$TMP" && cuobjdump -xelf "$UNIT" "$ROOT/planetmapper_b200/libpm_b200.so" >/dev/null)
+nvdisasm -gi -c "$TMP"/"$UNIT"*.cubin > "$1"
 rm -rf "$TMP"
