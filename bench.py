@@ -36,7 +36,7 @@ C2_NAMES = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'INCIDEN
             'AZIMUTH', 'LOCAL-SOLAR-TIME', 'DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER']
 METRIC = 'full-backplane Mpix/s (FP64) + mapped-cube voxels/s at 1-8 B200 vs host CPU'
 SZ = 2048
-CPU_SAMPLE_SZ = 512
+CPU_SAMPLE_SZ = 2048
 
 
 def load_bc():
@@ -122,9 +122,10 @@ def measured_peaks():
 
 
 def algorithmic_flops_per_frame(planes_host, frame):
-    """Algorithmic FLOPs of one C2 launch = per-class weighted flop counts of the
-    instrumented oracle (profiles/flops_per_pixel.json, tools/count_flops.cpp) x the
-    number of pixels of each class in this frame."""
+    """FP64 flops of one C2 launch = per-class flop counts (profiles/flops_per_pixel.json:
+    2 DFMA + DMUL + DADD this kernel executes per on-disc / in-circle-miss / outside pixel,
+    measured with ncu thread-instruction counters by tools/count_flops_ncu.py) x the number
+    of pixels of each class in the timed frame."""
     from planetmapper_b200 import frame as F
 
     path = os.path.join(ROOT, 'profiles', 'flops_per_pixel.json')
@@ -142,15 +143,22 @@ def algorithmic_flops_per_frame(planes_host, frame):
     c = fpp['c2_12plane']
     flops = n_on * c['on_disc'] + n_miss * c['in_circle_miss'] + n_out * c['outside_circle']
     return flops, {'on_disc_px': n_on, 'in_circle_miss_px': n_miss, 'outside_px': n_out,
-                   'flops_per_px': c, 'weights': fpp['weights']}
+                   'flops_per_px': c, 'flop_definition': fpp['flop_definition']}
 
 
-def ncu_traffic(key):
-    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+def ncu_summary(key):
+    """Counters of the committed ncu capture of this kernel (profiles/ncu_summary.json,
+    written by tools/ncu_summary.py from the .ncu-rep files of the same commands)."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f).get(key)
     return None
+
+
+def ncu_traffic(key):
+    s = ncu_summary(key)
+    return None if not s else s.get('dram_bytes_per_launch')
 
 
 def cpu_port_mpix(sz, threads=None, repeats=1):
@@ -193,8 +201,7 @@ def run_reference(args):
         O.backplanes_img(fr, CPU_SAMPLE_SZ, CPU_SAMPLE_SZ, mask)
     dt = (time.perf_counter() - t0) / args.steps
     value = CPU_SAMPLE_SZ * CPU_SAMPLE_SZ / dt / 1e6
-    sample = (f'{CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ} frame per step (1/16 of the C2 pixels, same disc fraction), '
-              f'12-plane stack, OpenMP over pixels')
+    sample = (f'one full C2 frame ({CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ}, 12-plane stack) per step, OpenMP over pixels')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
@@ -306,6 +313,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
@@ -388,7 +398,12 @@ def main():
                          'peak_source': 'pm_fp64_peak_probe: 8 independent DFMA chains/thread, full grid, measured '
                                         'in this run (MEASURED_PEAKS.json has no FP64 entry)',
                          'algorithmic_flops_per_launch': flops, 'pixel_classes': classes,
-                         'hbm_bytes_per_launch_algorithmic': int(k * SZ * SZ * 8)},
+                         'hbm_bytes_per_launch_algorithmic': int(k * SZ * SZ * 8),
+                         'note': 'frac counts flops (FMA = 2) against the DFMA-only peak; a third of the FP64-pipe '
+                                 'instructions are DMUL / DADD / DSETP (1 or 0 flop per issue slot), so the pipe '
+                                 'utilisation ncu reports (ncu.fp64_pipe_util) is the tighter measure of how '
+                                 'close the kernel is to the FP64 pipe',
+                         'ncu': ncu_summary('backplanes_img_c2')},
             'clocks': clocks,
         }
     if not args.skip_cube:
@@ -402,11 +417,13 @@ def main():
             result['mapped_cube'] = cube_res
     if rank == 0:
         if not args.skip_cpu:
-            mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ)
+            mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)
             result['cpu_baseline'] = {
                 'value': mp, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
-                'sample': f'{CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ} C2-like frame, one pass ({dt:.2f} s), OpenMP over pixels',
-                'note': 'C restatement in oracle/ (the Python+spiceypy reference is not installable here)'}
+                'sample': f'the full C2 frame ({CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ}, 12 planes), best of 3 passes '
+                          f'({dt:.2f} s wall each on {omp_threads()} OpenMP threads)',
+                'note': 'C restatement in oracle/ (the Python+spiceypy reference is not installable here; '
+                        'it is ~3 orders of magnitude slower than this port, SURVEY.md section 6)'}
         print(json.dumps(result))
     if world > 1:
         import torch.distributed as dist

@@ -624,7 +624,12 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
     if (mask & bit(PM_PIXEL_X)) out.put(PM_PIXEL_X, x);  // BodyXY.get_x_img / get_y_img (body_xy.py:3494-3531)
     if (mask & bit(PM_PIXEL_Y)) out.put(PM_PIXEL_Y, y);
 
-    const V3 v = xy2ray_local(fs, x, y);
+    // BodyXY._get_targvec_img's early-out circle (body_xy.py:3201-3203): pixels outside it
+    // never reach sincpt, and without sky planes they do not need the ray at all
+    const double dx = x - f.x0, dy = y - f.y0;
+    const bool try_disc = (mask & kSurfMask) && !(f.optimize_speed != 0.0 && fma(dx, dx, dy * dy) > f.r_cut2);
+    V3 v = mk(nan, nan, nan);
+    if (try_disc || (kSky && (mask & kSkyMask))) v = xy2ray_local(fs, x, y);
     V3 d2 = mk(nan, nan, nan);
     if (kSky && (mask & kSkyMask)) {
         // BodyXY._get_radec_img (body_xy.py:3413-3418)
@@ -651,10 +656,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
     // BodyXY._get_targvec_img (body_xy.py:3197-3225) incl. the early-out circle
     bool on_disc = false;
     Intercept it;
-    if (mask & kSurfMask) {
-        const double dx = x - f.x0, dy = y - f.y0;
-        if (!(f.optimize_speed != 0.0 && fma(dx, dx, dy * dy) > f.r_cut2)) on_disc = sincpt(fs, mxv(fs.G, v), it);
-    }
+    if (try_disc) on_disc = sincpt(fs, mxv(fs.G, v), it);
 
     double v_dist = nan;
     if (on_disc) {
