@@ -416,7 +416,7 @@ def main():
         if rank == 0:
             result['mapped_cube'] = cube_res
     if rank == 0:
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:  # the CPU baseline is an N = 1 measurement
             mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)
             result['cpu_baseline'] = {
                 'value': mp, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
