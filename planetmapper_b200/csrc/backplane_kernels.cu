@@ -52,7 +52,7 @@ struct PlaneSink {
 // ---------------------------------------------------------------------------------
 // Image direction: all requested backplanes for every pixel of every frame.
 // ---------------------------------------------------------------------------------
-template <bool kSky>
+template <bool kSky, uint64_t kFixedMask>
 __global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame *__restrict__ frames, uint32_t nx,
                                                                    uint32_t npx, int per_thread, uint64_t mask,
                                                                    const __grid_constant__ PlaneOffsets po,
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame
 #pragma unroll 1
     for (int r = 0; r < per_thread && idx < npx; r++) {
         PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
-        image_pixel<kSky>(fs, (double)xi, (double)yi, mask, sink);
+        image_pixel<kSky, kFixedMask>(fs, (double)xi, (double)yi, mask, sink);
         idx += kBlock;
         xi += kBlock;
         while (xi >= nx) {
@@ -194,6 +194,10 @@ static unsigned chunks_for(int64_t n) {
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// The default surface stack of BASELINE.json's headline config: lon / lat (graphic + centric),
+// incidence / emission / phase, azimuth, local solar time, distance, radial velocity, doppler
+constexpr uint64_t kDefaultStackMask = kLonLatMask | kCentricMask | kIllumMask | kStateMask;
+
 // Pixels per thread: as many as possible (amortises the per-CTA frame staging) while the
 // grid still has >= 3 waves of resident CTAs for the hardware scheduler to balance.
 static int pick_per_thread(int64_t n, int64_t n_batches, int sm_count) {
@@ -213,10 +217,14 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     const int per = forced > 0 ? forced : pick_per_thread(npx, n_frames, sm_count);
     const int64_t chunk = (int64_t)kBlock * per;
     dim3 grid((unsigned)((npx + chunk - 1) / chunk), n_frames);
-    if (mask & kSkyMask)
-        backplanes_img_kernel<true><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
+    static const bool no_fixed = getenv("PM_IMG_NO_FIXED_MASK") != nullptr;  // tuning only
+    if (mask == kDefaultStackMask && !no_fixed)
+        backplanes_img_kernel<false, kDefaultStackMask><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx,
+                                                                                   per, mask, po, out);
+    else if (mask & kSkyMask)
+        backplanes_img_kernel<true, 0><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
     else
-        backplanes_img_kernel<false><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
+        backplanes_img_kernel<false, 0><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
     count_launches(1);
     return cudaGetLastError();
 }

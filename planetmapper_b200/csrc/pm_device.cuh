@@ -616,11 +616,14 @@ constexpr uint64_t kSkyMask = bit(PM_RA) | bit(PM_DEC) | kKmMask | kLimbMask | k
 // kSky = false compiles out RA / DEC / KM / ANGULAR / LIMB / RING planes (the launcher
 // picks it when none is requested): smaller code, fewer registers for the default
 // surface stack.
-template <bool kSky, class Sink>
+// kFixedMask != 0 fixes the plane set at compile time (the launcher uses it for the
+// default surface stack): every `mask & bit` test folds away and the per-pixel code
+// becomes a handful of large basic blocks the scheduler can interleave freely.
+template <bool kSky, uint64_t kFixedMask = 0, class Sink>
 PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, Sink &out) {
     const PMFrame &f = fs.f;
     const double nan = NAN;
-    const uint64_t mask = kSky ? mask_in : (mask_in & ~kSkyMask);
+    const uint64_t mask = kFixedMask ? kFixedMask : (kSky ? mask_in : (mask_in & ~kSkyMask));
     if (mask & bit(PM_PIXEL_X)) out.put(PM_PIXEL_X, x);  // BodyXY.get_x_img / get_y_img (body_xy.py:3494-3531)
     if (mask & bit(PM_PIXEL_Y)) out.put(PM_PIXEL_Y, y);
 
