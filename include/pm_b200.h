@@ -202,7 +202,8 @@ int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
  * that replace CUDA's libm on the hot path) elementwise, so tests can measure their
  * ulp error on the device.  kind: 0 rcp(a), 1 rsqrt(a), 2 sqrt(a), 3 sin(a) and
  * 4 cos(a) for |a| <= pi/4, 5 atan2(a, b), 6 acos(a), 7 a / b, 8 sin(a), 9 cos(a)
- * for any |a| < 1e5.  `b` may be NULL for the one-argument kinds. */
+ * for any |a| < 1e5, 10 atan2(|a|, b) and 11 atan2(a, |b|) (the half-plane variants used
+ * for vector separations and latitudes).  `b` may be NULL for the one-argument kinds. */
 int pm_math_probe(int kind, const double *a, const double *b, int64_t n, double *out,
                   void *stream);
 

@@ -221,7 +221,7 @@ PM_HD V3 target_pos_b(const FrameD &fs, double dt) {
 // ---------------------------------------------------------------------------------
 // spice.recrad angles (base.py:902): RA in [0, 2pi), Dec
 PM_HD void recrad_angles(V3 v, double &ra, double &dec) {
-    dec = fast_atan2(v.z, fast_sqrt(fma(v.x, v.x, v.y * v.y)));
+    dec = fast_atan2_xpos(v.z, fast_sqrt(fma(v.x, v.x, v.y * v.y)));
     double lon = fast_atan2(v.y, v.x);
     if (lon < 0.0) lon += kTwoPi;
     ra = lon;
@@ -234,7 +234,7 @@ PM_HD V3 radrec1(double ra, double dec) {
     return mk(cr * cd, sr * cd, sd);
 }
 // spice.vsep for any two non-zero vectors: atan2(|a x b|, a.b)
-PM_HD double vsep(V3 a, V3 b) { return fast_atan2(norm(cross(a, b)), dot(a, b)); }
+PM_HD double vsep(V3 a, V3 b) { return fast_atan2_ypos(norm(cross(a, b)), dot(a, b)); }
 
 // spice.surfpt (inside sincpt, body.py:1010): nearest ray / ellipsoid intersection,
 // perpendicular-projection form.  o, u in the body frame.  `margin2` receives
@@ -328,7 +328,7 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
 PM_HD void geodetic_general(const FrameD &fs, double rho, double z, double &lat, double &alt) {
     const PMFrame &f = fs.f;
     if (f.f == 0.0) {
-        lat = fast_atan2(z, rho);
+        lat = fast_atan2_xpos(z, rho);
         alt = fast_sqrt(fma(rho, rho, z * z)) - f.re;
         return;
     }
@@ -365,7 +365,7 @@ PM_HD void recpgr(const FrameD &fs, V3 p, bool on_spheroid, double &lon, double 
     lon = l;
     if (on_spheroid) {
         // the point lies on the spheroid itself: its normal is the geodetic normal
-        lat = fast_atan2(p.z * fs.inv_omf2, rho);
+        lat = fast_atan2_xpos(p.z * fs.inv_omf2, rho);
         alt = 0.0;
     } else {
         geodetic_general(fs, rho, p.z, lat, alt);
@@ -385,7 +385,7 @@ PM_HD V3 pgrrec0(const FrameD &fs, double lon, double lat) {
 
 // spice.reclat angles (body.py:2912)
 PM_HD void reclat_angles(V3 v, double &lon, double &lat) {
-    lat = fast_atan2(v.z, fast_sqrt(fma(v.x, v.x, v.y * v.y)));
+    lat = fast_atan2_xpos(v.z, fast_sqrt(fma(v.x, v.x, v.y * v.y)));
     lon = fast_atan2(v.y, v.x);
 }
 
@@ -437,9 +437,9 @@ PM_HD void illum_angles(V3 n, V3 s, V3 e, bool want_az, Illum &out) {
     const V3 cse = cross(s, e), cns = cross(n, s), cne = cross(n, e);
     const double dse = dot(s, e), dns = dot(n, s), dne = dot(n, e);
     const double mns = norm(cns), mne = norm(cne);
-    out.phase = fast_atan2(norm(cse), dse);
-    out.incdnc = fast_atan2(mns, dns);
-    out.emissn = fast_atan2(mne, dne);
+    out.phase = fast_atan2_ypos(norm(cse), dse);
+    out.incdnc = fast_atan2_ypos(mns, dns);
+    out.emissn = fast_atan2_ypos(mne, dne);
     if (want_az) {
         // (cos g - cos e cos i) / (sin e sin i) with the common factor |n|^2 |s| |e|
         // cancelled: ((s.e)(n.n) - (n.e)(n.s)) / (|n x e| |n x s|)
@@ -675,7 +675,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
                 const double v_lon = l * kDpr;
                 double lat, alt;
                 if (fs.biaxial) {
-                    lat = fast_atan2(p.z * fs.inv_omf2, rho);
+                    lat = fast_atan2_xpos(p.z * fs.inv_omf2, rho);
                 } else {
                     geodetic_general(fs, rho, p.z, lat, alt);
                 }
@@ -684,7 +684,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
                 if (mask & bit(PM_LOCAL_SOLAR_TIME)) out.put(PM_LOCAL_SOLAR_TIME, local_solar_time(f, v_lon));
             }
             if (mask & bit(PM_LON_CENTRIC)) out.put(PM_LON_CENTRIC, lon_e * kDpr);
-            if (mask & bit(PM_LAT_CENTRIC)) out.put(PM_LAT_CENTRIC, fast_atan2(p.z, rho) * kDpr);
+            if (mask & bit(PM_LAT_CENTRIC)) out.put(PM_LAT_CENTRIC, fast_atan2_xpos(p.z, rho) * kDpr);
         }
         if (mask & (kIllumMask | kStateMask | kRingMask)) {
             // spkcpt's converged light time is the intercept's own: |X| = |p - o|
@@ -870,7 +870,7 @@ PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, bool not_vi
         // so that grazing cells agree with the map kernel
         const V3 e = spin_fwd(fs, g.r, -g.X0);
         const V3 n = mul3(tv, fs.nw);
-        if (!(fast_atan2(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return;
+        if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return;
     }
     const V3 ov = targvec2obsvec(fs, tv);
     if (!finite3(ov)) return;

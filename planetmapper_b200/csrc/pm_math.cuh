@@ -210,34 +210,81 @@ PM_HD void sincos_full(double x, double &s, double &c) {
     c = cr;
 }
 
-// atan2(y, x), full quadrant, atan2(0, 0) = 0 (the convention recrad / reclat / recgeo
-// apply explicitly).  One division; with a = min(|x|,|y|), b = max(|x|,|y|) the argument
-// is folded into |q| <= tan(pi/12) by
-//   atan(a/b) = pi/6 + atan((sqrt(3) a - b) / (sqrt(3) b + a))      for a/b > tan(pi/12).
-PM_HD double fast_atan2(double y, double x) {
-    // branch-free on purpose: independent calls then sit in one basic block and the
-    // scheduler interleaves their dependent FMA chains
-    const double ax = fabs(x), ay = fabs(y);
-    const bool sw = ay > ax;
-    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+// Bit-level helpers: keep sign / magnitude bookkeeping off the FP64 pipe
+PM_HD bool abs_gt(double a, double b) {  // |a| > |b| for non-NaN inputs (IEEE ordering == integer ordering)
+#ifdef __CUDA_ARCH__
+    return (__double_as_longlong(a) & 0x7fffffffffffffffll) > (__double_as_longlong(b) & 0x7fffffffffffffffll);
+#else
+    return fabs(a) > fabs(b);
+#endif
+}
+PM_HD double with_sign_of(double r, double y) {  // r >= 0: copysign(r, y)
+#ifdef __CUDA_ARCH__
+    const int hi = __double2hiint(r) | (__double2hiint(y) & 0x80000000);
+    return __hiloint2double(hi, __double2loint(r));
+#else
+    return copysign(r, y);
+#endif
+}
+PM_HD bool sign_bit(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x) < 0;
+#else
+    return signbit(x);
+#endif
+}
+
+// atan(a / b) for 0 <= a <= b, b > 0: one division; the argument is folded into
+// |q| <= tan(pi/12) by  atan(a/b) = pi/6 + atan((sqrt(3) a - b) / (sqrt(3) b + a)).
+// Branch-free on purpose: independent calls then sit in one basic block and the
+// scheduler interleaves their dependent FMA chains.
+PM_HD double atan_ratio(double mn, double mx) {
     const bool hi = mn > mx * PM_T(kMisc)[0];
     const double num = hi ? fma(PM_T(kMisc)[9], mn, -mx) : mn;
     const double den = hi ? fma(PM_T(kMisc)[9], mx, mn) : mx;
-    const double q = fast_div(num, den);  // 0 / 0 -> NaN, replaced below
+    const double q = fast_div(num, den);
     const double z = q * q;
     double p = PM_T(kAtanC)[7];
 #pragma unroll
     for (int i = 6; i >= 0; i--) p = fma(p, z, PM_T(kAtanC)[i]);
     double r = fma(q * z, p, q);
     if (hi) r += PM_T(kMisc)[10];
+    return r;
+}
+// atan2(y, x), full quadrant, atan2(0, 0) = 0 (the convention recrad / reclat / recgeo
+// apply explicitly).  NaN in -> NaN out.
+PM_HD double fast_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const bool sw = abs_gt(y, x);
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+    double r = atan_ratio(mn, mx);  // 0 / 0 -> NaN, replaced below
     if (sw) r = PM_T(kMisc)[2] - r;
-    if (x < 0.0) r = PM_T(kMisc)[3] - r;
-    r = (y < 0.0) ? -r : r;
+    if (sign_bit(x)) r = PM_T(kMisc)[3] - r;
+    r = with_sign_of(r, y);
     return (mx == 0.0) ? 0.0 : r;
+}
+// atan2(y, x) for y >= 0 and (x, y) != (0, 0): angle in [0, pi] (vector separations)
+PM_HD double fast_atan2_ypos(double y, double x) {
+    const double ax = fabs(x);
+    const bool sw = abs_gt(y, x);
+    const double mx = sw ? y : ax, mn = sw ? ax : y;
+    double r = atan_ratio(mn, mx);
+    if (sw) r = PM_T(kMisc)[2] - r;
+    if (sign_bit(x)) r = PM_T(kMisc)[3] - r;
+    return r;
+}
+// atan2(y, x) for x >= 0 and (x, y) != (0, 0): angle in [-pi/2, pi/2] (latitudes)
+PM_HD double fast_atan2_xpos(double y, double x) {
+    const double ay = fabs(y);
+    const bool sw = abs_gt(y, x);
+    const double mx = sw ? ay : x, mn = sw ? x : ay;
+    double r = atan_ratio(mn, mx);
+    if (sw) r = PM_T(kMisc)[2] - r;
+    return with_sign_of(r, y);
 }
 // acos(x); NaN for |x| > 1 like the libm routine
 PM_HD double fast_acos(double x) {
-    return fast_atan2(fast_sqrt_nan((1.0 - x) * (1.0 + x)), x);
+    return fast_atan2_ypos(fast_sqrt_nan((1.0 - x) * (1.0 + x)), x);
 }
 
 }  // namespace pm

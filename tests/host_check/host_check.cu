@@ -90,6 +90,8 @@ int hc_math(int kind, const double *a, const double *b, int64_t n, double *out) 
             case 3: pm::sincos_small(x, s, c); r = s; break;
             case 4: pm::sincos_small(x, s, c); r = c; break;
             case 5: r = pm::fast_atan2(x, y); break;
+            case 10: r = pm::fast_atan2_ypos(fabs(x), y); break;
+            case 11: r = pm::fast_atan2_xpos(x, fabs(y)); break;
             case 6: r = pm::fast_acos(x); break;
             case 7: r = pm::fast_div(x, y); break;
             case 8: pm::sincos_full(x, s, c); r = s; break;

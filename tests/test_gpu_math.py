@@ -45,11 +45,14 @@ def test_device_math_ulp_error():
         'cos': err(run(4, th), np.cos(th.astype(np.longdouble))),
         'atan2': err(run(5, a, b), np.arctan2(al, bl)),
         'acos': err(run(6, u), np.arccos(u.astype(np.longdouble))),
+        'atan2_ypos': err(run(10, a, b), np.arctan2(np.abs(al), bl)),
+        'atan2_xpos': err(run(11, a, b), np.arctan2(al, np.abs(bl))),
     }
     print('device ulp errors:', {k: round(v, 3) for k, v in report.items()})
     assert report['rcp'] <= 1.0 and report['div'] <= 1.0 and report['sqrt'] <= 1.0
     assert report['rsqrt'] <= 1.5 and report['sin'] <= 1.5 and report['cos'] <= 2.0
     assert report['atan2'] <= 3.0 and report['acos'] <= 4.0
+    assert report['atan2_ypos'] <= 3.0 and report['atan2_xpos'] <= 3.0
     assert np.max(np.abs(run(8, big) - np.sin(big.astype(np.longdouble)).astype(np.float64))) <= 3e-16
     assert np.max(np.abs(run(9, big) - np.cos(big.astype(np.longdouble)).astype(np.float64))) <= 3e-16
     assert run(2, np.array([0.0]))[0] == 0.0

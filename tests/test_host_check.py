@@ -89,6 +89,8 @@ def test_math_primitives_ulp(HC):
     assert err(run(3, th), np.sin(th.astype(np.longdouble))) <= 1.5
     assert err(run(4, th), np.cos(th.astype(np.longdouble))) <= 2.0
     assert err(run(5, a, b), np.arctan2(al, bl)) <= 3.0
+    assert err(run(10, a, b), np.arctan2(np.abs(al), bl)) <= 3.0
+    assert err(run(11, a, b), np.arctan2(al, np.abs(bl))) <= 3.0
     u = rng.uniform(-1, 1, n)
     u[::7] = 1 - 1e-9 * rng.uniform(0, 1, u[::7].size)
     assert err(run(6, u), np.arccos(u.astype(np.longdouble))) <= 4.0
