@@ -288,8 +288,9 @@ struct Intercept {
 //   pass 3 (e_2): e_2 - e_1 ~ 1e-5 s, so instead of a third ray / ellipsoid solve the
 //     body-fixed intercept is moved along the secant through passes 1 and 2,
 //     p(e_2) = p2 + (p2 - p1) (e_2 - e_1) / (e_1 - e_0); the neglected curvature term is
-//     omega^2 r (e_2 - e_1)(e_2 - e_0) / 2 ~ 3e-9 km, 40x below ulp(|P0|).  The observer
-//     position, the range and the light time are evaluated exactly at e_2.
+//     ~ V^2 r kappa / (2 c^2 cos(emission)) ~ 1e-8 km / cos(emission), an order below
+//     ulp(|P0|) with the same limb scaling as the intercept's own conditioning.  The
+//     observer position, the range and the light time are evaluated exactly at e_2.
 PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
     V3 p1, p2;
@@ -303,12 +304,19 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     if (!surfpt(fs, o2, spin_fwd(fs, r1, u0), p2)) return false;
     const double lt2 = norm(p2 - o2) * fs.inv_c;
 
-    const double den = f.lt0 - lt1, numer = lt1 - lt2;
-    const double ratio = (fabs(den) > 1.0e-7) ? fast_div(numer, den) : 0.0;
-    const V3 p = axpy(ratio, p2 - p1, p2);
+    // epochs as CSPICE forms them: et - lt rounded to a double (granularity ulp(et) ~ 3e-8 s,
+    // i.e. ~1e-6 km of target motion), so the secant runs between the QUANTISED epoch offsets
+    // dt1 (pass 2) and dt (pass 3); their difference is exact
     const double dt = (f.et - lt2) - f.t_ref;
     const Rot r = make_rot(fs, dt);
     const V3 Pb = target_pos_b(fs, dt);
+    V3 p;
+    if (fabs(dt1) > 1.0e-6) {
+        p = axpy(fast_div(dt - dt1, dt1), p2 - p1, p2);
+    } else {
+        // passes 1 and 2 (almost) coincide in epoch: no secant, solve the third intercept
+        if (!surfpt(fs, spin_fwd(fs, r, -Pb), spin_fwd(fs, r, u0), p)) return false;
+    }
     const V3 E = p - spin_fwd(fs, r, -Pb);
     const double L = norm(E);
     it.p = p;

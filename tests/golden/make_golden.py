@@ -130,7 +130,7 @@ def ephem_extract(ms):
     windows = [
         # the 2005-01-01 fixture +- a few days (covers bench time series of 4096 frames
         # 60 s apart = 2.85 days, ending at the fixture epoch; Saturn's SPK ends there)
-        ((10, 399, 3, 5, 599, 6, 699), et_fix - 6 * day, et_fix + 6 * day),
+        ((10, 399, 3, 5, 599, 6, 699, 7, 799, 301, 4, 499, 8, 899, 2, 299, 1, 199), et_fix - 6 * day, et_fix + 6 * day),
         # 2000-01-01 (docs example BodyXY('Jupiter','2000-01-01'), Saturn tests)
         ((10, 399, 3, 5, 599, 6, 699), -2 * day, 2 * day),
     ]
@@ -152,7 +152,7 @@ def ephem_extract(ms):
             continue
         body = key[4:].split('_')[0]
         if body in ('10', '399', '301', '3', '5', '599', '6', '699', '502', '501', '7',
-                    '799', '4', '499', '8', '899'):
+                    '799', '4', '499', '8', '899', '2', '299', '1', '199'):
             if all(isinstance(v, float) for v in val):
                 wanted[key] = val
     with open(os.path.join(ROOT, 'planetmapper_b200', 'data', 'pck_pool.json'), 'w') as f:

@@ -63,12 +63,14 @@ def lst_boundary(lon_deg, frame_lon_sign, sun_lon, prograde=True, tol_s=1e-6):
 # 2 ulp(|P0|) / (r cos e) radians.  The tolerances below are the stated bars, widened
 # ONLY by that amplification factor kappa = 1 / cos(emission) where it exceeds them.
 # ---------------------------------------------------------------------------------
-def surface_tolerances(ref_planes, p0_norm, r_min, omega_norm):
+def surface_tolerances(ref_planes, p0_norm, r_min, omega_norm, epoch_quantum_km=0.0):
     emi = ref_planes[PID['EMISSION']]
     latc = ref_planes[PID['LAT-CENTRIC']]
     with np.errstate(invalid='ignore', divide='ignore'):
         kappa = 1.0 / np.maximum(np.cos(np.deg2rad(emi)), 1e-12)
-        delta = 2.0 * np.spacing(p0_norm)                 # km, positional rounding noise
+        # km, positional rounding noise (+ optionally one epoch quantum of relative motion, see
+        # check_img_planes)
+        delta = 2.0 * np.spacing(p0_norm) + epoch_quantum_km
         ang = np.rad2deg(delta * kappa / r_min)           # deg, induced angle noise
         base = np.maximum(1e-9, 4.0 * ang)
         coslat = np.maximum(np.cos(np.deg2rad(latc)), 1e-12)
@@ -76,7 +78,8 @@ def surface_tolerances(ref_planes, p0_norm, r_min, omega_norm):
         'LAT-GRAPHIC': base, 'LAT-CENTRIC': base, 'INCIDENCE': base, 'EMISSION': base,
         'LON-GRAPHIC': base / coslat, 'LON-CENTRIC': base / coslat,
         'PHASE': np.full_like(base, 1e-9),
-        'DISTANCE': np.full_like(base, 1e-12 * p0_norm),
+        # a lateral shift d of the ray moves the intercept by d tan(e) along the line of sight
+        'DISTANCE': 1e-12 * p0_norm + 2.0 * delta * kappa,
         'RADIAL-VELOCITY': 1e-12 * np.abs(ref_planes[PID['RADIAL-VELOCITY']]) + 4.0 * omega_norm * delta * kappa + 1e-13,
     }
     tol['DOPPLER'] = tol['RADIAL-VELOCITY'] / 299792.458 + 4e-16
@@ -125,14 +128,40 @@ IMG_CASES = {
 }
 
 
-def check_img_planes(got, ref, margin, fr, label):
-    """Shared comparison of 26 image-direction planes (GPU `got` vs oracle `ref`)."""
+def epoch_quantum_km(fr):
+    """CSPICE forms every point epoch as et - lt in FP64: granularity ulp(et) ~ 3e-8 s.  The
+    target is evaluated at that epoch while the observer stays at et, so one quantum moves
+    the target by |V_target| ulp(et) ~ 1e-6 km (barycentric speed, ~13 km/s for Jupiter,
+    ~30 km/s for the inner planets and the Moon).  Both the oracle and the kernels carry that
+    noise relative to an extended-precision evaluation of the same algorithm
+    (tests/test_host_check.py::test_device_code_vs_extended_precision measures it), and two
+    FP64 evaluations land on different quanta in a few pixels per thousand."""
+    v = float(np.linalg.norm(F.frame_field(fr, 'VT')))
+    return v * float(np.spacing(F.frame_field(fr, 'et')[0]))
+
+
+OTHER_BODIES = [
+    # target, observer, nx, ny, x0, y0, r0, rotation: branches the Jupiter fixture never takes
+    ('Venus', 'EARTH', 80, 64, 40.0, 30.0, 25.0, 15.0),    # retrograde spin (et2lst sign), sphere
+    ('Moon', 'EARTH', 72, 72, 35.5, 35.5, 30.0, -20.0),    # near field (0.5 deg disc), sphere, east-positive
+    ('Earth', 'MOON', 64, 80, 30.0, 41.0, 26.0, 200.0),    # 1.9 deg disc, oblate, east-positive
+    ('Mars', 'EARTH', 90, 60, 44.5, 29.5, 24.0, 5.0),      # west-positive prograde, small flattening
+    ('Mercury', 'EARTH', 48, 48, 23.5, 23.5, 18.0, 90.0),
+]
+
+
+
+def check_img_planes(got, ref, margin, fr, label, allow_epoch_quantum=False):
+    """Shared comparison of 26 image-direction planes (GPU `got` vs oracle `ref`).
+    allow_epoch_quantum widens the positional noise term by one epoch quantum (used for
+    the bodies outside BASELINE.json's configs, whose |P0| / r conditioning is worse; the
+    named Jupiter / Saturn configs are held to the bare bar)."""
     grazing = np.abs(margin) < 1e-9
     grazing = np.where(np.isnan(margin), False, grazing)
     p0 = float(np.linalg.norm(F.frame_field(fr, 'P0')))
     r_min = float(np.min(F.frame_field(fr, 'radii')))
     w = float(np.linalg.norm(F.frame_field(fr, 'omega')))
-    tol, kappa = surface_tolerances(ref, p0, r_min, w)
+    tol, kappa = surface_tolerances(ref, p0, r_min, w, epoch_quantum_km(fr) if allow_epoch_quantum else 0.0)
     report = {}
     n_grazing_mismatch = 0
     for name in PLANE_NAMES:

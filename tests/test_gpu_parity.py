@@ -11,7 +11,7 @@ conditioning number only (tests/helpers.py:surface_tolerances explains why).
 import numpy as np
 import pytest
 
-from helpers import (IMG_CASES, PID, PLANE_NAMES, WRAP, angle_diff, check_img_planes, check_map_planes,
+from helpers import (IMG_CASES, OTHER_BODIES, PID, PLANE_NAMES, WRAP, angle_diff, check_img_planes, check_map_planes,
                      img_case as _img_case, masks_equal, surface_tolerances)
 from planetmapper_b200 import frame as F
 
@@ -52,6 +52,25 @@ def test_image_backplanes_earth_observer_saturn(L, oracle):
     check_img_planes(got, ref, margin, fr, 'saturn')
     ring = got[PID['RING-RADIUS']]
     assert np.isfinite(ring).sum() > 1000 and np.nanmax(ring) > 136780  # A ring is in frame
+
+
+@pytest.mark.parametrize('target,observer,nx,ny,x0,y0,r0,rot', OTHER_BODIES)
+def test_other_bodies_vs_oracle(L, oracle, target, observer, nx, ny, x0, y0, r0, rot):
+    """Bodies outside BASELINE.json's configs: retrograde spin, spheres, near field,
+    east-positive longitudes (image and map direction)."""
+    import planetmapper_b200 as pm
+
+    bc = F.build_body_constants(pm.get_default_provider(), target, '2004-12-31T00:00:00', observer)
+    fr = _img_case(bc, nx, ny, x0, y0, r0, rot)
+    ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+    got = L.backplanes_img(L.to_device(fr[None]), nx, ny).cpu().numpy()[0]
+    check_img_planes(got, ref, margin, fr, f'{target}/{observer}', allow_epoch_quantum=True)
+    lons = np.arange(2.5, 360, 5.0)[::-1]
+    lats = np.arange(-87.5, 90, 5.0)
+    lo, la = np.meshgrid(lons, lats)
+    refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+    gotm = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la)).cpu().numpy()
+    check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
 
 
 def test_plane_mask_subsets_match_full_stack(L, bc_hst):

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import (IMG_CASES, PID, angle_diff, check_img_planes, check_map_planes, img_case)
+from helpers import (IMG_CASES, OTHER_BODIES, PID, angle_diff, check_img_planes, check_map_planes, img_case)
 from planetmapper_b200 import frame as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -124,6 +124,24 @@ def test_device_code_saturn_rings_vs_oracle(HC, oracle):
     check_img_planes(got, ref, margin, fr, 'saturn')
 
 
+@pytest.mark.parametrize('target,observer,nx,ny,x0,y0,r0,rot', OTHER_BODIES)
+def test_device_code_other_bodies_vs_oracle(HC, oracle, target, observer, nx, ny, x0, y0, r0, rot):
+    import planetmapper_b200 as pm
+
+    bc = F.build_body_constants(pm.get_default_provider(), target, '2004-12-31T00:00:00', observer)
+    fr = img_case(bc, nx, ny, x0, y0, r0, rot)
+    ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+    got = hc_img(HC, fr, nx, ny)
+    check_img_planes(got, ref, margin, fr, f'{target}/{observer}', allow_epoch_quantum=True)
+    assert np.isfinite(got[PID['EMISSION']]).sum() > 0.3 * nx * ny * (r0 / max(nx, ny)) ** 2
+    lons = np.arange(2.5, 360, 5.0)[::-1]
+    lats = np.arange(-87.5, 90, 5.0)
+    lo, la = np.meshgrid(lons, lats)
+    refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+    gotm = hc_map(HC, fr, lo, la)
+    check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
+
+
 def test_device_code_plane_subsets(HC, bc_hst):
     fr = img_case(bc_hst, 60, 50, 29.5, 24.5, 22.0, 12.0)
     full = hc_img(HC, fr, 60, 50)
@@ -176,3 +194,106 @@ def test_device_code_point_transforms_vs_oracle(HC, oracle, bc_hst):
         assert np.array_equal(np.isnan(gx), np.isnan(rx))
         ok = np.isfinite(rx)
         assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9
+
+
+# ---------------------------------------------------------------------------------
+# Extended-precision referee.  The oracle (oracle/pm_oracle.c) is re-compiled with every
+# `double` turned into an 80-bit `long double` (sed + <tgmath.h>; the build lives under
+# tests/host_check/_build/), which evaluates the SAME algorithm with 11 more mantissa
+# bits and without the FP64 epoch quantisation.  Neither FP64 evaluation can be "more
+# right" than its distance to that result, so this pins how much of a kernel-vs-oracle
+# difference is FP64 noise of the algorithm itself, and checks that the kernels' own
+# formulation (secant third pass, atan2-based angles, MUFU-seeded primitives) is no
+# further from it than the CSPICE-shaped oracle is.
+# ---------------------------------------------------------------------------------
+LD_DRV = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include "pm_b200_ld.h"
+int pmo_backplanes_img(const PMFrame *f, int nx, int ny, uint64_t mask, long double *out, long double *margin);
+int main(int argc, char **argv) {
+    double fd[PM_FRAME_NDOUBLES];
+    FILE *fp = fopen(argv[1], "rb");
+    if (!fp || fread(fd, 8, PM_FRAME_NDOUBLES, fp) != PM_FRAME_NDOUBLES) return 1;
+    fclose(fp);
+    PMFrame f;
+    long double *fl = (long double *)&f;
+    for (int i = 0; i < PM_FRAME_NDOUBLES; i++) fl[i] = fd[i];
+    int nx = atoi(argv[2]), ny = atoi(argv[3]);
+    size_t n = (size_t)nx * ny;
+    long double *out = malloc(sizeof(long double) * 26 * n), *m = malloc(sizeof(long double) * n);
+    if (pmo_backplanes_img(&f, nx, ny, (1ull << 26) - 1, out, m)) return 2;
+    double *o = malloc(8 * 26 * n);
+    for (size_t i = 0; i < 26 * n; i++) o[i] = (double)out[i];
+    fp = fopen(argv[4], "wb");
+    fwrite(o, 8, 26 * n, fp);
+    fclose(fp);
+    return 0;
+}
+"""
+
+
+@pytest.fixture(scope='module')
+def ld_oracle():
+    import re
+
+    if not shutil.which('gcc'):
+        pytest.skip('gcc not available')
+    root = os.path.dirname(HERE)
+    bdir = os.path.join(HERE, 'host_check', '_build', 'ld')
+    os.makedirs(bdir, exist_ok=True)
+    exe = os.path.join(bdir, 'oracle_ld')
+    src_c = os.path.join(root, 'oracle', 'pm_oracle.c')
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src_c):
+        def ld(text):
+            return re.sub(r'\bdouble\b', 'long double', text)
+        c = ld(open(src_c).read()).replace('#include <math.h>', '#include <tgmath.h>')
+        c = c.replace('#define PI 3.14159265358979323846264338327950288\n',
+                      '#define PI 3.14159265358979323846264338327950288L\n')
+        h = ld(open(os.path.join(root, 'oracle', 'pm_oracle.h')).read()).replace('"../include/pm_b200.h"', '"pm_b200_ld.h"')
+        open(os.path.join(bdir, 'pm_oracle_ld.c'), 'w').write(c)
+        open(os.path.join(bdir, 'pm_oracle.h'), 'w').write(h)
+        open(os.path.join(bdir, 'pm_b200_ld.h'), 'w').write(ld(open(os.path.join(root, 'include', 'pm_b200.h')).read()))
+        open(os.path.join(bdir, 'drv.c'), 'w').write(LD_DRV)
+        subprocess.run(['gcc', '-O2', '-w', '-o', exe, 'drv.c', 'pm_oracle_ld.c', '-lm'], cwd=bdir, check=True,
+                       capture_output=True)
+
+    def run(fr, nx, ny):
+        fin, fout = os.path.join(bdir, 'frame.bin'), os.path.join(bdir, 'out.bin')
+        np.ascontiguousarray(fr, dtype=np.float64).tofile(fin)
+        subprocess.run([exe, fin, str(nx), str(ny), fout], check=True)
+        return np.fromfile(fout).reshape(26, ny, nx)
+    return run
+
+
+@pytest.mark.parametrize('target,observer,nx,ny,x0,y0,r0,rot', [('Jupiter', 'EARTH', 100, 100, 49.5, 49.5, 44.55, 0.0),
+                                                               ('Venus', 'EARTH', 80, 64, 40.0, 30.0, 25.0, 15.0),
+                                                               ('Moon', 'EARTH', 72, 72, 35.5, 35.5, 30.0, -20.0)])
+def test_device_code_vs_extended_precision(HC, oracle, ld_oracle, target, observer, nx, ny, x0, y0, r0, rot):
+    import planetmapper_b200 as pm
+    from helpers import epoch_quantum_km
+
+    bc = F.build_body_constants(pm.get_default_provider(), target, '2004-12-31T00:00:00', observer)
+    fr = img_case(bc, nx, ny, x0, y0, r0, rot)
+    exact = ld_oracle(fr, nx, ny)
+    ref = oracle.backplanes_img(fr, nx, ny)
+    got = hc_img(HC, fr, nx, ny)
+    emi = exact[PID['EMISSION']]
+    sel = np.isfinite(emi) & (emi < 70) & np.isfinite(got[PID['EMISSION']]) & np.isfinite(ref[PID['EMISSION']])
+    assert sel.sum() > 500
+    quantum = epoch_quantum_km(fr)
+    r_min = float(np.min(F.frame_field(fr, 'radii')))
+    report = {}
+    for name in ('LON-GRAPHIC', 'LAT-GRAPHIC', 'EMISSION', 'INCIDENCE', 'PHASE', 'DISTANCE', 'RADIAL-VELOCITY'):
+        k = PID[name]
+        e_dev = np.abs(got[k][sel] - exact[k][sel])
+        e_orc = np.abs(ref[k][sel] - exact[k][sel])
+        report[name] = (float(e_dev.max()), float(e_orc.max()))
+        # the kernels' formulation is no further from the extended-precision result than the oracle
+        assert np.sqrt(np.mean(e_dev ** 2)) <= 1.5 * np.sqrt(np.mean(e_orc ** 2)) + 1e-15, (name, report[name])
+    # and both sit within ~one epoch quantum of relative motion of it (the FP64 noise floor of the path)
+    assert report['DISTANCE'][0] <= 2.5 * quantum + 8 * np.spacing(float(np.linalg.norm(F.frame_field(fr, 'P0'))))
+    ang_floor = np.rad2deg(2.5 * quantum / r_min) / np.cos(np.deg2rad(70.0)) ** 2 + 1e-10
+    assert report['LAT-GRAPHIC'][0] <= ang_floor and report['EMISSION'][0] <= ang_floor
+    print(target, {k: (f'{a:.2e}', f'{b:.2e}') for k, (a, b) in report.items()}, 'quantum km', quantum)
