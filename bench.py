@@ -288,6 +288,113 @@ def bench_mapped_cube(L, torch, bc, rank, world):
     return res
 
 
+def bench_saturn_rings(L, torch, pm):
+    """C3: Saturn 4096 x 4096 with the ring planes, plus orthographic and azimuthal-equal-area
+    backplane maps (size 2048).  Saturn from EARTH 12 h before the end of the bundled SPK
+    (SURVEY 8(d)); r0 = 800 px so the A ring (2.27 r_eq) is in frame."""
+    from planetmapper_b200 import frame as F
+
+    bc = F.build_body_constants(pm.get_default_provider(), 'Saturn', '2004-12-30T12:00:00', 'EARTH')
+    sz, r0 = 4096, 800.0
+    fr = F.pack_frame(bc, nx=sz, ny=sz, x0=(sz - 1) / 2, y0=(sz - 1) / 2, r0=r0, rotation_radians=0.0)
+    names = ['RING-RADIUS', 'RING-LON-GRAPHIC', 'RING-DISTANCE', 'DISTANCE']
+    mask = L.mask_from_names(names)
+    fd = L.to_device(fr[None])
+    out = torch.empty((1, len(names), sz, sz), dtype=torch.float64, device='cuda')
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    img_ms = timed(lambda: L.backplanes_img(fd, sz, sz, mask, out=out))
+    ring_px = int(torch.isfinite(out[0, names.index('RING-RADIUS')]).sum())
+    res = {'workload': f'C3: Saturn / EARTH 2004-12-30T12:00, {sz}x{sz}, r0 = {r0:.0f} px, planes ' + ', '.join(names),
+           'img_ms': img_ms, 'img_mpix_per_s': sz * sz / img_ms / 1e3, 'ring_plane_px': ring_px}
+    size = 2048
+    c = np.linspace(-1.01 * max(1.0, bc.r_polar / bc.r_eq), 1.01 * max(1.0, bc.r_polar / bc.r_eq), size)
+    for kind, name in ((L.PROJ_ORTHOGRAPHIC, 'orthographic'), (L.PROJ_AZIMUTHAL_EQUAL_AREA, 'azimuthal equal area')):
+        cc = c if kind == L.PROJ_ORTHOGRAPHIC else np.linspace(-1.01, 1.01, size)
+        xx, yy = np.meshgrid(cc, cc)
+        xd, yd = L.to_device(xx), L.to_device(yy)
+        holder = {}
+
+        def proj():
+            holder['ll'] = L.proj_inverse(kind, bc.r_eq, bc.r_polar, 0.0, 30.0, bc.lon_sign, xd, yd)
+        proj_ms = timed(proj)
+        lon, lat = holder['ll']
+        lon = torch.remainder(lon, 360.0)
+        mmask = L.mask_from_names(names + ['PIXEL-X', 'PIXEL-Y', 'EMISSION'])
+        mout = torch.empty((L.popcount(mmask), size, size), dtype=torch.float64, device='cuda')
+        map_ms = timed(lambda: L.backplanes_map(fd[0], lon, lat, mmask, out=mout))
+        res[name] = {'size': size, 'proj_inverse_ms': proj_ms, 'backplanes_map_ms': map_ms,
+                     'mcells_per_s': size * size / (proj_ms + map_ms) / 1e3,
+                     'cells_on_body': int(torch.isfinite(lon).sum())}
+    return res
+
+
+def bench_time_series(L, torch, pm, rank, world, n_frames=256, batch=32):
+    """C5 (reduced): a time series of 1024 x 1024 frames 60 s apart ending at the fixture
+    epoch, sharded by frame across ranks, 12-plane stack per frame in batched launches plus a
+    1 deg rectangular nearest reprojection of one synthetic image per frame.  Europa has no
+    ephemeris in the bundled kernels (SURVEY section 0), so the series is Jupiter from EARTH;
+    the kernels only see constants.  4096 frames would write 412 GB of planes: the series is
+    cut to `n_frames` and each batch reuses one device buffer."""
+    from planetmapper_b200 import frame as F
+    from planetmapper_b200.shard import shard_range
+
+    sz = 1024
+    lo, hi = shard_range(n_frames, rank, world)
+    prov = pm.get_default_provider()
+    et_end = prov.utc2et('2005-01-01T00:00:00') - 3600.0
+    t0 = time.perf_counter()
+    frames = []
+    for i in range(lo, hi):
+        bc = F.build_body_constants(prov, 'Jupiter', None, 'EARTH', et=et_end - 60.0 * (n_frames - 1 - i))
+        frames.append(F.pack_frame(bc, nx=sz, ny=sz, x0=(sz - 1) / 2, y0=(sz - 1) / 2, r0=0.45 * sz,
+                                   rotation_radians=0.0))
+    host_s = time.perf_counter() - t0
+    frames = np.stack(frames)
+    fd = L.to_device(frames)
+    mask = plane_mask(C2_NAMES)
+    out = torch.empty((batch, len(C2_NAMES), sz, sz), dtype=torch.float64, device='cuda')
+    lons = np.arange(0.5, 360, 1.0)[::-1]
+    lats = np.arange(-89.5, 90, 1.0)
+    lo_g, la_g = np.meshgrid(lons, lats)
+    lod, lad = L.to_device(lo_g), L.to_device(la_g)
+    img = torch.rand((1, sz, sz), dtype=torch.float64, device='cuda')
+    xy = torch.empty((2,) + lo_g.shape, dtype=torch.float64, device='cuda')
+    mapped = torch.empty((1,) + lo_g.shape, dtype=torch.float64, device='cuda')
+    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+
+    def one_pass():
+        for s in range(0, hi - lo, batch):
+            n = min(batch, hi - lo - s)
+            L.backplanes_img(fd[s:s + n], sz, sz, mask, out=out[:n])
+    one_pass()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    one_pass()
+    e1.record()
+    for i in range(hi - lo):
+        L.backplanes_map(fd[i], lod, lad, xy_mask, out=xy)
+        L.gather(img, xy[0], xy[1], L.INTERP_NEAREST, out=mapped)
+    e2.record()
+    torch.cuda.synchronize()
+    return {'workload': f'C5 (reduced): {n_frames} Jupiter / EARTH frames of {sz}x{sz}, 60 s apart, 12-plane stack in '
+                        f'batches of {batch} frames + 1 deg nearest reprojection per frame; frames {lo}..{hi} on this rank',
+            'frames_this_rank': hi - lo, 'host_constants_s': host_s,
+            'backplanes_ms': e0.elapsed_time(e1), 'backplanes_mpix_per_s': (hi - lo) * sz * sz / e0.elapsed_time(e1) / 1e3,
+            'reprojection_ms': e1.elapsed_time(e2), 'reprojection_frames_per_s': (hi - lo) / e1.elapsed_time(e2) * 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -296,6 +403,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--skip-cube', action='store_true', help='skip the mapped-cube (C4) section')
     ap.add_argument('--skip-cpu', action='store_true', help='skip the bounded CPU baseline')
+    ap.add_argument('--skip-extra', action='store_true', help='skip the C3 (Saturn rings) and C5 (time series) sections')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -415,6 +523,13 @@ def main():
                 cube_res[name]['voxels_per_s'] = world * 3000 * 6480000 / (t * 1e-3)
         if rank == 0:
             result['mapped_cube'] = cube_res
+    if not args.skip_extra:
+        ts = bench_time_series(L, torch, pm, rank, world)
+        t_all = max_over_ranks(ts['backplanes_ms'], world, device='cuda')
+        if rank == 0:
+            ts['backplanes_mpix_per_s_all_ranks'] = 256 * 1024 * 1024 / t_all / 1e3
+            result['time_series'] = ts
+            result['saturn_rings'] = bench_saturn_rings(L, torch, pm)
     if rank == 0:
         if not args.skip_cpu and world == 1:  # the CPU baseline is an N = 1 measurement
             mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)
