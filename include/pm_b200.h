@@ -94,6 +94,7 @@ enum PMPlane {
 /* interpolation modes of pm_gather (BodyXY.map_img, body_xy.py:1414-1631) */
 #define PM_INTERP_NEAREST 0
 #define PM_INTERP_LINEAR 1
+#define PM_INTERP_QUADRATIC 2
 #define PM_INTERP_CUBIC 3
 
 /* projection kinds of pm_proj_inverse (BodyXY.generate_map_coordinates,
@@ -166,7 +167,7 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
  * Resamples planes [plane_begin, plane_begin + plane_count) of an n_planes cube:
  * xmap, ymap: [n_cells]; out: [plane_count][n_cells].
  *   NEAREST:  `src` is the raw cube [n_planes][ny][nx]; nanbits / plane_bits unused.
- *   LINEAR / CUBIC: `src`, `nanbits`, `plane_bits` are the three buffers filled by
+ *   LINEAR / QUADRATIC / CUBIC: `src`, `nanbits`, `plane_bits` are the three buffers filled by
  *   pm_spline_prepare for the same (n_planes, ny, nx); plane_begin must be a multiple
  *   of 4.  Their layout is private to the library (plane-quad interleaved coefficients
  *   [ceil(n/4)][ny][nx][4], NaN bit planes [ny*nx][ceil(n/32)], per-word plane bits).
@@ -178,8 +179,9 @@ int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_
 
 /*
  * NaN repair (BodyXY._replace_nans_with_interpolated_values, body_xy.py:1871-1904)
- * followed, for degree 3, by the separable not-a-knot B-spline fit scipy's
- * RectBivariateSpline(kx=ky=3, s=0) performs (body_xy.py:1673-1680), packed for
+ * followed, for degree 2 / 3, by the separable interpolating B-spline fit scipy's
+ * RectBivariateSpline(kx=ky=degree, s=0) performs (body_xy.py:1673-1680; FITPACK knots:
+ * not-a-knot for degree 3, mid-sample knots for degree 2), packed for
  * pm_gather.  In: cube [n_planes][ny][nx].  Out: coef (pm_spline_coef_bytes),
  * nanbits (pm_spline_nanbits_bytes), plane_bits (pm_spline_planebits_bytes).
  * `work` must hold pm_spline_work_bytes(...) bytes of device scratch.

@@ -699,11 +699,13 @@ def _interpolation_mode(interpolation, spline_smoothing) -> int:
                                       'accelerated; only interpolating splines are')
         if interpolation == 1:
             return L.INTERP_LINEAR
+        if interpolation == 2:
+            return L.INTERP_QUADRATIC
         if interpolation == 3:
             return L.INTERP_CUBIC
         raise NotImplementedError(
-            f'spline degree {interpolation} is on the "next" list (SURVEY.md 8(f)); '
-            "accelerated: 'nearest', 'linear' (1), 'cubic' (3)")
+            f'spline degree {interpolation} is not accelerated (SURVEY.md 8(f)); '
+            "accelerated: 'nearest', 'linear' (1), 'quadratic' (2), 'cubic' (3)")
     if interpolation == 'smooth':
         raise NotImplementedError("interpolation='smooth' is on the \"next\" list "
                                   '(SURVEY.md 8(f))')

@@ -101,9 +101,11 @@ int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_
     if (!src || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 ||
         plane_count < 0 || plane_begin + plane_count > n_planes)
         return PM_ERR_BAD_ARG;
-    if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR && mode != PM_INTERP_CUBIC)
+    if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR && mode != PM_INTERP_QUADRATIC &&
+        mode != PM_INTERP_CUBIC)
         return PM_ERR_UNSUPPORTED;
     if (mode == PM_INTERP_LINEAR && (nx < 2 || ny < 2)) return PM_ERR_BAD_ARG;
+    if (mode == PM_INTERP_QUADRATIC && (nx < 3 || ny < 3)) return PM_ERR_BAD_ARG;
     if (mode == PM_INTERP_CUBIC && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
     if (mode != PM_INTERP_NEAREST && (!nanbits || !plane_bits || (plane_begin & 3))) return PM_ERR_BAD_ARG;
     if (plane_count > 65535 * 128) return PM_ERR_BAD_ARG;
@@ -134,8 +136,8 @@ int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degr
                       uint32_t *nanbits, uint32_t *plane_bits, void *work, void *stream) {
     if (!cube || !coef || !nanbits || !plane_bits || !work || n_planes < 0 || ny <= 0 || nx <= 0)
         return PM_ERR_BAD_ARG;
-    if (degree != 1 && degree != 3) return PM_ERR_UNSUPPORTED;
-    if (degree == 3 && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
+    if (degree < 1 || degree > 3) return PM_ERR_UNSUPPORTED;
+    if (nx <= degree || ny <= degree) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_spline_prepare(cube, n_planes, ny, nx, degree, coef, nanbits, plane_bits, work, sms,

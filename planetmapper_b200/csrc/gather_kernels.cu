@@ -18,6 +18,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <utility>
 #include <mutex>
 #include <vector>
 
@@ -27,40 +28,48 @@ constexpr int kGatherBlock = 256;
 constexpr uint8_t kPlaneAllNan = 1;  // plane_skip bit0: np.all(np.isnan(img)) -> all NaN out
 constexpr uint8_t kPlaneHasNan = 2;  // plane_skip bit1: some NaN pixel -> consult nanmask
 
-// not-a-knot cubic knot vector for n samples at 0..n-1:
-// t = [0,0,0,0, 2,3,...,n-3, n-1,n-1,n-1,n-1]   (FITPACK, s = 0)
-__host__ __device__ __forceinline__ double nak_knot(int i, int n) {
-    return i <= 3 ? 0.0 : (i >= n ? (double)(n - 1) : (double)(i - 2));
+// FITPACK's interpolating-spline knot vectors (s = 0) for n samples at 0..n-1:
+//   degree 3 (not-a-knot):  t = [0,0,0,0, 2,3,...,n-3, n-1,n-1,n-1,n-1]
+//   degree 2 (knots between the samples): t = [0,0,0, 1.5,2.5,...,n-2.5, n-1,n-1,n-1]
+template <int DEG>
+__host__ __device__ __forceinline__ double spline_knot(int i, int n) {
+    if (i <= DEG) return 0.0;
+    if (i >= n) return (double)(n - 1);
+    return DEG == 3 ? (double)(i - 2) : (double)i - 1.5;
 }
 
-// FITPACK fpbspl: the 4 non-zero cubic B-splines at x; returns the first coefficient
+// FITPACK fpbspl: the DEG + 1 non-zero B-splines at x; returns the first coefficient
 // index.  x is clamped to [0, n-1] like bispev does.
-__host__ __device__ __forceinline__ int bspline3_weights(double x, int n, double h[4]) {
+template <int DEG>
+__host__ __device__ __forceinline__ int bspline_weights(double x, int n, double h[DEG + 1]) {
     double xe = fmin(fmax(x, 0.0), (double)(n - 1));
-    int j = (int)floor(xe);
-    int l = j + 2;
-    l = l < 3 ? 3 : (l > n - 1 ? n - 1 : l);
-    double hh[3];
+    int l = (DEG == 3) ? (int)floor(xe) + 2 : (int)floor(xe + 1.5);
+    l = l < DEG ? DEG : (l > n - 1 ? n - 1 : l);
+    double hh[DEG];
     h[0] = 1.0;
-    h[1] = h[2] = h[3] = 0.0;
 #pragma unroll
-    for (int jj = 1; jj <= 3; jj++) {
+    for (int i = 1; i <= DEG; i++) h[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+    for (int jj = 1; jj <= DEG; jj++) {
+#pragma unroll
+        for (int i = 0; i < DEG; i++)
             if (i < jj) hh[i] = h[i];
         h[0] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
+        for (int i = 0; i < DEG; i++) {
             if (i < jj) {
                 int li = l + 1 + i, lj = li - jj;
-                double tli = nak_knot(li, n), tlj = nak_knot(lj, n);
-                double f = fast_div(hh[i], tli - tlj);  // knot spans are 1, 2 or 3: exact or correctly rounded
+                double tli = spline_knot<DEG>(li, n), tlj = spline_knot<DEG>(lj, n);
+                double f = fast_div(hh[i], tli - tlj);  // knot spans are small half-integers: exact or correctly rounded
                 h[i] = h[i] + f * (tli - xe);
                 h[i + 1] = f * (xe - tlj);
             }
         }
     }
-    return l - 3;
+    return l - DEG;
+}
+__host__ __device__ __forceinline__ int bspline3_weights(double x, int n, double h[4]) {
+    return bspline_weights<3>(x, n, h);
 }
 
 // ---------------------------------------------------------------------------------
@@ -166,6 +175,9 @@ __device__ __forceinline__ void setup_cell(CellState<K> &c, double x, double y, 
         if (K == 4) {
             ix = bspline3_weights(x, nx, wx);
             iy = bspline3_weights(y, ny, wy);
+        } else if (K == 3) {
+            ix = bspline_weights<K == 3 ? 2 : 3>(x, nx, wx);
+            iy = bspline_weights<K == 3 ? 2 : 3>(y, ny, wy);
         } else {
             const double xe = fmin(fmax(x, 0.0), (double)(nx - 1));
             const double ye = fmin(fmax(y, 0.0), (double)(ny - 1));
@@ -561,6 +573,11 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                                                                       plane_begin, plane_count, xmap, ymap, n_cells,
                                                                       flags, out, ppg);
             break;
+        case PM_INTERP_QUADRATIC:
+            gather_spline_kernel<3, 1, 3><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                      plane_begin, plane_count, xmap, ymap, n_cells,
+                                                                      flags, out, ppg);
+            break;
         case PM_INTERP_CUBIC:
         {
             static const int v = getenv("PM_CUBIC_VARIANT") ? atoi(getenv("PM_CUBIC_VARIANT")) : -1;  // tuning only
@@ -843,19 +860,21 @@ __global__ void plane_bits_kernel(const uint8_t *__restrict__ plane_skip, int n_
     plane_bits[n_words + wd] = has;
 }
 
-// host: LU factors (no pivoting; the B-spline collocation matrix is totally positive)
-static const std::vector<double> &nak_lu(int n) {
-    static std::map<int, std::vector<double>> cache;
+// host: LU factors of the collocation matrix B_j(x_i) of degree `deg` (no pivoting; it is
+// totally positive); band storage fits both degrees (cubic: 2 + 2 off-diagonals,
+// quadratic: 1 + 1)
+static const std::vector<double> &spline_lu(int n, int deg) {
+    static std::map<std::pair<int, int>, std::vector<double>> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find(n);
+    auto it = cache.find({n, deg});
     if (it != cache.end()) return it->second;
     // band storage: A[i][j - i + 2] for |j - i| <= 2
     std::vector<double> A((size_t)n * 5, 0.0);
     for (int i = 0; i < n; i++) {
-        double h[4];
-        int first = bspline3_weights((double)i, n, h);
-        for (int m = 0; m < 4; m++) {
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+        int first = deg == 3 ? bspline_weights<3>((double)i, n, h) : bspline_weights<2>((double)i, n, h);
+        for (int m = 0; m <= deg; m++) {
             int j = first + m;
             if (j < 0 || j >= n) continue;
             int off = j - i + 2;
@@ -877,7 +896,7 @@ static const std::vector<double> &nak_lu(int n) {
         u1[i] = (i + 1 < n) ? at(i, i + 1) : 0.0;
         u2[i] = (i + 2 < n) ? at(i, i + 2) : 0.0;
     }
-    return cache.emplace(n, std::move(lu)).first->second;
+    return cache.emplace(std::make_pair(n, deg), std::move(lu)).first->second;
 }
 
 static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -893,7 +912,7 @@ int64_t spline_planebits_bytes(int n_planes) { return 2 * (int64_t)((n_planes + 
 int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree) {
     int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double)) +
                 align256((int64_t)n_planes) + align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
-    if (degree == 3) b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
+    if (degree >= 2) b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
     return b;
 }
 
@@ -918,12 +937,12 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
     repair_kernel<<<blocks, 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
     count_launches(3);
-    if (degree == 3) {
+    if (degree >= 2) {
         double *lu_x = reinterpret_cast<double *>(w);
         w += align256((int64_t)5 * nx * sizeof(double));
         double *lu_y = reinterpret_cast<double *>(w);
-        const std::vector<double> &hx = nak_lu(nx);
-        const std::vector<double> &hy = nak_lu(ny);
+        const std::vector<double> &hx = spline_lu(nx, degree);
+        const std::vector<double> &hy = spline_lu(ny, degree);
         cudaError_t e = cudaMemcpyAsync(lu_x, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(lu_y, hy.data(), hy.size() * sizeof(double), cudaMemcpyHostToDevice, st);

@@ -202,8 +202,8 @@ def test_gather_vs_scipy_oracle(L, oracle, bc_hst, nx, ny):
     sub = L.gather(cd, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=1, plane_count=2).cpu().numpy()
     assert np.array_equal(sub, ref[1:3], equal_nan=True)
     assert np.array_equal(oracle.gather_nearest(cube, xm, ym), ref, equal_nan=True)
-    for mode, name in ((L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
-        if name == 'cubic' and min(nx, ny) < 4:
+    for mode, name in ((L.INTERP_LINEAR, 'linear'), (L.INTERP_QUADRATIC, 'quadratic'), (L.INTERP_CUBIC, 'cubic')):
+        if mode >= min(nx, ny):
             continue
         for prop in (True, False):
             spline = L.spline_prepare(cd, mode)
@@ -309,7 +309,7 @@ def test_full_grid_gather_properties(L, bc_hst):
     near = L.gather(cube, xm, ym, L.INTERP_NEAREST)
     assert torch.equal(near[0][vis], torch.round(xm[vis])) and torch.equal(near[1][vis], torch.round(ym[vis]))
     assert torch.equal(torch.isfinite(near[0]), vis)
-    for mode in (L.INTERP_LINEAR, L.INTERP_CUBIC):
+    for mode in (L.INTERP_LINEAR, L.INTERP_QUADRATIC, L.INTERP_CUBIC):
         out = L.gather(L.spline_prepare(cube, mode), xm, ym, mode, propagate_nan=True)
         inside = vis & (xm >= 0) & (ym >= 0) & (xm <= sz - 1) & (ym <= sz - 1)
         assert torch.equal(torch.isfinite(out[0]), inside)
