@@ -106,6 +106,7 @@ enum PMPlane {
 /* flags */
 #define PM_FLAG_NOT_VISIBLE_NAN 1u /* lonlat2xy(not_visible_nan=True)               */
 #define PM_FLAG_PROPAGATE_NAN 2u   /* map_img(propagate_nan=True)                   */
+#define PM_FLAG_PLANETOCENTRIC 4u   /* lonlat2xy(planetocentric=True) inputs         */
 
 int pm_abi_version(void);
 const char *pm_error_string(int code);
@@ -149,6 +150,11 @@ int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t
                  double *lon, double *lat, int64_t *n_missed, void *stream);
 int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
                  uint32_t flags, double *x, double *y, void *stream);
+/* Same with a point altitude (km above the spheroid, pgrrec's `alt`): for alt != 0 the
+ * visibility test is the reference's ray cast (Body._test_if_targvec_visible,
+ * body.py:2131-2150) instead of illumf's `visibl`. */
+int pm_lonlat2xy_alt(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+                     double alt, uint32_t flags, double *x, double *y, void *stream);
 
 /*
  * Inverse map projections, replacing pyproj.Transformer.transform(...,

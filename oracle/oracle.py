@@ -81,7 +81,7 @@ def xy2lonlat(frame, x, y):
     return lon, lat, missed.value
 
 
-def lonlat2xy(frame, lon, lat, not_visible_nan=True):
+def lonlat2xy(frame, lon, lat, not_visible_nan=True, alt=0.0, planetocentric=False):
     f = _frame(frame)
     lon, lat = np.broadcast_arrays(np.asarray(lon, dtype=np.float64),
                                    np.asarray(lat, dtype=np.float64))
@@ -89,8 +89,9 @@ def lonlat2xy(frame, lon, lat, not_visible_nan=True):
     lat = np.ascontiguousarray(lat)
     x = np.empty(lon.shape)
     y = np.empty(lon.shape)
-    rc = lib().pmo_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size),
-                             ctypes.c_uint32(1 if not_visible_nan else 0), _p(x), _p(y))
+    flags = (1 if not_visible_nan else 0) | (4 if planetocentric else 0)
+    rc = lib().pmo_lonlat2xy_alt(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_double(alt),
+                                 ctypes.c_uint32(flags), _p(x), _p(y))
     assert rc == 0, rc
     return x, y
 

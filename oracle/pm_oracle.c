@@ -825,27 +825,67 @@ int pmo_xy2lonlat(const PMFrame *f, const double *x, const double *y, int64_t n,
     return PM_OK;
 }
 
-/* BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056)
- * with alt == 0 visibility through illumf.visibl (body.py:2124-2130) */
-int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_t n,
-                  uint32_t flags, double *x, double *y) {
+/* spice.latsrf on the ELLIPSOID (body.py:2970-2978): the surface point in the direction of
+ * planetocentric lon / lat (radians, east positive) */
+static void latsrf(const PMFrame *f, double lon, double lat, double p[3]) {
+    double d[3] = {cos(lat) * cos(lon), cos(lat) * sin(lon), sin(lat)};
+    double a = f->radii[0], b = f->radii[1], c = f->radii[2];
+    double s = 1.0 / sqrt((d[0] / a) * (d[0] / a) + (d[1] / b) * (d[1] / b) + (d[2] / c) * (d[2] / c));
+    for (int k = 0; k < 3; k++) p[k] = s * d[k];
+}
+
+/* Body._test_if_targvec_visible(on_surface=False) (body.py:2131-2150): cast the ray
+ * observer -> point; hidden iff it meets the surface and the surface is nearer */
+static int raycast_visible(const PMFrame *f, const double tv[3]) {
+    double ov[3], p[3], lt;
+    targvec2obsvec(f, tv, ov);
+    if (!sincpt(f, ov, p, &lt, NULL)) return 1;
+    PointState si, sp;
+    point_state(f, p, f->lt0, 0, &si);
+    point_state(f, tv, f->lt0, 0, &sp);
+    return sp.lt < si.lt;
+}
+
+/* BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056):
+ * alt == 0 visibility through illumf.visibl (body.py:2124-2130), alt != 0 through the ray
+ * cast (body.py:2131-2150); PM_FLAG_PLANETOCENTRIC converts the inputs with
+ * Body._centric2graphic_lonlat (body.py:2966-2982, alt == 0 only) */
+int pmo_lonlat2xy_alt(const PMFrame *f, const double *lon, const double *lat, int64_t n, double alt,
+                      uint32_t flags, double *x, double *y) {
     if (!f || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
 #pragma omp parallel for
     for (int64_t i = 0; i < n; i++) {
         x[i] = y[i] = kNaN;
         if (!(isfinite(lon[i]) && isfinite(lat[i]))) continue;
+        double lo = lon[i] * RPD, la = lat[i] * RPD;
+        if (flags & PM_FLAG_PLANETOCENTRIC) {
+            double sp[3], al;
+            latsrf(f, lo, la, sp);
+            recpgr(f, sp, &lo, &la, &al);
+            /* Body.targvec2lonlat returns degrees; _lonlat2obsvec converts back */
+            lo = (lo * DPR) * RPD;
+            la = (la * DPR) * RPD;
+        }
         double tv[3];
-        pgrrec(f, lon[i] * RPD, lat[i] * RPD, 0.0, tv);
+        pgrrec(f, lo, la, alt, tv);
         if (flags & PM_FLAG_NOT_VISIBLE_NAN) {
-            PointState s;
-            point_state(f, tv, f->lt0, 1, &s);
-            if (!s.visibl) continue;
+            if (alt == 0.0) {
+                PointState s;
+                point_state(f, tv, f->lt0, 1, &s);
+                if (!s.visibl) continue;
+            } else if (!raycast_visible(f, tv)) {
+                continue;
+            }
         }
         double ov[3];
         targvec2obsvec(f, tv, ov);
         obsvec2xy(f, ov, &x[i], &y[i]);
     }
     return PM_OK;
+}
+int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_t n,
+                  uint32_t flags, double *x, double *y) {
+    return pmo_lonlat2xy_alt(f, lon, lat, n, 0.0, flags, x, y);
 }
 
 /* ---------- projections ---------- */

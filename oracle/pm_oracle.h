@@ -20,6 +20,8 @@ int pmo_xy2lonlat(const PMFrame *f, const double *x, const double *y, int64_t n,
                   double *lon, double *lat, int64_t *n_missed);
 int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_t n,
                   uint32_t flags, double *x, double *y);
+int pmo_lonlat2xy_alt(const PMFrame *f, const double *lon, const double *lat, int64_t n, double alt,
+                      uint32_t flags, double *x, double *y);
 int pmo_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                      int64_t n, double *lon, double *lat);
 int pmo_gather_nearest(const double *cube, int n_planes, int ny, int nx,

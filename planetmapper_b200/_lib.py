@@ -23,6 +23,7 @@ INTERP_NEAREST, INTERP_LINEAR, INTERP_QUADRATIC, INTERP_CUBIC = 0, 1, 2, 3
 PROJ_ORTHOGRAPHIC, PROJ_AZIMUTHAL, PROJ_AZIMUTHAL_EQUAL_AREA = 1, 2, 3
 FLAG_NOT_VISIBLE_NAN = 1
 FLAG_PROPAGATE_NAN = 2
+FLAG_PLANETOCENTRIC = 4
 
 PLANE_NAMES = [
     'LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'RA', 'DEC', 'PIXEL-X',
@@ -36,7 +37,7 @@ PLANE_ID = {n: i for i, n in enumerate(PLANE_NAMES)}
 # every symbol include/pm_b200.h declares
 EXPORTED_SYMBOLS = [
     'pm_abi_version', 'pm_error_string', 'pm_launch_count', 'pm_backplanes_img',
-    'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_proj_inverse', 'pm_gather',
+    'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt', 'pm_proj_inverse', 'pm_gather',
     'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
 ]
@@ -70,6 +71,7 @@ def load_library() -> ctypes.CDLL:
     lib.pm_backplanes_map.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
     lib.pm_xy2lonlat.argtypes = [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
+    lib.pm_lonlat2xy_alt.argtypes = [c_p, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p]
     lib.pm_proj_inverse.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
     lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i64, c_i, c_u32,
                               c_p, c_p]
@@ -83,7 +85,7 @@ def load_library() -> ctypes.CDLL:
     lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
     lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
     lib.pm_math_probe.argtypes = [c_i, c_p, c_p, c_i64, c_p, c_p]
-    for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy',
+    for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe'):
         getattr(lib, fn).restype = c_i
@@ -176,15 +178,17 @@ def xy2lonlat(frame_dev, x_dev, y_dev):
     return lon, lat, missed
 
 
-def lonlat2xy(frame_dev, lon_dev, lat_dev, not_visible_nan: bool = True):
+def lonlat2xy(frame_dev, lon_dev, lat_dev, not_visible_nan: bool = True, *, alt: float = 0.0,
+              planetocentric: bool = False):
     torch = _torch()
     lib = load_library()
     x = torch.empty_like(lon_dev)
     y = torch.empty_like(lon_dev)
-    rc = lib.pm_lonlat2xy(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(),
-                          lon_dev.numel(), FLAG_NOT_VISIBLE_NAN if not_visible_nan else 0,
-                          x.data_ptr(), y.data_ptr(), _stream_ptr(torch))
-    _check(rc, 'pm_lonlat2xy')
+    flags = (FLAG_NOT_VISIBLE_NAN if not_visible_nan else 0) | (FLAG_PLANETOCENTRIC if planetocentric else 0)
+    rc = lib.pm_lonlat2xy_alt(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(),
+                              lon_dev.numel(), float(alt), flags, x.data_ptr(), y.data_ptr(),
+                              _stream_ptr(torch))
+    _check(rc, 'pm_lonlat2xy_alt')
     return x, y
 
 

@@ -349,16 +349,15 @@ class BodyXY:
     def lonlat2xy(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
                   planetocentric: bool = False):
         """Planetographic lon/lat -> image pixel coordinates (body_xy.py:498-560)."""
-        alt = self._check_alt(alt)
-        if alt != 0.0:
-            raise NotImplementedError(
-                'lonlat2xy(alt != 0) needs the ray-cast visibility test (body.py:2131-2150); '
-                'it is on the "next" list (SURVEY.md 8(f))')
-        if planetocentric:
-            raise NotImplementedError('planetocentric=True inputs (spice.latsrf) are on the '
-                                      '"next" list (SURVEY.md 8(f))')
+        alt = float(alt)
         scalar, lo, la = self._broadcast(lon, lat)
-        x, y = L.lonlat2xy(self._frame_dev(), L.to_device(lo), L.to_device(la), not_visible_nan)
+        if not math.isfinite(alt):   # Body._lonlat2targvec_radians: non-finite alt -> NaN (body.py:900-901)
+            return self._unbroadcast(scalar, np.full(lo.shape, np.nan), np.full(lo.shape, np.nan))
+        if planetocentric and alt != 0.0:
+            raise NotImplementedError('lonlat2xy(planetocentric=True, alt != 0) is not accelerated '
+                                      '(SURVEY.md 8(f))')
+        x, y = L.lonlat2xy(self._frame_dev(), L.to_device(lo), L.to_device(la), not_visible_nan,
+                           alt=alt, planetocentric=planetocentric)
         return self._unbroadcast(scalar, x.cpu().numpy(), y.cpu().numpy())
 
     def graphic2centric_lonlat(self, lon, lat, *, alt: float = 0.0):

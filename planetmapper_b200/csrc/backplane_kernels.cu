@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kBlock, 4) xy2lonlat_kernel(const PMFrame *__r
 __global__ void __launch_bounds__(kBlock, 4) lonlat2xy_kernel(const PMFrame *__restrict__ frame,
                                                               const double *__restrict__ lons,
                                                               const double *__restrict__ lats, int64_t n,
-                                                              uint32_t flags, double *__restrict__ x_out,
+                                                              double alt, uint32_t flags,
+                                                              double *__restrict__ x_out,
                                                               double *__restrict__ y_out) {
     __shared__ FrameD fs;
     load_frame(fs, frame);
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(kBlock, 4) lonlat2xy_kernel(const PMFrame *__r
         const double lon = lons[idx], lat = lats[idx];
         double x = NAN, y = NAN;
         if (fabs(lon) < INFINITY && fabs(lat) < INFINITY)
-            lonlat2xy_point(fs, lon, lat, (flags & PM_FLAG_NOT_VISIBLE_NAN) != 0, x, y);
+            lonlat2xy_point(fs, lon, lat, alt, (flags & PM_FLAG_NOT_VISIBLE_NAN) != 0,
+                            (flags & PM_FLAG_PLANETOCENTRIC) != 0, x, y);
         x_out[idx] = x;
         y_out[idx] = y;
     }
@@ -244,10 +246,10 @@ cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double
     count_launches(1);
     return cudaGetLastError();
 }
-cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
                              uint32_t flags, double *x, double *y, int sm_count, cudaStream_t st) {
     (void)sm_count;
-    lonlat2xy_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, flags, x, y);
+    lonlat2xy_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, alt, flags, x, y);
     count_launches(1);
     return cudaGetLastError();
 }

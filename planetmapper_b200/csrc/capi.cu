@@ -76,13 +76,18 @@ int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t
                                   (cudaStream_t)stream));
 }
 
-int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, uint32_t flags,
-                 double *x, double *y, void *stream) {
-    if (!frame || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+int pm_lonlat2xy_alt(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
+                     uint32_t flags, double *x, double *y, void *stream) {
+    if (!frame || !x || !y || !lon || !lat || n < 0 || !(alt == alt)) return PM_ERR_BAD_ARG;
+    if ((flags & PM_FLAG_PLANETOCENTRIC) && alt != 0.0) return PM_ERR_UNSUPPORTED;
     if (n == 0) return PM_OK;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
-    return check(launch_lonlat2xy(frame, lon, lat, n, flags, x, y, sms, (cudaStream_t)stream));
+    return check(launch_lonlat2xy(frame, lon, lat, n, alt, flags, x, y, sms, (cudaStream_t)stream));
+}
+int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, uint32_t flags,
+                 double *x, double *y, void *stream) {
+    return pm_lonlat2xy_alt(frame, lon, lat, n, 0.0, flags, x, y, stream);
 }
 
 int pm_proj_inverse(int kind, const double *params5_host, const double *xx, const double *yy, int64_t n,

@@ -866,19 +866,51 @@ PM_HD bool xy2lonlat_point(const FrameD &fs, double x, double y, double &lon, do
     return true;
 }
 
-// BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056),
-// alt == 0 visibility via illumf.visibl (body.py:2124-2130)
-PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, bool not_visible_nan, double &x, double &y) {
+// BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056).
+// Visibility: alt == 0 via illumf.visibl (body.py:2124-2130); alt != 0 via the ray cast
+// of Body._test_if_targvec_visible (body.py:2131-2150): hidden iff the ray observer ->
+// point meets the surface and the surface is nearer.  planetocentric inputs go through
+// spice.latsrf + recpgr first (Body._centric2graphic_lonlat, body.py:2966-2982).
+PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt, bool not_visible_nan,
+                           bool planetocentric, double &x, double &y) {
     x = y = NAN;
-    const V3 tv = pgrrec0(fs, lon * kRpd, lat * kRpd);
+    double lo = lon * kRpd, la = lat * kRpd;
+    if (planetocentric) {
+        double sl, cl, sb, cb;
+        sincos_full(lo, sl, cl);
+        sincos_full(la, sb, cb);
+        const V3 d = mk(cb * cl, cb * sl, sb);
+        const V3 ds = mul3(d, fs.inv_r);
+        const V3 sp = fast_rsqrt(dot(ds, ds)) * d;  // spice.latsrf on the ellipsoid
+        double al;
+        recpgr(fs, sp, fs.biaxial != 0, lo, la, al);
+        lo = (lo * kDpr) * kRpd;  // Body.targvec2lonlat returns degrees
+        la = (la * kDpr) * kRpd;
+    }
+    V3 tv = pgrrec0(fs, lo, la);
+    if (alt != 0.0) {  // spice.pgrrec with an altitude: along the spheroid normal
+        double sl, cl, sb, cb;
+        sincos_full(fs.f.lon_sign * lo, sl, cl);
+        sincos_full(la, sb, cb);
+        tv = axpy(alt, mk(cb * cl, cb * sl, sb), tv);
+    }
     if (not_visible_nan) {
         PointGeom g;
         point_geom(fs, tv, g);
-        // emission < pi/2  <=>  n . (point -> observer) > 0; evaluated as the angle itself
-        // so that grazing cells agree with the map kernel
-        const V3 e = spin_fwd(fs, g.r, -g.X0);
-        const V3 n = mul3(tv, fs.nw);
-        if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return;
+        if (alt == 0.0) {
+            // emission < pi/2  <=>  n . (point -> observer) > 0; evaluated as the angle itself
+            // so that grazing cells agree with the map kernel
+            const V3 e = spin_fwd(fs, g.r, -g.X0);
+            const V3 n = mul3(tv, fs.nw);
+            if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return;
+        } else {
+            Intercept it;
+            if (sincpt(fs, mxv(fs.f.R0, targvec2obsvec(fs, tv)), it)) {
+                PointGeom gi;
+                point_geom(fs, it.p, gi);
+                if (!(g.lt < gi.lt)) return;
+            }
+        }
     }
     const V3 ov = targvec2obsvec(fs, tv);
     if (!finite3(ov)) return;

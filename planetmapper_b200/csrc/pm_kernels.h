@@ -18,7 +18,7 @@ cudaError_t launch_backplanes_map(const PMFrame *frame, const double *lon, const
                                   uint64_t mask, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon,
                              double *lat, unsigned long long *n_missed, int sm_count, cudaStream_t st);
-cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
+cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
                              uint32_t flags, double *x, double *y, int sm_count, cudaStream_t st);
 cudaError_t launch_fp64_probe(double *scratch, int iters, int sm_count, cudaStream_t st);
 cudaError_t launch_math_probe(int kind, const double *a, const double *b, int64_t n, double *out,

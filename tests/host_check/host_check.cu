@@ -66,14 +66,15 @@ int hc_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t
     return 0;
 }
 
-int hc_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, uint32_t flags, double *x,
-                 double *y) {
+int hc_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt, uint32_t flags,
+                 double *x, double *y) {
     pm::FrameD fs;
     pm::load_frame_host(fs, frame);
     for (int64_t i = 0; i < n; i++) {
         x[i] = y[i] = NAN;
         if (fabs(lon[i]) < INFINITY && fabs(lat[i]) < INFINITY)
-            pm::lonlat2xy_point(fs, lon[i], lat[i], (flags & PM_FLAG_NOT_VISIBLE_NAN) != 0, x[i], y[i]);
+            pm::lonlat2xy_point(fs, lon[i], lat[i], alt, (flags & PM_FLAG_NOT_VISIBLE_NAN) != 0,
+                                (flags & PM_FLAG_PLANETOCENTRIC) != 0, x[i], y[i]);
     }
     return 0;
 }

@@ -110,8 +110,23 @@ def test_xy_conversions_known_answers(body):
             assert np.allclose(body.lonlat2xy(*lonlat), vis, rtol=0, atol=1e-9, equal_nan=True), lonlat
         assert np.allclose(body.lonlat2xy(*lonlat, not_visible_nan=False), allp, rtol=0, atol=1e-9,
                            equal_nan=True), lonlat
-    with pytest.raises(NotImplementedError):
-        body.lonlat2xy(0, 0, alt=10.0)
+    # points off the surface (tests/test_body_xy.py:396-410)
+    for (lon, lat, alt), e in [((42, 23.4, 0), (7.781497231832574, 8.015145501618983)),
+                               ((42, 23.4, -123.456), (7.776650117803703, 8.014878507462662)),
+                               ((42, 23.4, 1234.567), (7.829968623728911, 8.017815455484365)),
+                               ((42, 23.4, nan), (nan, nan))]:
+        got = body.lonlat2xy(lon, lat, alt=alt, not_visible_nan=False)
+        assert np.allclose(got, e, rtol=0, atol=1e-9, equal_nan=True), (alt, got)
+    # ray-cast visibility (sub-observer longitude is 153 deg): above the near side -> visible, above
+    # the far side -> hidden, 50 000 km above a point just behind the limb -> sticks out
+    assert np.all(np.isfinite(body.lonlat2xy(150.0, 0.0, alt=1234.567)))
+    assert np.all(np.isnan(body.lonlat2xy(330.0, 0.0, alt=1234.567)))
+    assert np.all(np.isnan(body.lonlat2xy(245.0, 0.0))) and np.all(np.isfinite(body.lonlat2xy(245.0, 0.0, alt=50000.0)))
+    # planetocentric inputs: the planetocentric image of a planetographic point maps to the same pixel
+    lon_c, lat_c = body.graphic2centric_lonlat(150.0, 23.4)
+    assert abs(lat_c - 23.4) > 1.0 and np.all(np.isfinite(body.lonlat2xy(150.0, 23.4)))
+    assert np.allclose(body.lonlat2xy(lon_c, lat_c, planetocentric=True), body.lonlat2xy(150.0, 23.4), rtol=0,
+                       atol=1e-9)
 
 
 @pytest.mark.parametrize('interp', ['nearest', 'linear', 'cubic', 1, 3, (3, 3)])

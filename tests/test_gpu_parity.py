@@ -141,6 +141,17 @@ def test_point_transforms_vs_oracle(L, oracle, bc_hst):
         assert np.array_equal(np.isnan(gx), np.isnan(rx))
         ok = np.isfinite(rx)
         assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9
+        # points above / below the surface (ray-cast visibility, body.py:2131-2150) and
+        # planetocentric inputs (spice.latsrf, body.py:2966-2982)
+        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True)):
+            rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=nvn, alt=alt, planetocentric=pc)
+            gx, gy = L.lonlat2xy(fd, L.to_device(lon), L.to_device(lat), nvn, alt=alt, planetocentric=pc)
+            gx, gy = gx.cpu().numpy(), gy.cpu().numpy()
+            assert (np.isnan(gx) != np.isnan(rx)).sum() <= 2, (alt, pc)   # only limb grazers may flip
+            ok = np.isfinite(rx) & np.isfinite(gx)
+            assert ok.sum() > 1000 or (alt < 0 and nvn)   # points below the surface are always hidden
+            if ok.any():
+                assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9, (alt, pc)
 
 
 @pytest.mark.parametrize('kind,lon0,lat0', [(1, 0, 0), (1, 123.456, -2), (1, -42, -21.3), (1, 10, 90), (1, 0, -90),

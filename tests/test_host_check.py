@@ -189,11 +189,24 @@ def test_device_code_point_transforms_vs_oracle(HC, oracle, bc_hst):
     for nvn in (True, False):
         rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=nvn)
         gx, gy = np.empty_like(lon), np.empty_like(lon)
-        assert HC.hc_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_uint32(1 if nvn else 0),
-                               _p(gx), _p(gy)) == 0
+        assert HC.hc_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_double(0.0),
+                               ctypes.c_uint32(1 if nvn else 0), _p(gx), _p(gy)) == 0
         assert np.array_equal(np.isnan(gx), np.isnan(rx))
         ok = np.isfinite(rx)
         assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9
+        # points above the surface (ray-cast visibility) and planetocentric inputs
+        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True)):
+            rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=nvn, alt=alt, planetocentric=pc)
+            flags = (1 if nvn else 0) | (4 if pc else 0)
+            assert HC.hc_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_double(alt),
+                                   ctypes.c_uint32(flags), _p(gx), _p(gy)) == 0
+            mism = np.isnan(gx) != np.isnan(rx)
+            assert mism.sum() <= 2, (alt, pc, int(mism.sum()))      # only limb grazers may flip
+            ok = np.isfinite(rx) & np.isfinite(gx)
+            assert ok.sum() > 1000 or (alt < 0 and nvn)   # points below the surface are always hidden
+            if not ok.any():
+                continue
+            assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9, (alt, pc)
 
 
 # ---------------------------------------------------------------------------------
