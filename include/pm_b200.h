@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 2
+#define PM_ABI_VERSION 3
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -171,7 +171,9 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
  * (body_xy.py:1633-1649) and _do_spline_interpolation (:1651-1702) applied per
  * wavelength plane by Observation._get_mapped_data (observation.py:876-905).
  * Resamples planes [plane_begin, plane_begin + plane_count) of an n_planes cube:
- * xmap, ymap: [n_cells]; out: [plane_count][n_cells].
+ * xmap, ymap: [n_cells]; out: [plane_count][n_cells].  cells_per_row = length of a map row
+ * when the cells form a regular 2-D grid (lets the dense-map cubic kernel work on 4 x 8
+ * cell blocks that share one footprint), 0 if unknown; results do not depend on it.
  *   NEAREST:  `src` is the raw cube [n_planes][ny][nx]; nanbits / plane_bits unused.
  *   LINEAR / QUADRATIC / CUBIC: `src`, `nanbits`, `plane_bits` are the three buffers filled by
  *   pm_spline_prepare for the same (n_planes, ny, nx); plane_begin must be a multiple
@@ -180,8 +182,8 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
  */
 int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits,
               int n_planes, int ny, int nx, int plane_begin, int plane_count,
-              const double *xmap, const double *ymap, int64_t n_cells, int mode,
-              uint32_t flags, double *out, void *stream);
+              const double *xmap, const double *ymap, int64_t n_cells,
+              int64_t cells_per_row, int mode, uint32_t flags, double *out, void *stream);
 
 /*
  * NaN repair (BodyXY._replace_nans_with_interpolated_values, body_xy.py:1871-1904)

@@ -73,7 +73,7 @@ def load_library() -> ctypes.CDLL:
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
     lib.pm_lonlat2xy_alt.argtypes = [c_p, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p]
     lib.pm_proj_inverse.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
-    lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i64, c_i, c_u32,
+    lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i64, c_i64, c_i, c_u32,
                               c_p, c_p]
     for fn in ('pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_work_bytes',
                'pm_spline_planebits_bytes'):
@@ -89,7 +89,7 @@ def load_library() -> ctypes.CDLL:
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 2:
+    if lib.pm_abi_version() != 3:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -279,8 +279,9 @@ def gather(src, xmap_dev, ymap_dev, mode: int, *, plane_begin: int = 0, plane_co
         out = torch.empty((plane_count,) + tuple(xmap_dev.shape), dtype=torch.float64,
                           device=xmap_dev.device)
     flags = FLAG_PROPAGATE_NAN if propagate_nan else 0
+    cells_per_row = int(xmap_dev.shape[-1]) if xmap_dev.dim() >= 2 else 0
     rc = lib.pm_gather(ptrs[0], ptrs[1], ptrs[2], nl, ny, nx, plane_begin, plane_count,
-                       xmap_dev.data_ptr(), ymap_dev.data_ptr(), n_cells, mode, flags,
+                       xmap_dev.data_ptr(), ymap_dev.data_ptr(), n_cells, cells_per_row, mode, flags,
                        out.data_ptr(), _stream_ptr(torch))
     _check(rc, 'pm_gather')
     return out

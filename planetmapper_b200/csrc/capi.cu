@@ -101,8 +101,8 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx, cons
 }
 
 int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes, int ny, int nx,
-              int plane_begin, int plane_count, const double *xmap, const double *ymap, int64_t n_cells, int mode,
-              uint32_t flags, double *out, void *stream) {
+              int plane_begin, int plane_count, const double *xmap, const double *ymap, int64_t n_cells,
+              int64_t cells_per_row, int mode, uint32_t flags, double *out, void *stream) {
     if (!src || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 ||
         plane_count < 0 || plane_begin + plane_count > n_planes)
         return PM_ERR_BAD_ARG;
@@ -117,7 +117,7 @@ int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_gather(src, nanbits, plane_bits, n_planes, ny, nx, plane_begin, plane_count, xmap, ymap,
-                               n_cells, mode, flags, out, sms, (cudaStream_t)stream));
+                               n_cells, cells_per_row, mode, flags, out, sms, (cudaStream_t)stream));
 }
 
 int64_t pm_spline_coef_bytes(int n_planes, int ny, int nx) {

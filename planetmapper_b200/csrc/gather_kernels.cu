@@ -341,12 +341,34 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
     gather_cubic_mma_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
                             const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int n_planes_padded,
                             int plane_begin, int plane_count, const double *__restrict__ xmap,
-                            const double *__restrict__ ymap, int64_t n_cells, uint32_t flags,
+                            const double *__restrict__ ymap, int64_t n_cells, int64_t row_len, uint32_t flags,
                             double *__restrict__ out, int planes_per_group) {
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int64_t warp_cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
-    if (warp_cell >= n_cells) return;  // whole warp
+    // Warp -> cells.  With a known map row length (row_len < n_cells) a warp owns a block of
+    // 4 map rows x 8 columns (tile i = row i of the block): neighbouring rows and columns
+    // almost always share one 4 x 4 footprint.  Otherwise it owns 32 consecutive cells
+    // (tile i = cells 8 i .. 8 i + 7).
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool grid2d = row_len < n_cells;
+    int64_t base0, tile_step;
+    int ncols[4];
+    if (grid2d) {
+        const int64_t col_tiles = (row_len + 7) / 8, n_rows = n_cells / row_len;
+        const int64_t rg = warp_id / col_tiles, ct = warp_id - rg * col_tiles;
+        if (4 * rg >= n_rows) return;  // whole warp
+        base0 = 4 * rg * row_len + 8 * ct;
+        tile_step = row_len;
+        const int nc = (int)min((int64_t)8, row_len - 8 * ct);
+#pragma unroll
+        for (int i = 0; i < 4; i++) ncols[i] = (4 * rg + i < n_rows) ? nc : 0;
+    } else {
+        base0 = 32 * warp_id;
+        if (base0 >= n_cells) return;  // whole warp
+        tile_step = 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) ncols[i] = (int)max((int64_t)0, min((int64_t)8, n_cells - base0 - 8 * i));
+    }
     const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 8
     const int l1 = min(l0 + planes_per_group, plane_count);
     const double nan = NAN;
@@ -360,8 +382,8 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
     uint32_t valid_mask[4];   // ballot of valid cells per tile
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int64_t cell = warp_cell + 8 * i + g;
-        const bool in_range = cell < n_cells;
+        const int64_t cell = base0 + i * tile_step + g;
+        const bool in_range = g < ncols[i];
         const double x = in_range ? __ldg(xmap + cell) : nan, y = in_range ? __ldg(ymap + cell) : nan;
         bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
         nbp[i] = 0;
@@ -388,15 +410,22 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
         cls[i] = __match_any_sync(kFull, origin[i]);
     }
     if ((valid_mask[0] | valid_mask[1] | valid_mask[2] | valid_mask[3]) == 0) {
-        // nothing visible in these 32 cells: stream NaN, 16 lanes x 16 B per plane row
-        const int64_t cell = warp_cell + 2 * (lane & 15);
-        for (int l = l0 + (lane >> 4); l < l1; l += 2) {
-            double *d = out + (int64_t)l * n_cells + cell;
-            if (((n_cells & 1) == 0) && cell + 1 < n_cells) {
+        // nothing visible in these 32 cells: stream NaN; 16 lanes x 16 B cover one plane
+        const int ti = (lane & 15) >> 2, pr = lane & 3;
+        const int nc = ti == 0 ? ncols[0] : (ti == 1 ? ncols[1] : (ti == 2 ? ncols[2] : ncols[3]));
+        const int64_t cell = base0 + ti * tile_step + 2 * pr;
+        const bool aligned = ((n_cells & 1) == 0) && (!grid2d || (row_len & 1) == 0);
+        double *d = out + (int64_t)(l0 + (lane >> 4)) * n_cells + cell;
+        const int64_t step2 = 2 * n_cells;
+        const int n_it = (l1 - l0 - (lane >> 4) + 1) / 2;  // planes l0 + (lane >> 4), + 2, ... < l1
+        if (aligned && 2 * pr + 1 < nc) {
+#pragma unroll 4
+            for (int it = 0; it < n_it; it++, d += step2)
                 asm volatile("st.global.cs.v2.f64 [%0], {%1, %1};" ::"l"(d), "d"(nan) : "memory");
-            } else {
-                if (cell < n_cells) __stcs(d, nan);
-                if (cell + 1 < n_cells) __stcs(d + 1, nan);
+        } else {
+            for (int it = 0; it < n_it; it++, d += step2) {
+                if (2 * pr < nc) __stcs(d, nan);
+                if (2 * pr + 1 < nc) __stcs(d + 1, nan);
             }
         }
         return;
@@ -406,7 +435,7 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
     const int64_t row_stride = (int64_t)nx * 4;
     // lane's fixed offset inside a footprint: plane (g & 3) of quad (g >> 2), column t
     const int64_t lane_off = (int64_t)(g >> 2) * quad_stride + t * 4 + (g & 3);
-    const bool pair_ok = (n_cells & 1) == 0;
+    const bool pair_ok = ((n_cells & 1) == 0) && (!grid2d || (row_len & 1) == 0);
 
     // ---- distinct footprints of the warp (plane independent): the usual case is one or
     // two (32 cells of a fine map straddle at most one pixel boundary)
@@ -442,7 +471,7 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
     uint32_t ok[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // per tile: bit p set = plane p of the word is good, for
                                                            // this lane's two OUTPUT cells (2t, 2t + 1)
     int cur_word = -1;
-    double *dst_row = out + (int64_t)(l0 + g) * n_cells + warp_cell + 2 * t;
+    double *dst_row = out + (int64_t)(l0 + g) * n_cells + base0 + 2 * t;
     const double *pbase = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + lane_off;
     const bool has1 = org1 != 0xffffffffu;
     auto load_a = [&](double (&a)[4], uint32_t org, const double *pb, bool in_coef) {
@@ -450,6 +479,87 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
 #pragma unroll
         for (int j = 0; j < 4; j++) a[j] = in_coef ? __ldg(p + j * row_stride) : 0.0;
     };
+    // NaN bits of the lane's output cells for the 32-plane word of plane gl + g
+    auto refresh_ok = [&](int word) {
+        const uint32_t skip = __ldg(plane_bits + word);
+        const bool consult = propagate && __ldg(plane_bits + n_words + word);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // bits of the cell this lane DESCRIBES (cell g), then exchanged to the lanes that STORE it
+            uint32_t bits = skip;
+            const bool v = (valid_mask[i] >> lane) & 1u;
+            if (consult && v) {
+                const int x0 = nbp[i] & 0x3fff, y0 = (nbp[i] >> 14) & 0x3fff;
+                const int dx = (nbp[i] >> 28) & 1, dy = (nbp[i] >> 29) & 1;
+                const uint32_t *nbw = nanbits + ((int64_t)y0 * nx + x0) * n_words + word;
+                bits |= __ldg(nbw) | __ldg(nbw + (int64_t)dx * n_words) | __ldg(nbw + (int64_t)dy * nx * n_words) |
+                        __ldg(nbw + ((int64_t)dy * nx + dx) * n_words);
+            }
+            const uint32_t good = v ? ~bits : 0u;
+            ok[i][0] = __shfl_sync(kFull, good, 4 * (2 * t));
+            ok[i][1] = __shfl_sync(kFull, good, 4 * (2 * t + 1));
+        }
+    };
+
+    // ---- fast path: every valid cell of the warp reads ONE footprint, full tiles, aligned pair
+    // stores, all planes inside the coefficient array.  No masks, no per-tile branches; the A
+    // fragments ping-pong between two register sets (software prefetch without copies).
+    const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
+    const bool planes_inside = plane_begin + l0 + ((l1 - l0 + 7) / 8) * 8 <= n_planes_padded;
+    if (simple && !has1 && full_tiles && pair_ok && planes_inside) {
+        const double *p0 = pbase + (int64_t)org0 * 4;
+        const int64_t tile_stride = 2 * quad_stride;
+        // three register sets rotate: the A fragment of plane tile n + 2 is requested while tile n
+        // is multiplied (L2 latency under 4 TB/s of streaming stores is several iterations long)
+        double fa[4], fb[4], fc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            fa[j] = __ldg(p0 + j * row_stride);
+            fb[j] = (l0 + 8 < l1) ? __ldg(p0 + tile_stride + j * row_stride) : 0.0;
+        }
+        int l = l0;
+        auto step = [&](const double (&cur)[4], double (&nxt)[4]) {
+            const int gl = plane_begin + l;
+            const int word = (gl + g) >> 5;
+            if (word != cur_word) {
+                cur_word = word;
+                refresh_ok(word);
+            }
+            if (l + 16 < l1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) nxt[j] = __ldg(p0 + 2 * tile_stride + j * row_stride);
+            }
+            double d[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                d[i][0] = d[i][1] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], cur[j], bw[i][j]);
+            }
+            if (l + g < l1) {
+                const int sh = (gl + g) & 31;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
+                    const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
+                    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst_row + i * tile_step), "d"(o0), "d"(o1)
+                                 : "memory");
+                }
+            }
+            p0 += tile_stride;
+            dst_row += 8 * n_cells;
+            l += 8;
+        };
+        while (l < l1) {
+            step(fa, fc);
+            if (l >= l1) break;
+            step(fb, fa);
+            if (l >= l1) break;
+            step(fc, fb);
+        }
+        return;
+    }
+
     // A fragment of footprint 0 is software-prefetched one plane tile ahead; footprint 1's is
     // issued at the top of the iteration and first needed after the footprint-0 products
     double a0[4];
@@ -459,24 +569,7 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
         const int word = (gl + g) >> 5;
         if (word != cur_word) {  // changes at most once per 32 planes (per lane: planes gl + g)
             cur_word = word;
-            const uint32_t skip = __ldg(plane_bits + word);
-            const bool consult = propagate && __ldg(plane_bits + n_words + word);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                // bits of the cell this lane DESCRIBES (cell g), then exchanged to the lanes that STORE it
-                uint32_t bits = skip;
-                const bool v = (valid_mask[i] >> lane) & 1u;
-                if (consult && v) {
-                    const int x0 = nbp[i] & 0x3fff, y0 = (nbp[i] >> 14) & 0x3fff;
-                    const int dx = (nbp[i] >> 28) & 1, dy = (nbp[i] >> 29) & 1;
-                    const uint32_t *nbw = nanbits + ((int64_t)y0 * nx + x0) * n_words + word;
-                    bits |= __ldg(nbw) | __ldg(nbw + (int64_t)dx * n_words) | __ldg(nbw + (int64_t)dy * nx * n_words) |
-                            __ldg(nbw + ((int64_t)dy * nx + dx) * n_words);
-                }
-                const uint32_t good = v ? ~bits : 0u;
-                ok[i][0] = __shfl_sync(kFull, good, 4 * (2 * t));
-                ok[i][1] = __shfl_sync(kFull, good, 4 * (2 * t + 1));
-            }
+            refresh_ok(word);
         }
         double d[4][2];
 #pragma unroll
@@ -536,15 +629,14 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
             const int sh = (gl + g) & 31;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int64_t cell = warp_cell + 8 * i + 2 * t;
                 const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
                 const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
-                double *dst = dst_row + 8 * i;
-                if (pair_ok && cell + 1 < n_cells) {
+                double *dst = dst_row + i * tile_step;
+                if (pair_ok && 2 * t + 1 < ncols[i]) {
                     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
                 } else {
-                    if (cell < n_cells) __stcs(dst, o0);
-                    if (cell + 1 < n_cells) __stcs(dst + 1, o1);
+                    if (2 * t < ncols[i]) __stcs(dst, o0);
+                    if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
                 }
             }
         }
@@ -555,7 +647,8 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
 
 cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
                           int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
-                          int64_t n_cells, int mode, uint32_t flags, double *out, int sm_count, cudaStream_t st) {
+                          int64_t n_cells, int64_t cells_per_row, int mode, uint32_t flags, double *out, int sm_count,
+                          cudaStream_t st) {
     (void)sm_count;
     if (n_cells == 0 || plane_count == 0) return cudaSuccess;
     int ppg = 128;  // planes per CTA: amortises the per-cell weights, bounds CTA run time
@@ -596,10 +689,19 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                 // heavier here than in the scalar kernel
                 static const int mma_ppg = getenv("PM_MMA_PPG") ? atoi(getenv("PM_MMA_PPG")) : 512;  // tuning only
                 const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
-                dim3 grid2(grid.x, (unsigned)((plane_count + g2 - 1) / g2));
+                // map row length known and regular -> 4 x 8 cell blocks per warp, else 32 consecutive cells
+                // (measured on C4: for long rows the 1-D order is ~4 % faster - longer contiguous store
+                // runs - so the blocks are only used when a warp's 32 cells would wrap across map rows)
+                const bool rows_ok = cells_per_row > 0 && cells_per_row < 64 && cells_per_row < n_cells &&
+                                     n_cells % cells_per_row == 0;
+                const int64_t row_len = rows_ok ? cells_per_row : n_cells;
+                const int64_t n_warps = rows_ok ? ((n_cells / row_len + 3) / 4) * ((row_len + 7) / 8) : (n_cells + 31) / 32;
+                dim3 grid2((unsigned)((n_warps + kGatherBlock / 32 - 1) / (kGatherBlock / 32)),
+                           (unsigned)((plane_count + g2 - 1) / g2));
                 gather_cubic_mma_kernel<<<grid2, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
                                                                         (n_planes + 3) / 4 * 4, plane_begin,
-                                                                        plane_count, xmap, ymap, n_cells, flags, out, g2);
+                                                                        plane_count, xmap, ymap, n_cells, row_len,
+                                                                        flags, out, g2);
             }
         }
             break;

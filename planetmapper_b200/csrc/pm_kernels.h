@@ -29,7 +29,8 @@ cudaError_t launch_proj_inverse(int kind, const double *params5, const double *x
 
 cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
                           int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
-                          int64_t n_cells, int mode, uint32_t flags, double *out, int sm_count, cudaStream_t st);
+                          int64_t n_cells, int64_t cells_per_row, int mode, uint32_t flags, double *out, int sm_count,
+                          cudaStream_t st);
 
 int64_t spline_coef_bytes(int n_planes, int ny, int nx);
 int64_t spline_nanbits_bytes(int n_planes, int ny, int nx);

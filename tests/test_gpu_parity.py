@@ -219,6 +219,9 @@ def test_gather_vs_scipy_oracle(L, oracle, bc_hst, nx, ny):
         for prop in (True, False):
             spline = L.spline_prepare(cd, mode)
             got = L.gather(spline, xy[0], xy[1], mode, propagate_nan=prop).cpu().numpy()
+            # the flat (unknown row length) cell order gives the same values as the 2-D grid
+            flat = L.gather(spline, xy[0].reshape(-1), xy[1].reshape(-1), mode, propagate_nan=prop).cpu().numpy()
+            assert np.array_equal(flat.reshape(got.shape), got, equal_nan=True), (name, prop)
             # a quad-aligned sub-range of planes equals the same planes of the full call
             if cube.shape[0] > 4:
                 sub = L.gather(spline, xy[0], xy[1], mode, plane_begin=4, plane_count=3,
@@ -322,6 +325,14 @@ def test_full_grid_gather_properties(L, bc_hst):
     assert torch.equal(torch.isfinite(near[0]), vis)
     for mode in (L.INTERP_LINEAR, L.INTERP_QUADRATIC, L.INTERP_CUBIC):
         out = L.gather(L.spline_prepare(cube, mode), xm, ym, mode, propagate_nan=True)
+        if mode == L.INTERP_CUBIC:
+            # narrow map (row length 40 < 64): 4 x 8 cell blocks per warp, ragged edges, odd row count
+            xs, ys = xm[:1799, 1000:1040].contiguous(), ym[:1799, 1000:1040].contiguous()
+            sub = L.gather(L.spline_prepare(cube, mode), xs, ys, mode, propagate_nan=True)
+            assert torch.equal(torch.nan_to_num(sub, nan=-7.0), torch.nan_to_num(out[:, :1799, 1000:1040], nan=-7.0))
+            xs, ys = xm[:1799, 1000:1037].contiguous(), ym[:1799, 1000:1037].contiguous()   # odd row length
+            sub = L.gather(L.spline_prepare(cube, mode), xs, ys, mode, propagate_nan=True)
+            assert torch.equal(torch.nan_to_num(sub, nan=-7.0), torch.nan_to_num(out[:, :1799, 1000:1037], nan=-7.0))
         inside = vis & (xm >= 0) & (ym >= 0) & (xm <= sz - 1) & (ym <= sz - 1)
         assert torch.equal(torch.isfinite(out[0]), inside)
         # both spline kinds reproduce linear functions: sampling the x / y ramps returns the map
