@@ -42,7 +42,7 @@ PM_HD V3 cross(V3 a, V3 b) {
 PM_HD V3 mul3(V3 a, const double *s) { return mk(a.x * s[0], a.y * s[1], a.z * s[2]); }
 // a + s b
 PM_HD V3 axpy(double s, V3 b, V3 a) { return mk(fma(s, b.x, a.x), fma(s, b.y, a.y), fma(s, b.z, a.z)); }
-PM_HD double norm(V3 a) { return fast_sqrt(dot(a, a)); }
+PM_HD double norm(V3 a) { return fast_sqrt_lite(dot(a, a)); }
 PM_HD V3 ld3(const double *p) { return mk(p[0], p[1], p[2]); }
 PM_HD bool finite3(V3 a) { return fabs(a.x) < INFINITY && fabs(a.y) < INFINITY && fabs(a.z) < INFINITY; }
 PM_HD V3 mxv(const double *m, V3 v) {
@@ -255,11 +255,11 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p) {
     if (ym2 > 1.0) {
         if (pm2 > 1.0) return false;
         if (yx > 0.0) return false;
-        q = axpy(-fast_sqrt((1.0 - pm2) * ixx), x, pp);
+        q = axpy(-fast_sqrt_lite((1.0 - pm2) * ixx), x, pp);
     } else if (ym2 == 1.0) {
         q = y;
     } else {
-        q = axpy(fast_sqrt(fmax(0.0, 1.0 - pm2) * ixx), x, pp);
+        q = axpy(fast_sqrt_lite(fmax(0.0, 1.0 - pm2) * ixx), x, pp);
     }
     p = mul3(q, fs.f.radii);
     return true;
@@ -312,7 +312,7 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const V3 Pb = target_pos_b(fs, dt);
     V3 p;
     if (fabs(dt1) > 1.0e-6) {
-        p = axpy(fast_div(dt - dt1, dt1), p2 - p1, p2);
+        p = axpy(fast_div_lite(dt - dt1, dt1), p2 - p1, p2);
     } else {
         // passes 1 and 2 (almost) coincide in epoch: no secant, solve the third intercept
         if (!surfpt(fs, spin_fwd(fs, r, -Pb), spin_fwd(fs, r, u0), p)) return false;
@@ -452,7 +452,7 @@ PM_HD void illum_angles(V3 n, V3 s, V3 e, bool want_az, Illum &out) {
         // (cos g - cos e cos i) / (sin e sin i) with the common factor |n|^2 |s| |e|
         // cancelled: ((s.e)(n.n) - (n.e)(n.s)) / (|n x e| |n x s|)
         const double a = fma(dse, dot(n, n), -dne * dns);
-        out.azimuth = kPi - fast_acos(fast_div(a, mne * mns));
+        out.azimuth = kPi - fast_acos(fast_div_lite(a, mne * mns));
     }
 }
 
@@ -675,7 +675,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
         if (mask & (kLonLatMask | kCentricMask)) {
             // _get_lonlat_img (body_xy.py:3284-3288), _get_lonlat_centric_img (:3349): the
             // east longitude and the cylindrical radius are shared by recpgr and reclat
-            const double rho = fast_sqrt(fma(p.x, p.x, p.y * p.y));
+            const double rho = fast_sqrt_lite(fma(p.x, p.x, p.y * p.y));
             const double lon_e = fast_atan2(p.y, p.x);
             if (mask & kLonLatMask) {
                 double l = f.lon_sign * lon_e;
