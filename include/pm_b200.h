@@ -96,6 +96,10 @@ enum PMPlane {
 #define PM_INTERP_LINEAR 1
 #define PM_INTERP_QUADRATIC 2
 #define PM_INTERP_CUBIC 3
+/* mixed spline degrees, RectBivariateSpline(kx = ky_rows, ky = kx_cols): degree along image
+ * rows (y) in bits 4-7, along columns (x) in bits 0-3, each 1..3 */
+#define PM_INTERP_MIXED 0x100
+#define PM_INTERP_MIXED_MODE(deg_rows, deg_cols) (PM_INTERP_MIXED | ((deg_rows) << 4) | (deg_cols))
 
 /* projection kinds of pm_proj_inverse (BodyXY.generate_map_coordinates,
  * body_xy.py:2899-2969) */

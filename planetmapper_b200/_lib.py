@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, 'libpm_b200.so')
 N_PLANES = 26
 ALL_PLANES = (1 << N_PLANES) - 1
 INTERP_NEAREST, INTERP_LINEAR, INTERP_QUADRATIC, INTERP_CUBIC = 0, 1, 2, 3
+INTERP_MIXED = 0x100   # | degree along rows << 4 | degree along columns
 PROJ_ORTHOGRAPHIC, PROJ_AZIMUTHAL, PROJ_AZIMUTHAL_EQUAL_AREA = 1, 2, 3
 FLAG_NOT_VISIBLE_NAN = 1
 FLAG_PROPAGATE_NAN = 2

@@ -687,11 +687,19 @@ def _interpolation_mode(interpolation, spline_smoothing) -> int:
     if interpolation == 'nearest':
         return L.INTERP_NEAREST
     if isinstance(interpolation, tuple):
-        if len(interpolation) == 2 and interpolation[0] == interpolation[1]:
-            interpolation = interpolation[0]
-        else:
-            raise NotImplementedError(
-                f'mixed spline degrees {interpolation!r} are on the "next" list (SURVEY 8(f))')
+        # (kx, ky) as handed to RectBivariateSpline(np.arange(ny), np.arange(nx), img, kx=, ky=)
+        # (body_xy.py:1673-1680): the FIRST degree runs along image rows (y)
+        if len(interpolation) != 2:
+            raise ValueError(f'Unknown interpolation method {interpolation!r}')
+        if spline_smoothing != 0:
+            raise NotImplementedError('spline_smoothing != 0 (FITPACK smoothing) is not '
+                                      'accelerated; only interpolating splines are')
+        k_rows, k_cols = (int(k) for k in interpolation)
+        if not (1 <= k_rows <= 3 and 1 <= k_cols <= 3):
+            raise NotImplementedError(f'spline degrees {interpolation!r} are not accelerated (1..3 are)')
+        if k_rows == k_cols:
+            return k_rows
+        return L.INTERP_MIXED | (k_rows << 4) | k_cols
     if isinstance(interpolation, (int, np.integer)) and not isinstance(interpolation, bool):
         if spline_smoothing != 0:
             raise NotImplementedError('spline_smoothing != 0 (FITPACK smoothing) is not '

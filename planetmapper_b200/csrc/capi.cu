@@ -106,12 +106,15 @@ int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_
     if (!src || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 ||
         plane_count < 0 || plane_begin + plane_count > n_planes)
         return PM_ERR_BAD_ARG;
-    if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR && mode != PM_INTERP_QUADRATIC &&
-        mode != PM_INTERP_CUBIC)
+    int ky = mode, kx = mode;
+    if (mode & PM_INTERP_MIXED) {
+        ky = (mode >> 4) & 0xF;
+        kx = mode & 0xF;
+        if ((mode & ~0x1FF) || ky < 1 || ky > 3 || kx < 1 || kx > 3) return PM_ERR_UNSUPPORTED;
+    } else if (mode < PM_INTERP_NEAREST || mode > PM_INTERP_CUBIC) {
         return PM_ERR_UNSUPPORTED;
-    if (mode == PM_INTERP_LINEAR && (nx < 2 || ny < 2)) return PM_ERR_BAD_ARG;
-    if (mode == PM_INTERP_QUADRATIC && (nx < 3 || ny < 3)) return PM_ERR_BAD_ARG;
-    if (mode == PM_INTERP_CUBIC && (nx < 4 || ny < 4)) return PM_ERR_BAD_ARG;
+    }
+    if (mode != PM_INTERP_NEAREST && (nx <= kx || ny <= ky)) return PM_ERR_BAD_ARG;
     if (mode != PM_INTERP_NEAREST && (!nanbits || !plane_bits || (plane_begin & 3))) return PM_ERR_BAD_ARG;
     if (plane_count > 65535 * 128) return PM_ERR_BAD_ARG;
     int sms = sm_count();
@@ -141,8 +144,14 @@ int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degr
                       uint32_t *nanbits, uint32_t *plane_bits, void *work, void *stream) {
     if (!cube || !coef || !nanbits || !plane_bits || !work || n_planes < 0 || ny <= 0 || nx <= 0)
         return PM_ERR_BAD_ARG;
-    if (degree < 1 || degree > 3) return PM_ERR_UNSUPPORTED;
-    if (nx <= degree || ny <= degree) return PM_ERR_BAD_ARG;
+    int ky = degree, kx = degree;
+    if (degree & PM_INTERP_MIXED) {
+        ky = (degree >> 4) & 0xF;
+        kx = degree & 0xF;
+        if (degree & ~0x1FF) return PM_ERR_UNSUPPORTED;
+    }
+    if (ky < 1 || ky > 3 || kx < 1 || kx > 3) return PM_ERR_UNSUPPORTED;
+    if (nx <= kx || ny <= ky) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_spline_prepare(cube, n_planes, ny, nx, degree, coef, nanbits, plane_bits, work, sms,

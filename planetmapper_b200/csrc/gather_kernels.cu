@@ -144,17 +144,34 @@ __device__ __forceinline__ Quad ldg_quad(const double *p) {
     return q;
 }
 
-// Per-cell state of the spline gather (weights, footprint origin, NaN-test pixels)
+// The K = degree + 1 non-zero basis functions of one axis at coordinate x (n samples);
+// returns the first coefficient index.  K = 2 is the degree-1 spline = linear interpolation
+// with bispev's clamping.
 template <int K>
+__device__ __forceinline__ int axis_weights(double x, int n, double w[K]) {
+    if (K == 2) {
+        const double xe = fmin(fmax(x, 0.0), (double)(n - 1));
+        const int i = min((int)floor(xe), n - 2);
+        const double fx = xe - i;
+        w[0] = 1.0 - fx;
+        w[1] = fx;
+        return i;
+    }
+    return bspline_weights<(K == 2 ? 2 : K - 1)>(x, n, w);
+}
+
+// Per-cell state of the spline gather (weights, footprint origin, NaN-test pixels)
+template <int KY, int KX>
 struct CellState {
-    double w[K * K];     // wy[a] * wx[b], FITPACK fpbisp order (rows outer)
+    double w[KY * KX];   // wy[a] * wx[b], FITPACK fpbisp order (rows outer)
     int64_t origin;      // ((iy * nx + ix) * 4): offset of the footprint inside a plane quad
     uint32_t nb[4];      // pixel indices floor/ceil(x, y) for _should_propagate_nan_to_map
     uint32_t bad;        // NaN bits of the current 32-plane word
     bool valid;
 };
-template <int K>
-__device__ __forceinline__ void setup_cell(CellState<K> &c, double x, double y, int ny, int nx, bool propagate) {
+template <int KY, int KX>
+__device__ __forceinline__ void setup_cell(CellState<KY, KX> &c, double x, double y, int ny, int nx,
+                                           bool propagate) {
     c.valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
     c.bad = 0;
     c.origin = 0;
@@ -170,141 +187,70 @@ __device__ __forceinline__ void setup_cell(CellState<K> &c, double x, double y, 
         c.nb[3] = (uint32_t)(y1 * nx + x1);
     }
     if (c.valid) {
-        double wx[K], wy[K];
-        int ix, iy;
-        if (K == 4) {
-            ix = bspline3_weights(x, nx, wx);
-            iy = bspline3_weights(y, ny, wy);
-        } else if (K == 3) {
-            ix = bspline_weights<K == 3 ? 2 : 3>(x, nx, wx);
-            iy = bspline_weights<K == 3 ? 2 : 3>(y, ny, wy);
-        } else {
-            const double xe = fmin(fmax(x, 0.0), (double)(nx - 1));
-            const double ye = fmin(fmax(y, 0.0), (double)(ny - 1));
-            ix = min((int)floor(xe), nx - 2);
-            iy = min((int)floor(ye), ny - 2);
-            const double fx = xe - ix, fy = ye - iy;
-            wx[0] = 1.0 - fx;
-            wx[1] = fx;
-            wy[0] = 1.0 - fy;
-            wy[1] = fy;
-        }
+        double wx[KX], wy[KY];
+        const int ix = axis_weights<KX>(x, nx, wx);
+        const int iy = axis_weights<KY>(y, ny, wy);
 #pragma unroll
-        for (int a = 0; a < K; a++)
+        for (int a = 0; a < KY; a++)
 #pragma unroll
-            for (int b = 0; b < K; b++) c.w[a * K + b] = wy[a] * wx[b];
+            for (int b = 0; b < KX; b++) c.w[a * KX + b] = wy[a] * wx[b];
         c.origin = ((int64_t)iy * nx + ix) * 4;
     } else {
 #pragma unroll
-        for (int k = 0; k < K * K; k++) c.w[k] = 0.0;
+        for (int k = 0; k < KY * KX; k++) c.w[k] = 0.0;
     }
 }
 
-// C = cells per thread.  With C == 2 a thread owns two adjacent cells: map grids are
-// usually much finer than the image (C4: 0.1 deg cells on ~3 deg pixels), so both cells
-// read the same K x K footprint and every 256-bit coefficient load feeds 8 FMAs.  That
-// matters for the cubic case, where the L1 -> register return path (128 B/clk/SM), not
-// HBM, bounds a one-cell-per-thread kernel: 16 coefficients x 8 B per voxel.
-template <int K, int C, int kMinBlocks>
-__global__ void __launch_bounds__(kGatherBlock / C, kMinBlocks)
+// One cell per thread, KY x KX footprint (KY = row degree + 1, KX = column degree + 1)
+template <int KY, int KX, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
     gather_spline_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
                          const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int plane_begin,
                          int plane_count, const double *__restrict__ xmap, const double *__restrict__ ymap,
                          int64_t n_cells, uint32_t flags, double *__restrict__ out, int planes_per_group) {
-    const int64_t cell0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * C;
-    if (cell0 >= n_cells) return;
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
     const int l0 = blockIdx.y * planes_per_group;  // relative to plane_begin, multiple of 4
     const int l1 = min(l0 + planes_per_group, plane_count);
     const double nan = NAN;
     const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
-    CellState<K> cs[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        const bool in_range = cell0 + c < n_cells;
-        const double x = in_range ? __ldg(xmap + cell0 + c) : nan, y = in_range ? __ldg(ymap + cell0 + c) : nan;
-        setup_cell<K>(cs[c], x, y, ny, nx, propagate);
-    }
-    const bool shared_patch = (C == 2) && cs[0].valid && cs[C - 1].valid && cs[0].origin == cs[C - 1].origin;
+    CellState<KY, KX> cs;
+    setup_cell<KY, KX>(cs, __ldg(xmap + cell), __ldg(ymap + cell), ny, nx, propagate);
     const int64_t quad_stride = (int64_t)ny * nx * 4;  // doubles per plane quad
     const int64_t row_stride = (int64_t)nx * 4;
-    const double *src = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride;
-    double *dst = out + (int64_t)l0 * n_cells + cell0;
-    const bool pair_store = (C == 2) && (cell0 + 1 < n_cells) && ((n_cells & 1) == 0);
+    const double *src = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + cs.origin;
+    double *dst = out + (int64_t)l0 * n_cells + cell;
     int cur_word = -1;
     for (int l = l0; l < l1; l += 4) {
         const int gl = plane_begin + l;  // global plane index of this quad (multiple of 4)
         const int word = gl >> 5;
         if (word != cur_word) {  // uniform: once per 32 planes
             cur_word = word;
-            const uint32_t skip = __ldg(plane_bits + word);
-            const bool consult = propagate && __ldg(plane_bits + n_words + word);
+            uint32_t bad = __ldg(plane_bits + word);
+            if (cs.valid && propagate && __ldg(plane_bits + n_words + word)) {
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                uint32_t bad = skip;
-                if (cs[c].valid && consult) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) bad |= __ldg(nanbits + (int64_t)cs[c].nb[k] * n_words + word);
-                }
-                cs[c].bad = bad;
+                for (int k = 0; k < 4; k++) bad |= __ldg(nanbits + (int64_t)cs.nb[k] * n_words + word);
             }
+            cs.bad = bad;
         }
-        double acc[C][4];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (cs.valid) {
 #pragma unroll
-        for (int c = 0; c < C; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
-        if (shared_patch) {
-            const double *p = src + cs[0].origin;
+            for (int a = 0; a < KY; a++) {
 #pragma unroll
-            for (int a = 0; a < K; a++) {
+                for (int b = 0; b < KX; b++) {
+                    const Quad q = ldg_quad(src + a * row_stride + b * 4);
+                    const double ww = cs.w[a * KX + b];
 #pragma unroll
-                for (int b = 0; b < K; b++) {
-                    const Quad q = ldg_quad(p + a * row_stride + b * 4);
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const double ww = cs[c].w[a * K + b];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[c][j] = fma(q.v[j], ww, acc[c][j]);
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                if (cs[c].valid) {
-                    const double *p = src + cs[c].origin;
-#pragma unroll
-                    for (int a = 0; a < K; a++) {
-#pragma unroll
-                        for (int b = 0; b < K; b++) {
-                            const Quad q = ldg_quad(p + a * row_stride + b * 4);
-                            const double ww = cs[c].w[a * K + b];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) acc[c][j] = fma(q.v[j], ww, acc[c][j]);
-                        }
-                    }
+                    for (int j = 0; j < 4; j++) acc[j] = fma(q.v[j], ww, acc[j]);
                 }
             }
         }
+        const uint32_t nib = cs.valid ? ((cs.bad >> (gl & 31)) & 0xFu) : 0xFu;
         const int left = l1 - l;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const uint32_t nib = cs[c].valid ? ((cs[c].bad >> (gl & 31)) & 0xFu) : 0xFu;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((nib >> j) & 1u) acc[c][j] = nan;
-        }
-#pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (j < left) {
-                double *d = dst + (int64_t)j * n_cells;
-                if (pair_store) {
-                    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(d), "d"(acc[0][j]), "d"(acc[C - 1][j])
-                                 : "memory");
-                } else {
-#pragma unroll
-                    for (int c = 0; c < C; c++)
-                        if (cell0 + c < n_cells) __stcs(d + c, acc[c][j]);
-                }
-            }
+            if (j < left) __stcs(dst + (int64_t)j * n_cells, ((nib >> j) & 1u) ? nan : acc[j]);
         }
         src += quad_stride;
         dst += 4 * n_cells;
@@ -656,58 +602,56 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
     // every CTA covers kGatherBlock cells (128 threads x 2 cells for the cubic kernel)
     dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)((plane_count + ppg - 1) / ppg));
     const int n_words = (n_planes + 31) / 32;
-    switch (mode) {
-        case PM_INTERP_NEAREST:
-            gather_nearest_kernel<<<grid, kGatherBlock, 0, st>>>(src, ny, nx, plane_begin, plane_count, xmap, ymap,
-                                                                 n_cells, out, ppg);
-            break;
-        case PM_INTERP_LINEAR:
-            gather_spline_kernel<2, 1, 4><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                      plane_begin, plane_count, xmap, ymap, n_cells,
-                                                                      flags, out, ppg);
-            break;
-        case PM_INTERP_QUADRATIC:
-            gather_spline_kernel<3, 1, 3><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                      plane_begin, plane_count, xmap, ymap, n_cells,
-                                                                      flags, out, ppg);
-            break;
-        case PM_INTERP_CUBIC:
-        {
-            static const int v = getenv("PM_CUBIC_VARIANT") ? atoi(getenv("PM_CUBIC_VARIANT")) : -1;  // tuning only
-            // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel
-            const bool dense = n_cells >= (int64_t)8 * nx * ny && nx < 16384 && ny < 16384;
-            if (v == 0 || (v < 0 && !dense)) {
-                gather_spline_kernel<4, 1, 2><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                             plane_begin, plane_count, xmap, ymap,
-                                                                             n_cells, flags, out, ppg);
-            } else if (v == 3) {
-                gather_spline_kernel<4, 2, 3><<<grid, kGatherBlock / 2, 0, st>>>(src, nanbits, plane_bits, n_words, ny,
-                                                                                 nx, plane_begin, plane_count, xmap,
-                                                                                 ymap, n_cells, flags, out, ppg);
-            } else {
-                // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is
-                // heavier here than in the scalar kernel
-                static const int mma_ppg = getenv("PM_MMA_PPG") ? atoi(getenv("PM_MMA_PPG")) : 512;  // tuning only
-                const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
-                // map row length known and regular -> 4 x 8 cell blocks per warp, else 32 consecutive cells
-                // (measured on C4: for long rows the 1-D order is ~4 % faster - longer contiguous store
-                // runs - so the blocks are only used when a warp's 32 cells would wrap across map rows)
-                const bool rows_ok = cells_per_row > 0 && cells_per_row < 64 && cells_per_row < n_cells &&
-                                     n_cells % cells_per_row == 0;
-                const int64_t row_len = rows_ok ? cells_per_row : n_cells;
-                const int64_t n_warps = rows_ok ? ((n_cells / row_len + 3) / 4) * ((row_len + 7) / 8) : (n_cells + 31) / 32;
-                dim3 grid2((unsigned)((n_warps + kGatherBlock / 32 - 1) / (kGatherBlock / 32)),
-                           (unsigned)((plane_count + g2 - 1) / g2));
-                gather_cubic_mma_kernel<<<grid2, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                        (n_planes + 3) / 4 * 4, plane_begin,
-                                                                        plane_count, xmap, ymap, n_cells, row_len,
-                                                                        flags, out, g2);
-            }
-        }
-            break;
-        default:
-            return cudaErrorInvalidValue;
+    int ky = mode, kx = mode;  // spline degree along image rows (y) / columns (x)
+    if (mode & PM_INTERP_MIXED) {
+        ky = (mode >> 4) & 0xF;
+        kx = mode & 0xF;
     }
+    if (mode == PM_INTERP_NEAREST) {
+        gather_nearest_kernel<<<grid, kGatherBlock, 0, st>>>(src, ny, nx, plane_begin, plane_count, xmap, ymap, n_cells,
+                                                             out, ppg);
+        count_launches(1);
+        return cudaGetLastError();
+    }
+    if (ky < 1 || ky > 3 || kx < 1 || kx > 3) return cudaErrorInvalidValue;
+#define PM_SPLINE(KY, KX, MB)                                                                                     \
+    gather_spline_kernel<KY, KX, MB><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,    \
+                                                                    plane_begin, plane_count, xmap, ymap, n_cells, \
+                                                                    flags, out, ppg)
+    static const int v = getenv("PM_CUBIC_VARIANT") ? atoi(getenv("PM_CUBIC_VARIANT")) : -1;  // tuning only
+    // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel
+    const bool dense = n_cells >= (int64_t)8 * nx * ny && nx < 16384 && ny < 16384;
+    if (ky == 3 && kx == 3 && v != 0 && (dense || v > 0)) {
+        // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is heavier here
+        // than in the scalar kernel
+        static const int mma_ppg = getenv("PM_MMA_PPG") ? atoi(getenv("PM_MMA_PPG")) : 512;  // tuning only
+        const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
+        // map row length known and regular -> 4 x 8 cell blocks per warp, else 32 consecutive cells
+        // (measured on C4: for long rows the 1-D order is ~4 % faster - longer contiguous store
+        // runs - so the blocks are only used when a warp's 32 cells would wrap across map rows)
+        const bool rows_ok = cells_per_row > 0 && cells_per_row < 64 && cells_per_row < n_cells &&
+                             n_cells % cells_per_row == 0;
+        const int64_t row_len = rows_ok ? cells_per_row : n_cells;
+        const int64_t n_warps = rows_ok ? ((n_cells / row_len + 3) / 4) * ((row_len + 7) / 8) : (n_cells + 31) / 32;
+        dim3 grid2((unsigned)((n_warps + kGatherBlock / 32 - 1) / (kGatherBlock / 32)),
+                   (unsigned)((plane_count + g2 - 1) / g2));
+        gather_cubic_mma_kernel<<<grid2, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+                                                                (n_planes + 3) / 4 * 4, plane_begin, plane_count, xmap,
+                                                                ymap, n_cells, row_len, flags, out, g2);
+    } else {
+        switch (ky * 4 + kx) {
+            case 1 * 4 + 1: PM_SPLINE(2, 2, 4); break;
+            case 1 * 4 + 2: PM_SPLINE(2, 3, 3); break;
+            case 1 * 4 + 3: PM_SPLINE(2, 4, 3); break;
+            case 2 * 4 + 1: PM_SPLINE(3, 2, 3); break;
+            case 2 * 4 + 2: PM_SPLINE(3, 3, 3); break;
+            case 2 * 4 + 3: PM_SPLINE(3, 4, 2); break;
+            case 3 * 4 + 1: PM_SPLINE(4, 2, 3); break;
+            case 3 * 4 + 2: PM_SPLINE(4, 3, 2); break;
+            default: PM_SPLINE(4, 4, 2); break;
+        }
+    }
+#undef PM_SPLINE
     count_launches(1);
     return cudaGetLastError();
 }
@@ -1014,7 +958,7 @@ int64_t spline_planebits_bytes(int n_planes) { return 2 * (int64_t)((n_planes + 
 int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree) {
     int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double)) +
                 align256((int64_t)n_planes) + align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
-    if (degree >= 2) b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
+    b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
     return b;
 }
 
@@ -1039,22 +983,32 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
     repair_kernel<<<blocks, 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
     count_launches(3);
-    if (degree >= 2) {
+    int deg_y = degree, deg_x = degree;  // rows (image y) / columns (image x)
+    if (degree & PM_INTERP_MIXED) {
+        deg_y = (degree >> 4) & 0xF;
+        deg_x = degree & 0xF;
+    }
+    {
         double *lu_x = reinterpret_cast<double *>(w);
         w += align256((int64_t)5 * nx * sizeof(double));
         double *lu_y = reinterpret_cast<double *>(w);
-        const std::vector<double> &hx = spline_lu(nx, degree);
-        const std::vector<double> &hy = spline_lu(ny, degree);
-        cudaError_t e = cudaMemcpyAsync(lu_x, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(lu_y, hy.data(), hy.size() * sizeof(double), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return e;
         int64_t rows = (int64_t)n_planes * ny, cols = (int64_t)n_planes * nx;
         int rb = (int)std::min<int64_t>((rows + 127) / 128, (int64_t)sm_count * 16);
         int cb = (int)std::min<int64_t>((cols + 127) / 128, (int64_t)sm_count * 16);
-        prefilter_rows_kernel<<<rb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_x);
-        prefilter_cols_kernel<<<cb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_y);
-        count_launches(2);
+        if (deg_x >= 2) {  // solve along x (within image rows) with the column-axis degree
+            const std::vector<double> &hx = spline_lu(nx, deg_x);
+            cudaError_t e = cudaMemcpyAsync(lu_x, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            prefilter_rows_kernel<<<rb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_x);
+            count_launches(1);
+        }
+        if (deg_y >= 2) {
+            const std::vector<double> &hy = spline_lu(ny, deg_y);
+            cudaError_t e = cudaMemcpyAsync(lu_y, hy.data(), hy.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            prefilter_cols_kernel<<<cb, 128, 0, st>>>(coef, plane_skip, n_planes, ny, nx, lu_y);
+            count_launches(1);
+        }
     }
     const int64_t quads_total = (int64_t)((n_planes + 3) / 4) * plane_px;
     pack_quads_kernel<<<(int)std::min<int64_t>((quads_total + 255) / 256, (int64_t)sm_count * 32), 256, 0, st>>>(

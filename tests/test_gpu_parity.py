@@ -213,8 +213,9 @@ def test_gather_vs_scipy_oracle(L, oracle, bc_hst, nx, ny):
     sub = L.gather(cd, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=1, plane_count=2).cpu().numpy()
     assert np.array_equal(sub, ref[1:3], equal_nan=True)
     assert np.array_equal(oracle.gather_nearest(cube, xm, ym), ref, equal_nan=True)
-    for mode, name in ((L.INTERP_LINEAR, 'linear'), (L.INTERP_QUADRATIC, 'quadratic'), (L.INTERP_CUBIC, 'cubic')):
-        if mode >= min(nx, ny):
+    mixed = [(L.INTERP_MIXED | (a << 4) | b, (a, b)) for a in (1, 2, 3) for b in (1, 2, 3) if a != b]
+    for mode, name in [(L.INTERP_LINEAR, 'linear'), (L.INTERP_QUADRATIC, 'quadratic'), (L.INTERP_CUBIC, 'cubic')] + mixed:
+        if (max(name) if isinstance(name, tuple) else mode) >= min(nx, ny):
             continue
         for prop in (True, False):
             spline = L.spline_prepare(cd, mode)
