@@ -206,6 +206,28 @@ int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degr
                       double *coef, uint32_t *nanbits, uint32_t *plane_bits, void *work,
                       void *stream);
 
+/*
+ * map_img(interpolation='smooth') (BodyXY._do_smooth_interpolation, body_xy.py:1704-1790):
+ *   pm_nan_minmax         np.nanmin / np.nanmax of a device array -> out2[2] (device), the x / y
+ *                         map limits the host needs to size the oversampled grid (:1720-1721);
+ *   pm_pchip_resample     BodyXY._pchip_grid_interp2d (:1792-1853): PchipInterpolator over the
+ *                         finite pixels of columns x_first..x_last of every row y_first..y_last,
+ *                         then of every column, evaluated on np.linspace(first, last, n) grids;
+ *                         fine: [n_planes][n_ys][n_xs]; `work`: pm_pchip_work_bytes(...) bytes;
+ *   pm_gather_grid_linear RegularGridInterpolator(method='linear', bounds_error=False,
+ *                         fill_value=nan) on `fine` at (ymap, xmap) with the propagate_nan rule
+ *                         evaluated on the original cube (:1761-1790); out: [n_planes][n_cells].
+ */
+int pm_nan_minmax(const double *x, int64_t n, double *out2, void *stream);
+int64_t pm_pchip_work_bytes(int n_planes, int ny, int nx, int n_xs);
+int pm_pchip_resample(const double *cube, int n_planes, int ny, int nx, int x_first, int x_last,
+                      int y_first, int y_last, int n_xs, int n_ys, double *fine, void *work,
+                      void *stream);
+int pm_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, int x_first,
+                          int x_last, int y_first, int y_last, const double *cube, int ny, int nx,
+                          const double *xmap, const double *ymap, int64_t n_cells, uint32_t flags,
+                          double *out, void *stream);
+
 /* FP64 FMA throughput probe used by bench.py for the compute roofline
  * denominator: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the kernel time in ms through *ms_host (synchronises). */

@@ -53,11 +53,13 @@ def should_propagate_nan_to_map(x, y, nans, nx, ny) -> bool:
 
 
 def map_img(img, x_map, y_map, interpolation='nearest', propagate_nan=True,
-            spline_smoothing=0.0) -> np.ndarray:
+            spline_smoothing=0.0, smooth_oversample_by=5,
+            smooth_max_oversampled_img_size=10_000) -> np.ndarray:
     img = np.asarray(img)
     if img.ndim == 3:
         return np.array([map_img(s, x_map, y_map, interpolation, propagate_nan,
-                                 spline_smoothing) for s in img])
+                                 spline_smoothing, smooth_oversample_by,
+                                 smooth_max_oversampled_img_size) for s in img])
     ny, nx = img.shape
     projected = np.full(x_map.shape, np.nan)
     spline_k = {'linear': 1, 'quadratic': 2, 'cubic': 3}
@@ -74,6 +76,9 @@ def map_img(img, x_map, y_map, interpolation='nearest', propagate_nan=True,
                     continue
                 projected[a, b] = img[ym[a, b], x]
         return projected
+    if interpolation == 'smooth':
+        return _smooth(img, x_map, y_map, projected, propagate_nan, smooth_oversample_by,
+                       smooth_max_oversampled_img_size)
     if isinstance(interpolation, int):
         kx = ky = interpolation
     else:
@@ -99,6 +104,78 @@ def map_img(img, x_map, y_map, interpolation='nearest', propagate_nan=True,
             y_vals.append(y)
     if a_vals:
         projected[a_vals, b_vals] = interpolator.ev(y_vals, x_vals)
+    return projected
+
+
+def smooth_grid(n, limits, oversample_by, max_size, limit_padding=5.0):
+    """get_xy_pchip of BodyXY._do_smooth_interpolation (body_xy.py:1723-1741): the oversampled
+    1-D grid.  Returns (first original index, last original index, grid)."""
+    original = np.arange(n)
+    original = original[(original >= limits[0] - limit_padding) & (original <= limits[1] + limit_padding)]
+    old_size = len(original)
+    for oversample_to_use in range(oversample_by, 1, -1):
+        new_size = old_size * oversample_to_use - (oversample_to_use - 1)
+        if new_size <= max_size:
+            return original[0], original[-1], np.linspace(original[0], original[-1], new_size)
+    return original[0], original[-1], original.astype(float)
+
+
+def pchip_grid_interp2d(xs_original, ys_original, img, xs, ys, xlim, ylim, limit_padding):
+    """BodyXY._pchip_grid_interp2d (body_xy.py:1792-1853) with the real scipy PCHIP."""
+    intermediate = np.full((len(ys_original), len(xs)), np.nan, dtype=np.float64)
+    x_mask = (xs_original >= xlim[0] - limit_padding) & (xs_original <= xlim[1] + limit_padding)
+    for i, y in enumerate(ys_original):
+        if y < ylim[0] - limit_padding or y > ylim[1] + limit_padding:
+            continue
+        mask = np.isfinite(img[i]) & x_mask
+        if np.sum(mask) < 2:
+            continue
+        interpolator = scipy.interpolate.PchipInterpolator(xs_original[mask], img[i, mask], extrapolate=False)
+        intermediate[i] = interpolator(xs)
+    final = np.full((len(ys), len(xs)), np.nan, dtype=np.float64)
+    y_mask = (ys_original >= ylim[0] - limit_padding) & (ys_original <= ylim[1] + limit_padding)
+    for j, x in enumerate(xs):
+        if x < xlim[0] - limit_padding or x > xlim[1] + limit_padding:
+            continue
+        mask = np.isfinite(intermediate[:, j]) & y_mask
+        if np.sum(mask) < 2:
+            continue
+        interpolator = scipy.interpolate.PchipInterpolator(ys_original[mask], intermediate[mask, j],
+                                                           extrapolate=False)
+        final[:, j] = interpolator(ys)
+    return final
+
+
+def _smooth(img, x_map, y_map, projected, propagate_nan, oversample_by, max_size, limit_padding=5.0):
+    """BodyXY._do_smooth_interpolation (body_xy.py:1704-1790): PCHIP oversampling on a regular
+    grid followed by linear interpolation, with the real scipy calls."""
+    ny, nx = img.shape
+    nans = np.isnan(img)
+    if np.all(nans) or not np.any(np.isfinite(x_map)):
+        return projected
+    xlim = (np.nanmin(x_map), np.nanmax(x_map))
+    ylim = (np.nanmin(y_map), np.nanmax(y_map))
+    xs_original, ys_original = np.arange(nx), np.arange(ny)
+    _, _, xs_pchip = smooth_grid(nx, xlim, oversample_by, max_size, limit_padding)
+    _, _, ys_pchip = smooth_grid(ny, ylim, oversample_by, max_size, limit_padding)
+    pchip_img = pchip_grid_interp2d(xs_original, ys_original, img, xs_pchip, ys_pchip, xlim, ylim, limit_padding)
+    interpolator = scipy.interpolate.RegularGridInterpolator(
+        (ys_pchip, xs_pchip), pchip_img, bounds_error=False, fill_value=np.nan, method='linear')
+    a_vals, b_vals, x_vals, y_vals = [], [], [], []
+    for a in range(projected.shape[0]):
+        for b in range(projected.shape[1]):
+            x = x_map[a, b]
+            if math.isnan(x):
+                continue
+            y = y_map[a, b]
+            if propagate_nan and should_propagate_nan_to_map(x, y, nans, nx, ny):
+                continue
+            a_vals.append(a)
+            b_vals.append(b)
+            x_vals.append(x)
+            y_vals.append(y)
+    if a_vals:
+        projected[a_vals, b_vals] = interpolator((y_vals, x_vals))
     return projected
 
 

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = [
     'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt', 'pm_proj_inverse', 'pm_gather',
     'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
+    'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
 ]
 
 
@@ -86,9 +87,15 @@ def load_library() -> ctypes.CDLL:
     lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
     lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
     lib.pm_math_probe.argtypes = [c_i, c_p, c_p, c_i64, c_p, c_p]
+    lib.pm_nan_minmax.argtypes = [c_p, c_i64, c_p, c_p]
+    lib.pm_pchip_work_bytes.restype = c_i64
+    lib.pm_pchip_work_bytes.argtypes = [c_i, c_i, c_i, c_i]
+    lib.pm_pchip_resample.argtypes = [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+    lib.pm_gather_grid_linear.argtypes = [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i64,
+                                          c_u32, c_p, c_p]
     for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
-               'pm_math_probe'):
+               'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
     if lib.pm_abi_version() != 3:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
@@ -306,4 +313,59 @@ def math_probe(kind: int, a_dev, b_dev=None):
     rc = lib.pm_math_probe(kind, a_dev.data_ptr(), b_dev.data_ptr() if b_dev is not None else None,
                            a_dev.numel(), out.data_ptr(), _stream_ptr(torch))
     _check(rc, 'pm_math_probe')
+    return out
+
+
+def nan_minmax(x_dev):
+    """(np.nanmin, np.nanmax) of a CUDA tensor, NaN if it holds no finite value."""
+    torch = _torch()
+    lib = load_library()
+    out = torch.empty(2, dtype=torch.float64, device=x_dev.device)
+    _check(lib.pm_nan_minmax(x_dev.data_ptr(), x_dev.numel(), out.data_ptr(), _stream_ptr(torch)), 'pm_nan_minmax')
+    lo, hi = out.cpu().tolist()
+    return lo, hi
+
+
+def smooth_grid(n: int, limits, oversample_by: int, max_size: int, limit_padding: float = 5.0):
+    """get_xy_pchip of BodyXY._do_smooth_interpolation (body_xy.py:1723-1741): (first original
+    index, last original index, number of points of np.linspace(first, last, num))."""
+    import math
+
+    first = max(int(math.ceil(limits[0] - limit_padding)), 0)
+    last = min(int(math.floor(limits[1] + limit_padding)), n - 1)
+    old_size = last - first + 1
+    if old_size <= 0:
+        return None
+    for oversample_to_use in range(int(oversample_by), 1, -1):
+        new_size = old_size * oversample_to_use - (oversample_to_use - 1)
+        if new_size <= max_size:
+            return first, last, new_size
+    return first, last, old_size
+
+
+def map_smooth(cube_dev, xmap_dev, ymap_dev, *, propagate_nan: bool = True, oversample_by: int = 5,
+               max_oversampled_img_size: int = 10_000, out=None):
+    """BodyXY._do_smooth_interpolation for every plane of a CUDA cube (nl, ny, nx)."""
+    torch = _torch()
+    lib = load_library()
+    nl, ny, nx = cube_dev.shape
+    n_cells = xmap_dev.numel()
+    if out is None:
+        out = torch.empty((nl,) + tuple(xmap_dev.shape), dtype=torch.float64, device=cube_dev.device)
+    xlim, ylim = nan_minmax(xmap_dev), nan_minmax(ymap_dev)
+    gx = None if xlim[0] != xlim[0] else smooth_grid(nx, xlim, oversample_by, max_oversampled_img_size)
+    gy = None if ylim[0] != ylim[0] else smooth_grid(ny, ylim, oversample_by, max_oversampled_img_size)
+    if gx is None or gy is None or gx[2] < 2 or gy[2] < 2:
+        out.fill_(float('nan'))   # nothing of the map falls on the image
+        return out
+    (x0, x1, n_xs), (y0, y1, n_ys) = gx, gy
+    fine = torch.empty((nl, n_ys, n_xs), dtype=torch.float64, device=cube_dev.device)
+    work = torch.empty((max(int(lib.pm_pchip_work_bytes(nl, ny, nx, n_xs)), 256),), dtype=torch.uint8,
+                       device=cube_dev.device)
+    _check(lib.pm_pchip_resample(cube_dev.data_ptr(), nl, ny, nx, x0, x1, y0, y1, n_xs, n_ys, fine.data_ptr(),
+                                 work.data_ptr(), _stream_ptr(torch)), 'pm_pchip_resample')
+    flags = FLAG_PROPAGATE_NAN if propagate_nan else 0
+    _check(lib.pm_gather_grid_linear(fine.data_ptr(), nl, n_ys, n_xs, x0, x1, y0, y1, cube_dev.data_ptr(), ny, nx,
+                                     xmap_dev.data_ptr(), ymap_dev.data_ptr(), n_cells, flags, out.data_ptr(),
+                                     _stream_ptr(torch)), 'pm_gather_grid_linear')
     return out

@@ -647,12 +647,15 @@ class BodyXY:
         out = self.map_img_device(img, interpolation=interpolation,
                                   spline_smoothing=spline_smoothing,
                                   propagate_nan=propagate_nan, warn_nan=warn_nan,
+                                  smooth_oversample_by=smooth_oversample_by,
+                                  smooth_max_oversampled_img_size=smooth_max_oversampled_img_size,
                                   **map_kwargs)
         res = out.cpu().numpy()
         return res[0] if np.ndim(img) == 2 else res
 
     def map_img_device(self, img, *, interpolation='linear', spline_smoothing: float = 0,
                        propagate_nan: bool = True, warn_nan: bool = False, out=None,
+                       smooth_oversample_by: int = 5, smooth_max_oversampled_img_size: int = 10_000,
                        **map_kwargs):
         """Same as :func:`map_img` but takes/returns device tensors shaped (n, ...)."""
         torch = L._torch()
@@ -674,10 +677,17 @@ class BodyXY:
         xmap, ymap = xy[0], xy[1]
         if mode == L.INTERP_NEAREST:
             return L.gather(cube, xmap, ymap, mode, out=out)
+        if mode == INTERP_SMOOTH:   # body_xy.py:1616-1629
+            return L.map_smooth(cube, xmap, ymap, propagate_nan=propagate_nan,
+                                oversample_by=smooth_oversample_by,
+                                max_oversampled_img_size=smooth_max_oversampled_img_size, out=out)
         if warn_nan and bool(torch.isfinite(cube).logical_not().any()):
             print('Warning, image contains NaN values which will be corrected')
         spline = L.spline_prepare(cube, mode)
         return L.gather(spline, xmap, ymap, mode, propagate_nan=propagate_nan, out=out)
+
+
+INTERP_SMOOTH = -1   # host-side marker: PCHIP oversampling + linear (its own entry points)
 
 
 def _interpolation_mode(interpolation, spline_smoothing) -> int:
@@ -714,8 +724,7 @@ def _interpolation_mode(interpolation, spline_smoothing) -> int:
             f'spline degree {interpolation} is not accelerated (SURVEY.md 8(f)); '
             "accelerated: 'nearest', 'linear' (1), 'quadratic' (2), 'cubic' (3)")
     if interpolation == 'smooth':
-        raise NotImplementedError("interpolation='smooth' is on the \"next\" list "
-                                  '(SURVEY.md 8(f))')
+        return INTERP_SMOOTH
     raise ValueError(f'Unknown interpolation method {interpolation!r}')
 
 

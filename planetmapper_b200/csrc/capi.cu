@@ -158,6 +158,39 @@ int pm_spline_prepare(const double *cube, int n_planes, int ny, int nx, int degr
                                        (cudaStream_t)stream));
 }
 
+int pm_nan_minmax(const double *x, int64_t n, double *out2, void *stream) {
+    if (!x || !out2 || n <= 0) return PM_ERR_BAD_ARG;
+    return check(launch_nan_minmax(x, n, out2, (cudaStream_t)stream));
+}
+
+int64_t pm_pchip_work_bytes(int n_planes, int ny, int nx, int n_xs) {
+    if (n_planes < 0 || ny <= 0 || nx <= 0 || n_xs <= 0) return PM_ERR_BAD_ARG;
+    return pchip_work_bytes(n_planes, ny, nx, n_xs);
+}
+
+int pm_pchip_resample(const double *cube, int n_planes, int ny, int nx, int x_first, int x_last, int y_first,
+                      int y_last, int n_xs, int n_ys, double *fine, void *work, void *stream) {
+    if (!cube || !fine || !work || n_planes < 0 || ny <= 0 || nx <= 0 || n_xs < 1 || n_ys < 1 || x_first < 0 ||
+        x_last >= nx || x_first > x_last || y_first < 0 || y_last >= ny || y_first > y_last)
+        return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_pchip_resample(cube, n_planes, ny, nx, x_first, x_last, y_first, y_last, (double)x_first,
+                                       (double)x_last, n_xs, (double)y_first, (double)y_last, n_ys, fine, work, sms,
+                                       (cudaStream_t)stream));
+}
+
+int pm_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, int x_first, int x_last, int y_first,
+                          int y_last, const double *cube, int ny, int nx, const double *xmap, const double *ymap,
+                          int64_t n_cells, uint32_t flags, double *out, void *stream) {
+    if (!fine || !cube || !xmap || !ymap || !out || n_planes < 0 || n_ys < 1 || n_xs < 1 || ny <= 0 || nx <= 0 ||
+        n_cells < 0)
+        return PM_ERR_BAD_ARG;
+    return check(launch_gather_grid_linear(fine, n_planes, n_ys, n_xs, (double)x_first, (double)x_last, (double)y_first,
+                                           (double)y_last, cube, ny, nx, xmap, ymap, n_cells, flags, out,
+                                           (cudaStream_t)stream));
+}
+
 int pm_math_probe(int kind, const double *a, const double *b, int64_t n, double *out, void *stream) {
     if (!a || !out || n < 0 || kind < 0 || kind > 11) return PM_ERR_BAD_ARG;
     if ((kind == 5 || kind == 7 || kind == 10 || kind == 11) && !b) return PM_ERR_BAD_ARG;

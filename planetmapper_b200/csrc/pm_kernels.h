@@ -40,4 +40,16 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
                                   uint32_t *nanbits, uint32_t *plane_bits, void *work, int sm_count,
                                   cudaStream_t st);
 
+
+// map_img(interpolation='smooth') (smooth_kernels.cu)
+cudaError_t launch_nan_minmax(const double *x, int64_t n, double *out2, cudaStream_t st);
+int64_t pchip_work_bytes(int n_planes, int ny, int nx, int n_xs);
+cudaError_t launch_pchip_resample(const double *cube, int n_planes, int ny, int nx, int i0, int i1, int j0, int j1,
+                                  double x_start, double x_stop, int n_xs, double y_start, double y_stop, int n_ys,
+                                  double *fine, void *work, int sm_count, cudaStream_t st);
+cudaError_t launch_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, double x_start,
+                                      double x_stop, double y_start, double y_stop, const double *cube, int ny, int nx,
+                                      const double *xmap, const double *ymap, int64_t n_cells, uint32_t flags,
+                                      double *out, cudaStream_t st);
+
 }  // namespace pm

@@ -45,17 +45,21 @@ class Observation(BodyXY):
         """Map every plane of ``data`` (copy returned; observation.py:826-874)."""
         return np.array(self._get_mapped_data(
             interpolation, spline_smoothing=spline_smoothing, propagate_nan=propagate_nan,
-            warn_nan=warn_nan, **map_kwargs), copy=True)
+            warn_nan=warn_nan, smooth_oversample_by=smooth_oversample_by,
+            smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs), copy=True)
 
     def _get_mapped_data(self, interpolation, *, spline_smoothing, propagate_nan, warn_nan,
+                         smooth_oversample_by=5, smooth_max_oversampled_img_size=10_000,
                          **map_kwargs) -> np.ndarray:
         # alt-keyed clearable cache (observation.py:876-890)
-        key = ('mapped_data', repr(interpolation), spline_smoothing, propagate_nan,
-               self._map_key(map_kwargs), self._alt_adjustment)
+        key = ('mapped_data', repr(interpolation), spline_smoothing, propagate_nan, smooth_oversample_by,
+               smooth_max_oversampled_img_size, self._map_key(map_kwargs), self._alt_adjustment)
         if key not in self._cache:
             out = self.map_img_device(self._get_data_device(), interpolation=interpolation,
                                       spline_smoothing=spline_smoothing,
                                       propagate_nan=propagate_nan, warn_nan=warn_nan,
+                                      smooth_oversample_by=smooth_oversample_by,
+                                      smooth_max_oversampled_img_size=smooth_max_oversampled_img_size,
                                       **map_kwargs)
             self._cache[key] = out.cpu().numpy()
         return self._cache[key]

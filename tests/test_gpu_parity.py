@@ -236,6 +236,34 @@ def test_gather_vs_scipy_oracle(L, oracle, bc_hst, nx, ny):
             assert rel <= 1e-10, f'{name} propagate={prop}: rel {rel:.3e}'
 
 
+@pytest.mark.parametrize('nx,ny,step,oversample,max_size', [(12, 9, 4.0, 5, 10_000), (64, 64, 4.0, 5, 10_000),
+                                                             (64, 64, 2.0, 3, 150), (40, 30, 5.0, 5, 20)])
+def test_smooth_vs_scipy_oracle(L, bc_hst, nx, ny, step, oversample, max_size):
+    """map_img(interpolation='smooth'): PCHIP oversampling + linear against the real scipy
+    PchipInterpolator / RegularGridInterpolator arranged as the reference arranges them."""
+    from oracle import map_img_oracle as MO
+
+    fr = _img_case(bc_hst, nx, ny, (nx - 1) / 2 + 0.3, (ny - 1) / 2 - 0.2, 0.4 * min(nx, ny), 33.0)
+    lo, la = _grid(step)
+    xy = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la),
+                          L.mask_from_names(['PIXEL-X', 'PIXEL-Y']))
+    xm, ym = xy[0].cpu().numpy(), xy[1].cpu().numpy()
+    rng = np.random.default_rng(11)
+    cube = _cube(rng, 9, ny, nx)
+    cube[8, :, nx // 2] = np.nan                      # a NaN column splits every row's PCHIP
+    cd = L.to_device(cube)
+    for prop in (True, False):
+        got = L.map_smooth(cd, xy[0], xy[1], propagate_nan=prop, oversample_by=oversample,
+                           max_oversampled_img_size=max_size).cpu().numpy()
+        ref = MO.map_img(cube, xm, ym, 'smooth', propagate_nan=prop, smooth_oversample_by=oversample,
+                         smooth_max_oversampled_img_size=max_size)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (prop, int((np.isnan(got) != np.isnan(ref)).sum()))
+        ok = np.isfinite(ref)
+        assert ok.sum() > 100
+        rel = np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1.0))
+        assert rel <= 1e-10, f'smooth propagate={prop}: rel {rel:.3e}'
+
+
 def test_nan_repair_matches_reference_recipe(L, bc_hst):
     from oracle import map_img_oracle as MO
 

@@ -76,6 +76,7 @@ MAP_FILES = {
     'map_rectangular-linear.fits': (('rectangular', 30), 0.0, 'linear'),
     'map_rectangular-cubic.fits': (('rectangular', 30), 0.0, 'cubic'),
     'map_rectangular-quadratic.fits': (('rectangular', 30), 0.0, 'quadratic'),
+    'map_rectangular-smooth.fits': (('rectangular', 30), 0.0, 'smooth'),
     'map_orthographic-1.fits': (('orthographic', 0, 0, 10), 0.0, 'linear'),
     'map_orthographic-2.fits': (('orthographic', 0, 90, 5), 0.0, 'linear'),
     'map_orthographic-3.fits': (('orthographic', -42, -21.3, 4), 0.0, 'linear'),
