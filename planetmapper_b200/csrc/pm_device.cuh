@@ -239,7 +239,7 @@ PM_HD double vsep(V3 a, V3 b) { return fast_atan2_ypos(norm(cross(a, b)), dot(a,
 // spice.surfpt (inside sincpt, body.py:1010): nearest ray / ellipsoid intersection,
 // perpendicular-projection form.  o, u in the body frame.  `margin2` receives
 // |p_perp|^2 (scaled space): < 1 hit, > 1 miss.
-PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p) {
+PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr) {
     // scaled space (unit sphere); the direction x is deliberately NOT normalised: the
     // three dot products are independent and a single reciprocal serves both the
     // projection and the half-chord
@@ -251,6 +251,7 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p) {
     const V3 pp = axpy(-(yx * ixx), x, y);  // component of y perpendicular to the ray
     const double pm2 = dot(pp, pp);
     if (!(pm2 < INFINITY)) return false;
+    if (cos2) *cos2 = 1.0 - pm2;  // squared half-chord in the unit-sphere space: -> 0 at tangency
     V3 q;
     if (ym2 > 1.0) {
         if (pm2 > 1.0) return false;
@@ -301,21 +302,35 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const double dt1 = (f.et - lt1) - f.t_ref;
     const Rot r1 = make_rot(fs, dt1);
     const V3 o2 = spin_fwd(fs, r1, -target_pos_b(fs, dt1));
-    if (!surfpt(fs, o2, spin_fwd(fs, r1, u0), p2)) return false;
+    double cos2;
+    if (!surfpt(fs, o2, spin_fwd(fs, r1, u0), p2, &cos2)) return false;
     const double lt2 = norm(p2 - o2) * fs.inv_c;
 
     // epochs as CSPICE forms them: et - lt rounded to a double (granularity ulp(et) ~ 3e-8 s,
     // i.e. ~1e-6 km of target motion), so the secant runs between the QUANTISED epoch offsets
     // dt1 (pass 2) and dt (pass 3); their difference is exact
-    const double dt = (f.et - lt2) - f.t_ref;
-    const Rot r = make_rot(fs, dt);
-    const V3 Pb = target_pos_b(fs, dt);
+    double dt = (f.et - lt2) - f.t_ref;
+    Rot r = make_rot(fs, dt);
+    V3 Pb = target_pos_b(fs, dt);
     V3 p;
-    if (fabs(dt1) > 1.0e-6) {
+    if (fabs(dt1) > 1.0e-6 && cos2 > 1.0e-3) {
         p = axpy(fast_div_lite(dt - dt1, dt1), p2 - p1, p2);
     } else {
-        // passes 1 and 2 (almost) coincide in epoch: no secant, solve the third intercept
-        if (!surfpt(fs, spin_fwd(fs, r, -Pb), spin_fwd(fs, r, u0), p)) return false;
+        // Passes 1 and 2 (almost) coincide in epoch, or the ray grazes the limb (emission > ~88 deg,
+        // ~0.1 % of the disc pixels).  There the light time depends on the epoch through
+        // V_lateral tan(emission) / c, which is no longer tiny: iterate full intercepts until the
+        // FP64 epoch et - lt stops changing, exactly like CSPICE's loop (at most 10 passes).
+        double t = f.et - lt2;
+        for (int it = 0; it < 8; it++) {
+            if (!surfpt(fs, spin_fwd(fs, r, -Pb), spin_fwd(fs, r, u0), p)) return false;
+            const double t_new = f.et - norm(p - spin_fwd(fs, r, -Pb)) * fs.inv_c;
+            const bool moved = fabs(t_new - t) > 1.0e-17 * fabs(t_new);
+            if (!moved) break;
+            t = t_new;
+            dt = t - f.t_ref;
+            r = make_rot(fs, dt);
+            Pb = target_pos_b(fs, dt);
+        }
     }
     const V3 E = p - spin_fwd(fs, r, -Pb);
     const double L = norm(E);

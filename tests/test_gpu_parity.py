@@ -326,6 +326,49 @@ def test_full_size_2048_properties(L, bc_hst):
     assert (lst - torch.round(lst)).abs().max().item() < 1e-6
 
 
+def test_full_size_2048_vs_oracle(L, oracle, bc_hst):
+    """C2 at full size against the oracle itself (4.19 Mpix x 12 planes; the C oracle needs
+    ~0.2 s on 16 threads), with the same bars as the small cases."""
+    sz = 2048
+    fr = _img_case(bc_hst, sz, sz, (sz - 1) / 2, (sz - 1) / 2, 0.9 * (sz - 1) / 2, 0.0)
+    names = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'INCIDENCE', 'EMISSION', 'PHASE',
+             'AZIMUTH', 'LOCAL-SOLAR-TIME', 'DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER']
+    mask = L.mask_from_names(names + ['KM-X', 'KM-Y'])   # KM-X / KM-Y feed the comparison helper only
+    ref_k, margin = oracle.backplanes_img(fr, sz, sz, mask, with_margin=True)
+    got_k = L.backplanes_img(L.to_device(fr[None]), sz, sz, mask).cpu().numpy()[0]
+    ids = sorted(PID[n] for n in names + ['KM-X', 'KM-Y'])
+    ref = np.full((len(PLANE_NAMES), sz, sz), np.nan)
+    got = np.full((len(PLANE_NAMES), sz, sz), np.nan)
+    for slot, pid in enumerate(ids):
+        ref[pid], got[pid] = ref_k[slot], got_k[slot]
+    report, n_graz, n_mis = check_img_planes(got, ref, margin, fr, 'C2-2048')
+    on = np.isfinite(ref[PID['EMISSION']])
+    assert 2.4e6 < on.sum() < 2.6e6
+    print('C2 full size: grazing px excluded', n_graz, 'mask flips there', n_mis,
+          {k: round(float(v), 3) for k, v in report.items()})
+
+
+def test_full_size_saturn_4096_rings_vs_oracle(L, oracle):
+    """C3 at full size: Saturn 4096 x 4096, ring planes + DISTANCE against the oracle."""
+    import planetmapper_b200 as pm
+
+    bc = F.build_body_constants(pm.get_default_provider(), 'Saturn', '2004-12-30T12:00:00', 'EARTH')
+    sz = 4096
+    fr = _img_case(bc, sz, sz, (sz - 1) / 2, (sz - 1) / 2, 800.0, 0.0)
+    names = ['RING-RADIUS', 'RING-LON-GRAPHIC', 'RING-DISTANCE', 'DISTANCE', 'EMISSION', 'LAT-CENTRIC', 'KM-X', 'KM-Y']
+    mask = L.mask_from_names(names)
+    ref_k, margin = oracle.backplanes_img(fr, sz, sz, mask, with_margin=True)
+    got_k = L.backplanes_img(L.to_device(fr[None]), sz, sz, mask).cpu().numpy()[0]
+    ids = sorted(PID[n] for n in names)
+    ref = np.full((len(PLANE_NAMES), sz, sz), np.nan)
+    got = np.full((len(PLANE_NAMES), sz, sz), np.nan)
+    for slot, pid in enumerate(ids):
+        ref[pid], got[pid] = ref_k[slot], got_k[slot]
+    check_img_planes(got, ref, margin, fr, 'C3-4096')
+    ring = got[PID['RING-RADIUS']]
+    assert np.isfinite(ring).sum() > 1.5e6 and np.nanmax(ring) > 136780   # the A ring is in frame
+
+
 def test_full_grid_gather_properties(L, bc_hst):
     """C4 geometry: 64 x 64 cube -> 0.1 deg grid (6.48 M cells); a few planes."""
     import torch
