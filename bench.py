@@ -339,6 +339,58 @@ def bench_saturn_rings(L, torch, pm):
     return res
 
 
+def bench_save_observation(L, torch, pm, bc, sz=2048):
+    """Observation.save_observation of a 2048 x 2048 frame, all 26 backplanes
+    + the image itself = 27 float64 HDUs (906 MB file).  Reports the three stages separately:
+    the fused backplane launch, the big-endian staging launch (HBM-bound: 16 B per element) and
+    the single device->host copy of the file image, then the whole call including the disk write."""
+    import tempfile
+    import time
+
+    from planetmapper_b200 import fits_stage as FS
+
+    img = np.random.default_rng(3).normal(1.0, 0.1, (1, sz, sz))
+    obs = pm.Observation(data=img, constants=bc)
+    data_dev = obs._get_data_device()
+    have, planes = obs.get_backplanes_img_device(L.ALL_PLANES)
+    hdus = [FS.ImageHDU(data_dev)] + [FS.ImageHDU(planes[i], name=L.PLANE_NAMES[i]) for i in range(planes.shape[0])]
+    headers, hoff, doff, size = FS.file_layout(hdus)
+    arrays = [h.data for h in hdus]
+    image = torch.empty(size, dtype=torch.uint8, device='cuda')
+    host = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+
+    def timed(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    stage_ms = timed(lambda: L.fits_stage(arrays, doff, image))
+    copy_ms = timed(lambda: host.copy_(image, non_blocking=True), reps=5)
+    fd = obs._frame_dev().reshape(1, -1)
+    out = torch.empty((1, L.N_PLANES, sz, sz), dtype=torch.float64, device='cuda')
+    planes_ms = timed(lambda: L.backplanes_img(fd, sz, sz, L.ALL_PLANES, out=out))
+    n_elems = sum(a.numel() for a in arrays)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, 'nav.fits')
+        obs.save_observation(path, print_info=False)   # warm (page cache, pinned allocator)
+        obs._clear_cache()
+        t0 = time.perf_counter()
+        obs.save_observation(path, print_info=False)
+        call_s = time.perf_counter() - t0
+        file_bytes = os.path.getsize(path)
+    return {'workload': f'save_observation: {sz}x{sz} frame, 27 float64 HDUs (image + 26 backplanes)',
+            'file_bytes': file_bytes, 'backplanes_26_ms': planes_ms, 'stage_ms': stage_ms,
+            'stage_gb_per_s': 16.0 * n_elems / stage_ms / 1e6, 'd2h_ms': copy_ms,
+            'd2h_gb_per_s': size / copy_ms / 1e6, 'launches': 2,
+            'whole_call_s_incl_disk_write': call_s}
+
+
 def bench_time_series(L, torch, pm, rank, world, n_frames=256, batch=32):
     """C5 (reduced): a time series of 1024 x 1024 frames 60 s apart ending at the fixture
     epoch, sharded by frame across ranks, 12-plane stack per frame in batched launches plus a
@@ -530,6 +582,7 @@ def main():
             ts['backplanes_mpix_per_s_all_ranks'] = 256 * 1024 * 1024 / t_all / 1e3
             result['time_series'] = ts
             result['saturn_rings'] = bench_saturn_rings(L, torch, pm)
+            result['save_observation'] = bench_save_observation(L, torch, pm, bc)
     if rank == 0:
         if not args.skip_cpu and world == 1:  # the CPU baseline is an N = 1 measurement
             mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)

@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 3
+#define PM_ABI_VERSION 4
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -232,6 +232,26 @@ int pm_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, 
  * denominator: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the kernel time in ms through *ms_host (synchronises). */
 int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
+
+/*
+ * FITS staging for Observation.save_observation (observation.py:1185-1303) and
+ * save_mapped_observation (:1315-1474).  Both append one `fits.ImageHDU(data=float64 array)`
+ * per backplane (EXTNAME = backplane name, :1281-1284 / :1434-1441) after the primary HDU and
+ * let astropy (third party, astropy.io.fits) write them: each data unit is the array as
+ * big-endian IEEE-754 doubles zero-padded to a multiple of 2880 bytes.
+ * pm_fits_stage converts n_units device arrays into their data units inside ONE
+ * device-resident image of the file, so the file leaves the device in a single copy:
+ *   src[u]         device pointer to the n_elems[u] doubles of unit u (native byte order)
+ *   dst_offset[u]  byte offset of unit u's data unit inside `image` (a multiple of 8; FITS
+ *                  layouts make it a multiple of 2880)
+ *   image          device buffer holding the file; header blocks are the caller's (host-built)
+ * src, n_elems and dst_offset are HOST arrays of n_units entries (read before returning).
+ * pm_fits_data_unit_bytes(n) = the padded size of an n-element float64 data unit.
+ */
+#define PM_FITS_MAX_UNITS 32 /* units per launch; more are split over several launches */
+int64_t pm_fits_data_unit_bytes(int64_t n_elems);
+int pm_fits_stage(const double *const *src, const int64_t *n_elems, const int64_t *dst_offset,
+                  int n_units, uint8_t *image, void *stream);
 
 /* Diagnostic: evaluates one of the library's own FP64 primitives (the MUFU-seeded
  * reciprocal / rsqrt / sqrt / division and the polynomial sin / cos / atan2 / acos

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpm_b200.so')
+LIB_PATH = os.environ.get('PM_B200_LIBRARY') or os.path.join(_HERE, 'libpm_b200.so')
 
 N_PLANES = 26
 ALL_PLANES = (1 << N_PLANES) - 1
@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
+    'pm_fits_data_unit_bytes', 'pm_fits_stage',
 ]
 
 
@@ -93,11 +94,15 @@ def load_library() -> ctypes.CDLL:
     lib.pm_pchip_resample.argtypes = [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     lib.pm_gather_grid_linear.argtypes = [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i64,
                                           c_u32, c_p, c_p]
+    lib.pm_fits_data_unit_bytes.restype = c_i64
+    lib.pm_fits_data_unit_bytes.argtypes = [c_i64]
+    lib.pm_fits_stage.argtypes = [c_p, c_p, c_p, c_i, c_p, c_p]
+    lib.pm_fits_stage.restype = c_i
     for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 3:
+    if lib.pm_abi_version() != 4:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -324,6 +329,26 @@ def nan_minmax(x_dev):
     _check(lib.pm_nan_minmax(x_dev.data_ptr(), x_dev.numel(), out.data_ptr(), _stream_ptr(torch)), 'pm_nan_minmax')
     lo, hi = out.cpu().tolist()
     return lo, hi
+
+
+def fits_stage(arrays, offsets, image) -> None:
+    """Byte-swap the float64 CUDA tensors ``arrays`` into their FITS data units at byte
+    ``offsets`` of the uint8 CUDA tensor ``image`` (zero-padded to 2880-byte blocks)."""
+    torch = _torch()
+    lib = load_library()
+    n = len(arrays)
+    if n != len(offsets):
+        raise ValueError('one offset per array')
+    for a in arrays:
+        if a.dtype != torch.float64 or not a.is_contiguous() or a.device != image.device:
+            raise ValueError('FITS staging needs contiguous float64 tensors on the image device')
+    src = (ctypes.c_void_p * n)(*[a.data_ptr() if a.numel() else None for a in arrays])
+    cnt = (ctypes.c_int64 * n)(*[a.numel() for a in arrays])
+    off = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+    for a, o in zip(arrays, offsets):
+        if o + lib.pm_fits_data_unit_bytes(a.numel()) > image.numel():
+            raise ValueError('data unit does not fit in the file image')
+    _check(lib.pm_fits_stage(src, cnt, off, n, image.data_ptr(), _stream_ptr(torch)), 'pm_fits_stage')
 
 
 def smooth_grid(n: int, limits, oversample_by: int, max_size: int, limit_padding: float = 5.0):

@@ -168,6 +168,7 @@ class BodyXY:
         self._cache: dict = {}         # cleared when a disc parameter changes
         self._stable_cache: dict = {}  # never cleared
         self.backplanes: dict[str, Backplane] = {}
+        self._builtin_getters: dict[str, tuple] = {}
         self._register_default_backplanes()
         # body_xy.py:226-232: centre the disc if an image size was given
         if self._nx > 0 and self._ny > 0:
@@ -178,7 +179,21 @@ class BodyXY:
     # ---- attributes mirrored from Body (body.py:347-436) ---------------------------
     target = property(lambda self: self._bc.target)
     observer = property(lambda self: self._bc.observer)
-    utc = property(lambda self: self._bc.utc)
+    @property
+    def dtm(self):
+        """Observation time as a timezone-aware datetime (base.py:815-822)."""
+        import datetime
+
+        text = str(self._bc.utc).strip().replace(' ', 'T').rstrip('Zz')
+        date, _, time = text.partition('T')
+        hms = (time.split(':') + ['0', '0', '0'])[:3] if time else ['0', '0', '0']
+        sec = float(hms[2] or 0)
+        y, mo, d = (int(v) for v in date.split('-'))
+        return (datetime.datetime(y, mo, d, int(hms[0] or 0), int(hms[1] or 0), tzinfo=datetime.timezone.utc)
+                + datetime.timedelta(seconds=sec))
+
+    # 'YYYY-MM-DDTHH:MM:SS.ffffff', the reference's standardised form of the input time
+    utc = property(lambda self: self.dtm.strftime('%Y-%m-%dT%H:%M:%S.%f'))
     et = property(lambda self: self._bc.et)
     target_body_id = property(lambda self: self._bc.target_id)
     radii = property(lambda self: self._bc.radii + self._alt_adjustment)
@@ -196,6 +211,8 @@ class BodyXY:
     subpoint_distance = property(lambda self: self._bc.sub_dist)
     subpoint_lon = property(lambda self: self._bc.subpoint_lon)
     subpoint_lat = property(lambda self: self._bc.subpoint_lat)
+    subsol_lon = property(lambda self: self._bc.subsol_lon)
+    subsol_lat = property(lambda self: self._bc.subsol_lat)
 
     def north_pole_angle(self) -> float:
         return self._bc.north_pole_angle
@@ -471,13 +488,22 @@ class BodyXY:
         return '\n'.join(f'{bp.name}: {bp.description}' for bp in self.backplanes.values())
 
     def _register_default_backplanes(self) -> None:
-        ew = {'W': 'west', 'E': 'east'}[self.positive_longitude_direction]
+        ew = self.positive_longitude_direction  # body_xy.py:4201-4203
         for pid, (name, desc, stem) in enumerate(_PLANE_DESCRIPTIONS):
             get_img = self._make_img_getter(pid)
             get_map = self._make_map_getter(pid)
             setattr(self, f'get_{stem}_img', get_img)
             setattr(self, f'get_{stem}_map', get_map)
             self.register_backplane(name, desc.format(ew=ew), get_img, get_map)
+            self._builtin_getters[name] = (get_img, get_map)
+
+    def _is_builtin_backplane(self, name: str, mapped: bool) -> bool:
+        """True while ``backplanes[name]`` is still the kernel-backed default getter."""
+        getters = self._builtin_getters.get(name)
+        bp = self.backplanes.get(name)
+        if getters is None or bp is None:
+            return False
+        return (bp.get_map is getters[1]) if mapped else (bp.get_img is getters[0])
 
     def _make_img_getter(self, pid: int):
         def get_img() -> np.ndarray:

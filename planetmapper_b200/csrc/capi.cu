@@ -191,6 +191,23 @@ int pm_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, 
                                            (cudaStream_t)stream));
 }
 
+int64_t pm_fits_data_unit_bytes(int64_t n_elems) {
+    if (n_elems < 0) return PM_ERR_BAD_ARG;
+    return (n_elems * 8 + 2879) / 2880 * 2880;
+}
+
+int pm_fits_stage(const double *const *src, const int64_t *n_elems, const int64_t *dst_offset, int n_units,
+                  uint8_t *image, void *stream) {
+    if (n_units < 0 || (n_units > 0 && (!src || !n_elems || !dst_offset || !image))) return PM_ERR_BAD_ARG;
+    for (int u = 0; u < n_units; u++)
+        if (n_elems[u] < 0 || dst_offset[u] < 0 || (dst_offset[u] & 7) || (n_elems[u] > 0 && !src[u]))
+            return PM_ERR_BAD_ARG;
+    if (n_units == 0) return PM_OK;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_fits_stage(src, n_elems, dst_offset, n_units, image, sms, (cudaStream_t)stream));
+}
+
 int pm_math_probe(int kind, const double *a, const double *b, int64_t n, double *out, void *stream) {
     if (!a || !out || n < 0 || kind < 0 || kind > 11) return PM_ERR_BAD_ARG;
     if ((kind == 5 || kind == 7 || kind == 10 || kind == 11) && !b) return PM_ERR_BAD_ARG;

@@ -292,6 +292,9 @@ struct Intercept {
 //     ~ V^2 r kappa / (2 c^2 cos(emission)) ~ 1e-8 km / cos(emission), an order below
 //     ulp(|P0|) with the same limb scaling as the intercept's own conditioning.  The
 //     observer position, the range and the light time are evaluated exactly at e_2.
+//   Grazing rays (cos^2 of the scaled-space emission <= 1e-3, i.e. emission > ~88 deg) are the
+//   exception: there d(lt)/d(epoch) = V_lateral tan(emission) / c reaches ~0.1 and three passes
+//   are not converged, so those pixels run CSPICE's loop as written (until et - lt is stable).
 PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
     V3 p1, p2;

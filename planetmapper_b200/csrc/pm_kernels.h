@@ -52,4 +52,8 @@ cudaError_t launch_gather_grid_linear(const double *fine, int n_planes, int n_ys
                                       const double *xmap, const double *ymap, int64_t n_cells, uint32_t flags,
                                       double *out, cudaStream_t st);
 
+// FITS data-unit staging (stage_kernels.cu)
+cudaError_t launch_fits_stage(const double *const *src, const int64_t *n_elems, const int64_t *dst_offset, int n_units,
+                              uint8_t *image, int sm_count, cudaStream_t st);
+
 }  // namespace pm

@@ -185,6 +185,8 @@ class BodyConstants:
     north_pole_angle: float
     subpoint_lon: float = math.nan
     subpoint_lat: float = math.nan
+    subsol_lon: float = math.nan
+    subsol_lat: float = math.nan
     extra: dict = field(default_factory=dict)
 
     @property
@@ -403,6 +405,28 @@ def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
     sp_lat = math.degrees(math.atan2(sub_t[2] / ((1 - flat) ** 2),
                                      math.hypot(sub_t[0], sub_t[1])))
 
+    # sub-solar point for metadata: spice.subslr('INTERCEPT/ELLIPSOID', ..., 'CN') at
+    # body.py:559-567 - the point where the Sun -> target-centre line meets the surface, at
+    # the epoch et - lt with lt the light time from that point to the observer
+    ss_lon = ss_lat = math.nan
+    if target_id != 10:
+        lt = lt0
+        for _ in range(12):
+            t = et - lt
+            ts = provider.ssb_state(target_id, t)
+            rmat, _ = provider.orientation(target_id, t)
+            sun_t, _ = _light_time_state(provider, 10, t, ts[:3])
+            s_b = rmat @ (sun_t[:3] - ts[:3])
+            p = _surfpt(s_b, -s_b / np.linalg.norm(s_b), *radii)
+            o = rmat @ (obs_pos - ts[:3])
+            new_lt = float(np.linalg.norm(p - o)) / c
+            done = abs(new_lt - lt) <= 1e-17 * abs(t)
+            lt = new_lt
+            if done:
+                break
+        ss_lon = math.degrees(math.atan2(p[1], p[0]) * lon_sign) % 360.0
+        ss_lat = math.degrees(math.atan2(p[2] / ((1 - flat) ** 2), math.hypot(p[0], p[1])))
+
     return BodyConstants(
         target=provider.bodc2n(target_id), target_id=target_id,
         observer=str(observer).upper(), utc=str(utc), et=et, clight=c, lt0=lt0,
@@ -413,6 +437,7 @@ def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
         target_ra=target_ra, target_dec=target_dec, target_distance=target_distance,
         target_diameter_arcsec=target_diameter_arcsec, km_per_arcsec=km_per_arcsec,
         north_pole_angle=theta, subpoint_lon=sp_lon, subpoint_lat=sp_lat,
+        subsol_lon=ss_lon, subsol_lat=ss_lat,
     )
 
 

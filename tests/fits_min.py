@@ -51,3 +51,31 @@ def read_fits(path):
         pos += (n + 2879) // 2880 * 2880
         hdus.append((hdr, arr))
     return hdus
+
+
+def read_cards(path, max_hdus=None):
+    """Raw 80-character header cards (END excluded) of every HDU, as a list of lists."""
+    data = open(path, 'rb').read()
+    pos = 0
+    out = []
+    while pos < len(data) and (max_hdus is None or len(out) < max_hdus):
+        cards = []
+        done = False
+        while not done:
+            block = data[pos:pos + 2880]
+            pos += 2880
+            for i in range(36):
+                c = block[i * 80:(i + 1) * 80].decode('ascii')
+                if c.startswith('END '):
+                    done = True
+                    break
+                cards.append(c)
+        kv = {c[:8].strip(): c[10:30].strip() for c in cards if c[8:10] == '= '}
+        n = abs(int(kv['BITPIX'])) // 8
+        for i in range(int(kv['NAXIS'])):
+            n *= int(kv['NAXIS%d' % (i + 1)])
+        if int(kv['NAXIS']) == 0:
+            n = 0
+        pos += (n + 2879) // 2880 * 2880
+        out.append(cards)
+    return out

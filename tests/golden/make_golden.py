@@ -15,6 +15,9 @@ tests/golden/ref_outputs.npz
     tests/data/inputs/test.fits, as float64 arrays keyed "<file>/<EXTNAME>".
 tests/golden/ref_headers.json
     The primary-header cards of those files (disc parameters, ET, light time ...).
+tests/golden/ref_cards.json
+    Raw 80-character header cards (primary HDU + first two extensions) and the EXTNAME order
+    of a few of those files: the pin for the FITS staging's card formatting and HDU layout.
 tests/golden/jupiter_hst_2005.json
     BodyConstants for the reference's main fixture, Jupiter from HST at
     2005-01-01T00:00:00 (tests/test_body_xy.py:69-76).  HST's ephemeris is an SPK
@@ -40,7 +43,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-from fits_min import read_fits  # noqa: E402
+from fits_min import read_cards, read_fits  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 from planetmapper_b200 import frame as F  # noqa: E402
 from planetmapper_b200.minispice import MiniSpice, daf  # noqa: E402
@@ -69,6 +72,17 @@ def export_fits():
     arrays['inputs/test.fits/PRIMARY'] = np.asarray(hdus[0][1], dtype=np.float64)
     headers['inputs/test.fits'] = {k: v for k, v in hdus[0][0].items()
                                    if isinstance(v, (int, float, str, bool))}
+    # raw header cards (primary + first two extensions) of the saved files the FITS staging
+    # tests pin their card formatting and HDU structure against
+    cards = {fn: read_cards(os.path.join(out_dir, fn), 3)
+             for fn in ('test_nav.fits', 'map_rectangular-linear.fits', 'map_rectangular-smooth.fits',
+                        'map_rectangular-cubic.fits', 'map_orthographic-1.fits', 'map_azimuthal-1.fits')}
+    extnames = {fn: [h[0].get('EXTNAME', 'PRIMARY') for h in read_fits(os.path.join(out_dir, fn))]
+                for fn in cards}
+    with open(os.path.join(HERE, 'ref_cards.json'), 'w') as f:
+        about = {h[0]['EXTNAME']: h[0]['ABOUT']
+                 for h in read_fits(os.path.join(out_dir, 'test_nav.fits'))[1:]}
+        json.dump({'cards': cards, 'extnames': extnames, 'about': about}, f, indent=0)
     np.savez_compressed(os.path.join(HERE, 'ref_outputs.npz'), **arrays)
     with open(os.path.join(HERE, 'ref_headers.json'), 'w') as f:
         json.dump(headers, f, indent=1, sort_keys=True)
