@@ -278,6 +278,27 @@ struct Intercept {
     double lt;   // L / c
 };
 
+// cos^2 (scaled-space emission) below which sincpt iterates to convergence: emission > ~89.1 deg
+constexpr double kGrazingCos2 = 2.5e-4;
+
+// Slow path of sincpt for grazing rays and for frames whose first two passes coincide in
+// epoch: CSPICE's loop as written - full intercepts until the FP64 epoch et - lt stops
+// changing (at most 10 passes in total).  dt (in: epoch offset of the next pass) and p come
+// back for the converged pass.  Kept out of line so the common path keeps its registers.
+PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p) {
+    const PMFrame &f = fs.f;
+    for (int it = 0; it < 8; it++) {
+        const Rot r = make_rot(fs, dt);
+        const V3 o = spin_fwd(fs, r, -target_pos_b(fs, dt));
+        if (!surfpt(fs, o, spin_fwd(fs, r, u0), p)) return false;
+        const double t = dt + f.t_ref;
+        const double t_new = f.et - norm(p - o) * fs.inv_c;
+        if (!(fabs(t_new - t) > 1.0e-17 * fabs(t_new))) break;
+        dt = t_new - f.t_ref;
+    }
+    return true;
+}
+
 // spice.sincpt(..., 'CN', ..., d) (body.py:1008-1020): intercept with the light time
 // iterated on the intercept point.  u0: ray direction in the body frame at t_ref.
 //
@@ -313,28 +334,18 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     // i.e. ~1e-6 km of target motion), so the secant runs between the QUANTISED epoch offsets
     // dt1 (pass 2) and dt (pass 3); their difference is exact
     double dt = (f.et - lt2) - f.t_ref;
-    Rot r = make_rot(fs, dt);
-    V3 Pb = target_pos_b(fs, dt);
     V3 p;
-    if (fabs(dt1) > 1.0e-6 && cos2 > 1.0e-3) {
+    if (fabs(dt1) > 1.0e-6 && cos2 > kGrazingCos2) {
         p = axpy(fast_div_lite(dt - dt1, dt1), p2 - p1, p2);
     } else {
-        // Passes 1 and 2 (almost) coincide in epoch, or the ray grazes the limb (emission > ~88 deg,
-        // ~0.1 % of the disc pixels).  There the light time depends on the epoch through
-        // V_lateral tan(emission) / c, which is no longer tiny: iterate full intercepts until the
-        // FP64 epoch et - lt stops changing, exactly like CSPICE's loop (at most 10 passes).
-        double t = f.et - lt2;
-        for (int it = 0; it < 8; it++) {
-            if (!surfpt(fs, spin_fwd(fs, r, -Pb), spin_fwd(fs, r, u0), p)) return false;
-            const double t_new = f.et - norm(p - spin_fwd(fs, r, -Pb)) * fs.inv_c;
-            const bool moved = fabs(t_new - t) > 1.0e-17 * fabs(t_new);
-            if (!moved) break;
-            t = t_new;
-            dt = t - f.t_ref;
-            r = make_rot(fs, dt);
-            Pb = target_pos_b(fs, dt);
-        }
+        double dt_c = dt;  // address-taken copies: keep dt and p themselves in registers
+        V3 p_c;
+        if (!sincpt_converge(fs, u0, dt_c, p_c)) return false;
+        dt = dt_c;
+        p = p_c;
     }
+    const Rot r = make_rot(fs, dt);
+    const V3 Pb = target_pos_b(fs, dt);
     const V3 E = p - spin_fwd(fs, r, -Pb);
     const double L = norm(E);
     it.p = p;
