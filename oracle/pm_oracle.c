@@ -849,7 +849,7 @@ static int raycast_visible(const PMFrame *f, const double tv[3]) {
 /* BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056):
  * alt == 0 visibility through illumf.visibl (body.py:2124-2130), alt != 0 through the ray
  * cast (body.py:2131-2150); PM_FLAG_PLANETOCENTRIC converts the inputs with
- * Body._centric2graphic_lonlat (body.py:2966-2982, alt == 0 only) */
+ * Body._centric2graphic_lonlat (body.py:2966-2982) */
 int pmo_lonlat2xy_alt(const PMFrame *f, const double *lon, const double *lat, int64_t n, double alt,
                       uint32_t flags, double *x, double *y) {
     if (!f || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
@@ -861,7 +861,16 @@ int pmo_lonlat2xy_alt(const PMFrame *f, const double *lon, const double *lat, in
         if (flags & PM_FLAG_PLANETOCENTRIC) {
             double sp[3], al;
             latsrf(f, lo, la, sp);
-            recpgr(f, sp, &lo, &la, &al);
+            if (alt == 0.0) {
+                recpgr(f, sp, &lo, &la, &al);
+            } else {
+                /* Body.targvec2lonlat(targvec, alt=alt) (body.py:1279-1283): recpgr against the
+                 * spheroid with every radius raised by alt (_AdjustedSurfaceAltitude, :210-229) */
+                double re_a = f->re + alt, rp_a = (f->re - f->f * f->re) + alt;
+                recgeo(sp, re_a, (re_a - rp_a) / re_a, &lo, &la, &al);
+                lo = f->lon_sign * lo;
+                if (lo < 0.0) lo += TWOPI;
+            }
             /* Body.targvec2lonlat returns degrees; _lonlat2obsvec converts back */
             lo = (lo * DPR) * RPD;
             la = (la * DPR) * RPD;

@@ -370,9 +370,6 @@ class BodyXY:
         scalar, lo, la = self._broadcast(lon, lat)
         if not math.isfinite(alt):   # Body._lonlat2targvec_radians: non-finite alt -> NaN (body.py:900-901)
             return self._unbroadcast(scalar, np.full(lo.shape, np.nan), np.full(lo.shape, np.nan))
-        if planetocentric and alt != 0.0:
-            raise NotImplementedError('lonlat2xy(planetocentric=True, alt != 0) is not accelerated '
-                                      '(SURVEY.md 8(f))')
         x, y = L.lonlat2xy(self._frame_dev(), L.to_device(lo), L.to_device(la), not_visible_nan,
                            alt=alt, planetocentric=planetocentric)
         return self._unbroadcast(scalar, x.cpu().numpy(), y.cpu().numpy())
@@ -439,10 +436,13 @@ class BodyXY:
             lons, lats = lo.cpu().numpy(), la.cpu().numpy()
             info = dict(projection=projection, lon=lon, lat=lat, size=size)
         else:
-            raise ProjStringError(
-                f'custom proj string {projection!r}: arbitrary PROJ pipelines are out of scope '
-                'of the accelerated path (SURVEY.md section 2); use rectangular, orthographic, '
-                'azimuthal, azimuthal equal area or manual')
+            # custom proj string (body_xy.py:2970-2980)
+            if projection_x_coords is None:
+                raise ValueError('x coords must be provided')
+            lons, lats, xx, yy = self._custom_proj_map_coords(projection, projection_x_coords,
+                                                             projection_y_coords)
+            info = dict(projection=projection, projection_x_coords=projection_x_coords,
+                        projection_y_coords=projection_y_coords)
         info['xlim'] = xlim
         info['ylim'] = ylim
         if xlim is not None:
@@ -463,6 +463,91 @@ class BodyXY:
         if alt != 0.0:
             info['alt'] = alt
         return _readonly(lons), _readonly(lats), _readonly(xx), _readonly(yy), None, info
+
+    def create_proj_string(self, proj: str, **parameters) -> str:
+        """Proj string with this body's radii and axis direction filled in
+        (body_xy.py:3056-3095): ``a``, ``b`` and ``axis`` default to the body's values and a
+        parameter given as ``None`` is left out."""
+        merged = dict(parameters)
+        merged.setdefault('a', self.r_eq)
+        merged.setdefault('b', self.r_polar)
+        merged.setdefault('axis', f'{self.positive_longitude_direction.lower()}nu')
+        parts = [f'+proj={proj}'] + [f'+{k}={v}' for k, v in merged.items() if v is not None]
+        return ' '.join(parts + ['+type=crs'])
+
+    def _check_proj_string_for_axis(self, projection: str) -> None:
+        expected_axis = f'+axis={self.positive_longitude_direction.lower()}nu'   # body_xy.py:3097-3104
+        if expected_axis not in projection:
+            raise ProjStringError(
+                f'Projection string {projection!r} does not have the expected axis orientation '
+                f'{expected_axis!r} for positive {self.positive_longitude_direction} coordinates.')
+
+    # proj parameters the device kernels cover (pm_proj_inverse): ortho on an ellipsoid, aeqd /
+    # laea on a sphere, with the linear +to_meter / +x_0 / +y_0 terms folded into the grid
+    _PROJ_KINDS = {'ortho': L.PROJ_ORTHOGRAPHIC, 'aeqd': L.PROJ_AZIMUTHAL, 'laea': L.PROJ_AZIMUTHAL_EQUAL_AREA}
+
+    def _custom_proj_map_coords(self, projection: str, xx, yy):
+        """``_get_pyproj_map_coords`` (body_xy.py:3106-3128) for the proj strings whose inverse the
+        CUDA kernels implement; anything else raises ProjStringError (there is no PROJ here)."""
+        if yy is None:
+            yy = xx
+        xx, yy = np.asarray(xx), np.asarray(yy)
+        if xx.ndim != yy.ndim:
+            raise ValueError('x and y coords must have the same number of dimensions')
+        if xx.ndim == 1:
+            xx, yy = np.meshgrid(xx, yy)
+        if xx.ndim != 2:
+            raise ValueError('x and y coords must be 1D or 2D arrays')
+        if xx.shape != yy.shape:
+            raise ValueError('x and y coords must have the same shape')
+        self._check_proj_string_for_axis(projection)
+        par: dict[str, str | None] = {}
+        for token in projection.split():
+            key, sep, value = token.lstrip('+').partition('=')
+            par[key] = value if sep else None
+        known = {'proj', 'R', 'a', 'b', 'lon_0', 'lat_0', 'x_0', 'y_0', 'to_meter', 'axis', 'type', 'units',
+                 'no_defs'}
+        unknown = sorted(set(par) - known)
+        kind = self._PROJ_KINDS.get(par.get('proj') or '')
+        if kind is None or unknown or par.get('units') not in (None, 'm'):
+            raise ProjStringError(
+                f'proj string {projection!r} is outside the accelerated subset: +proj=ortho|aeqd|laea with '
+                f'+R | +a +b, +lon_0, +lat_0, +x_0, +y_0, +to_meter, +axis (unsupported: '
+                f'{unknown or par.get("proj") or par.get("units")})')
+
+        def num(key: str, default: float) -> float:
+            v = par.get(key)
+            try:
+                return default if v is None else float(v)
+            except ValueError as exc:
+                raise ProjStringError(f'bad value for +{key} in {projection!r}') from exc
+
+        if 'R' in par:
+            a = b = num('R', 1.0)
+        elif 'a' in par:
+            a = num('a', 1.0)
+            b = num('b', a) if 'b' in par else a   # PROJ: +a without a second shape parameter is a sphere
+        else:
+            # PROJ would silently fall back to the GRS80 Earth ellipsoid here
+            raise ProjStringError(f'{projection!r} needs an explicit +R or +a (create_proj_string adds them)')
+        if not (a > 0 and b > 0):
+            raise ProjStringError(f'radii must be positive in {projection!r}')
+        if kind != L.PROJ_ORTHOGRAPHIC and a != b:
+            raise ProjStringError(f'+proj={par["proj"]} is only accelerated on a sphere (+R or +a without +b)')
+        lon0, lat0 = num('lon_0', 0.0), num('lat_0', 0.0)
+        tm = num('to_meter', 1.0)
+        # PROJ inverse: internal = (user * to_meter - false origin) / a; then the units the
+        # kernels take (the reference's own strings: to_meter = a, a pi and 2 a; y_0 of the ortho)
+        xi = (np.asarray(xx, dtype=float) * tm - num('x_0', 0.0)) / a
+        yi = (np.asarray(yy, dtype=float) * tm - num('y_0', 0.0)) / a
+        if kind == L.PROJ_ORTHOGRAPHIC:
+            yi = yi + (b / a - 1.0) * np.sin(np.radians(lat0 * 2))
+        elif kind == L.PROJ_AZIMUTHAL:
+            xi, yi = xi / np.pi, yi / np.pi
+        else:
+            xi, yi = xi / 2.0, yi / 2.0
+        lo, la = L.proj_inverse(kind, a, b, lon0, lat0, self._bc.lon_sign, L.to_device(xi), L.to_device(yi))
+        return lo.cpu().numpy(), la.cpu().numpy(), xx, yy
 
     # ---- backplane registry (body_xy.py:2512-2584) -------------------------------------
     @staticmethod

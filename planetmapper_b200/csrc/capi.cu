@@ -79,7 +79,6 @@ int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t
 int pm_lonlat2xy_alt(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
                      uint32_t flags, double *x, double *y, void *stream) {
     if (!frame || !x || !y || !lon || !lat || n < 0 || !(alt == alt)) return PM_ERR_BAD_ARG;
-    if ((flags & PM_FLAG_PLANETOCENTRIC) && alt != 0.0) return PM_ERR_UNSUPPORTED;
     if (n == 0) return PM_OK;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;

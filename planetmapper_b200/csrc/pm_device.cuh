@@ -394,6 +394,34 @@ PM_HD void geodetic_general(const FrameD &fs, double rho, double z, double &lat,
     alt = fma(rho, cp, z * sp) - f.re * fast_sqrt(fma(-fs.e2 * sp, sp, 1.0));
 }
 
+// Geodetic latitude w.r.t. an arbitrary spheroid (re, re, rp): the same iteration with the
+// constants derived on the spot.  Only used by the point transforms (planetocentric inputs
+// combined with an altitude), never per pixel.
+PM_HD double geodetic_lat_spheroid(double re, double rp, double rho, double z) {
+    if (re == rp) return fast_atan2_xpos(z, rho);
+    const double q = fast_div(rp, re), qi = fast_div(re, rp);
+    const double e2 = fma(-q, q, 1.0), ep2 = fma(qi, qi, -1.0);
+    double sb = re * z, cb = rp * rho;
+    double n = fast_rsqrt(fma(sb, sb, cb * cb) + 1.0e-300);
+    sb *= n;
+    cb *= n;
+    double num = z, den = rho;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        num = fma(ep2 * rp, sb * sb * sb, z);
+        den = fma(-e2 * re, cb * cb * cb, rho);
+        double nsb = q * num, ncb = den;
+        n = fast_rsqrt(fma(nsb, nsb, ncb * ncb) + 1.0e-300);
+        nsb *= n;
+        ncb *= n;
+        const double change = fabs(nsb - sb) + fabs(ncb - cb);
+        sb = nsb;
+        cb = ncb;
+        if (change <= 4.0e-16) break;
+    }
+    return fast_atan2(num, den);
+}
+
 // spice.recpgr (body.py:1030): planetographic lon in [0, 2pi), lat, alt
 PM_HD void recpgr(const FrameD &fs, V3 p, bool on_spheroid, double &lon, double &lat, double &alt) {
     const double rho = fast_sqrt(fma(p.x, p.x, p.y * p.y));
@@ -912,7 +940,15 @@ PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt,
         const V3 ds = mul3(d, fs.inv_r);
         const V3 sp = fast_rsqrt(dot(ds, ds)) * d;  // spice.latsrf on the ellipsoid
         double al;
-        recpgr(fs, sp, fs.biaxial != 0, lo, la, al);
+        if (alt == 0.0) {
+            recpgr(fs, sp, fs.biaxial != 0, lo, la, al);
+        } else {
+            // Body.targvec2lonlat(targvec, alt=alt) (body.py:1279-1283): recpgr against the
+            // spheroid with every radius raised by alt (_AdjustedSurfaceAltitude, :210-229)
+            lo = fs.f.lon_sign * fast_atan2(sp.y, sp.x);
+            if (lo < 0.0) lo += kTwoPi;
+            la = geodetic_lat_spheroid(fs.f.re + alt, fs.rp + alt, fast_sqrt(fma(sp.x, sp.x, sp.y * sp.y)), sp.z);
+        }
         lo = (lo * kDpr) * kRpd;  // Body.targvec2lonlat returns degrees
         la = (la * kDpr) * kRpd;
     }

@@ -127,6 +127,11 @@ def test_xy_conversions_known_answers(body):
     assert abs(lat_c - 23.4) > 1.0 and np.all(np.isfinite(body.lonlat2xy(150.0, 23.4)))
     assert np.allclose(body.lonlat2xy(lon_c, lat_c, planetocentric=True), body.lonlat2xy(150.0, 23.4), rtol=0,
                        atol=1e-9)
+    # planetocentric + altitude (body.py:1048-1056): the surface point of the planetocentric direction is
+    # re-expressed against the raised spheroid, then lifted along the original spheroid's normal
+    got = body.lonlat2xy(lon_c, lat_c, planetocentric=True, alt=5000.0)
+    assert np.all(np.isfinite(got)) and not np.allclose(got, body.lonlat2xy(150.0, 23.4, alt=5000.0), rtol=0, atol=1e-6)
+    assert np.allclose(got, body.lonlat2xy(150.0, 23.4, alt=5000.0), rtol=0, atol=0.05)
 
 
 @pytest.mark.parametrize('interp', ['nearest', 'linear', 'cubic', 1, 3, (3, 3)])
@@ -183,6 +188,50 @@ def test_generate_map_coordinates_known_answers(body, case):
     assert not lons.flags.writeable and not xx.flags.writeable
     assert info == dict(projection=proj, lon=lon0, lat=lat0, size=size, xlim=None, ylim=None)
     assert xx.shape == (size, size) and np.allclose(xx[0], np.linspace(xx[0, 0], -xx[0, 0], size))
+
+
+def test_custom_proj_strings(body):
+    """Custom proj strings (body_xy.py:2970-2980): the strings the reference itself builds for its
+    named projections (:2932-2968) must give exactly the named projection, and a unit-sphere
+    orthographic string the textbook inverse."""
+    g = body.generate_map_coordinates
+    a, b = body.r_eq, body.r_polar
+    for lon0, lat0 in ((0, 0), (-42, -21.3), (123.4, 90), (10, -90)):
+        named = g('orthographic', lon=lon0, lat=lat0, size=41)
+        proj = body.create_proj_string('ortho', to_meter=a, lon_0=lon0, lat_0=lat0,
+                                       y_0=a * (b / a - 1) * np.sin(np.radians(lat0 * 2)))
+        lim = max(1, b / a) * 1.01
+        custom = g(proj, projection_x_coords=np.linspace(-lim, lim, 41))
+        for i in range(4):
+            # (xx * to_meter - x_0) / a rounds differently from xx itself: 1e-10 deg, not bitwise
+            assert np.allclose(named[i], custom[i], rtol=0, atol=1e-10, equal_nan=True), (lon0, lat0, i)
+        for name, pj, tm in (('azimuthal', 'aeqd', a * np.pi), ('azimuthal equal area', 'laea', a * 2)):
+            named = g(name, lon=lon0, lat=lat0, size=33)
+            proj = body.create_proj_string(pj, to_meter=tm, b=None, lon_0=lon0, lat_0=lat0)
+            custom = g(proj, projection_x_coords=np.linspace(-1.01, 1.01, 33))
+            for i in range(4):
+                assert np.allclose(named[i], custom[i], rtol=0, atol=1e-10, equal_nan=True), (name, lon0, lat0, i)
+    # +R=1, default origin: lon = -atan2(x, sqrt(1 - x^2 - y^2)) (west-positive axis), lat = asin(y)
+    c = np.array([0, 0.25, 0.5])
+    out_a = g('+proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=c)
+    out_b = g('+proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=c, projection_y_coords=c)
+    xx, yy = np.meshgrid(c, c)
+    assert np.array_equal(out_a[2], xx) and np.array_equal(out_a[3], yy)
+    assert np.allclose(out_a[1], np.degrees(np.arcsin(yy)), rtol=0, atol=1e-12)
+    assert np.allclose(out_a[0], -np.degrees(np.arctan2(xx, np.sqrt(1 - xx**2 - yy**2))), rtol=0, atol=1e-12)
+    for i in range(4):
+        assert np.array_equal(out_a[i], out_b[i]) and not out_a[i].flags.writeable
+    assert out_a[5]['projection_y_coords'] is None and out_a[4] is None
+    # false origin and units: x_0 / y_0 in metres, to_meter scaling the user coordinates
+    shifted = g('+proj=ortho +R=2 +x_0=1 +y_0=-0.5 +to_meter=4 +axis=wnu', projection_x_coords=(c * 2 + 1) / 4,
+                projection_y_coords=(c * 2 - 0.5) / 4)
+    assert np.allclose(shifted[0], out_a[0], rtol=0, atol=1e-12) and np.allclose(shifted[1], out_a[1], rtol=0, atol=1e-12)
+    # a mapped backplane through a custom string equals the named projection's
+    proj = body.create_proj_string('ortho', to_meter=a, lon_0=30, lat_0=10, y_0=a * (b / a - 1) * np.sin(np.radians(20)))
+    lim = max(1, b / a) * 1.01
+    m1 = body.get_backplane_map('EMISSION', projection='orthographic', lon=30, lat=10, size=21)
+    m2 = body.get_backplane_map('EMISSION', projection=proj, projection_x_coords=np.linspace(-lim, lim, 21))
+    assert np.allclose(m1, m2, rtol=0, atol=1e-9, equal_nan=True)
 
 
 def test_backplane_values_known_answers(body):
@@ -244,4 +293,5 @@ def test_unsupported_options_raise(bc_hst):
             pm.BodyXY(constants=bc_hst, sz=5, **kw)
     b = pm.BodyXY(constants=bc_hst, sz=5)
     with pytest.raises(pm.ProjStringError):
-        b.generate_map_coordinates('+proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=np.arange(3.0))
+        # proj strings outside the kernels' subset fail loudly (there is no PROJ fallback)
+        b.generate_map_coordinates('+proj=moll +R=1 +axis=wnu +type=crs', projection_x_coords=np.arange(3.0))

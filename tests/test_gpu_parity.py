@@ -143,7 +143,8 @@ def test_point_transforms_vs_oracle(L, oracle, bc_hst):
         assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9
         # points above / below the surface (ray-cast visibility, body.py:2131-2150) and
         # planetocentric inputs (spice.latsrf, body.py:2966-2982)
-        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True)):
+        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True), (2345.6, True),
+                        (-150.0, True)):
             rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=nvn, alt=alt, planetocentric=pc)
             gx, gy = L.lonlat2xy(fd, L.to_device(lon), L.to_device(lat), nvn, alt=alt, planetocentric=pc)
             gx, gy = gx.cpu().numpy(), gy.cpu().numpy()

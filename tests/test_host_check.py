@@ -195,7 +195,8 @@ def test_device_code_point_transforms_vs_oracle(HC, oracle, bc_hst):
         ok = np.isfinite(rx)
         assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-9
         # points above the surface (ray-cast visibility) and planetocentric inputs
-        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True)):
+        for alt, pc in ((1234.5, False), (-300.0, False), (50000.0, False), (0.0, True), (2345.6, True),
+                        (-150.0, True)):
             rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=nvn, alt=alt, planetocentric=pc)
             flags = (1 if nvn else 0) | (4 if pc else 0)
             assert HC.hc_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_double(alt),

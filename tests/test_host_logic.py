@@ -49,6 +49,46 @@ def test_rectangular_and_manual_grids_known_answers(body):
             body.generate_map_coordinates('manual', **kw)
 
 
+def test_create_proj_string_literals(body):
+    """tests/test_body_xy.py:1990-2029 (the Jupiter literals; Earth's follow the same code)."""
+    f = body.create_proj_string
+    assert f('ortho') == '+proj=ortho +a=71492.0 +b=66854.0 +axis=wnu +type=crs'
+    assert f('ortho', axis=None) == '+proj=ortho +a=71492.0 +b=66854.0 +type=crs'
+    assert f('ortho', a=None, axis=None) == '+proj=ortho +b=66854.0 +type=crs'
+    assert f('ortho', axis='123') == '+proj=ortho +axis=123 +a=71492.0 +b=66854.0 +type=crs'
+    assert (f('eqc', string='a_string', number=123, lat_0=-1.234)
+            == '+proj=eqc +string=a_string +number=123 +lat_0=-1.234 +a=71492.0 +b=66854.0 +axis=wnu +type=crs')
+    assert f('ortho', lon_0=180, lat_0=45, axis=None, a=None, b=None) == '+proj=ortho +lon_0=180 +lat_0=45 +type=crs'
+
+
+def test_custom_proj_string_validation_needs_no_device(body):
+    """Argument and axis checks of generate_map_coordinates for proj strings
+    (tests/test_body_xy.py:1563-1590, :1948-1988) happen before any device work."""
+    import planetmapper_b200 as pm
+
+    g = body.generate_map_coordinates
+    with pytest.raises(ValueError):
+        g('+proj=ortho +R=1 +axis=wnu +type=crs')                       # x coords must be provided
+    with pytest.raises(ValueError):
+        g('proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=np.array([1, 2, 3]),
+          projection_y_coords=np.array([[1, 2, 3], [4, 5, 6]]))
+    with pytest.raises(ValueError):
+        g('proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=np.array([[[1, 2, 3]]]))
+    with pytest.raises(ValueError):
+        g('proj=ortho +R=1 +axis=wnu +type=crs', projection_x_coords=np.array([[1, 2, 3]]),
+          projection_y_coords=np.array([[1, 2, 3], [4, 5, 6]]))
+    for bad_axis in ('+proj=ortho +R=1 +type=crs', '+proj=ortho +R=1 +axis=enu +type=crs',
+                     '+proj=ortho +R=1 +axis=neu +type=crs'):
+        with pytest.raises(pm.ProjStringError):
+            g(bad_axis, projection_x_coords=np.array([0, 0.25, 0.5]))
+    # outside the accelerated subset: a clear error, never a silent approximation
+    for unsupported in ('+proj=eqc +axis=wnu +type=crs', '+proj=ortho +k_0=2 +axis=wnu', '+proj=aeqd +axis=wnu',
+                        '+proj=laea +a=2 +b=1 +axis=wnu', '+proj=ortho +R=abc +axis=wnu',
+                        '+proj=ortho +units=km +axis=wnu'):
+        with pytest.raises(pm.ProjStringError):
+            g(unsupported, projection_x_coords=np.array([0, 0.25, 0.5]))
+
+
 def test_disc_parameter_interface(body):
     """tests/test_body_xy.py set/get behaviour incl. centre_disc (body_xy.py:791-803)."""
     assert body.get_disc_params() == (7.0, 4.5, 0.9 * 4.5, 0.0)
