@@ -283,7 +283,27 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kGatherBlock, 2)
+// The A fragments are staged through shared memory with cp.async: one 8-byte copy per lane and
+// coefficient row, each lane reading back exactly what it copied (no cross-lane exchange, no
+// barrier).  What this buys is the GROUP accounting: `cp.async.wait_group N` waits for the
+// oldest group only, so kCubicStages - 1 plane tiles are genuinely in flight.  The earlier
+// register-prefetch version compiled to loads that all shared one hardware scoreboard (SASS:
+// every LDG of the three rotating register sets wrote SB5); waiting for the tile about to be
+// multiplied therefore also waited for the prefetches just issued.
+constexpr int kCubicBlock = 128;   // threads per CTA: 4 CTAs / SM at <= 128 registers, fine-grained tail
+constexpr int kCubicStages = 4;    // plane tiles in flight per warp (power of two)
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(kCubicBlock, 4)
     gather_cubic_mma_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
                             const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int n_planes_padded,
                             int plane_begin, int plane_count, const double *__restrict__ xmap,
@@ -447,69 +467,114 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
         }
     };
 
-    // ---- fast path: every valid cell of the warp reads ONE footprint, full tiles, aligned pair
-    // stores, all planes inside the coefficient array.  No masks, no per-tile branches; the A
-    // fragments ping-pong between two register sets (software prefetch without copies).
-    const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
-    const bool planes_inside = plane_begin + l0 + ((l1 - l0 + 7) / 8) * 8 <= n_planes_padded;
-    if (simple && !has1 && full_tiles && pair_ok && planes_inside) {
+    // ---- pipelined path: at most two distinct footprints in the warp (the rule for a dense map:
+    // 32 consecutive cells straddle at most one pixel boundary)
+    if (simple) {
+        __shared__ double stage[kCubicStages][2][4][kCubicBlock];
+        const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
+        const bool fast_store = full_tiles && pair_ok;
+        const int n_it = (l1 - l0 + 7) / 8;
         const double *p0 = pbase + (int64_t)org0 * 4;
+        const double *p1 = pbase + (int64_t)(has1 ? org1 : org0) * 4;
         const int64_t tile_stride = 2 * quad_stride;
-        // three register sets rotate: the A fragment of plane tile n + 2 is requested while tile n
-        // is multiplied (L2 latency under 4 TB/s of streaming stores is several iterations long)
-        double fa[4], fb[4], fc[4];
+        int issued = 0;
+        auto issue = [&]() {
+            if (issued < n_it) {
+                const int slot = issued & (kCubicStages - 1);
+                const bool in_coef = (plane_begin + l0 + 8 * issued + g) < n_planes_padded;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            fa[j] = __ldg(p0 + j * row_stride);
-            fb[j] = (l0 + 8 < l1) ? __ldg(p0 + tile_stride + j * row_stride) : 0.0;
-        }
-        int l = l0;
-        auto step = [&](const double (&cur)[4], double (&nxt)[4]) {
-            const int gl = plane_begin + l;
+                for (int j = 0; j < 4; j++) {
+                    double *dst = &stage[slot][0][j][threadIdx.x];
+                    if (in_coef)
+                        cp_async8(dst, p0 + j * row_stride);
+                    else
+                        *dst = 0.0;
+                }
+                if (has1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        double *dst = &stage[slot][1][j][threadIdx.x];
+                        if (in_coef)
+                            cp_async8(dst, p1 + j * row_stride);
+                        else
+                            *dst = 0.0;
+                    }
+                }
+                p0 += tile_stride;
+                p1 += tile_stride;
+            }
+            issued++;
+            cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
+        };
+#pragma unroll
+        for (int k = 0; k < kCubicStages - 1; k++) issue();
+        for (int it = 0; it < n_it; it++) {
+            const int l = l0 + 8 * it;
+            const int gl = plane_begin + l;  // global plane of row 0 of this plane tile
+            issue();
             const int word = (gl + g) >> 5;
-            if (word != cur_word) {
+            if (word != cur_word) {  // changes at most once per 32 planes (per lane: planes gl + g)
                 cur_word = word;
                 refresh_ok(word);
             }
-            if (l + 16 < l1) {
+            cp_async_wait<kCubicStages - 1>();  // the group of plane tile `it` has landed
+            const int slot = it & (kCubicStages - 1);
+            double a0[4], a1[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) nxt[j] = __ldg(p0 + 2 * tile_stride + j * row_stride);
-            }
+            for (int j = 0; j < 4; j++) a0[j] = stage[slot][0][j][threadIdx.x];
             double d[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                d[i][0] = d[i][1] = 0.0;
+            for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
+            if (!has1) {
+                // every valid cell reads footprint 0 and invalid cells carry zero weights: no masks
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], cur[j], bw[i][j]);
+                for (int j = 0; j < 4; j++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dmma8x8x4(d[i][0], d[i][1], a0[j], bw[i][j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) a1[j] = stage[slot][1][j][threadIdx.x];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (tiles & (1u << i)) {
+                        const bool keep = (tiles & (1u << (8 + i))) || ((mine01 >> i) & 1u);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a0[j], keep ? bw[i][j] : 0.0);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (tiles & (1u << (4 + i))) {
+                        const bool keep = (mine01 >> (4 + i)) & 1u;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a1[j], keep ? bw[i][j] : 0.0);
+                    }
+                }
             }
+            // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
             if (l + g < l1) {
                 const int sh = (gl + g) & 31;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
                     const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
-                    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst_row + i * tile_step), "d"(o0), "d"(o1)
-                                 : "memory");
+                    double *dst = dst_row + i * tile_step;
+                    if (fast_store || (pair_ok && 2 * t + 1 < ncols[i])) {
+                        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
+                    } else {
+                        if (2 * t < ncols[i]) __stcs(dst, o0);
+                        if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
+                    }
                 }
             }
-            p0 += tile_stride;
             dst_row += 8 * n_cells;
-            l += 8;
-        };
-        while (l < l1) {
-            step(fa, fc);
-            if (l >= l1) break;
-            step(fb, fa);
-            if (l >= l1) break;
-            step(fc, fb);
         }
         return;
     }
 
-    // A fragment of footprint 0 is software-prefetched one plane tile ahead; footprint 1's is
-    // issued at the top of the iteration and first needed after the footprint-0 products
-    double a0[4];
-    if (simple) load_a(a0, org0, pbase, (plane_begin + l0 + g) < n_planes_padded);
+    // ---- general path (three or more footprints in the warp): one pass per distinct footprint
+    // among each tile's cells
     for (int l = l0; l < l1; l += 8) {
         const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (multiple of 4)
         const int word = (gl + g) >> 5;
@@ -521,35 +586,7 @@ __global__ void __launch_bounds__(kGatherBlock, 2)
 #pragma unroll
         for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
         const bool in_coef = (gl + g) < n_planes_padded;
-        if (simple) {
-            double a1[4], n0[4];
-            if (has1) load_a(a1, org1, pbase, in_coef);
-            const bool more = l + 8 < l1;
-            if (more) load_a(n0, org0, pbase + 2 * quad_stride, (gl + 8 + g) < n_planes_padded);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (tiles & (1u << i)) {
-                    const bool keep = (tiles & (1u << (8 + i))) || ((mine01 >> i) & 1u);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a0[j], keep ? bw[i][j] : 0.0);
-                }
-            }
-            if (has1) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (tiles & (1u << (4 + i))) {
-                        const bool keep = (mine01 >> (4 + i)) & 1u;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a1[j], keep ? bw[i][j] : 0.0);
-                    }
-                }
-            }
-            if (more) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) a0[j] = n0[j];
-            }
-        } else {
-            // general case: one pass per distinct footprint among each tile's cells
+        {
             uint32_t a_origin = 0xffffffffu;
             double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -633,9 +670,9 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                              n_cells % cells_per_row == 0;
         const int64_t row_len = rows_ok ? cells_per_row : n_cells;
         const int64_t n_warps = rows_ok ? ((n_cells / row_len + 3) / 4) * ((row_len + 7) / 8) : (n_cells + 31) / 32;
-        dim3 grid2((unsigned)((n_warps + kGatherBlock / 32 - 1) / (kGatherBlock / 32)),
+        dim3 grid2((unsigned)((n_warps + kCubicBlock / 32 - 1) / (kCubicBlock / 32)),
                    (unsigned)((plane_count + g2 - 1) / g2));
-        gather_cubic_mma_kernel<<<grid2, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
+        gather_cubic_mma_kernel<<<grid2, kCubicBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
                                                                 (n_planes + 3) / 4 * 4, plane_begin, plane_count, xmap,
                                                                 ymap, n_cells, row_len, flags, out, g2);
     } else {
