@@ -1,0 +1,152 @@
+"""
+Frame constants for a TIME SERIES (BASELINE config C5: thousands of frames, a fresh
+``BodyXY`` per epoch in the reference).
+
+Once the per-pixel work takes ~40 microseconds per 1024 x 1024 frame on the GPU, the serial
+host extraction of each frame's 92 constants (about 55 ephemeris / orientation evaluations,
+~3 ms in Python, the same order through spiceypy: SURVEY.md 8(e) "limited only by serial
+host constant extraction") is the whole cost of a series.  Epochs are independent, so the
+extraction shards over host processes exactly like frames shard over GPUs: contiguous
+blocks of epochs, no exchange, the SAME scalar code per epoch (``frame.build_body_constants``
++ ``frame.pack_frame``), hence bit-identical constants.  SPICE itself is not re-entrant
+(SURVEY.md 8(b) "Threading"), which is why the workers are processes, each with its own
+provider, and never threads.
+"""
+from __future__ import annotations
+
+import atexit
+import os
+import pickle
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+from . import frame as F
+from .shard import shard_range
+
+
+def _block(provider, target, observer, ets, disc) -> np.ndarray:
+    out = np.empty((len(ets), F.PMFRAME_NDOUBLES))
+    for i, et in enumerate(ets):
+        bc = F.build_body_constants(provider, target, None, observer, et=float(et))
+        out[i] = F.pack_frame(bc, **disc)
+    return out
+
+
+# ---- worker processes ---------------------------------------------------------------------
+# Plain child interpreters running `python -m planetmapper_b200.series` and talking
+# length-prefixed pickles over their pipes.  (multiprocessing's spawn / forkserver start
+# methods re-import the caller's __main__, which breaks unguarded user scripts, and fork is not
+# safe once the parent holds a CUDA context.)
+def _send(stream, obj) -> None:
+    data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    stream.write(struct.pack('<Q', len(data)))
+    stream.write(data)
+    stream.flush()
+
+
+def _recv(stream):
+    head = stream.read(8)
+    if len(head) < 8:
+        raise EOFError('series worker closed its pipe')
+    (n,) = struct.unpack('<Q', head)
+    return pickle.loads(stream.read(n))
+
+
+def _worker_main() -> None:
+    import planetmapper_b200 as pm
+
+    inp, out = sys.stdin.buffer, sys.stdout.buffer
+    sys.stdout = sys.stderr  # stray prints must not corrupt the reply stream
+    provider = None
+    while True:
+        try:
+            msg = _recv(inp)
+        except EOFError:
+            return
+        try:
+            kernel_path, target, observer, ets, disc = msg
+            if provider is None:
+                if kernel_path is not None:
+                    pm.set_kernel_path(kernel_path)
+                provider = pm.get_default_provider()
+            _send(out, ('ok', _block(provider, target, observer, ets, disc)))
+        except Exception as exc:  # reported to the parent, which raises
+            _send(out, ('error', f'{type(exc).__name__}: {exc}'))
+
+
+_WORKERS: list[subprocess.Popen] = []
+
+
+def _workers(n: int) -> list[subprocess.Popen]:
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''),
+               OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+    _WORKERS[:] = [w for w in _WORKERS if w.poll() is None]
+    while len(_WORKERS) < n:
+        _WORKERS.append(subprocess.Popen([sys.executable, '-m', 'planetmapper_b200.series'], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, env=env))
+    return _WORKERS[:n]
+
+
+def shutdown_pool() -> None:
+    """Stop the worker processes (they are otherwise kept for the next series)."""
+    for w in _WORKERS:
+        try:
+            w.stdin.close()
+            w.wait(timeout=10)
+        except Exception:
+            w.kill()
+    _WORKERS.clear()
+
+
+atexit.register(shutdown_pool)
+
+
+def default_workers() -> int:
+    """Host processes to use: the cores this process may run on, shared between the ranks
+    of a torchrun job (LOCAL_WORLD_SIZE)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    return max(1, cores // ranks)
+
+
+def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: float, y0: float,
+                        r0: float, rotation_radians: float = 0.0, alt: float = 0.0,
+                        workers: int | None = None, provider=None) -> np.ndarray:
+    """PMFrame constants, shape (len(ets), 92), for ``target`` seen from ``observer`` at the
+    ephemeris times ``ets`` with one set of disc parameters.
+
+    ``workers`` host processes (default: :func:`default_workers`) each take one contiguous
+    block of epochs; ``workers <= 1``, a short series, or an explicit in-process ``provider``
+    runs serially in this process.  The result does not depend on ``workers``.
+    """
+    import planetmapper_b200 as pm
+
+    ets = np.asarray(ets, dtype=np.float64).reshape(-1)
+    disc = dict(nx=nx, ny=ny, x0=x0, y0=y0, r0=r0, rotation_radians=rotation_radians, alt=alt)
+    workers = default_workers() if workers is None else int(workers)
+    workers = min(workers, max(1, len(ets) // 16))   # a block under ~16 epochs does not pay for the hand-off
+    if provider is not None or workers <= 1:
+        return _block(provider if provider is not None else pm.get_default_provider(), target, observer, ets, disc)
+    procs = _workers(workers)
+    for w, proc in enumerate(procs):
+        block = ets[slice(*shard_range(len(ets), w, workers))]
+        _send(proc.stdin, (pm.get_kernel_path(), str(target), str(observer), block, disc))
+    parts = []
+    for proc in procs:
+        status, payload = _recv(proc.stdout)
+        if status != 'ok':
+            shutdown_pool()
+            raise RuntimeError(f'series worker failed: {payload}')
+        parts.append(payload)
+    return np.concatenate(parts, axis=0)
+
+
+if __name__ == '__main__':
+    _worker_main()

@@ -109,6 +109,32 @@ def test_disc_parameter_interface(body):
     assert body.get_rotation() == pytest.approx(24.15516987997688, abs=1e-8)
 
 
+def test_series_frames_over_host_processes_are_bit_identical():
+    """planetmapper_b200.series: epochs sharded over worker processes give exactly the serial
+    constants, in order; worker errors surface in the parent."""
+    import planetmapper_b200 as pm
+    from planetmapper_b200 import frame as F
+    from planetmapper_b200 import series as S
+
+    prov = pm.get_default_provider()
+    ets = prov.utc2et('2005-01-01T00:00:00') - 3600.0 - 60.0 * np.arange(70)[::-1]
+    disc = dict(nx=64, ny=48, x0=31.5, y0=23.5, r0=20.0, rotation_radians=0.3)
+    serial = S.build_series_frames('Jupiter', ets, 'EARTH', workers=1, **disc)
+    assert serial.shape == (70, F.PMFRAME_NDOUBLES)
+    bc = F.build_body_constants(prov, 'Jupiter', None, 'EARTH', et=float(ets[5]))
+    assert np.array_equal(serial[5], F.pack_frame(bc, **disc))
+    try:
+        for workers in (2, 3):
+            assert np.array_equal(S.build_series_frames('Jupiter', ets, 'EARTH', workers=workers, **disc), serial)
+        assert np.array_equal(S.build_series_frames('Jupiter', ets[:5], 'EARTH', workers=4, **disc), serial[:5])
+        with pytest.raises(RuntimeError, match='unknown body'):
+            S.build_series_frames('Nosuchbody', ets, 'EARTH', workers=2, **disc)
+        assert np.array_equal(S.build_series_frames('Jupiter', ets, 'EARTH', workers=2, **disc), serial)  # pool restarts
+    finally:
+        S.shutdown_pool()
+    assert S.default_workers() >= 1
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 3000, 4096, 4097):
         for w in (1, 2, 3, 4, 8):
