@@ -148,5 +148,28 @@ def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: 
     return np.concatenate(parts, axis=0)
 
 
+def iter_backplane_batches(frames: np.ndarray, nx: int, ny: int, names, batch: int = 32):
+    """Backplane images of a series, ``batch`` frames per fused launch.
+
+    Yields ``(first, planes)`` with ``planes`` a CUDA tensor of shape
+    ``(n, len(set(names)), ny, nx)`` holding frames ``first .. first + n`` (planes in
+    backplane-registration order, like ``BodyXY.get_backplane_imgs``).  The tensor is REUSED by
+    the next iteration (a 4096-frame series of 12 planes would be 412 GB): consume or copy it
+    before advancing.  Equivalent to ``BodyXY(target, utc_i, ...).get_backplane_img(name)`` for
+    every epoch and name in the reference (body_xy.py:2586), one launch per batch instead of one
+    Python loop per pixel, stage and frame.
+    """
+    from . import _lib as L
+
+    torch = L._torch()
+    mask = L.mask_from_names([str(n).strip().upper() for n in names])
+    fd = L.to_device(np.ascontiguousarray(frames, dtype=np.float64))
+    out = torch.empty((min(batch, len(frames)), L.popcount(mask), ny, nx), dtype=torch.float64, device=fd.device)
+    for first in range(0, len(frames), batch):
+        n = min(batch, len(frames) - first)
+        L.backplanes_img(fd[first:first + n], nx, ny, mask, out=out[:n])
+        yield first, out[:n]
+
+
 if __name__ == '__main__':
     _worker_main()

@@ -190,6 +190,35 @@ def test_generate_map_coordinates_known_answers(body, case):
     assert xx.shape == (size, size) and np.allclose(xx[0], np.linspace(xx[0, 0], -xx[0, 0], size))
 
 
+def test_series_batches_equal_one_bodyxy_per_epoch():
+    """planetmapper_b200.series: a time series in batched launches gives, frame by frame, exactly
+    what a fresh BodyXY per epoch returns (the reference's only way to do a series)."""
+    import planetmapper_b200 as pm
+    from planetmapper_b200 import series as S
+
+    prov = pm.get_default_provider()
+    utcs = ['2004-12-31T2%d:%02d:00' % (h, m) for h in (1, 2) for m in (0, 20, 40)] + ['2004-12-30T03:00:00']
+    ets = np.array([prov.utc2et(u) for u in utcs])
+    names = ['EMISSION', 'LON-GRAPHIC', 'DOPPLER', 'RING-RADIUS']
+    disc = dict(nx=40, ny=30, x0=19.5, y0=14.5, r0=12.0, rotation_radians=np.deg2rad(25.0))
+    try:
+        frames = S.build_series_frames('Jupiter', ets, 'EARTH', workers=2, **disc)
+    finally:
+        S.shutdown_pool()
+    seen = 0
+    for first, planes in S.iter_backplane_batches(frames, 40, 30, names, batch=3):
+        got = planes.cpu().numpy()
+        for k in range(got.shape[0]):
+            body = pm.BodyXY('Jupiter', utcs[first + k], 'EARTH', nx=40, ny=30)
+            body.set_disc_params(19.5, 14.5, 12.0, 25.0)
+            ref = body.get_backplane_imgs(names)
+            order = sorted(names, key=PLANE_NAMES.index)
+            for j, n in enumerate(order):
+                assert np.array_equal(got[k, j], ref[n], equal_nan=True), (first + k, n)
+            seen += 1
+    assert seen == len(utcs)
+
+
 def test_custom_proj_strings(body):
     """Custom proj strings (body_xy.py:2970-2980): the strings the reference itself builds for its
     named projections (:2932-2968) must give exactly the named projection, and a unit-sphere
