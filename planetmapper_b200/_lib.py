@@ -134,8 +134,14 @@ def launch_count() -> int:
 
 def to_device(arr, device=None):
     torch = _torch()
+    import warnings
+
     a = np.ascontiguousarray(arr, dtype=np.float64)
-    return torch.from_numpy(a).to(device or 'cuda', non_blocking=False)
+    with warnings.catch_warnings():
+        # read-only views of cached arrays are only ever read (copied to the device) here
+        warnings.simplefilter('ignore')
+        t = torch.from_numpy(a)
+    return t.to(device or 'cuda', non_blocking=False)
 
 
 def popcount(mask: int) -> int:
@@ -377,6 +383,8 @@ def map_smooth(cube_dev, xmap_dev, ymap_dev, *, propagate_nan: bool = True, over
     n_cells = xmap_dev.numel()
     if out is None:
         out = torch.empty((nl,) + tuple(xmap_dev.shape), dtype=torch.float64, device=cube_dev.device)
+    if n_cells == 0 or nl == 0:
+        return out   # a map without cells (xlim / ylim excluded everything)
     xlim, ylim = nan_minmax(xmap_dev), nan_minmax(ymap_dev)
     gx = None if xlim[0] != xlim[0] else smooth_grid(nx, xlim, oversample_by, max_oversampled_img_size)
     gy = None if ylim[0] != ylim[0] else smooth_grid(ny, ylim, oversample_by, max_oversampled_img_size)

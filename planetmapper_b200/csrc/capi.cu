@@ -57,10 +57,11 @@ int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint6
 
 int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n_cells,
                       uint64_t plane_mask, double *out, void *stream) {
-    if (!frame || !lon || !lat || !out || n_cells < 0) return PM_ERR_BAD_ARG;
+    if (!frame || n_cells < 0) return PM_ERR_BAD_ARG;
     plane_mask &= PM_ALL_PLANES;
     if (!plane_mask) return PM_ERR_BAD_ARG;
-    if (n_cells == 0) return PM_OK;
+    if (n_cells == 0) return PM_OK;  // empty inputs are valid (and carry null pointers)
+    if (!lon || !lat || !out) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_backplanes_map(frame, lon, lat, n_cells, plane_mask, out, sms, (cudaStream_t)stream));
@@ -68,8 +69,9 @@ int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat
 
 int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon, double *lat,
                  int64_t *n_missed, void *stream) {
-    if (!frame || !x || !y || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (!frame || n < 0) return PM_ERR_BAD_ARG;
     if (n == 0) return PM_OK;
+    if (!x || !y || !lon || !lat) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_xy2lonlat(frame, x, y, n, lon, lat, (unsigned long long *)n_missed, sms,
@@ -78,8 +80,9 @@ int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t
 
 int pm_lonlat2xy_alt(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
                      uint32_t flags, double *x, double *y, void *stream) {
-    if (!frame || !x || !y || !lon || !lat || n < 0 || !(alt == alt)) return PM_ERR_BAD_ARG;
+    if (!frame || n < 0 || !(alt == alt)) return PM_ERR_BAD_ARG;
     if (n == 0) return PM_OK;
+    if (!x || !y || !lon || !lat) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_lonlat2xy(frame, lon, lat, n, alt, flags, x, y, sms, (cudaStream_t)stream));
@@ -91,9 +94,10 @@ int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int
 
 int pm_proj_inverse(int kind, const double *params5_host, const double *xx, const double *yy, int64_t n,
                     double *lon, double *lat, void *stream) {
-    if (!params5_host || !xx || !yy || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;
+    if (!params5_host || n < 0) return PM_ERR_BAD_ARG;
     if (kind < PM_PROJ_ORTHOGRAPHIC || kind > PM_PROJ_AZIMUTHAL_EQUAL_AREA) return PM_ERR_UNSUPPORTED;
     if (n == 0) return PM_OK;
+    if (!xx || !yy || !lon || !lat) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     return check(launch_proj_inverse(kind, params5_host, xx, yy, n, lon, lat, sms, (cudaStream_t)stream));
@@ -102,9 +106,11 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx, cons
 int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes, int ny, int nx,
               int plane_begin, int plane_count, const double *xmap, const double *ymap, int64_t n_cells,
               int64_t cells_per_row, int mode, uint32_t flags, double *out, void *stream) {
-    if (!src || !xmap || !ymap || !out || n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 ||
-        plane_count < 0 || plane_begin + plane_count > n_planes)
+    if (n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || plane_begin < 0 || plane_count < 0 ||
+        plane_begin + plane_count > n_planes)
         return PM_ERR_BAD_ARG;
+    const bool empty = n_cells == 0 || plane_count == 0;  // valid, and the empty arrays carry null pointers
+    if (!empty && (!src || !xmap || !ymap || !out)) return PM_ERR_BAD_ARG;
     int ky = mode, kx = mode;
     if (mode & PM_INTERP_MIXED) {
         ky = (mode >> 4) & 0xF;
@@ -114,6 +120,7 @@ int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_
         return PM_ERR_UNSUPPORTED;
     }
     if (mode != PM_INTERP_NEAREST && (nx <= kx || ny <= ky)) return PM_ERR_BAD_ARG;
+    if (empty) return PM_OK;
     if (mode != PM_INTERP_NEAREST && (!nanbits || !plane_bits || (plane_begin & 3))) return PM_ERR_BAD_ARG;
     if (plane_count > 65535 * 128) return PM_ERR_BAD_ARG;
     int sms = sm_count();

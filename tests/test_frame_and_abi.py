@@ -51,6 +51,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.pm_backplanes_img(None, 1, 4, 4, 1, None, None) == -1
     assert lib.pm_gather(None, None, None, 1, 4, 4, 0, 1, None, None, 4, 0, 0, 0, None, None) == -1
     assert lib.pm_spline_work_bytes(3, 8, 8, 3) > 0
+    # empty inputs are valid and carry null pointers: accepted before any device work
+    import ctypes
+
+    frame = (ctypes.c_double * F.PMFRAME_NDOUBLES)()
+    assert lib.pm_gather(None, None, None, 1, 4, 4, 0, 1, None, None, 0, 0, 0, 0, None, None) == 0
+    assert lib.pm_xy2lonlat(frame, None, None, 0, None, None, None, None) == 0
+    assert lib.pm_lonlat2xy(frame, None, None, 0, 0, None, None, None) == 0
+    assert lib.pm_backplanes_map(frame, None, None, 0, 1, None, None) == 0
+    assert lib.pm_xy2lonlat(frame, None, None, 3, None, None, None, None) == -1
 
 
 def test_oracle_library_exports():

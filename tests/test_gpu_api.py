@@ -190,6 +190,34 @@ def test_generate_map_coordinates_known_answers(body, case):
     assert xx.shape == (size, size) and np.allclose(xx[0], np.linspace(xx[0, 0], -xx[0, 0], size))
 
 
+def test_empty_and_degenerate_inputs(body, bc_hst):
+    """Empty point sets, maps with no cells (xlim / ylim excluding everything, body_xy.py:2985-2998)
+    and a one-pixel image go through every entry point and keep their shapes."""
+    import planetmapper_b200 as pm
+
+    e = np.array([], dtype=float)
+    for out in (body.xy2lonlat(e, e), body.lonlat2xy(e, e), body.lonlat2xy(e, e, alt=10.0, planetocentric=True)):
+        assert all(o.shape == (0,) and o.dtype == np.float64 for o in out)
+    lon2, lat2 = body.xy2lonlat(np.zeros((0, 3)), np.zeros((1, 3)))
+    assert lon2.shape == lat2.shape == (0, 3)
+    kw = dict(projection='orthographic', size=5, xlim=(5, 6))
+    lons, lats, xx, yy, _t, _info = body.generate_map_coordinates(**kw)
+    assert lons.shape == lats.shape == xx.shape == yy.shape == (5, 0)
+    assert body.get_backplane_map('EMISSION', **kw).shape == (5, 0)
+    img = np.arange(150.0).reshape(10, 15)
+    for interp in ('nearest', 'linear', 'cubic', 'smooth'):
+        assert body.map_img(img, interpolation=interp, **kw).shape == (5, 0)
+    assert body.map_img(np.stack([img, img]), degree_interval=90, ylim=(100, 200)).shape == (2, 0, 4)
+    one = pm.BodyXY(constants=bc_hst)   # (nx = ny = 1 in the constructor fails in centre_disc, as in the reference)
+    one.set_img_size(1, 1)
+    one.set_disc_params(0.0, 0.0, 5.0, 0.0)
+    lon = one.get_backplane_img('LON-GRAPHIC')
+    assert lon.shape == (1, 1) and np.isfinite(lon[0, 0])
+    # the disc-centre pixel: the reference's literal for it (tests/test_body_xy.py:278) - not exactly the
+    # sub-observer longitude, which is evaluated at its own light time
+    assert abs(lon[0, 0] - 153.1235185909613) < 1e-8 and abs(one.get_backplane_img('EMISSION')[0, 0]) < 1.0
+
+
 def test_series_batches_equal_one_bodyxy_per_epoch():
     """planetmapper_b200.series: a time series in batched launches gives, frame by frame, exactly
     what a fresh BodyXY per epoch returns (the reference's only way to do a series)."""
