@@ -188,6 +188,13 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return 0
+    # all the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its workers);
+    # set before the OpenMP runtime of the oracle library is loaded
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    os.environ['OMP_NUM_THREADS'] = str(cores)
     from oracle import oracle as O
 
     O.build()
@@ -468,6 +475,13 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back
+    # (NCCL prints its version banner there at NCCL_DEBUG=VERSION / WARN), so descriptor 1 is pointed at
+    # stderr for the whole run and the result goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
 
     import planetmapper_b200 as pm
@@ -481,9 +495,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries exactly one JSON line: keep NCCL's version banner off it
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
@@ -600,7 +611,7 @@ def main():
                           f'({dt:.2f} s wall each on {omp_threads()} OpenMP threads)',
                 'note': 'C restatement in oracle/ (the Python+spiceypy reference is not installable here; '
                         'it is ~3 orders of magnitude slower than this port, SURVEY.md section 6)'}
-        print(json.dumps(result))
+        os.write(result_fd, (json.dumps(result) + '\n').encode())
     if world > 1:
         import torch.distributed as dist
 

@@ -121,6 +121,11 @@ class Header:
     def keys(self) -> list[str]:
         return [c[0] for c in self.cards]
 
+    @property
+    def comments(self) -> '_Comments':
+        """``header.comments[keyword]`` like astropy.io.fits.Header.comments."""
+        return _Comments(self)
+
     def __len__(self) -> int:
         return len(self.cards)
 
@@ -165,6 +170,18 @@ class Header:
         for k, v, c in self.cards:
             out += self.format_card(k, v, c)
         return out
+
+
+class _Comments:
+    def __init__(self, header: Header) -> None:
+        self._header = header
+
+    def __getitem__(self, keyword: str) -> str:
+        k = Header._norm(keyword)
+        for c in self._header.cards:
+            if c[0] == k:
+                return c[2] or ''
+        raise KeyError(keyword)
 
 
 def _structural_cards(shape: tuple[int, ...], primary: bool, extend: bool) -> list[tuple]:

@@ -169,8 +169,9 @@ class Observation(BodyXY):
         """e.g. ``'JUPITER_2000-01-01T123456.fits'`` (observation.py:1159-1182)."""
         return f'{prefix}{self.target}_{self.dtm.strftime("%Y-%m-%dT%H%M%S")}{suffix}{extension}'
 
-    def _add_map_header_metadata(self, header: Header, *, interpolation, spline_smoothing, propagate_nan,
-                                 smooth_oversample_by, smooth_max_oversampled_img_size, **map_kwargs) -> None:
+    def _add_map_header_metadata(self, header: Header, *, interpolation, spline_smoothing: float,
+                                 propagate_nan: bool, smooth_oversample_by: int,
+                                 smooth_max_oversampled_img_size: int, **map_kwargs) -> None:
         """observation.py:1476-1571."""
         *_, info = self.generate_map_coordinates(**map_kwargs)
         put = lambda k, v, c: self.append_to_header(k, v, c, header=header)  # noqa: E731

@@ -158,6 +158,83 @@ def test_backplane_descriptions_match_golden_about_cards(bc_hst, ref_cards):
     assert {n: bp.description for n, bp in body.backplanes.items()} == about
 
 
+def test_map_function_params_are_consistent(bc_hst, golden_arrays, golden_headers):
+    """tests/test_observation.py:815-860: map_img, get_mapped_data, save_mapped_observation and
+    _add_map_header_metadata share parameter names, annotations and defaults."""
+    import inspect
+
+    obs = _observation(bc_hst, golden_arrays, golden_headers)
+
+    def compare(p1, p2, allow_empty_default=False):
+        assert p1.name == p2.name and p1.annotation == p2.annotation, p1.name
+        empty = inspect.Parameter.empty
+        if not allow_empty_default or (p1.default is not empty and p2.default is not empty):
+            assert p1.default == p2.default, p1.name
+
+    map_img = inspect.signature(obs.map_img).parameters
+    func = inspect.signature(obs.get_mapped_data).parameters
+    for k in set(func) | (set(map_img) - {'img', 'warn_nan'}):
+        compare(func[k], map_img[k])
+    func = inspect.signature(obs.save_mapped_observation).parameters
+    for k in set(map_img) - {'img', 'warn_nan'}:
+        compare(func[k], map_img[k])
+    func = inspect.signature(obs._add_map_header_metadata).parameters
+    for k in set(map_img) - {'img', 'warn_nan'}:
+        compare(func[k], map_img[k], allow_empty_default=True)
+
+
+def test_append_to_header_make_filename_and_names_to_save(bc_hst):
+    """tests/test_observation.py:862-1014."""
+    import planetmapper_b200 as pm
+
+    obs = pm.Observation(data=np.ones((5, 10, 8)), constants=bc_hst)
+    obs.append_to_header('TESTING', 123, 'Testing comment')
+    assert obs.header['HIERARCH PLANMAP TESTING'] == 123
+    assert obs.header.comments['HIERARCH PLANMAP TESTING'] == 'Testing comment'
+    header = FS.Header()
+    obs.append_to_header('TESTING', 123, 'Testing comment', header=header)
+    assert header['HIERARCH PLANMAP TESTING'] == 123 and 'TESTING' not in header
+    header = FS.Header()
+    obs.append_to_header('TESTING', 123, 'Testing comment', header=header, hierarch_keyword=False)
+    assert header['TESTING'] == 123 and header.comments['TESTING'] == 'Testing comment'
+    assert 'HIERARCH PLANMAP TESTING' not in header
+    header = FS.Header()
+    obs.append_to_header('A', 0, header=header, hierarch_keyword=False)
+    obs.append_to_header('B', 1, header=header, hierarch_keyword=False)
+    obs.append_to_header('A', 1, header=header, hierarch_keyword=False)
+    assert header['A'] == 1 and header.keys() == ['B', 'A']
+    header = FS.Header()
+    obs.append_to_header('A', 0, header=header, hierarch_keyword=False)
+    obs.append_to_header('B', 1, header=header, hierarch_keyword=False)
+    obs.append_to_header('A', 1, header=header, hierarch_keyword=False, remove_existing=False)
+    assert header['A'] == 0 and header.keys() == ['A', 'B', 'A']
+    for n in range(100):
+        s = 'x' * n
+        obs.append_to_header('TESTING', s)
+        if n >= 53:
+            s = 'x' * 49 + '...'
+        assert obs.header['HIERARCH PLANMAP TESTING'] == s
+        assert all(len(c) == 80 for c in obs.header.card_images())
+    obs.append_to_header('TESTING', 'x' * 100, truncate_strings=False)
+    assert obs.header['HIERARCH PLANMAP TESTING'] == 'x' * 100
+    with pytest.raises(ValueError):   # astropy < 7.1 behaviour: no CONTINUE cards for HIERARCH keywords
+        obs.header.card_images()
+
+    obs = pm.Observation(data=np.ones((5, 10, 8)), constants=bc_hst)
+    obs.add_header_metadata()
+    assert 'HIERARCH PLANMAP INFILE' not in obs.header and obs.header['PLANMAP TARGET'] == 'JUPITER'
+    assert obs.make_filename() == 'JUPITER_2005-01-01T000000.fits'
+    assert obs.make_filename(extension='.txt') == 'JUPITER_2005-01-01T000000.txt'
+    assert obs.make_filename(prefix='pre_', suffix='_post') == 'pre_JUPITER_2005-01-01T000000_post.fits'
+
+    assert obs._get_backplane_names_to_save(None, frozenset()) == set(PLANE_NAMES)
+    assert obs._get_backplane_names_to_save(['RA', 'DEC'], frozenset()) == {'RA', 'DEC'}
+    assert obs._get_backplane_names_to_save(['RA', 'DEC'], ['RA']) == {'DEC'}
+    assert obs._get_backplane_names_to_save(
+        backplanes_to_save=['RA', '   dec   ', 'DISTANCE', 'radial-VELOCITY', '<some other backplane>'],
+        backplanes_to_skip=['DEC', 'dISTANCE   ', 'LIMB-DISTANCE']) == {'RA', 'RADIAL-VELOCITY', '<SOME OTHER BACKPLANE>'}
+
+
 def test_file_layout_offsets():
     hdus = [FS.ImageHDU(np.zeros((10, 10, 7))), FS.ImageHDU(np.zeros((10, 7)), name='A'),
             FS.ImageHDU(np.zeros((0, 7)), name='EMPTY'), FS.ImageHDU(np.zeros((360, 1)), name='B')]
