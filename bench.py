@@ -433,29 +433,35 @@ def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     lons = np.arange(0.5, 360, 1.0)[::-1]
     lats = np.arange(-89.5, 90, 1.0)
     lo_g, la_g = np.meshgrid(lons, lats)
-    lod, lad = L.to_device(lo_g), L.to_device(la_g)
-    img = torch.rand((1, sz, sz), dtype=torch.float64, device='cuda')
-    xy = torch.empty((2,) + lo_g.shape, dtype=torch.float64, device='cuda')
-    mapped = torch.empty((1,) + lo_g.shape, dtype=torch.float64, device='cuda')
-    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+    # one synthetic image per frame (1 % NaN pixels), resident on the device like the frames
+    imgs = torch.empty((hi - lo, sz, sz), dtype=torch.float64, device='cuda')
+    for s in range(0, hi - lo, 128):
+        part = torch.rand(imgs[s:s + 128].shape, dtype=torch.float64, device='cuda')
+        part[torch.rand(part.shape, device='cuda') < 0.01] = float('nan')
+        imgs[s:s + 128] = part
+    del part
+    mapped = torch.empty((hi - lo,) + lo_g.shape, dtype=torch.float64, device='cuda')
 
     def one_pass():
         for s in range(0, hi - lo, batch):
             n = min(batch, hi - lo - s)
             L.backplanes_img(fd[s:s + n], sz, sz, mask, out=out[:n])
+
+    def reproject():
+        S.map_series(frames, imgs, sz, sz, lo_g, la_g, interpolation='linear', batch=batch, out=mapped)
     one_pass()
+    reproject()
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     one_pass()
     e1.record()
-    for i in range(hi - lo):
-        L.backplanes_map(fd[i], lod, lad, xy_mask, out=xy)
-        L.gather(img, xy[0], xy[1], L.INTERP_NEAREST, out=mapped)
+    reproject()
     e2.record()
     torch.cuda.synchronize()
     return {'workload': f'C5: {n_frames} Jupiter / EARTH frames of {sz}x{sz}, 60 s apart, 12-plane stack in '
-                        f'batches of {batch} frames + 1 deg nearest reprojection per frame; frames {lo}..{hi} on this rank',
+                        f'batches of {batch} frames + map_img(img, degree_interval=1) (linear) of one image per frame, batched '
+                        f'(series.map_series); frames {lo}..{hi} on this rank',
             'frames_this_rank': hi - lo, 'host_constants_s': host_s, 'host_workers': host_workers,
             'host_constants_serial_ms_per_frame': serial_ms_per_frame,
             'backplanes_ms': e0.elapsed_time(e1), 'backplanes_mpix_per_s': (hi - lo) * sz * sz / e0.elapsed_time(e1) / 1e3,

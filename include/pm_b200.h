@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 4
+#define PM_ABI_VERSION 5
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -142,6 +142,23 @@ int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny,
  */
 int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat,
                       int64_t n_cells, uint64_t plane_mask, double *out, void *stream);
+
+/*
+ * Time series (BASELINE config C5: a fresh BodyXY per epoch, then map_img of that epoch's image,
+ * i.e. body_xy.py:3482-3491 + :1414-1631 once per frame in the reference).
+ *   pm_backplanes_map_batch  pm_backplanes_map for n_frames frames sharing one lon / lat grid, one
+ *                            launch; out: [n_frames][popcount(mask)][n_cells].
+ *   pm_gather_paired         map_img where plane l of the cube is mapped with ITS OWN x / y map
+ *                            (xmaps + l * map_stride): nearest (src = the cube as is) or linear
+ *                            (src / nanbits / plane_bits = pm_spline_prepare(degree 1) outputs);
+ *                            out: [n_planes][n_cells].  Same arithmetic per cell as pm_gather.
+ */
+int pm_backplanes_map_batch(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
+                            int64_t n_cells, uint64_t plane_mask, double *out, void *stream);
+int pm_gather_paired(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits,
+                     int n_planes, int ny, int nx, const double *xmaps, const double *ymaps,
+                     int64_t map_stride, int64_t n_cells, int mode, uint32_t flags, double *out,
+                     void *stream);
 
 /*
  * Vectorised point transforms: replace SpiceBase._maybe_transform_as_arrays

@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
-    'pm_fits_data_unit_bytes', 'pm_fits_stage',
+    'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
 ]
 
 
@@ -98,11 +98,15 @@ def load_library() -> ctypes.CDLL:
     lib.pm_fits_data_unit_bytes.argtypes = [c_i64]
     lib.pm_fits_stage.argtypes = [c_p, c_p, c_p, c_i, c_p, c_p]
     lib.pm_fits_stage.restype = c_i
+    lib.pm_backplanes_map_batch.argtypes = [c_p, c_i, c_p, c_p, c_i64, c_u64, c_p, c_p]
+    lib.pm_backplanes_map_batch.restype = c_i
+    lib.pm_gather_paired.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i64, c_i64, c_i, c_u32, c_p, c_p]
+    lib.pm_gather_paired.restype = c_i
     for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 4:
+    if lib.pm_abi_version() != 5:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -181,6 +185,48 @@ def backplanes_map(frame_dev, lon_dev, lat_dev, mask: int = ALL_PLANES, out=None
     rc = lib.pm_backplanes_map(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(), n,
                                mask, out.data_ptr(), _stream_ptr(torch))
     _check(rc, 'pm_backplanes_map')
+    return out
+
+
+def backplanes_map_batch(frames_dev, lon_dev, lat_dev, mask: int = ALL_PLANES, out=None):
+    """pm_backplanes_map for every frame of ``frames_dev`` (n_frames, 92) over one lon / lat grid in
+    one launch; returns (n_frames, popcount(mask)) + grid shape."""
+    torch = _torch()
+    lib = load_library()
+    assert frames_dev.dim() == 2 and frames_dev.is_contiguous()
+    n_frames = frames_dev.shape[0]
+    if out is None:
+        out = torch.empty((n_frames, popcount(mask)) + tuple(lon_dev.shape), dtype=torch.float64,
+                          device=lon_dev.device)
+    _check(lib.pm_backplanes_map_batch(frames_dev.data_ptr(), n_frames, lon_dev.data_ptr(), lat_dev.data_ptr(),
+                                       lon_dev.numel(), mask, out.data_ptr(), _stream_ptr(torch)),
+           'pm_backplanes_map_batch')
+    return out
+
+
+def gather_paired(src, xmaps, ymaps, mode: int, propagate_nan: bool = True, out=None):
+    """Plane l of ``src`` mapped with its own maps ``xmaps[l]``, ``ymaps[l]`` (a time series: one image
+    and one disc position per frame).  ``src``: CUDA cube (n, ny, nx) for nearest, a :class:`Spline`
+    of degree 1 for linear; ``xmaps`` / ``ymaps``: (n,) + map shape, possibly strided along axis 0."""
+    torch = _torch()
+    lib = load_library()
+    spline = src if isinstance(src, Spline) else None
+    n, ny, nx = (spline.n_planes, spline.ny, spline.nx) if spline is not None else tuple(src.shape)
+    if mode not in (INTERP_NEAREST, INTERP_LINEAR) or (mode == INTERP_LINEAR) != (spline is not None):
+        raise ValueError('gather_paired: nearest takes the cube, linear a degree-1 Spline')
+    if xmaps.shape != ymaps.shape or xmaps.shape[0] != n or xmaps.stride(0) != ymaps.stride(0):
+        raise ValueError('one x / y map per plane, laid out alike')
+    n_cells = xmaps[0].numel() if n else 0
+    if n and not (xmaps[0].is_contiguous() and ymaps[0].is_contiguous()):
+        raise ValueError('each map must be contiguous')
+    if out is None:
+        out = torch.empty((n,) + tuple(xmaps.shape[1:]), dtype=torch.float64, device=xmaps.device)
+    flags = FLAG_PROPAGATE_NAN if propagate_nan else 0
+    data = spline.coef if spline is not None else src
+    _check(lib.pm_gather_paired(data.data_ptr(), spline.nanbits.data_ptr() if spline is not None else None,
+                                spline.plane_bits.data_ptr() if spline is not None else None, n, ny, nx,
+                                xmaps.data_ptr(), ymaps.data_ptr(), xmaps.stride(0) if n else n_cells, n_cells, mode,
+                                flags, out.data_ptr(), _stream_ptr(torch)), 'pm_gather_paired')
     return out
 
 

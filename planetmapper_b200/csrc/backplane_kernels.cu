@@ -29,6 +29,7 @@ __device__ __forceinline__ int slot(uint64_t mask, int k) { return __popcll(mask
 // operand) instead of a popcount, a 64-bit multiply and a shared-memory load per store.
 struct PlaneOffsets {
     int64_t byte_off[PM_N_PLANES];
+    int64_t frame_stride;  // doubles between the plane blocks of consecutive frames
 };
 static PlaneOffsets make_plane_offsets(uint64_t mask, int64_t plane_stride) {
     PlaneOffsets po;
@@ -37,6 +38,7 @@ static PlaneOffsets make_plane_offsets(uint64_t mask, int64_t plane_stride) {
         po.byte_off[k] = (int64_t)slot * plane_stride * (int64_t)sizeof(double);
         if (mask & bit(k)) slot++;
     }
+    po.frame_stride = (int64_t)slot * plane_stride;
     return po;
 }
 
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_map_kernel(const PMFrame
                                                                    const __grid_constant__ PlaneOffsets po,
                                                                    double *__restrict__ out) {
     __shared__ FrameD fs;
-    load_frame(fs, frame);
+    // blockIdx.y = frame of a series sharing the lon / lat grid (pm_backplanes_map_batch); each
+    // frame's planes follow the previous frame's: po.frame_stride doubles apart
+    load_frame(fs, frame + blockIdx.y);
+    out += (int64_t)blockIdx.y * po.frame_stride;
     const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
 #pragma unroll 1
     for (int r = 0; r < kPerThread; r++) {
@@ -232,10 +237,11 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     count_launches(1);
     return cudaGetLastError();
 }
-cudaError_t launch_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
-                                  uint64_t mask, double *out, int sm_count, cudaStream_t st) {
+cudaError_t launch_backplanes_map(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
+                                  int64_t n, uint64_t mask, double *out, int sm_count, cudaStream_t st) {
     (void)sm_count;
-    backplanes_map_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, mask, make_plane_offsets(mask, n), out);
+    const dim3 grid(chunks_for(n), (unsigned)n_frames);
+    backplanes_map_kernel<<<grid, kBlock, 0, st>>>(frames, lon, lat, n, mask, make_plane_offsets(mask, n), out);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -64,7 +64,33 @@ int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat
     if (!lon || !lat || !out) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
-    return check(launch_backplanes_map(frame, lon, lat, n_cells, plane_mask, out, sms, (cudaStream_t)stream));
+    return check(launch_backplanes_map(frame, 1, lon, lat, n_cells, plane_mask, out, sms, (cudaStream_t)stream));
+}
+
+int pm_backplanes_map_batch(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
+                            int64_t n_cells, uint64_t plane_mask, double *out, void *stream) {
+    if (!frames || n_frames <= 0 || n_frames > 65535 || n_cells < 0) return PM_ERR_BAD_ARG;
+    plane_mask &= PM_ALL_PLANES;
+    if (!plane_mask) return PM_ERR_BAD_ARG;
+    if (n_cells == 0) return PM_OK;
+    if (!lon || !lat || !out) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_backplanes_map(frames, n_frames, lon, lat, n_cells, plane_mask, out, sms,
+                                       (cudaStream_t)stream));
+}
+
+int pm_gather_paired(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes, int ny,
+                     int nx, const double *xmaps, const double *ymaps, int64_t map_stride, int64_t n_cells, int mode,
+                     uint32_t flags, double *out, void *stream) {
+    if (n_planes < 0 || ny <= 0 || nx <= 0 || n_cells < 0 || map_stride < n_cells) return PM_ERR_BAD_ARG;
+    if (mode != PM_INTERP_NEAREST && mode != PM_INTERP_LINEAR) return PM_ERR_UNSUPPORTED;
+    if (n_planes == 0 || n_cells == 0) return PM_OK;
+    if (!src || !xmaps || !ymaps || !out) return PM_ERR_BAD_ARG;
+    if (mode == PM_INTERP_LINEAR && (!nanbits || !plane_bits || nx < 2 || ny < 2)) return PM_ERR_BAD_ARG;
+    if (n_planes > 65535) return PM_ERR_BAD_ARG;
+    return check(launch_gather_paired(src, nanbits, plane_bits, n_planes, ny, nx, xmaps, ymaps, map_stride, n_cells,
+                                      mode, flags, out, (cudaStream_t)stream));
 }
 
 int pm_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon, double *lat,

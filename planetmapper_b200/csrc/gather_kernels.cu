@@ -628,6 +628,72 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Paired gather for a time series: plane l of the cube is mapped with its own x / y map
+// (pm_gather_paired).  One thread per (plane, cell); per cell the same arithmetic, in the same
+// order, as gather_nearest_kernel / gather_spline_kernel<2, 2>, so results are bit-identical to
+// n_planes single-plane pm_gather calls.  Each voxel reads one (nearest) or four (linear) cube
+// values that neighbouring threads share through L1 / L2; the store is coalesced.
+// ---------------------------------------------------------------------------------
+template <bool kLinear>
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_paired_kernel(const double *__restrict__ src, const uint32_t *__restrict__ nanbits,
+                         const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx,
+                         const double *__restrict__ xmaps, const double *__restrict__ ymaps, int64_t map_stride,
+                         int64_t n_cells, uint32_t flags, double *__restrict__ out) {
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const int l = blockIdx.y;
+    const double x = __ldg(xmaps + (int64_t)l * map_stride + cell), y = __ldg(ymaps + (int64_t)l * map_stride + cell);
+    double v = NAN;
+    if (!kLinear) {
+        if (!isnan(x)) {
+            long xi = (long)rint(x), yi = isnan(y) ? -999 : (long)rint(y);
+            if (xi < 0) xi += nx;
+            if (yi < 0) yi += ny;
+            if (xi >= 0 && xi < nx && yi >= 0 && yi < ny) v = __ldg(src + ((int64_t)l * ny + yi) * nx + xi);
+        }
+    } else {
+        const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
+        CellState<2, 2> cs;
+        setup_cell<2, 2>(cs, x, y, ny, nx, propagate);
+        if (cs.valid) {
+            const int word = l >> 5;
+            uint32_t bad = __ldg(plane_bits + word);
+            if (propagate && __ldg(plane_bits + n_words + word)) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) bad |= __ldg(nanbits + (int64_t)cs.nb[k] * n_words + word);
+            }
+            if (!((bad >> (l & 31)) & 1u)) {
+                const int64_t row_stride = (int64_t)nx * 4;
+                const double *p = src + (int64_t)(l >> 2) * ny * row_stride + cs.origin + (l & 3);
+                double acc = 0.0;
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) acc = fma(__ldg(p + a * row_stride + b * 4), cs.w[a * 2 + b], acc);
+                v = acc;
+            }
+        }
+    }
+    __stcs(out + (int64_t)l * n_cells + cell, v);
+}
+
+cudaError_t launch_gather_paired(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
+                                 int ny, int nx, const double *xmaps, const double *ymaps, int64_t map_stride,
+                                 int64_t n_cells, int mode, uint32_t flags, double *out, cudaStream_t st) {
+    const dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)n_planes);
+    const int n_words = (n_planes + 31) / 32;
+    if (mode == PM_INTERP_LINEAR)
+        gather_paired_kernel<true><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx, xmaps, ymaps,
+                                                                   map_stride, n_cells, flags, out);
+    else
+        gather_paired_kernel<false><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx, xmaps,
+                                                                    ymaps, map_stride, n_cells, flags, out);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
                           int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
                           int64_t n_cells, int64_t cells_per_row, int mode, uint32_t flags, double *out, int sm_count,
@@ -701,16 +767,17 @@ struct PlaneStats {
     long long n_bad;
 };
 
-// pass 1: NaN mask, bad-pixel counts, plane flags, copy into the coefficient buffer
+// Planes of a cube are small (C4: 64 x 64) and many, planes of a time series are large (C5:
+// 1024 x 1024) and few per batch: a plane is spread over `gridDim.y` CTAs so that both shapes
+// fill the machine.
+// pass 1: NaN mask, bad-pixel counts (atomically into zeroed `stats`), copy into the coefficient buffer
 __global__ void __launch_bounds__(256) classify_kernel(const double *__restrict__ cube, int64_t plane_px,
-                                                       double *__restrict__ coef,
-                                                       uint8_t *__restrict__ plane_skip,
-                                                       PlaneStats *__restrict__ stats) {
+                                                       double *__restrict__ coef, PlaneStats *__restrict__ stats) {
     const int l = blockIdx.x;
     const double *src = cube + (int64_t)l * plane_px;
     double *dst = coef + (int64_t)l * plane_px;
     long long n_nan = 0, n_bad = 0;
-    for (int64_t i = threadIdx.x; i < plane_px; i += blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < plane_px; i += (int64_t)gridDim.y * blockDim.x) {
         double v = src[i];
         bool isn = isnan(v);
         n_nan += isn;
@@ -728,14 +795,19 @@ __global__ void __launch_bounds__(256) classify_kernel(const double *__restrict_
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        stats[l].n_nan = s_nan[0];
-        stats[l].n_bad = s_bad[0];
-        uint8_t flag = 0;
-        if (s_nan[0] == plane_px) flag |= kPlaneAllNan;
-        if (s_nan[0] > 0) flag |= kPlaneHasNan;
-        plane_skip[l] = flag;
+    if (threadIdx.x == 0 && (s_nan[0] | s_bad[0])) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&stats[l].n_nan), (unsigned long long)s_nan[0]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&stats[l].n_bad), (unsigned long long)s_bad[0]);
     }
+}
+__global__ void plane_flags_kernel(const PlaneStats *__restrict__ stats, int n_planes, int64_t plane_px,
+                                   uint8_t *__restrict__ plane_skip) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_planes) return;
+    uint8_t flag = 0;
+    if (stats[l].n_nan == plane_px) flag |= kPlaneAllNan;
+    if (stats[l].n_nan > 0) flag |= kPlaneHasNan;
+    plane_skip[l] = flag;
 }
 
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -809,6 +881,94 @@ __global__ void __launch_bounds__(256) median_kernel(const double *__restrict__ 
         }
     }
     if (threadIdx.x == 0) median[l] = med;
+}
+
+// pass 2 for LARGE planes: the same MSB-first radix select with the histogram of every pass built
+// by many CTAs per plane (shared-memory histogram per CTA, merged with global atomics) and the
+// bucket chosen by a one-thread-per-plane kernel in between: 1 + 2 x 8 small launches that each
+// stream the batch once, instead of one CTA walking a megapixel plane sixteen times.
+struct SelectState {
+    unsigned long long prefix[2], mask;
+    long long k[2];
+    int n_sel;  // 0: nothing to select, 1: odd count (one order statistic), 2: even count (two)
+};
+__global__ void select_init_kernel(const PlaneStats *__restrict__ stats, int n_planes, int64_t plane_px,
+                                   SelectState *__restrict__ state, unsigned int *__restrict__ hist,
+                                   double *__restrict__ median) {
+    const int l = blockIdx.x;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[(int64_t)l * 512 + i] = 0;
+    if (threadIdx.x != 0) return;
+    SelectState st;
+    st.prefix[0] = st.prefix[1] = st.mask = 0;
+    st.k[0] = st.k[1] = 0;
+    st.n_sel = 0;
+    const long long n_bad = stats[l].n_bad, m = plane_px - n_bad;
+    if (n_bad > 0) {
+        if (m <= 0) {
+            median[l] = 0.0;  // np.all(bad) -> 0.0 (body_xy.py:1890-1891)
+        } else if (m & 1) {
+            st.n_sel = 1;
+            st.k[0] = m / 2;
+        } else {
+            st.n_sel = 2;
+            st.k[0] = m / 2 - 1;
+            st.k[1] = m / 2;
+        }
+    }
+    state[l] = st;
+}
+__global__ void __launch_bounds__(256) select_hist_kernel(const double *__restrict__ cube, int64_t plane_px,
+                                                          const SelectState *__restrict__ state,
+                                                          unsigned int *__restrict__ hist, int pass) {
+    const int l = blockIdx.x;
+    const SelectState st = state[l];
+    if (st.n_sel == 0) return;  // uniform for the CTA
+    __shared__ unsigned int sh[2][256];
+    sh[0][threadIdx.x] = 0;
+    sh[1][threadIdx.x] = 0;
+    __syncthreads();
+    const double *src = cube + (int64_t)l * plane_px;
+    const bool same = st.n_sel == 2 && st.prefix[0] == st.prefix[1];  // both statistics still in one bucket
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < plane_px; i += (int64_t)gridDim.y * blockDim.x) {
+        const double v = src[i];
+        if (isfinite(v)) {
+            const unsigned long long key = order_key(v);
+            const unsigned d = (unsigned)((key >> (8 * pass)) & 255ull);
+            if ((key & st.mask) == st.prefix[0]) atomicAdd(&sh[0][d], 1u);
+            if (st.n_sel == 2 && !same && (key & st.mask) == st.prefix[1]) atomicAdd(&sh[1][d], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned int *g = hist + (int64_t)l * 512;
+    if (sh[0][threadIdx.x]) atomicAdd(&g[threadIdx.x], sh[0][threadIdx.x]);
+    const unsigned int second = same ? sh[0][threadIdx.x] : sh[1][threadIdx.x];
+    if (st.n_sel == 2 && second) atomicAdd(&g[256 + threadIdx.x], second);
+}
+__global__ void select_pick_kernel(SelectState *__restrict__ state, unsigned int *__restrict__ hist, int n_planes,
+                                   int pass, double *__restrict__ median) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_planes) return;
+    SelectState st = state[l];
+    if (st.n_sel == 0) return;
+    unsigned int *g = hist + (int64_t)l * 512;
+    for (int s = 0; s < st.n_sel; s++) {
+        long long cum = 0;
+        int b = 0;
+        for (; b < 256; b++) {
+            if (cum + (long long)g[256 * s + b] > st.k[s]) break;
+            cum += g[256 * s + b];
+        }
+        if (b > 255) b = 255;
+        st.k[s] -= cum;
+        st.prefix[s] |= (unsigned long long)b << (8 * pass);
+    }
+    st.mask |= 0xffull << (8 * pass);
+    for (int i = 0; i < 512; i++) g[i] = 0;
+    state[l] = st;
+    if (pass == 0) {
+        const double a = key_to_double(st.prefix[0]);
+        median[l] = st.n_sel == 1 ? a : (a + key_to_double(st.prefix[1])) / 2.0;
+    }
 }
 
 // pass 3: replace bad pixels (body_xy.py:1893-1903)
@@ -996,6 +1156,7 @@ int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree) {
     int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double)) +
                 align256((int64_t)n_planes) + align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
     b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
+    b += align256((int64_t)n_planes * sizeof(SelectState)) + align256((int64_t)n_planes * 512 * sizeof(unsigned int));
     return b;
 }
 
@@ -1014,8 +1175,29 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     w += align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
     const int64_t plane_px = (int64_t)ny * nx;
     const int n_words = (n_planes + 31) / 32;
-    classify_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, coef, plane_skip, stats);
-    median_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, stats, median);
+    // CTAs per plane: enough to fill the machine when the planes are few and large
+    const int chunks = (int)std::max<int64_t>(
+        1, std::min<int64_t>((plane_px + 4095) / 4096, ((int64_t)sm_count * 8 + n_planes - 1) / n_planes));
+    cudaError_t me = cudaMemsetAsync(stats, 0, (size_t)n_planes * sizeof(PlaneStats), st);
+    if (me != cudaSuccess) return me;
+    classify_kernel<<<dim3(n_planes, chunks), 256, 0, st>>>(cube, plane_px, coef, stats);
+    plane_flags_kernel<<<(n_planes + 255) / 256, 256, 0, st>>>(stats, n_planes, plane_px, plane_skip);
+    count_launches(1);
+    if (chunks == 1) {
+        median_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, stats, median);
+    } else {
+        char *tail = static_cast<char *>(work) + spline_work_bytes(n_planes, ny, nx, degree) -
+                     align256((int64_t)n_planes * sizeof(SelectState)) -
+                     align256((int64_t)n_planes * 512 * sizeof(unsigned int));
+        SelectState *state = reinterpret_cast<SelectState *>(tail);
+        unsigned int *hist = reinterpret_cast<unsigned int *>(tail + align256((int64_t)n_planes * sizeof(SelectState)));
+        select_init_kernel<<<n_planes, 256, 0, st>>>(stats, n_planes, plane_px, state, hist, median);
+        for (int pass = 7; pass >= 0; pass--) {
+            select_hist_kernel<<<dim3(n_planes, chunks), 256, 0, st>>>(cube, plane_px, state, hist, pass);
+            select_pick_kernel<<<(n_planes + 127) / 128, 128, 0, st>>>(state, hist, n_planes, pass, median);
+        }
+        count_launches(16);
+    }
     int64_t total = plane_px * n_planes;
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
     repair_kernel<<<blocks, 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);

@@ -14,8 +14,8 @@ void count_launches(int n);
 
 cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t mask,
                                   double *out, int sm_count, cudaStream_t st);
-cudaError_t launch_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
-                                  uint64_t mask, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_backplanes_map(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
+                                  int64_t n, uint64_t mask, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon,
                              double *lat, unsigned long long *n_missed, int sm_count, cudaStream_t st);
 cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,
@@ -31,6 +31,10 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                           int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
                           int64_t n_cells, int64_t cells_per_row, int mode, uint32_t flags, double *out, int sm_count,
                           cudaStream_t st);
+
+cudaError_t launch_gather_paired(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
+                                 int ny, int nx, const double *xmaps, const double *ymaps, int64_t map_stride,
+                                 int64_t n_cells, int mode, uint32_t flags, double *out, cudaStream_t st);
 
 int64_t spline_coef_bytes(int n_planes, int ny, int nx);
 int64_t spline_nanbits_bytes(int n_planes, int ny, int nx);

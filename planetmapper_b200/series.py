@@ -171,5 +171,42 @@ def iter_backplane_batches(frames: np.ndarray, nx: int, ny: int, names, batch: i
         yield first, out[:n]
 
 
+def map_series(frames: np.ndarray, imgs, nx: int, ny: int, lons, lats, *, interpolation='linear',
+               propagate_nan: bool = True, batch: int = 32, out=None):
+    """``BodyXY(...).map_img(img_f, ...)`` for every frame f of a series (body_xy.py:1414-1631 once per
+    epoch in the reference): frame f's image is mapped onto the lon / lat grid with frame f's own
+    disc geometry.  Per batch of frames: ONE launch for all x / y maps (``pm_backplanes_map_batch``),
+    the NaN repair of the batch's images (linear), ONE paired gather.
+
+    ``imgs``: (n_frames, ny, nx) array or CUDA tensor; ``lons`` / ``lats``: the map grid (degrees,
+    e.g. from ``generate_map_coordinates``); ``interpolation``: 'nearest' or 'linear'.  Returns a CUDA
+    tensor (n_frames,) + grid shape (``out`` if given).
+    """
+    from . import _lib as L
+
+    torch = L._torch()
+    mode = {'nearest': L.INTERP_NEAREST, 'linear': L.INTERP_LINEAR, 1: L.INTERP_LINEAR}.get(interpolation)
+    if mode is None:
+        raise NotImplementedError("map_series: interpolation must be 'nearest' or 'linear'")
+    fd = L.to_device(np.ascontiguousarray(frames, dtype=np.float64))
+    if not isinstance(imgs, torch.Tensor):
+        imgs = L.to_device(imgs)
+    if tuple(imgs.shape) != (len(frames), ny, nx):
+        raise ValueError(f'imgs must have shape ({len(frames)}, {ny}, {nx})')
+    lod = L.to_device(np.asarray(lons, dtype=np.float64) % 360)
+    lad = L.to_device(lats)
+    if out is None:
+        out = torch.empty((len(frames),) + tuple(lod.shape), dtype=torch.float64, device=fd.device)
+    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+    xy = torch.empty((min(batch, len(frames)), 2) + tuple(lod.shape), dtype=torch.float64, device=fd.device)
+    for first in range(0, len(frames), batch):
+        n = min(batch, len(frames) - first)
+        L.backplanes_map_batch(fd[first:first + n], lod, lad, xy_mask, out=xy[:n])
+        cube = imgs[first:first + n].contiguous()
+        src = cube if mode == L.INTERP_NEAREST else L.spline_prepare(cube, 1)
+        L.gather_paired(src, xy[:n, 0], xy[:n, 1], mode, propagate_nan=propagate_nan, out=out[first:first + n])
+    return out
+
+
 if __name__ == '__main__':
     _worker_main()

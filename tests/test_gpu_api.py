@@ -247,6 +247,52 @@ def test_series_batches_equal_one_bodyxy_per_epoch():
     assert seen == len(utcs)
 
 
+def test_map_series_equals_map_img_per_epoch():
+    """series.map_series (batched x / y maps + paired gather) gives, frame by frame, exactly what
+    BodyXY(...).map_img(img_f) returns for that epoch (body_xy.py:1414-1631)."""
+    import planetmapper_b200 as pm
+    from planetmapper_b200 import _lib as L
+    from planetmapper_b200 import series as S
+
+    prov = pm.get_default_provider()
+    utcs = ['2004-12-31T2%d:%02d:00' % (h, m) for h in (0, 1, 2) for m in (0, 30)] + ['2004-12-29T12:00:00']
+    ets = np.array([prov.utc2et(u) for u in utcs])
+    nx, ny = 36, 28
+    disc = dict(nx=nx, ny=ny, x0=17.0, y0=13.5, r0=11.0, rotation_radians=np.deg2rad(40.0))
+    frames = S.build_series_frames('Jupiter', ets, 'EARTH', workers=1, **disc)
+    rng = np.random.default_rng(11)
+    imgs = rng.normal(1.0, 0.3, (len(utcs), ny, nx))
+    imgs[rng.random(imgs.shape) < 0.03] = np.nan
+    imgs[3] = np.nan                                         # an all-NaN image
+    bodies = []
+    for u in utcs:
+        b = pm.BodyXY('Jupiter', u, 'EARTH', nx=nx, ny=ny)
+        b.set_disc_params(17.0, 13.5, 11.0, 40.0)
+        bodies.append(b)
+    lons, lats, *_ = bodies[0].generate_map_coordinates(degree_interval=7.5)
+    for interp in ('nearest', 'linear'):
+        for prop in (True, False):
+            before = L.launch_count()
+            got = S.map_series(frames, imgs, nx, ny, lons, lats, interpolation=interp, propagate_nan=prop,
+                               batch=4).cpu().numpy()
+            launches = L.launch_count() - before
+            assert got.shape == (len(utcs),) + lons.shape
+            for f, b in enumerate(bodies):
+                ref = b.map_img(imgs[f], interpolation=interp, propagate_nan=prop, degree_interval=7.5)
+                assert np.array_equal(got[f], ref, equal_nan=True), (interp, prop, f)
+            assert np.isfinite(got[0]).sum() > 100 and not np.isfinite(got[3]).any()
+            if interp == 'nearest':
+                assert launches == 2 * 2   # two batches x (maps + gather), not two launches per frame
+    with pytest.raises(NotImplementedError):
+        S.map_series(frames, imgs, nx, ny, lons, lats, interpolation='cubic')
+    # the batched map kernel alone: every plane of every frame equals the single-frame call
+    fd, lod, lad = L.to_device(frames), L.to_device(np.asarray(lons) % 360), L.to_device(lats)
+    mask = L.mask_from_names(['PIXEL-X', 'EMISSION', 'DISTANCE', 'RING-RADIUS'])
+    both = L.backplanes_map_batch(fd, lod, lad, mask).cpu().numpy()
+    for f in range(len(utcs)):
+        assert np.array_equal(both[f], L.backplanes_map(fd[f], lod, lad, mask).cpu().numpy(), equal_nan=True)
+
+
 def test_custom_proj_strings(body):
     """Custom proj strings (body_xy.py:2970-2980): the strings the reference itself builds for its
     named projections (:2932-2968) must give exactly the named projection, and a unit-sphere

@@ -284,6 +284,41 @@ def test_nan_repair_matches_reference_recipe(L, bc_hst):
         assert np.allclose(coef[l], ref, rtol=1e-14, atol=0), l
 
 
+def test_nan_repair_large_planes_multi_cta_median(L):
+    """Time-series images are few and large: classify / nanmedian spread a plane over many CTAs
+    (multi-pass radix select with global histograms).  Same recipe, same answers: odd and even
+    counts of finite pixels, inf treated as bad, an isolated 3 x 3 block of NaN (median fill),
+    an all-NaN plane and a plane without NaN."""
+    from oracle import map_img_oracle as MO
+
+    rng = np.random.default_rng(17)
+    ny, nx = 301, 299
+    # positive values over seven decades (no cancellation in the 3 x 3 means, so 1e-14 relative is meaningful)
+    cube = rng.lognormal(0.0, 1.0, (5, ny, nx)) * 10.0 ** rng.integers(-3, 4, (5, ny, nx))
+    cube[0][rng.random((ny, nx)) < 0.02] = np.nan
+    cube[0, 100:103, 50:53] = np.nan                       # all nine neighbours bad -> nanmedian
+    if np.isfinite(cube[0]).sum() % 2 == 0:
+        cube[0, 0, 0] = np.nan                             # odd number of finite pixels
+    cube[1][rng.random((ny, nx)) < 0.3] = np.nan
+    cube[1, 5, 5] = np.inf
+    if np.isfinite(cube[1]).sum() % 2 == 1:
+        cube[1, 0, 0] = np.nan                             # even: mean of the two middle values
+    cube[2] = np.nan
+    cube[4, 7, 7] = np.nan
+    cube[4, 200:203, 200:203] = np.inf
+    spline = L.spline_prepare(L.to_device(cube), L.INTERP_LINEAR)
+    coef = spline.planes().cpu().numpy()
+    assert np.array_equal(spline.nanmask().cpu().numpy()[:5], np.isnan(cube))
+    assert list(spline.all_nan_planes().cpu().numpy()[:5]) == [False, False, True, False, False]
+    for l in (0, 1, 3, 4):
+        ref = MO.replace_nans_with_interpolated_values(cube[l])
+        assert np.array_equal(coef[l], ref) or np.allclose(coef[l], ref, rtol=1e-14, atol=0), l
+        if l in (0, 4):   # the isolated block is filled with exactly np.nanmedian of the finite pixels
+            r, c = (101, 51) if l == 0 else (201, 201)
+            finite = cube[l][np.isfinite(cube[l])]
+            assert coef[l][r, c] == np.median(finite)
+
+
 # ---- size-independent properties at BASELINE.json's full sizes ------------------------
 def test_full_size_2048_properties(L, bc_hst):
     """C2: 2048 x 2048, 12-plane stack."""
