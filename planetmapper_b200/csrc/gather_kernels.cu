@@ -944,30 +944,59 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const double *__restri
     const unsigned int second = same ? sh[0][threadIdx.x] : sh[1][threadIdx.x];
     if (st.n_sel == 2 && second) atomicAdd(&g[256 + threadIdx.x], second);
 }
-__global__ void select_pick_kernel(SelectState *__restrict__ state, unsigned int *__restrict__ hist, int n_planes,
-                                   int pass, double *__restrict__ median) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_planes) return;
+// one warp per plane: lane i owns buckets 8 i .. 8 i + 7; the bucket holding rank k is found from
+// the warp prefix sum of the lane totals
+__global__ void __launch_bounds__(128) select_pick_kernel(SelectState *__restrict__ state,
+                                                          unsigned int *__restrict__ hist, int n_planes, int pass,
+                                                          double *__restrict__ median) {
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= n_planes) return;  // whole warp
     SelectState st = state[l];
     if (st.n_sel == 0) return;
     unsigned int *g = hist + (int64_t)l * 512;
     for (int s = 0; s < st.n_sel; s++) {
-        long long cum = 0;
-        int b = 0;
-        for (; b < 256; b++) {
-            if (cum + (long long)g[256 * s + b] > st.k[s]) break;
-            cum += g[256 * s + b];
+        unsigned int c[8];
+        long long mine = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            c[b] = g[256 * s + 8 * lane + b];
+            mine += c[b];
         }
-        if (b > 255) b = 255;
-        st.k[s] -= cum;
-        st.prefix[s] |= (unsigned long long)b << (8 * pass);
+        long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const long long before = incl - mine;   // counts in the buckets below this lane's
+        const bool holds = before <= st.k[s] && st.k[s] < incl;
+        const unsigned owner = __ballot_sync(0xffffffffu, holds);
+        int bucket = 255;
+        long long cum = before;
+        if (holds) {
+            bucket = 8 * lane;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                if (cum + (long long)c[b] > st.k[s]) break;
+                cum += c[b];
+                bucket = 8 * lane + b + 1;
+            }
+        }
+        const int src = owner ? __ffs(owner) - 1 : 31;   // rank beyond the count cannot happen; bucket 255 as before
+        bucket = __shfl_sync(0xffffffffu, bucket, src);
+        cum = __shfl_sync(0xffffffffu, cum, src);
+        if (!owner) cum = incl;  // (defensive) everything is below
+        st.k[s] -= __shfl_sync(0xffffffffu, cum, src);
+        st.prefix[s] |= (unsigned long long)min(bucket, 255) << (8 * pass);
     }
     st.mask |= 0xffull << (8 * pass);
-    for (int i = 0; i < 512; i++) g[i] = 0;
-    state[l] = st;
-    if (pass == 0) {
-        const double a = key_to_double(st.prefix[0]);
-        median[l] = st.n_sel == 1 ? a : (a + key_to_double(st.prefix[1])) / 2.0;
+    for (int i = lane; i < 512; i += 32) g[i] = 0;
+    if (lane == 0) {
+        state[l] = st;
+        if (pass == 0) {
+            const double a = key_to_double(st.prefix[0]);
+            median[l] = st.n_sel == 1 ? a : (a + key_to_double(st.prefix[1])) / 2.0;
+        }
     }
 }
 
@@ -976,16 +1005,15 @@ __global__ void __launch_bounds__(256) repair_kernel(const double *__restrict__ 
                                                      int nx, const PlaneStats *__restrict__ stats,
                                                      const double *__restrict__ median,
                                                      double *__restrict__ coef) {
+    // blockIdx.y = plane; rows are walked with 32-bit arithmetic (no 64-bit division per pixel)
+    const int l = blockIdx.y;
+    if (stats[l].n_bad == 0) return;
     const int64_t plane_px = (int64_t)ny * nx;
-    const int64_t total = plane_px * n_planes;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int l = (int)(idx / plane_px);
-        if (stats[l].n_bad == 0) continue;
-        const int64_t r = idx - (int64_t)l * plane_px;
-        const int i = (int)(r / nx), j = (int)(r - (int64_t)i * nx);
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < plane_px; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t idx = (int64_t)l * plane_px + r;
         const double *img = cube + (int64_t)l * plane_px;
         if (isfinite(img[r])) continue;
+        const int i = (int)(r / nx), j = (int)(r - (int64_t)i * nx);   // bad pixels only
         // uniform_filter(bad, size=3) on a bool array is True only when all nine
         // reflected neighbours are bad; reflect == clamp for size 3
         bool all_bad = true;
@@ -1194,13 +1222,13 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
         select_init_kernel<<<n_planes, 256, 0, st>>>(stats, n_planes, plane_px, state, hist, median);
         for (int pass = 7; pass >= 0; pass--) {
             select_hist_kernel<<<dim3(n_planes, chunks), 256, 0, st>>>(cube, plane_px, state, hist, pass);
-            select_pick_kernel<<<(n_planes + 127) / 128, 128, 0, st>>>(state, hist, n_planes, pass, median);
+            select_pick_kernel<<<(n_planes + 3) / 4, 128, 0, st>>>(state, hist, n_planes, pass, median);
         }
         count_launches(16);
     }
-    int64_t total = plane_px * n_planes;
-    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
-    repair_kernel<<<blocks, 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
+    const int rblocks = (int)std::max<int64_t>(
+        1, std::min<int64_t>((plane_px + 255) / 256, ((int64_t)sm_count * 16 + n_planes - 1) / n_planes));
+    repair_kernel<<<dim3(rblocks, n_planes), 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
     count_launches(3);
     int deg_y = degree, deg_x = degree;  // rows (image y) / columns (image x)
     if (degree & PM_INTERP_MIXED) {
