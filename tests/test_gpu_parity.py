@@ -73,6 +73,23 @@ def test_other_bodies_vs_oracle(L, oracle, target, observer, nx, ny, x0, y0, r0,
     check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
 
 
+@pytest.mark.parametrize('target,observer', [('Moon', 'EARTH'), ('Venus', 'EARTH'), ('Earth', 'MOON'), ('Mars', 'EARTH')])
+def test_other_bodies_large_disc_limb_vs_oracle(L, oracle, target, observer):
+    """The same bodies with a 700-pixel disc: thousands of limb pixels per body, so the grazing-ray
+    branch of sincpt (light time iterated to convergence) is exercised on near-field, retrograde and
+    east-positive geometries, all 26 planes."""
+    import planetmapper_b200 as pm
+
+    bc = F.build_body_constants(pm.get_default_provider(), target, '2004-12-31T00:00:00', observer)
+    sz = 768
+    fr = _img_case(bc, sz, sz, 380.3, 390.7, 350.0, 33.0)
+    ref, margin = oracle.backplanes_img(fr, sz, sz, with_margin=True)
+    got = L.backplanes_img(L.to_device(fr[None]), sz, sz).cpu().numpy()[0]
+    report, n_graz, n_mis = check_img_planes(got, ref, margin, fr, f'{target}/{observer} 768', allow_epoch_quantum=True)
+    emi = ref[PID['EMISSION']]
+    assert (emi > 89.1).sum() > 20, 'no grazing pixels in this frame'
+
+
 def test_plane_mask_subsets_match_full_stack(L, bc_hst):
     fr = _img_case(bc_hst, 60, 50, 29.5, 24.5, 22.0, 12.0)
     fd = L.to_device(fr[None])

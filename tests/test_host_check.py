@@ -142,6 +142,22 @@ def test_device_code_other_bodies_vs_oracle(HC, oracle, target, observer, nx, ny
     check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
 
 
+@pytest.mark.parametrize('target,observer', [('Moon', 'EARTH'), ('Venus', 'EARTH'), ('Jupiter', 'EARTH')])
+def test_device_code_large_disc_limb_vs_oracle(HC, oracle, target, observer):
+    """700-pixel discs: dozens of pixels with emission > 89.1 deg take sincpt's grazing-ray branch
+    (light time iterated to convergence like CSPICE; the fixed three-pass scheme was off by up to 66
+    tolerances on such pixels of the 2048 x 2048 frame)."""
+    import planetmapper_b200 as pm
+
+    bc = F.build_body_constants(pm.get_default_provider(), target, '2004-12-31T00:00:00', observer)
+    sz = 768
+    fr = img_case(bc, sz, sz, 380.3, 390.7, 350.0, 33.0)
+    ref, margin = oracle.backplanes_img(fr, sz, sz, with_margin=True)
+    got = hc_img(HC, fr, sz, sz)
+    check_img_planes(got, ref, margin, fr, f'{target}/{observer} 768', allow_epoch_quantum=True)
+    assert (ref[PID['EMISSION']] > 89.1).sum() > 20
+
+
 def test_device_code_plane_subsets(HC, bc_hst):
     fr = img_case(bc_hst, 60, 50, 29.5, 24.5, 22.0, 12.0)
     full = hc_img(HC, fr, 60, 50)
