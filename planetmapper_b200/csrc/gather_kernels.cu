@@ -340,40 +340,48 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
     const double nan = NAN;
     const bool propagate = (flags & PM_FLAG_PROPAGATE_NAN) != 0;
 
-    // ---- per-cell setup: the four lanes of group g all describe cell 8 i + g of tile i
+    // ---- per-cell setup.  Lane L works out cell (tile L >> 3, column L & 7) ONCE - map load, validity,
+    // NaN-test pixels, B-spline weights (the not-a-knot weights are ~250 instructions per axis) -
+    // then the values travel to the four lanes (g, t = 0..3) that describe that cell in the MMA.
     double bw[4][4];          // B fragments: bw[i][j] = wy[j] * wx[t] of tile i's cell g
     uint32_t origin[4];       // iy * nx + ix of the footprint (pixel index)
     uint32_t nbp[4];          // NaN-test pixels, packed: x0 | y0 << 14 | (x1 - x0) << 28 | (y1 - y0) << 29
     uint32_t cls[4];          // lanes of the tile sharing this lane's footprint
     uint32_t valid_mask[4];   // ballot of valid cells per tile
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int64_t cell = base0 + i * tile_step + g;
-        const bool in_range = g < ncols[i];
+    {
+        const int ti = lane >> 3, col = lane & 7;
+        const int nc = ti == 0 ? ncols[0] : (ti == 1 ? ncols[1] : (ti == 2 ? ncols[2] : ncols[3]));
+        const int64_t cell = base0 + ti * tile_step + col;
+        const bool in_range = col < nc;
         const double x = in_range ? __ldg(xmap + cell) : nan, y = in_range ? __ldg(ymap + cell) : nan;
         bool valid = !isnan(x);  // y is never NaN when x is not (body_xy.py:1646, :1697)
-        nbp[i] = 0;
+        uint32_t my_nbp = 0, my_origin = 0xffffffffu;
         if (valid && propagate) {
             // BodyXY._should_propagate_nan_to_map (body_xy.py:1855-1866)
             if (x < 0.0 || y < 0.0 || x > nx - 1 || y > ny - 1) valid = false;
             const int x0 = max((int)floor(x), 0), x1 = min((int)ceil(x), nx - 1);
             const int y0 = max((int)floor(y), 0), y1 = min((int)ceil(y), ny - 1);
-            nbp[i] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(x1 > x0) << 28) | ((uint32_t)(y1 > y0) << 29);
+            my_nbp = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(x1 > x0) << 28) | ((uint32_t)(y1 > y0) << 29);
         }
-        origin[i] = 0xffffffffu;
-#pragma unroll
-        for (int j = 0; j < 4; j++) bw[i][j] = 0.0;
+        double wx[4] = {0.0, 0.0, 0.0, 0.0}, wy[4] = {0.0, 0.0, 0.0, 0.0};
         if (valid) {
-            double wx[4], wy[4];
             const int ix = bspline3_weights(x, nx, wx);
             const int iy = bspline3_weights(y, ny, wy);
-            const double wxt = t == 0 ? wx[0] : (t == 1 ? wx[1] : (t == 2 ? wx[2] : wx[3]));
-#pragma unroll
-            for (int j = 0; j < 4; j++) bw[i][j] = wy[j] * wxt;
-            origin[i] = (uint32_t)(iy * nx + ix);
+            my_origin = (uint32_t)(iy * nx + ix);
         }
-        valid_mask[i] = __ballot_sync(kFull, valid);
-        cls[i] = __match_any_sync(kFull, origin[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int src = 8 * i + g;  // the lane that worked out cell g of tile i
+            origin[i] = __shfl_sync(kFull, my_origin, src);
+            nbp[i] = __shfl_sync(kFull, my_nbp, src);
+            valid_mask[i] = __ballot_sync(kFull, origin[i] != 0xffffffffu);
+            const double w0 = __shfl_sync(kFull, wx[0], src), w1 = __shfl_sync(kFull, wx[1], src);
+            const double w2 = __shfl_sync(kFull, wx[2], src), w3 = __shfl_sync(kFull, wx[3], src);
+            const double wxt = t == 0 ? w0 : (t == 1 ? w1 : (t == 2 ? w2 : w3));
+#pragma unroll
+            for (int j = 0; j < 4; j++) bw[i][j] = __shfl_sync(kFull, wy[j], src) * wxt;  // zero for invalid cells
+            cls[i] = __match_any_sync(kFull, origin[i]);
+        }
     }
     if ((valid_mask[0] | valid_mask[1] | valid_mask[2] | valid_mask[3]) == 0) {
         // nothing visible in these 32 cells: stream NaN; 16 lanes x 16 B cover one plane
@@ -445,25 +453,34 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
 #pragma unroll
         for (int j = 0; j < 4; j++) a[j] = in_coef ? __ldg(p + j * row_stride) : 0.0;
     };
-    // NaN bits of the lane's output cells for the 32-plane word of plane gl + g
+    // NaN bits of the lane's OUTPUT cells (2t, 2t + 1 of every tile) for the 32-plane word of plane
+    // gl + g: OR over the (up to) four pixels of _should_propagate_nan_to_map.  The eight lanes
+    // sharing t split the loads: lane (g, t) reads neighbour pixel (g & 3) of cell 2t + (g >> 2), two
+    // xor-shuffles OR the neighbours, a third swaps the two cells: one load per tile and word.
+    uint32_t pixel[4];  // that neighbour's pixel index; 0xffffffff: cell not valid
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int src = 4 * (2 * t + (g >> 2));
+        const uint32_t nb = __shfl_sync(kFull, nbp[i], src);
+        const bool v = (valid_mask[i] >> src) & 1u;
+        const uint32_t x0 = nb & 0x3fff, y0 = (nb >> 14) & 0x3fff;
+        const uint32_t dx = (g & 1) ? ((nb >> 28) & 1u) : 0u, dy = (g & 2) ? ((nb >> 29) & 1u) : 0u;
+        pixel[i] = v ? (y0 + dy) * (uint32_t)nx + x0 + dx : 0xffffffffu;
+    }
     auto refresh_ok = [&](int word) {
+        word = min(word, n_words - 1);  // lanes past the last plane never store
         const uint32_t skip = __ldg(plane_bits + word);
         const bool consult = propagate && __ldg(plane_bits + n_words + word);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            // bits of the cell this lane DESCRIBES (cell g), then exchanged to the lanes that STORE it
-            uint32_t bits = skip;
-            const bool v = (valid_mask[i] >> lane) & 1u;
-            if (consult && v) {
-                const int x0 = nbp[i] & 0x3fff, y0 = (nbp[i] >> 14) & 0x3fff;
-                const int dx = (nbp[i] >> 28) & 1, dy = (nbp[i] >> 29) & 1;
-                const uint32_t *nbw = nanbits + ((int64_t)y0 * nx + x0) * n_words + word;
-                bits |= __ldg(nbw) | __ldg(nbw + (int64_t)dx * n_words) | __ldg(nbw + (int64_t)dy * nx * n_words) |
-                        __ldg(nbw + ((int64_t)dy * nx + dx) * n_words);
-            }
-            const uint32_t good = v ? ~bits : 0u;
-            ok[i][0] = __shfl_sync(kFull, good, 4 * (2 * t));
-            ok[i][1] = __shfl_sync(kFull, good, 4 * (2 * t + 1));
+            uint32_t w = 0;
+            if (consult && pixel[i] != 0xffffffffu) w = __ldg(nanbits + (int64_t)pixel[i] * n_words + word);
+            w |= __shfl_xor_sync(kFull, w, 4);
+            w |= __shfl_xor_sync(kFull, w, 8);
+            const uint32_t good = pixel[i] != 0xffffffffu ? ~(w | skip) : 0u;
+            const uint32_t other = __shfl_xor_sync(kFull, good, 16);
+            ok[i][0] = (g >> 2) ? other : good;
+            ok[i][1] = (g >> 2) ? good : other;
         }
     };
 
@@ -474,34 +491,29 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
         const bool fast_store = full_tiles && pair_ok;
         const int n_it = (l1 - l0 + 7) / 8;
-        const double *p0 = pbase + (int64_t)org0 * 4;
-        const double *p1 = pbase + (int64_t)(has1 ? org1 : org0) * 4;
+        // Lanes whose plane lies past the padded coefficient array (second quad of the last plane tile)
+        // read the first quad instead and stop advancing: their rows of D are never stored, and the
+        // rows of the product are independent.
+        const int planes_ahead = n_planes_padded - (plane_begin + l0 + g);  // > 0: the lane's first plane exists
+        const double *p0 = pbase + (int64_t)org0 * 4 - (planes_ahead > 0 ? 0 : (int64_t)(g >> 2) * quad_stride);
+        const double *p1 = p0 + ((int64_t)(has1 ? org1 : org0) - (int64_t)org0) * 4;
         const int64_t tile_stride = 2 * quad_stride;
+        double *const my_stage = &stage[0][0][0][threadIdx.x];
+        constexpr int kRow = kCubicBlock, kFoot = 4 * kCubicBlock, kSlot = 8 * kCubicBlock;  // in doubles
         int issued = 0;
         auto issue = [&]() {
             if (issued < n_it) {
-                const int slot = issued & (kCubicStages - 1);
-                const bool in_coef = (plane_begin + l0 + 8 * issued + g) < n_planes_padded;
+                double *dst = my_stage + (issued & (kCubicStages - 1)) * kSlot;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    double *dst = &stage[slot][0][j][threadIdx.x];
-                    if (in_coef)
-                        cp_async8(dst, p0 + j * row_stride);
-                    else
-                        *dst = 0.0;
-                }
+                for (int j = 0; j < 4; j++) cp_async8(dst + j * kRow, p0 + j * row_stride);
                 if (has1) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        double *dst = &stage[slot][1][j][threadIdx.x];
-                        if (in_coef)
-                            cp_async8(dst, p1 + j * row_stride);
-                        else
-                            *dst = 0.0;
-                    }
+                    for (int j = 0; j < 4; j++) cp_async8(dst + kFoot + j * kRow, p1 + j * row_stride);
                 }
-                p0 += tile_stride;
-                p1 += tile_stride;
+                if (8 * (issued + 1) < planes_ahead) {
+                    p0 += tile_stride;
+                    p1 += tile_stride;
+                }
             }
             issued++;
             cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
