@@ -292,6 +292,7 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
 // multiplied therefore also waited for the prefetches just issued.
 constexpr int kCubicBlock = 128;   // threads per CTA: 4 CTAs / SM at <= 128 registers, fine-grained tail
 constexpr int kCubicStages = 4;    // plane tiles in flight per warp (power of two)
+constexpr int kCubicFoot = 3;      // distinct 4 x 4 footprints per warp in the pipelined path (48 KB of stages)
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -411,12 +412,14 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
     const int64_t lane_off = (int64_t)(g >> 2) * quad_stride + t * 4 + (g & 3);
     const bool pair_ok = ((n_cells & 1) == 0) && (!grid2d || (row_len & 1) == 0);
 
-    // ---- distinct footprints of the warp (plane independent): the usual case is one or
-    // two (32 cells of a fine map straddle at most one pixel boundary)
-    uint32_t org0 = 0xffffffffu, org1 = 0xffffffffu;
-    uint32_t mine01 = 0;   // bit i: this lane's cell of tile i uses footprint 0; bit 4 + i: footprint 1
-    uint32_t tiles = 0;    // (uniform) bit i: tile i has footprint-0 cells; bit 4 + i: footprint-1 cells;
-                           // bit 8 + i: every valid cell of tile i uses footprint 0 (no masking needed)
+    // ---- distinct footprints of the warp (plane independent).  32 consecutive cells of a dense map
+    // cover one to three image pixels along the row: up to three footprints are kept for the
+    // pipelined path; more (a map coarser than the launcher's density rule expects) take the
+    // general path at the end.
+    uint32_t org0 = 0xffffffffu, org1 = 0xffffffffu, org2 = 0xffffffffu;
+    uint32_t mine = 0;     // bit 4 f + i: this lane's cell of tile i reads footprint f
+    uint32_t tiles = 0;    // (uniform) bit 4 f + i: tile i has cells of footprint f;
+                           // bit 12 + i: every valid cell of tile i reads ONE footprint (no masking needed)
     bool simple = true;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -426,15 +429,19 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
             const uint32_t members = __shfl_sync(kFull, cls[i], leader);
             const uint32_t org = __shfl_sync(kFull, origin[i], leader);
             const uint32_t me = (members >> lane) & 1u;
+            if (members == valid_mask[i]) tiles |= 1u << (12 + i);
             if (org0 == 0xffffffffu || org == org0) {
                 org0 = org;
-                mine01 |= me << i;
+                mine |= me << i;
                 tiles |= 1u << i;
-                if (members == valid_mask[i]) tiles |= 1u << (8 + i);
             } else if (org1 == 0xffffffffu || org == org1) {
                 org1 = org;
-                mine01 |= me << (4 + i);
+                mine |= me << (4 + i);
                 tiles |= 1u << (4 + i);
+            } else if (org2 == 0xffffffffu || org == org2) {
+                org2 = org;
+                mine |= me << (8 + i);
+                tiles |= 1u << (8 + i);
             } else {
                 simple = false;
             }
@@ -484,36 +491,38 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         }
     };
 
-    // ---- pipelined path: at most two distinct footprints in the warp (the rule for a dense map:
-    // 32 consecutive cells straddle at most one pixel boundary)
+    // ---- pipelined path: at most three distinct footprints in the warp
     if (simple) {
-        __shared__ double stage[kCubicStages][2][4][kCubicBlock];
+        __shared__ double stage[kCubicStages][kCubicFoot][4][kCubicBlock];
         const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
         const bool fast_store = full_tiles && pair_ok;
         const int n_it = (l1 - l0 + 7) / 8;
+        const int nf = org2 != 0xffffffffu ? 3 : (has1 ? 2 : 1);
         // Lanes whose plane lies past the padded coefficient array (second quad of the last plane tile)
         // read the first quad instead and stop advancing: their rows of D are never stored, and the
         // rows of the product are independent.
         const int planes_ahead = n_planes_padded - (plane_begin + l0 + g);  // > 0: the lane's first plane exists
         const double *p0 = pbase + (int64_t)org0 * 4 - (planes_ahead > 0 ? 0 : (int64_t)(g >> 2) * quad_stride);
-        const double *p1 = p0 + ((int64_t)(has1 ? org1 : org0) - (int64_t)org0) * 4;
+        // footprints 1 and 2 as element offsets from footprint 0 (they fit 32 bits: nx, ny < 16384)
+        const int d1 = nf > 1 ? ((int)org1 - (int)org0) * 4 : 0, d2 = nf > 2 ? ((int)org2 - (int)org0) * 4 : 0;
         const int64_t tile_stride = 2 * quad_stride;
         double *const my_stage = &stage[0][0][0][threadIdx.x];
-        constexpr int kRow = kCubicBlock, kFoot = 4 * kCubicBlock, kSlot = 8 * kCubicBlock;  // in doubles
+        constexpr int kRow = kCubicBlock, kFoot = 4 * kCubicBlock, kSlot = kCubicFoot * 4 * kCubicBlock;  // doubles
         int issued = 0;
         auto issue = [&]() {
             if (issued < n_it) {
                 double *dst = my_stage + (issued & (kCubicStages - 1)) * kSlot;
 #pragma unroll
                 for (int j = 0; j < 4; j++) cp_async8(dst + j * kRow, p0 + j * row_stride);
-                if (has1) {
+                if (nf > 1) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) cp_async8(dst + kFoot + j * kRow, p1 + j * row_stride);
+                    for (int j = 0; j < 4; j++) cp_async8(dst + kFoot + j * kRow, p0 + d1 + j * row_stride);
                 }
-                if (8 * (issued + 1) < planes_ahead) {
-                    p0 += tile_stride;
-                    p1 += tile_stride;
+                if (nf > 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) cp_async8(dst + 2 * kFoot + j * kRow, p0 + d2 + j * row_stride);
                 }
+                if (8 * (issued + 1) < planes_ahead) p0 += tile_stride;
             }
             issued++;
             cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
@@ -530,37 +539,35 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                 refresh_ok(word);
             }
             cp_async_wait<kCubicStages - 1>();  // the group of plane tile `it` has landed
-            const int slot = it & (kCubicStages - 1);
-            double a0[4], a1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) a0[j] = stage[slot][0][j][threadIdx.x];
+            const double *src = my_stage + (it & (kCubicStages - 1)) * kSlot;
             double d[4][2];
 #pragma unroll
             for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
-            if (!has1) {
+            if (nf == 1) {
                 // every valid cell reads footprint 0 and invalid cells carry zero weights: no masks
+                double a[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = src[j * kRow];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) dmma8x8x4(d[i][0], d[i][1], a0[j], bw[i][j]);
+                    for (int i = 0; i < 4; i++) dmma8x8x4(d[i][0], d[i][1], a[j], bw[i][j]);
                 }
             } else {
+#pragma unroll 1
+                for (int f = 0; f < nf; f++) {   // rolled: the footprint only enters through bit positions
+                    {
+                        double a[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) a1[j] = stage[slot][1][j][threadIdx.x];
+                        for (int j = 0; j < 4; j++) a[j] = src[f * kFoot + j * kRow];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (tiles & (1u << i)) {
-                        const bool keep = (tiles & (1u << (8 + i))) || ((mine01 >> i) & 1u);
+                        for (int i = 0; i < 4; i++) {
+                            if (tiles & (1u << (4 * f + i))) {
+                                const bool keep = (tiles & (1u << (12 + i))) || ((mine >> (4 * f + i)) & 1u);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a0[j], keep ? bw[i][j] : 0.0);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (tiles & (1u << (4 + i))) {
-                        const bool keep = (mine01 >> (4 + i)) & 1u;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a1[j], keep ? bw[i][j] : 0.0);
+                                for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a[j], keep ? bw[i][j] : 0.0);
+                            }
+                        }
                     }
                 }
             }
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         return;
     }
 
-    // ---- general path (three or more footprints in the warp): one pass per distinct footprint
+    // ---- general path (four or more footprints in the warp): one pass per distinct footprint
     // among each tile's cells
     for (int l = l0; l < l1; l += 8) {
         const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (multiple of 4)
