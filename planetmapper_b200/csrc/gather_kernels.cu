@@ -574,18 +574,28 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
             // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
             if (l + g < l1) {
                 const int sh = (gl + g) & 31;
+                auto store_tiles = [&](const int64_t step, const bool all_pairs) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
-                    const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
-                    double *dst = dst_row + i * tile_step;
-                    if (fast_store || (pair_ok && 2 * t + 1 < ncols[i])) {
-                        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
-                    } else {
-                        if (2 * t < ncols[i]) __stcs(dst, o0);
-                        if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
+                    for (int i = 0; i < 4; i++) {
+                        const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
+                        const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
+                        double *dst = dst_row + i * step;
+                        if (all_pairs || (pair_ok && 2 * t + 1 < ncols[i])) {
+                            asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
+                        } else {
+                            if (2 * t < ncols[i]) __stcs(dst, o0);
+                            if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
+                        }
                     }
-                }
+                };
+                // the usual case - full tiles of consecutive cells, aligned pairs - is straight-line code
+                // whose tile offsets are immediates of the stores
+                if (fast_store && !grid2d)
+                    store_tiles(8, true);
+                else if (fast_store)
+                    store_tiles(tile_step, true);
+                else
+                    store_tiles(tile_step, false);
             }
             dst_row += 8 * n_cells;
         }
