@@ -271,7 +271,8 @@ def obsvec2angular(M: np.ndarray, obsvec: np.ndarray) -> tuple[float, float]:
 
 def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
                          et: float | None = None,
-                         observer_state: np.ndarray | None = None) -> BodyConstants:
+                         observer_state: np.ndarray | None = None,
+                         with_subsol: bool = True) -> BodyConstants:
     """Derive BodyConstants. ``observer_state`` (6-vector, SSB J2000 at et) overrides
     the provider's observer ephemeris (used for observers whose SPK type the
     provider cannot read, e.g. HST's type-10 TLE segment)."""
@@ -409,7 +410,7 @@ def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
     # body.py:559-567 - the point where the Sun -> target-centre line meets the surface, at
     # the epoch et - lt with lt the light time from that point to the observer
     ss_lon = ss_lat = math.nan
-    if target_id != 10:
+    if target_id != 10 and with_subsol:   # header metadata only: a time series skips it
         lt = lt0
         for _ in range(12):
             t = et - lt

@@ -135,6 +135,10 @@ class MiniSpice:
     def __init__(self, segments: list[daf.Segment], pool: dict[str, list]):
         self.segments = segments  # in load order; later entries take precedence
         self.pool = pool
+        # per body, highest precedence first (same order as scanning `segments` backwards)
+        self._by_target: dict[int, list[daf.Segment]] = {}
+        for seg in reversed(segments):
+            self._by_target.setdefault(seg.target, []).append(seg)
 
     # ---- construction -----------------------------------------------------------
     @classmethod
@@ -194,8 +198,8 @@ class MiniSpice:
 
     # ---- ephemeris -----------------------------------------------------------------
     def _find_segment(self, target: int, et: float) -> daf.Segment:
-        for seg in reversed(self.segments):
-            if seg.target == target and seg.covers(et):
+        for seg in self._by_target.get(target, ()):
+            if seg.covers(et):
                 return seg
         raise LookupError(
             f'no SPK data for body {target} at et={et!r} (types 2/3 only)'

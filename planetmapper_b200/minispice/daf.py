@@ -70,17 +70,16 @@ class Segment:
 def _cheby_with_derivative(coefs: np.ndarray, s: float) -> tuple[np.ndarray, np.ndarray]:
     """Evaluate sum_k c_k T_k(s) and its derivative d/ds for each row of coefs."""
     n = coefs.shape[1]
-    t = np.empty(n)
-    dt = np.empty(n)
-    t[0] = 1.0
-    dt[0] = 0.0
-    if n > 1:
-        t[1] = s
-        dt[1] = 1.0
+    s = float(s)
+    # the recurrences run on Python floats (same IEEE arithmetic as float64 scalars, a fraction of
+    # the per-element cost of indexing an ndarray); only the two matrix-vector products use numpy
+    t = [1.0, s][:n]
+    dt = [0.0, 1.0][:n]
+    two_s = 2.0 * s
     for k in range(2, n):
-        t[k] = 2.0 * s * t[k - 1] - t[k - 2]
-        dt[k] = 2.0 * t[k - 1] + 2.0 * s * dt[k - 1] - dt[k - 2]
-    return coefs @ t, coefs @ dt
+        t.append(two_s * t[k - 1] - t[k - 2])
+        dt.append(2.0 * t[k - 1] + two_s * dt[k - 1] - dt[k - 2])
+    return coefs @ np.array(t), coefs @ np.array(dt)
 
 
 def read_spk(path: str, keep_types: tuple[int, ...] = (2, 3)) -> list[Segment]:

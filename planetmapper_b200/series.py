@@ -30,7 +30,7 @@ from .shard import shard_range
 def _block(provider, target, observer, ets, disc) -> np.ndarray:
     out = np.empty((len(ets), F.PMFRAME_NDOUBLES))
     for i, et in enumerate(ets):
-        bc = F.build_body_constants(provider, target, None, observer, et=float(et))
+        bc = F.build_body_constants(provider, target, None, observer, et=float(et), with_subsol=False)
         out[i] = F.pack_frame(bc, **disc)
     return out
 
