@@ -9,7 +9,7 @@ import pytest
 
 from conftest import GOLDEN_ALT
 from helpers import PLANE_NAMES, max_diff
-from test_oracle_golden import (GOLDEN_TOL, LONLAT2XY, MAP_EXPECTED, MAP_EXPECTED_NO_PROPAGATE,
+from test_oracle_golden import (GOLDEN_TOL, LONLAT2XY, MAP_EXPECTED, MAP_EXPECTED_NO_PROPAGATE, check_body_point_literals,
                                 MAP_FILES, MAP_IMG, PROJ_CASES, WRAP, XY_COORDINATES)
 
 pytestmark = pytest.mark.gpu
@@ -335,6 +335,17 @@ def test_custom_proj_strings(body):
     m1 = body.get_backplane_map('EMISSION', projection='orthographic', lon=30, lat=10, size=21)
     m2 = body.get_backplane_map('EMISSION', projection=proj, projection_x_coords=np.linspace(-lim, lim, 21))
     assert np.allclose(m1, m2, rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_map_planes_match_body_method_literals(body):
+    """The scalar Body methods' 16-digit literals (reference tests/test_body.py:679, :1828-1868, :1902-1905,
+    :2488-2524, :2560-2566) through get_backplane_map on a one-point manual grid."""
+    names = list(body.backplanes)
+
+    def planes_at(lon, lat):
+        kw = dict(projection='manual', lon_coords=np.array([lon]), lat_coords=np.array([lat]))
+        return np.array([body.get_backplane_map(n, **kw)[0, 0] for n in names])
+    check_body_point_literals(planes_at)
 
 
 def test_backplane_values_known_answers(body):

@@ -293,3 +293,55 @@ def test_frame_scalars_known_answers(bc_hst, golden_headers):
     hdr = golden_headers['test_nav.fits']
     assert abs(bc_hst.north_pole_angle - hdr['PLANMAP NP-ANGLE']) < 1e-9
     assert bc_hst.positive_longitude_direction == 'W' and bc_hst.prograde
+
+
+# ---- known-answer literals of the scalar Body methods (reference tests/test_body.py), which are the
+# per-point arithmetic of the map-direction backplanes: Body('Jupiter', observer='HST', utc='2005-01-01T00:00:00')
+BODY_POINT_LITERALS = [
+    # (lon, lat), {plane: 16-digit value}           reference tests/test_body.py line
+    ((0.0, 0.0), {'PHASE': 10.31594976458697, 'INCIDENCE': 163.2795134457034, 'EMISSION': 152.99822832991876,   # :1828
+                  'AZIMUTH': 177.66817822757469,                                                                 # :1867
+                  'RADIAL-VELOCITY': -20.796924908179438,                                                        # :2488
+                  'DISTANCE': 819701772.0279644,                                                                 # :2523
+                  'LOCAL-SOLAR-TIME': 22.89638888888889}),                                                       # :1902
+    ((123.456, -78.9), {'PHASE': 10.316968817304499, 'INCIDENCE': 79.16351827229181, 'EMISSION': 77.68583738495468,  # :1831
+                        'AZIMUTH': 169.57651996164563,                                                               # :1868
+                        'LOCAL-SOLAR-TIME': 14.666111111111112}),                                                    # :1904
+    ((45.0, 45.0), {'RADIAL-VELOCITY': -17.75706386255955, 'DISTANCE': 819656453.7301536}),                         # :2489, :2524
+    ((-90.0 % 360, 0.0), {'LOCAL-SOLAR-TIME': 4.896388888888889}),                                                   # :1903
+    ((999.999 % 360, 0.0), {'LOCAL-SOLAR-TIME': 4.229722222222223}),                                                 # :1905
+    ((123.456, -56.789), {'RA': 196.3691609381441, 'DEC': -5.5685956879058764}),                                     # :679 (visible)
+    ((123.4, 56.789), {'LON-CENTRIC': -123.4, 'LAT-CENTRIC': 53.17999536010973}),                                    # :2560
+    ((1.0, 40.0), {'LON-CENTRIC': -1.0, 'LAT-CENTRIC': 36.26969371}),                                                # :2563-2566 (8 decimals)
+    ((3.0, 60.0), {'LON-CENTRIC': -3.0, 'LAT-CENTRIC': 56.56575448}),
+]
+# Most of these literals agree with the oracle to 1e-10 or better.  PHASE / INCIDENCE / EMISSION are
+# the exception (1e-7 / 1e-5 deg): the reference asserts them with np.allclose's default rtol = 1e-5
+# and the golden FITS files - written by v1.12.5 and matched at 1e-8 deg above - show that the
+# literals, not the files, are the older numbers.
+BODY_POINT_TOL = {'PHASE': 2e-7, 'INCIDENCE': 2e-5, 'EMISSION': 2e-5, 'AZIMUTH': 1e-9, 'RADIAL-VELOCITY': 1e-9,
+                  'DISTANCE': 1e-6, 'RA': 1e-12, 'DEC': 1e-12, 'LON-CENTRIC': 1e-12, 'LAT-CENTRIC': 1e-12,
+                  'LOCAL-SOLAR-TIME': 0.0}
+
+
+def check_body_point_literals(planes_at):
+    """planes_at(lon, lat) -> all 26 map-direction planes at one point."""
+    for (lon, lat), expected in BODY_POINT_LITERALS:
+        got = planes_at(lon, lat)
+        for name, value in expected.items():
+            g = float(got[PID[name]])
+            tol = BODY_POINT_TOL[name]
+            if name == 'LOCAL-SOLAR-TIME':
+                assert abs(g - value) < 1e-12, (lon, lat, name, g, value)
+            elif name == 'LAT-CENTRIC' and len(repr(value)) < 14:
+                assert abs(g - value) < 5e-9, (lon, lat, name, g, value)     # literal has 8 decimals
+            else:
+                d = abs(g - value)
+                if name in WRAP:
+                    d = min(d, abs(d - 360.0))
+                assert d <= tol, (lon, lat, name, g, value, d)
+
+
+def test_map_planes_match_body_method_literals(oracle, bc_hst):
+    fr = _frame(bc_hst)
+    check_body_point_literals(lambda lon, lat: oracle.backplanes_map(fr, np.array([[lon]]), np.array([[lat]]))[:, 0, 0])
