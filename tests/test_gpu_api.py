@@ -10,6 +10,7 @@ import pytest
 from conftest import GOLDEN_ALT
 from helpers import PLANE_NAMES, max_diff
 from test_oracle_golden import (GOLDEN_TOL, LONLAT2XY, MAP_EXPECTED, MAP_EXPECTED_NO_PROPAGATE, check_body_point_literals,
+                                check_radec_point_literals, frame_looking_at,
                                 MAP_FILES, MAP_IMG, PROJ_CASES, WRAP, XY_COORDINATES)
 
 pytestmark = pytest.mark.gpu
@@ -346,6 +347,15 @@ def test_map_planes_match_body_method_literals(body):
         kw = dict(projection='manual', lon_coords=np.array([lon]), lat_coords=np.array([lat]))
         return np.array([body.get_backplane_map(n, **kw)[0, 0] for n in names])
     check_body_point_literals(planes_at)
+
+
+def test_image_planes_match_body_radec_literals(bc_hst):
+    """Body.ring_plane_coordinates / limb_coordinates_from_radec literals (reference tests/test_body.py:2008-2030,
+    :1683-1697) through the image kernel: a one-pixel frame looking along each (ra, dec)."""
+    from planetmapper_b200 import _lib as L
+
+    check_radec_point_literals(
+        lambda ra, dec: L.backplanes_img(L.to_device(frame_looking_at(bc_hst, ra, dec)[None]), 1, 1).cpu().numpy()[0, :, 0, 0])
 
 
 def test_backplane_values_known_answers(body):

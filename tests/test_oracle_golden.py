@@ -9,6 +9,8 @@ reference's own golden data:
 
 The golden arrays were exported by tests/golden/make_golden.py.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -345,3 +347,54 @@ def check_body_point_literals(planes_at):
 def test_map_planes_match_body_method_literals(oracle, bc_hst):
     fr = _frame(bc_hst)
     check_body_point_literals(lambda lon, lat: oracle.backplanes_map(fr, np.array([[lon]]), np.array([[lat]]))[:, 0, 0])
+
+
+# Image-direction literals: Body.ring_plane_coordinates(ra, dec) (reference tests/test_body.py:2008-2030) and
+# Body.limb_coordinates_from_radec(ra, dec) (:1683-1697).  A one-pixel frame is placed so that its pixel
+# looks exactly along (ra, dec).
+RADEC_POINT_LITERALS = [
+    ((196.37347182693253, -5.561472466522512), {'RING-RADIUS': 1377914.753652832, 'RING-LON-GRAPHIC': 152.91772706249577,
+                                                'RING-DISTANCE': 818261707.8278764}),
+    ((196.3, -5.5), {'RING-RADIUS': 9305877.091704229, 'RING-LON-GRAPHIC': 145.3644753085151,
+                     'RING-DISTANCE': 810435703.2382222,
+                     'LIMB-LON-GRAPHIC': 64.1290135632679, 'LIMB-LAT-GRAPHIC': 20.79992677586983,
+                     'LIMB-DISTANCE': 1320579.9259661217}),
+    ((196.37198562427025, -5.565793847134351), {'RING-RADIUS': nan, 'RING-LON-GRAPHIC': nan, 'RING-DISTANCE': nan}),  # behind the disc
+    ((196.3696997398314, -5.569843641306982), {'RING-RADIUS': nan}),
+    ((196.3719829300016, -5.565779946690757), {'LIMB-LON-GRAPHIC': 67.23274105785333, 'LIMB-LAT-GRAPHIC': 58.34599234749429,
+                                               'LIMB-DISTANCE': -68089.8880967631}),
+    ((196.372, -5.566), {'LIMB-LON-GRAPHIC': 248.13985326986065, 'LIMB-LAT-GRAPHIC': -64.83923990338549,
+                         'LIMB-DISTANCE': -64857.80811442864}),
+]
+
+
+def frame_looking_at(bc, ra_deg, dec_deg):
+    """PMFrame of a 1 x 1 image whose only pixel looks along (ra, dec)."""
+    obsvec = F._radrec(1.0, math.radians(ra_deg), math.radians(dec_deg))
+    ax, ay = F.obsvec2angular(bc.M, obsvec)
+    a3 = F.xy2angular_matrix(bc, 0.0, 0.0, 10.0, 0.0)
+    px, py, _ = np.linalg.solve(a3, np.array([ax, ay, 1.0]))   # pixel coordinates of that direction when x0 = y0 = 0
+    return F.pack_frame(bc, nx=1, ny=1, x0=-px, y0=-py, r0=10.0, rotation_radians=0.0)
+
+
+def check_radec_point_literals(planes_at):
+    """planes_at(frame) -> the 26 image-direction planes of the frame's single pixel."""
+    for (ra, dec), expected in RADEC_POINT_LITERALS:
+        got = planes_at(ra, dec)
+        assert abs(got[PID['RA']] - ra) < 1e-9 and abs(got[PID['DEC']] - dec) < 1e-9, (ra, dec, got[PID['RA']], got[PID['DEC']])
+        for name, value in expected.items():
+            g = float(got[PID[name]])
+            if value != value:
+                assert g != g, (ra, dec, name, g)
+                continue
+            # the literals are asserted at rtol 1e-5 by the reference; they agree far better than that
+            tol = {'RING-RADIUS': 1e-9 * abs(value), 'RING-DISTANCE': 1e-11 * abs(value), 'LIMB-DISTANCE': 1e-5}.get(name, 1e-7)
+            d = abs(g - value)
+            if name in WRAP:
+                d = min(d, abs(d - 360.0))
+            assert d <= tol, (ra, dec, name, g, value, d)
+
+
+def test_image_planes_match_body_radec_literals(oracle, bc_hst):
+    check_radec_point_literals(
+        lambda ra, dec: oracle.backplanes_img(frame_looking_at(bc_hst, ra, dec), 1, 1)[:, 0, 0])
