@@ -772,7 +772,7 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                                                                 ymap, n_cells, row_len, flags, out, g2);
     } else {
         switch (ky * 4 + kx) {
-            case 1 * 4 + 1: PM_SPLINE(2, 2, 4); break;
+            case 1 * 4 + 1: PM_SPLINE(2, 2, 5); break;
             case 1 * 4 + 2: PM_SPLINE(2, 3, 3); break;
             case 1 * 4 + 3: PM_SPLINE(2, 4, 3); break;
             case 2 * 4 + 1: PM_SPLINE(3, 2, 3); break;
