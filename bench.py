@@ -291,6 +291,28 @@ def bench_mapped_cube(L, torch, bc, rank, world):
                          'traffic': ncu_traffic(f'gather_{name}'),
                          'algorithmic_bytes_per_voxel': alg_bytes / vox},
         }
+    if world > 1:
+        # result assembly: 64 mapped planes of every rank into one device buffer on rank 0,
+        # NCCL point-to-point straight into the destination slices (GPU-to-GPU over NVLink)
+        import torch.distributed as dist
+
+        from planetmapper_b200.shard import gather_blocks
+
+        per = 64
+        whole = torch.empty((per * world,) + lo.shape, dtype=torch.float64, device='cuda') if rank == 0 else None
+        for timed in (False, True):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            gather_blocks(out[:per], per * world, world, rank, dst=0, out=whole)
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+        nbytes = per * (world - 1) * n_cells * 8
+        res['assemble_on_rank0'] = {'planes_per_rank': per, 'bytes_received': nbytes, 'ms': e0.elapsed_time(e1),
+                                    'gb_per_s': nbytes / e0.elapsed_time(e1) / 1e6,
+                                    'how': 'NCCL send / irecv into slices of one buffer (shard.gather_blocks)'}
+        del whole
     del out
     return res
 

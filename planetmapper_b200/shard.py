@@ -39,6 +39,44 @@ def gather_shard_results(obj, world_size: int):
     return out
 
 
+def gather_blocks(local, n_units: int, world_size: int, rank: int, dst: int = 0, out=None):
+    """Assemble the contiguous per-rank blocks of :func:`shard_range` into ONE tensor on rank `dst`
+    ("cudaMemcpyPeer over NVLink 5 if the caller wants one device buffer").
+
+    ``local``: this rank's block, shape (hi - lo, ...) for ``lo, hi = shard_range(n_units, rank, W)``.
+    Returns the (n_units, ...) tensor on rank ``dst`` (``out`` if given), None elsewhere.  Point-to-point
+    sends straight into the destination slices - with the NCCL backend that is a GPU-to-GPU copy
+    over NVLink, with no staging buffer and no padding of unequal blocks.  This is result assembly
+    after the path has run; the path itself has no exchange step.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if world_size == 1:
+        if out is None:
+            return local
+        out.copy_(local)
+        return out
+    if rank == dst:
+        if out is None:
+            out = torch.empty((n_units,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        ops = []
+        for src in range(world_size):
+            lo, hi = shard_range(n_units, src, world_size)
+            if src == dst:
+                out[lo:hi].copy_(local)
+            elif hi > lo:
+                ops.append(dist.P2POp(dist.irecv, out[lo:hi], src))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):   # batched: the receives run concurrently
+                req.wait()
+        return out
+    if local.shape[0] > 0:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+            req.wait()
+    return None
+
+
 def max_over_ranks(value: float, world_size: int, device=None) -> float:
     if world_size == 1:
         return float(value)

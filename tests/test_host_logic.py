@@ -158,7 +158,7 @@ def test_two_process_gloo_sharding(tmp_path):
         import numpy as np, torch, torch.distributed as dist
         import planetmapper_b200 as pm
         from planetmapper_b200 import frame as F
-        from planetmapper_b200.shard import env_rank_world, shard_range, gather_shard_results, max_over_ranks
+        from planetmapper_b200.shard import env_rank_world, shard_range, gather_shard_results, max_over_ranks, gather_blocks
         rank, local_rank, world = env_rank_world()
         dist.init_process_group('gloo')
         n_frames = 9
@@ -173,6 +173,13 @@ def test_two_process_gloo_sharding(tmp_path):
         dist.barrier()
         t = max_over_ranks(float(rank + 1), world)
         allsums = gather_shard_results((lo, hi, sums), world)
+        # result assembly: each rank's block of planes lands in one tensor on rank 0
+        local = torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64)
+        whole = gather_blocks(local, n_frames, world, rank)
+        if rank == 0:
+            assert whole.shape == (n_frames, 3) and torch.equal(whole[:, 0], torch.arange(n_frames, dtype=torch.float64))
+        else:
+            assert whole is None
         if rank == 0:
             flat = [s for _, _, ss in sorted(allsums) for s in ss]
             print('RESULT ' + json.dumps(dict(t=t, n=len(flat), checksum=sum(flat), blocks=[(a, b) for a, b, _ in sorted(allsums)])))
