@@ -221,7 +221,7 @@ class BodyXY:
         return self._bc.clight
 
     def __repr__(self) -> str:
-        return (f'BodyXY({self.target!r}, {self.utc!r}, observer={self.observer!r}, '
+        return (f'{type(self).__name__}({self.target!r}, {self.utc!r}, observer={self.observer!r}, '
                 f'nx={self._nx}, ny={self._ny})')
 
     # ---- disc parameters (body_xy.py:696-1080) --------------------------------------
