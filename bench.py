@@ -443,7 +443,7 @@ def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     t0 = time.perf_counter()
     S.build_series_frames('Jupiter', ets[:16], 'EARTH', workers=1, **disc)
     serial_ms_per_frame = (time.perf_counter() - t0) / min(16, len(ets)) * 1e3
-    S.build_series_frames('Jupiter', ets[:64], 'EARTH', **disc)   # starts the worker processes
+    S.build_series_frames('Jupiter', ets[:16 * S.default_workers()], 'EARTH', **disc)   # starts every worker process
     t0 = time.perf_counter()
     frames = S.build_series_frames('Jupiter', ets, 'EARTH', **disc)
     host_s = time.perf_counter() - t0

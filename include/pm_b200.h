@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 5
+#define PM_ABI_VERSION 6
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -269,6 +269,36 @@ int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
 int64_t pm_fits_data_unit_bytes(int64_t n_elems);
 int pm_fits_stage(const double *const *src, const int64_t *n_elems, const int64_t *dst_offset,
                   int n_units, uint8_t *image, void *stream);
+
+/*
+ * HOST functions (no device work): the two ephemeris primitives behind the once-per-frame
+ * constants when spiceypy is not the provider.  They replace, for SPK types 2 / 3 and the text-PCK
+ * IAU orientation model, the CSPICE calls the reference makes through spiceypy: spkssb / spkezr
+ * (planetmapper/base.py:828) and the pxform / sxform rotations (body.py:935-945, base.py:815-837).
+ *   pm_host_ssb_state    state (km, km/s) of `body` relative to the solar-system barycentre, J2000,
+ *                        summed along the centre chain; `segs` in precedence order (the last
+ *                        loaded kernel first), `records` the concatenated Chebyshev records.
+ *                        PM_ERR_UNSUPPORTED: no segment covers (body, et).
+ *   pm_host_orientation  J2000 -> body-fixed rotation R (row major, v_body = R v_j2000) at et and the
+ *                        angular velocity omega of the body frame in body axes (dR/dt = -[omega]x R).
+ */
+#define PM_MAX_NUT_TERMS 64
+typedef struct PMEphemSegment {
+    int32_t target, center, spk_type, rsize; /* NAIF ids, SPK type 2 or 3, doubles per record        */
+    int32_t n, first_record, n_kept, pad;    /* records in the segment; kept slice [first, first + kept) */
+    double et_start, et_end, init, intlen;   /* coverage; first record start and record length (s)   */
+    int64_t rec_offset;                      /* index of the first kept record in `records` (doubles) */
+} PMEphemSegment;
+typedef struct PMOrientationModel {
+    double pole_ra[3], pole_dec[3], pm[3];   /* BODYnnn_POLE_RA / POLE_DEC / PM (deg, deg/century or /day) */
+    int32_t n_ra, n_dec, n_pm, n_nut;        /* polynomial lengths; number of NUT_PREC_ANGLES pairs   */
+    int32_t n_nut_ra, n_nut_dec, n_nut_pm, pad;
+    double nut_ra[PM_MAX_NUT_TERMS], nut_dec[PM_MAX_NUT_TERMS], nut_pm[PM_MAX_NUT_TERMS];
+    double nut_angles[2 * PM_MAX_NUT_TERMS]; /* (deg, deg/century) pairs of the system barycentre     */
+} PMOrientationModel;
+int pm_host_ssb_state(const PMEphemSegment *segs, int n_segs, const double *records, int body,
+                      double et, double *state6);
+int pm_host_orientation(const PMOrientationModel *model, double et, double *rmat9, double *omega3);
 
 /* Diagnostic: evaluates one of the library's own FP64 primitives (the MUFU-seeded
  * reciprocal / rsqrt / sqrt / division and the polynomial sin / cos / atan2 / acos

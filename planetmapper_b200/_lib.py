@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
     'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
+    'pm_host_ssb_state', 'pm_host_orientation',
 ]
 
 
@@ -102,11 +103,15 @@ def load_library() -> ctypes.CDLL:
     lib.pm_backplanes_map_batch.restype = c_i
     lib.pm_gather_paired.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i64, c_i64, c_i, c_u32, c_p, c_p]
     lib.pm_gather_paired.restype = c_i
+    lib.pm_host_ssb_state.argtypes = [c_p, c_i, c_p, c_i, ctypes.c_double, c_p]
+    lib.pm_host_ssb_state.restype = c_i
+    lib.pm_host_orientation.argtypes = [c_p, ctypes.c_double, c_p, c_p]
+    lib.pm_host_orientation.restype = c_i
     for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 5:
+    if lib.pm_abi_version() != 6:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -33,9 +33,10 @@ def test_subpoint_lon_known_answer_from_extract():
 @pytest.mark.skipif(not os.path.isdir(REF_KERNELS), reason='reference kernels not present')
 def test_extract_reproduces_full_kernels():
     full = MiniSpice.from_kernel_dir(REF_KERNELS)
-    ext = pm.get_default_provider()
-    if not isinstance(ext, MiniSpice):
+    if not isinstance(pm.get_default_provider(), MiniSpice):
         pytest.skip('default provider is spiceypy')
+    ext = MiniSpice.from_extract(os.path.join(pm._DATA_DIR, 'ephem_extract.npz'),
+                                 os.path.join(pm._DATA_DIR, 'pck_pool.json'))   # the pure-Python reader on both sides
     for body in (10, 399, 599, 699):
         for et in (157809664.1839331 - 3 * 86400, 157809000.0, 0.0):
             assert np.array_equal(full.ssb_state(body, et), ext.ssb_state(body, et)), (body, et)
@@ -87,3 +88,40 @@ def test_saturn_frame_builds_before_spk_edge():
     bc = F.build_body_constants(ms, 'Saturn', '2004-12-30T00:00:00', 'EARTH')
     assert bc.radii[0] == 60268.0 and bc.prograde
     assert 1.1e9 < bc.target_distance < 1.7e9
+
+
+def test_native_primitives_match_the_python_reader():
+    """NativeSpice (pm_host_ssb_state / pm_host_orientation in libpm_b200.so) evaluates the same
+    tables with the same formulas: agreement to the last bit or two, same errors, and frames whose
+    constants differ only where the formulas themselves amplify rounding (the finite-difference
+    acceleration, the ring-plane constant)."""
+    from planetmapper_b200.minispice.native import NativeSpice
+
+    py = MiniSpice.from_extract(os.path.join(pm._DATA_DIR, 'ephem_extract.npz'),
+                                os.path.join(pm._DATA_DIR, 'pck_pool.json'))
+    nat = NativeSpice.from_minispice(py)
+    assert isinstance(pm.get_default_provider(), (NativeSpice,)) or not isinstance(pm.get_default_provider(), MiniSpice)
+    et0 = utc2et('2005-01-01T00:00:00')
+    for body in (10, 399, 301, 599, 699, 499, 299, 199, 5, 3):
+        for dt in (-10.0, -1234.5, -86400 * 3.3, -86400 * 5.9):   # the extract ends at 2005-01-01 for some bodies
+            a, b = py.ssb_state(body, et0 + dt), nat.ssb_state(body, et0 + dt)
+            assert np.allclose(a, b, rtol=2e-14, atol=0), (body, dt, a, b)
+    for body in (599, 399, 301, 299, 499, 199, 699):
+        for dt in (0.0, -1234.5, -86400 * 3.3):
+            (ra, wa), (rb, wb) = py.orientation(body, et0 + dt), nat.orientation(body, et0 + dt)
+            assert np.max(np.abs(ra - rb)) < 1e-15 and np.allclose(wa, wb, rtol=1e-13, atol=1e-12 * np.max(np.abs(wa))), (body, dt)
+    for bad_call in (lambda p: p.ssb_state(599, et0 + 400 * 86400), lambda p: p.ssb_state(12345, et0)):
+        with pytest.raises(LookupError):
+            bad_call(py)
+        with pytest.raises(LookupError):
+            bad_call(nat)
+    loose = {'AT': 1e-8, 'ring_c': 1e-9, 'ring_n': 1e-10, 'ang2km': 1e-9, 'km2ang': 1e-9}
+    for target, observer in (('Jupiter', 'EARTH'), ('Saturn', 'EARTH'), ('Moon', 'EARTH'), ('Earth', 'MOON')):
+        fa = F.pack_frame(F.build_body_constants(py, target, None, observer, et=et0 - 2 * 86400), nx=64, ny=64,
+                          x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.3)
+        fb = F.pack_frame(F.build_body_constants(nat, target, None, observer, et=et0 - 2 * 86400), nx=64, ny=64,
+                          x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.3)
+        for name, (o, n) in F.PMFRAME_OFFSETS.items():
+            a, b = fa[o:o + n], fb[o:o + n]
+            scale = np.max(np.abs(a)) or 1.0
+            assert np.max(np.abs(a - b)) / scale <= loose.get(name, 1e-11), (target, name)
