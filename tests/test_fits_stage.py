@@ -72,6 +72,40 @@ def test_value_formatting_rules():
         f('BAD*KEY', 1, None)
 
 
+def test_card_format_round_trip_property():
+    """Property (hypothesis): every value the formatter accepts parses back to itself - floats
+    bit-exactly whenever their shortest repr fits FITS's 20-character value field - and every card
+    is exactly 80 ASCII characters."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    keys = st.sampled_from(['NAXIS1', 'CRVAL1', 'PLANMAP DISC X0', 'PLANMAP MAP SMOOTH-MAX-OVERSAMPLED-IMG-SIZE', 'A'])
+    text = st.text(alphabet=st.characters(min_codepoint=32, max_codepoint=126), max_size=18)
+    values = st.one_of(st.booleans(), st.integers(min_value=-10**15, max_value=10**15),
+                       st.floats(allow_nan=False, allow_infinity=False), text)
+
+    @settings(max_examples=400, deadline=None)
+    @given(keys, values, st.one_of(st.none(), text.filter(lambda t: t.strip() == t and t != '' and '/' not in t)))
+    def check(key, value, comment):
+        cards = FS.Header.format_card(key, value, comment)
+        assert len(cards) == 1 and len(cards[0]) == 80 and cards[0].isascii()
+        k, v, c = FO.parse_card(cards[0])
+        assert k == key
+        if isinstance(value, str):
+            assert v == value.rstrip()
+        elif isinstance(value, float):
+            assert isinstance(v, (float, int))
+            if len(str(value)) <= 20:
+                assert float(v) == value
+            else:
+                assert float(v) == pytest.approx(value, rel=1e-11)   # astropy keeps 20 characters: >= 12 digits
+        else:
+            assert v == value and type(v) is type(value)
+        assert FS.Header.format_card(k, v if not isinstance(value, float) else float(v), c) == cards or isinstance(value, float)
+
+    check()
+
+
 def test_header_object_semantics():
     h = FS.Header([('A', 1, None)])
     h['B'] = 2.0
