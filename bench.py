@@ -606,6 +606,10 @@ def main():
                                         'in this run (MEASURED_PEAKS.json has no FP64 entry)',
                          'algorithmic_flops_per_launch': flops, 'pixel_classes': classes,
                          'hbm_bytes_per_launch_algorithmic': int(k * SZ * SZ * 8),
+                         # the same launch seen as an HBM kernel (why the bound is the FP64 pipe, not memory)
+                         'hbm_view': {'bound': 'hbm', 'achieved': k * SZ * SZ * 8 / (ms * 1e-3) / 1e9,
+                                      'peak': measured_peaks()[0]['hbm_gbs'], 'unit': 'GB/s',
+                                      'frac': k * SZ * SZ * 8 / (ms * 1e-3) / 1e9 / measured_peaks()[0]['hbm_gbs']},
                          'note': 'frac counts flops (FMA = 2) against the DFMA-only peak; a third of the FP64-pipe '
                                  'instructions are DMUL / DADD / DSETP (1 or 0 flop per issue slot), so the pipe '
                                  'utilisation ncu reports (ncu.fp64_pipe_util) is the tighter measure of how '
