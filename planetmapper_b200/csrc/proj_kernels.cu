@@ -110,21 +110,23 @@ __device__ __forceinline__ bool proj_inverse_one(int kind, const ProjParams &pp,
             if (x * x + yr * yr > 1.0 + 1e-11) return false;
             if (!ortho_sph_inverse(x, yr, phi0, sinph0, cosph0, phi, lam)) return false;
             bool ok = false;
+            // Newton on (phi, lam): own FP64 primitives (pm_math.cuh; 1-2 ulp) instead of libm's sincos /
+            // division / sqrt slow paths - this loop is the whole cost of an oblique orthographic map
             for (int it = 0; it < 20; it++) {
                 double sp, cp, sl, cl;
-                sincos(phi, &sp, &cp);
-                sincos(lam, &sl, &cl);
+                sincos_full(phi, sp, cp);
+                sincos_full(lam, sl, cl);
                 double w = 1.0 - es * sp * sp;
-                double nu = 1.0 / sqrt(w);
+                double nu = fast_rsqrt(w);
                 double fx = nu * cp * sl;
                 double fy = nu * (sp * cosph0 - cp * sinph0 * cl) + es * (nu0 * sinph0 - nu * sp) * cosph0;
-                double rho = one_es * nu / w;
+                double rho = one_es * nu * (nu * nu);
                 double J11 = -rho * sp * sl, J12 = nu * cp * cl;
                 double J21 = rho * (cp * cosph0 + sp * sinph0 * cl), J22 = nu * sinph0 * cp * sl;
-                double D = J11 * J22 - J12 * J21;
+                double iD = fast_rcp(J11 * J22 - J12 * J21);
                 double dx = x - fx, dy = y - fy;
-                double dphi = (J22 * dx - J12 * dy) / D;
-                double dlam = (-J21 * dx + J11 * dy) / D;
+                double dphi = (J22 * dx - J12 * dy) * iD;
+                double dlam = (-J21 * dx + J11 * dy) * iD;
                 phi += dphi;
                 if (phi > kHalfPi)
                     phi = kHalfPi - (phi - kHalfPi);
