@@ -420,6 +420,35 @@ def bench_save_observation(L, torch, pm, bc, sz=2048):
             'whole_call_s_incl_disk_write': call_s}
 
 
+def bench_point_transforms(L, torch, bc, n=10_000_000):
+    """the vectorised point transforms (xy2lonlat / lonlat2xy over arrays,
+    base.py:718-757 in the reference: np.nditer + one ctypes call per element), n points each."""
+    fr = c2_frame(bc)
+    fd = L.to_device(fr)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * SZ
+    y = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * SZ
+    lon = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 360.0
+    lat = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 180.0 - 90.0
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_fwd = timed(lambda: L.xy2lonlat(fd, x, y))
+    t_inv = timed(lambda: L.lonlat2xy(fd, lon, lat, True))
+    t_alt = timed(lambda: L.lonlat2xy(fd, lon, lat, True, alt=1000.0))
+    return {'workload': f'{n} random points on the C2 frame', 'xy2lonlat_mpoints_per_s': n / t_fwd / 1e3,
+            'lonlat2xy_mpoints_per_s': n / t_inv / 1e3, 'lonlat2xy_alt_raycast_mpoints_per_s': n / t_alt / 1e3}
+
+
 def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     """C5: the time series of BASELINE.json - 4096 frames of 1024 x 1024, 60 s apart, ending one
     hour before the fixture epoch, sharded by frame across ranks: the 12-plane stack per frame in
@@ -634,6 +663,7 @@ def main():
             result['time_series'] = ts
             result['saturn_rings'] = bench_saturn_rings(L, torch, pm)
             result['save_observation'] = bench_save_observation(L, torch, pm, bc)
+            result['point_transforms'] = bench_point_transforms(L, torch, bc)
     if rank == 0:
         if not args.skip_cpu and world == 1:  # the CPU baseline is an N = 1 measurement
             mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)
