@@ -731,7 +731,7 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
     if (n_cells == 0 || plane_count == 0) return cudaSuccess;
     int ppg = 128;  // planes per CTA: amortises the per-cell weights, bounds CTA run time
     if (plane_count < ppg) ppg = (plane_count + 3) / 4 * 4;
-    // every CTA covers kGatherBlock cells (128 threads x 2 cells for the cubic kernel)
+    // every CTA of the scalar kernels covers kGatherBlock cells (the DMMA kernel sizes its own grid below)
     dim3 grid((unsigned)((n_cells + kGatherBlock - 1) / kGatherBlock), (unsigned)((plane_count + ppg - 1) / ppg));
     const int n_words = (n_planes + 31) / 32;
     int ky = mode, kx = mode;  // spline degree along image rows (y) / columns (x)
