@@ -422,6 +422,34 @@ def test_full_size_saturn_4096_rings_vs_oracle(L, oracle):
     assert np.isfinite(ring).sum() > 1.5e6 and np.nanmax(ring) > 136780   # the A ring is in frame
 
 
+def test_very_large_frame_indexing(L, bc_hst):
+    """16384 x 16384 (268 Mpix, two planes = 4.3 GB): plane offsets and pixel indices beyond 2^31
+    bytes / 2^28 elements.  A window of the big frame must equal a small frame whose disc centre is
+    shifted by the window origin (same rays, same arithmetic up to the rounding of x0)."""
+    import torch
+
+    sz = 16384
+    names = ['EMISSION', 'LON-GRAPHIC']
+    mask = L.mask_from_names(names)
+    big_fr = _img_case(bc_hst, sz, sz, 8000.25, 8100.5, 7000.0, 20.0)
+    big = L.backplanes_img(L.to_device(big_fr[None]), sz, sz, mask)[0]
+    assert big.shape == (2, sz, sz)
+    on = torch.isfinite(big[0])
+    frac = float(on.double().mean())
+    assert abs(frac - np.pi * 7000.0 ** 2 * (bc_hst.r_polar / bc_hst.r_eq) / sz ** 2) < 0.02    # an ellipse of that size
+    for (oy, ox) in ((0, 0), (8100 - 32, 8000 - 32), (sz - 64, sz - 64), (12000, 3000), (14000, 9000)):
+        small_fr = _img_case(bc_hst, 64, 64, 8000.25 - ox, 8100.5 - oy, 7000.0, 20.0)
+        small = L.backplanes_img(L.to_device(small_fr[None]), 64, 64, mask)[0].cpu().numpy()
+        win = big[:, oy:oy + 64, ox:ox + 64].cpu().numpy()
+        assert np.array_equal(np.isnan(win), np.isnan(small)), (oy, ox)
+        ok = np.isfinite(small)
+        if ok.any():
+            d = np.abs(win[ok] - small[ok])
+            d = np.minimum(d, np.abs(d - 360.0))
+            assert d.max() < 1e-7, (oy, ox, d.max())     # x0 - ox rounds differently: ~1e-12 px -> well below this
+    del big
+
+
 def test_full_grid_gather_properties(L, bc_hst):
     """C4 geometry: 64 x 64 cube -> 0.1 deg grid (6.48 M cells); a few planes."""
     import torch
