@@ -68,6 +68,8 @@ class NativeSpice(MiniSpice):
 
     # ---- ephemeris ---------------------------------------------------------------------
     def ssb_state(self, body: int, et: float) -> np.ndarray:
+        if self._other_frames:   # segments in other frames: precedence and errors are the Python reader's business
+            return super().ssb_state(body, et)
         rc = self._lib.pm_host_ssb_state(self._segs, self._n_segs, self._rec_ptr, int(body), float(et), self._state)
         if rc != 0:
             return super().ssb_state(body, et)   # raises the reader's own LookupError / NotImplementedError
