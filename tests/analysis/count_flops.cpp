@@ -69,7 +69,7 @@ static inline bool isfinite(C a) { return std::isfinite(a.v); }
 static inline bool isnan(C a) { return std::isnan(a.v); }
 
 #define double C
-#include "../oracle/pm_oracle.c"
+#include "../../oracle/pm_oracle.c"
 #undef double
 
 int main(int argc, char **argv) {
