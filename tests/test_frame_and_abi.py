@@ -73,13 +73,13 @@ def test_oracle_library_exports():
 
 def test_product_never_imports_the_oracle():
     """The product path must not route through oracle/ (no CPU fallback)."""
-    pkg = os.path.join(ROOT, 'planetmapper_b200')
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
-                text = open(os.path.join(dirpath, fn), encoding='utf-8').read()
-                assert 'import oracle' not in text and 'from oracle' not in text, fn
-                assert 'pm_oracle' not in text, fn
+    for top in ('planetmapper_b200', 'tools', 'include'):   # only tests/, smoke() and bench.py's CPU legs may use it
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for fn in files:
+                if fn.endswith(('.py', '.cu', '.cuh', '.h', '.sh')):
+                    text = open(os.path.join(dirpath, fn), encoding='utf-8').read()
+                    assert 'import oracle' not in text and 'from oracle' not in text, fn
+                    assert 'pm_oracle' not in text, fn
 
 
 @pytest.mark.skipif(__import__('torch').cuda.is_available(), reason='CPU-only check')
