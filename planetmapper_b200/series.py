@@ -135,17 +135,18 @@ def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: 
     if provider is not None or workers <= 1:
         return _block(provider if provider is not None else pm.get_default_provider(), target, observer, ets, disc)
     procs = _workers(workers)
-    for w, proc in enumerate(procs):
-        block = ets[slice(*shard_range(len(ets), w, workers))]
-        _send(proc.stdin, (pm.get_kernel_path(), str(target), str(observer), block, disc))
-    parts = []
-    for proc in procs:
-        status, payload = _recv(proc.stdout)
-        if status != 'ok':
-            shutdown_pool()
-            raise RuntimeError(f'series worker failed: {payload}')
-        parts.append(payload)
-    return np.concatenate(parts, axis=0)
+    try:
+        for w, proc in enumerate(procs):
+            block = ets[slice(*shard_range(len(ets), w, workers))]
+            _send(proc.stdin, (pm.get_kernel_path(), str(target), str(observer), block, disc))
+        replies = [_recv(proc.stdout) for proc in procs]   # every reply is drained before any error is raised
+    except BaseException:
+        shutdown_pool()   # a dead or half-read worker must not serve the next call
+        raise
+    failed = [payload for status, payload in replies if status != 'ok']
+    if failed:
+        raise RuntimeError(f'series worker failed: {failed[0]}')
+    return np.concatenate([payload for _, payload in replies], axis=0)
 
 
 def iter_backplane_batches(frames: np.ndarray, nx: int, ny: int, names, batch: int = 32):
