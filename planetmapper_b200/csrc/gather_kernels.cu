@@ -917,6 +917,11 @@ __global__ void __launch_bounds__(256) median_kernel(const double *__restrict__ 
 // by many CTAs per plane (shared-memory histogram per CTA, merged with global atomics) and the
 // bucket chosen by a one-thread-per-plane kernel in between: 1 + 2 x 8 small launches that each
 // stream the batch once, instead of one CTA walking a megapixel plane sixteen times.
+// 11-bit digits: six passes over the batch instead of eight with bytes (the last digit has 9 bits)
+constexpr int kSelBits = 11, kSelBins = 1 << kSelBits, kSelPasses = 6;
+__host__ __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 0 : 64 - kSelBits * (kSelPasses - pass); }
+__host__ __device__ __forceinline__ unsigned sel_width_mask(int pass) { return pass == 0 ? (1u << 9) - 1u : (unsigned)kSelBins - 1u; }
+
 struct SelectState {
     unsigned long long prefix[2], mask;
     long long k[2];
@@ -926,7 +931,7 @@ __global__ void select_init_kernel(const PlaneStats *__restrict__ stats, int n_p
                                    SelectState *__restrict__ state, unsigned int *__restrict__ hist,
                                    double *__restrict__ median) {
     const int l = blockIdx.x;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[(int64_t)l * 512 + i] = 0;
+    for (int i = threadIdx.x; i < 2 * kSelBins; i += blockDim.x) hist[(int64_t)l * 2 * kSelBins + i] = 0;
     if (threadIdx.x != 0) return;
     SelectState st;
     st.prefix[0] = st.prefix[1] = st.mask = 0;
@@ -953,45 +958,49 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const double *__restri
     const int l = blockIdx.x;
     const SelectState st = state[l];
     if (st.n_sel == 0) return;  // uniform for the CTA
-    __shared__ unsigned int sh[2][256];
-    sh[0][threadIdx.x] = 0;
-    sh[1][threadIdx.x] = 0;
+    __shared__ unsigned int sh[2][kSelBins];
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) {
+        sh[0][i] = 0;
+        sh[1][i] = 0;
+    }
     __syncthreads();
     const double *src = cube + (int64_t)l * plane_px;
     const bool same = st.n_sel == 2 && st.prefix[0] == st.prefix[1];  // both statistics still in one bucket
+    const int shift = sel_shift(pass);
+    const unsigned wmask = sel_width_mask(pass);
     for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < plane_px; i += (int64_t)gridDim.y * blockDim.x) {
         const double v = src[i];
         if (isfinite(v)) {
             const unsigned long long key = order_key(v);
-            const unsigned d = (unsigned)((key >> (8 * pass)) & 255ull);
+            const unsigned d = (unsigned)(key >> shift) & wmask;
             if ((key & st.mask) == st.prefix[0]) atomicAdd(&sh[0][d], 1u);
             if (st.n_sel == 2 && !same && (key & st.mask) == st.prefix[1]) atomicAdd(&sh[1][d], 1u);
         }
     }
     __syncthreads();
-    unsigned int *g = hist + (int64_t)l * 512;
-    if (sh[0][threadIdx.x]) atomicAdd(&g[threadIdx.x], sh[0][threadIdx.x]);
-    const unsigned int second = same ? sh[0][threadIdx.x] : sh[1][threadIdx.x];
-    if (st.n_sel == 2 && second) atomicAdd(&g[256 + threadIdx.x], second);
+    unsigned int *g = hist + (int64_t)l * 2 * kSelBins;
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) {
+        if (sh[0][i]) atomicAdd(&g[i], sh[0][i]);
+        const unsigned int second = same ? sh[0][i] : sh[1][i];
+        if (st.n_sel == 2 && second) atomicAdd(&g[kSelBins + i], second);
+    }
 }
-// one warp per plane: lane i owns buckets 8 i .. 8 i + 7; the bucket holding rank k is found from
-// the warp prefix sum of the lane totals
+// one warp per plane: lane i owns buckets kPer i .. kPer i + kPer - 1; the bucket holding rank k is
+// found from the warp prefix sum of the lane totals
 __global__ void __launch_bounds__(128) select_pick_kernel(SelectState *__restrict__ state,
                                                           unsigned int *__restrict__ hist, int n_planes, int pass,
                                                           double *__restrict__ median) {
+    constexpr int kPer = kSelBins / 32;
     const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (l >= n_planes) return;  // whole warp
     SelectState st = state[l];
     if (st.n_sel == 0) return;
-    unsigned int *g = hist + (int64_t)l * 512;
+    unsigned int *g = hist + (int64_t)l * 2 * kSelBins;
+    const int shift = sel_shift(pass);
     for (int s = 0; s < st.n_sel; s++) {
-        unsigned int c[8];
+        const unsigned int *c = g + kSelBins * s + kPer * lane;
         long long mine = 0;
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            c[b] = g[256 * s + 8 * lane + b];
-            mine += c[b];
-        }
+        for (int b = 0; b < kPer; b++) mine += c[b];
         long long incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1001,26 +1010,25 @@ __global__ void __launch_bounds__(128) select_pick_kernel(SelectState *__restric
         const long long before = incl - mine;   // counts in the buckets below this lane's
         const bool holds = before <= st.k[s] && st.k[s] < incl;
         const unsigned owner = __ballot_sync(0xffffffffu, holds);
-        int bucket = 255;
+        int bucket = kSelBins - 1;
         long long cum = before;
         if (holds) {
-            bucket = 8 * lane;
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
+            bucket = kPer * lane;
+            for (int b = 0; b < kPer; b++) {
                 if (cum + (long long)c[b] > st.k[s]) break;
                 cum += c[b];
-                bucket = 8 * lane + b + 1;
+                bucket = kPer * lane + b + 1;
             }
         }
-        const int src = owner ? __ffs(owner) - 1 : 31;   // rank beyond the count cannot happen; bucket 255 as before
+        const int src = owner ? __ffs(owner) - 1 : 31;   // a rank beyond the count cannot happen
         bucket = __shfl_sync(0xffffffffu, bucket, src);
         cum = __shfl_sync(0xffffffffu, cum, src);
-        if (!owner) cum = incl;  // (defensive) everything is below
-        st.k[s] -= __shfl_sync(0xffffffffu, cum, src);
-        st.prefix[s] |= (unsigned long long)min(bucket, 255) << (8 * pass);
+        st.k[s] -= cum;
+        st.prefix[s] |= (unsigned long long)min(bucket, (int)sel_width_mask(pass)) << shift;
     }
-    st.mask |= 0xffull << (8 * pass);
-    for (int i = lane; i < 512; i += 32) g[i] = 0;
+    st.mask |= (unsigned long long)sel_width_mask(pass) << shift;
+    __syncwarp();
+    for (int i = lane; i < 2 * kSelBins; i += 32) g[i] = 0;
     if (lane == 0) {
         state[l] = st;
         if (pass == 0) {
@@ -1214,7 +1222,8 @@ int64_t spline_work_bytes(int n_planes, int ny, int nx, int degree) {
     int64_t b = align256((int64_t)n_planes * sizeof(PlaneStats)) + align256((int64_t)n_planes * sizeof(double)) +
                 align256((int64_t)n_planes) + align256((int64_t)n_planes * ny * nx * (int64_t)sizeof(double));
     b += align256((int64_t)5 * nx * sizeof(double)) + align256((int64_t)5 * ny * sizeof(double));
-    b += align256((int64_t)n_planes * sizeof(SelectState)) + align256((int64_t)n_planes * 512 * sizeof(unsigned int));
+    b += align256((int64_t)n_planes * sizeof(SelectState)) +
+         align256((int64_t)n_planes * 2 * kSelBins * sizeof(unsigned int));
     return b;
 }
 
@@ -1246,15 +1255,15 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     } else {
         char *tail = static_cast<char *>(work) + spline_work_bytes(n_planes, ny, nx, degree) -
                      align256((int64_t)n_planes * sizeof(SelectState)) -
-                     align256((int64_t)n_planes * 512 * sizeof(unsigned int));
+                     align256((int64_t)n_planes * 2 * kSelBins * sizeof(unsigned int));
         SelectState *state = reinterpret_cast<SelectState *>(tail);
         unsigned int *hist = reinterpret_cast<unsigned int *>(tail + align256((int64_t)n_planes * sizeof(SelectState)));
         select_init_kernel<<<n_planes, 256, 0, st>>>(stats, n_planes, plane_px, state, hist, median);
-        for (int pass = 7; pass >= 0; pass--) {
+        for (int pass = kSelPasses - 1; pass >= 0; pass--) {
             select_hist_kernel<<<dim3(n_planes, chunks), 256, 0, st>>>(cube, plane_px, state, hist, pass);
             select_pick_kernel<<<(n_planes + 3) / 4, 128, 0, st>>>(state, hist, n_planes, pass, median);
         }
-        count_launches(16);
+        count_launches(2 * kSelPasses);
     }
     const int rblocks = (int)std::max<int64_t>(
         1, std::min<int64_t>((plane_px + 255) / 256, ((int64_t)sm_count * 16 + n_planes - 1) / n_planes));
