@@ -70,6 +70,10 @@ _PLANE_DESCRIPTIONS = [
 assert [p[0] for p in _PLANE_DESCRIPTIONS] == L.PLANE_NAMES
 
 _XY_PLANES = (L.PLANE_ID['PIXEL-X'], L.PLANE_ID['PIXEL-Y'])
+# the default surface stack (BASELINE config C2): the planes that need the ray / ellipsoid intercept only
+_SURFACE_STACK = L.mask_from_names(['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'PHASE', 'INCIDENCE',
+                                    'EMISSION', 'AZIMUTH', 'LOCAL-SOLAR-TIME', 'DISTANCE', 'RADIAL-VELOCITY',
+                                    'DOPPLER'])
 _MAP_KWARG_KEYS = ('projection', 'degree_interval', 'lon', 'lat', 'size', 'lon_coords',
                    'lat_coords', 'projection_x_coords', 'projection_y_coords', 'xlim', 'ylim',
                    'alt')
@@ -86,6 +90,34 @@ class ProjStringError(ValueError):
 class NotFoundError(Exception):
     """Stands in for spiceypy's NotFoundError: a ray missed the target
     (Body._obsvec_norm2lonlat with not_found_nan=False, body.py:1073-1078)."""
+
+
+def mjd2dtm(mjd: float):
+    """Modified Julian Date -> timezone-aware UTC datetime (SpiceBase.mjd2dtm, base.py:500-512; the
+    reference goes through astropy.time.Time(mjd, format='mjd').datetime, i.e. the UTC scale with
+    MJD 0 = 1858-11-17T00:00:00)."""
+    import datetime
+
+    days = math.floor(mjd)
+    micro = round((float(mjd) - days) * 86400e6)
+    return (datetime.datetime(1858, 11, 17, tzinfo=datetime.timezone.utc)
+            + datetime.timedelta(days=days, microseconds=micro))
+
+
+def standardise_utc_to_string(utc) -> str:
+    """BodyBase._standardise_utc_to_string (base.py:841-861): MJD numbers and datetimes (naive ones
+    are taken as UTC, aware ones converted to UTC) become '%Y-%m-%dT%H:%M:%S.%f' strings; strings
+    pass through."""
+    import datetime
+    import numbers
+
+    if isinstance(utc, numbers.Number) and not isinstance(utc, bool):
+        utc = mjd2dtm(float(utc))
+    if isinstance(utc, datetime.datetime):
+        if utc.tzinfo is None:
+            utc = utc.replace(tzinfo=datetime.timezone.utc)
+        utc = utc.astimezone(tz=datetime.timezone.utc).strftime('%Y-%m-%dT%H:%M:%S.%f')
+    return str(utc)
 
 
 class Backplane(NamedTuple):
@@ -124,7 +156,7 @@ class BodyXY:
       ``minispice.MiniSpice``); default = :func:`planetmapper_b200.get_default_provider`.
     """
 
-    def __init__(self, target=None, utc=None, observer='EARTH', *, nx: int = 0, ny: int = 0,
+    def __init__(self, target=None, utc=None, observer='EARTH', nx: int = 0, ny: int = 0, *,
                  sz: int | None = None, constants: F.BodyConstants | None = None,
                  provider=None, optimize_speed: bool = True, aberration_correction: str = 'CN',
                  observer_frame: str = 'J2000', target_frame: str | None = None,
@@ -153,12 +185,14 @@ class BodyXY:
                 raise TypeError('target is required')
             if utc is None:
                 raise NotImplementedError('utc=None (current time) needs a live SPICE setup')
-            constants = F.build_body_constants(provider, target, str(utc), observer)
+            constants = F.build_body_constants(provider, target, standardise_utc_to_string(utc), observer)
         if target_frame is not None and target_frame.upper() != 'IAU_' + constants.target:
             raise NotImplementedError('only the default IAU_<target> frame is accelerated')
         self._bc = constants
         self._optimize_speed = bool(optimize_speed)
         if sz is not None:
+            if nx != 0 or ny != 0:   # body_xy.py:199-201
+                raise ValueError('`sz` cannot be used if `nx` and/or `ny` are nonzero')
             nx = ny = sz
         self._nx, self._ny = int(nx), int(ny)
         self._x0 = self._y0 = 0.0
@@ -621,20 +655,24 @@ class BodyXY:
         if entry is None or (entry[0] & mask) != mask:
             have = entry[0] if entry else 0
             new_mask = have | mask
+            if have:
+                # second distinct request: escalate to the whole group the planes belong to (the
+                # 12-plane surface stack has a specialised kernel; anything else -> all 26), so a
+                # sequence of single-plane getters costs at most three launches
+                new_mask = _SURFACE_STACK if (new_mask & ~_SURFACE_STACK) == 0 else L.ALL_PLANES
             fd = self._frame_dev(alt).reshape(1, -1)
             planes = L.backplanes_img(fd, self._nx, self._ny, new_mask)[0]
             entry = (new_mask, planes)
-            self._cache[key] = entry
-            for k in [k for k in self._cache if isinstance(k, tuple) and k[:1] == ('img_host',)
-                      and k[2] == alt]:
-                del self._cache[k]
+            self._cache[key] = entry   # host copies already handed out stay valid (same values)
         return entry
 
     def _get_img_plane(self, pid: int) -> np.ndarray:
         alt = self._alt_adjustment
         key = ('img_host', pid, alt)
         if key not in self._cache:
-            have, planes = self.get_backplanes_img_device(L.ALL_PLANES, alt)
+            # only the requested plane is added to what the cache already holds (a single
+            # get_backplane_img('EMISSION') must not pay for the 26-plane stack)
+            have, planes = self.get_backplanes_img_device(1 << pid, alt)
             slot = L.popcount(have & ((1 << pid) - 1))
             self._cache[key] = _readonly(planes[slot].cpu().numpy())
         return self._cache[key]

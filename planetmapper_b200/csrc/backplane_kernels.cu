@@ -222,11 +222,11 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     const int64_t npx = (int64_t)nx * ny;
     if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
     const PlaneOffsets po = make_plane_offsets(mask, npx);
-    static const int forced = getenv("PM_IMG_PER_THREAD") ? atoi(getenv("PM_IMG_PER_THREAD")) : 0;  // tuning only
+    static const int forced = tune_int("PM_IMG_PER_THREAD", 0);
     const int per = forced > 0 ? forced : pick_per_thread(npx, n_frames, sm_count);
     const int64_t chunk = (int64_t)kBlock * per;
     dim3 grid((unsigned)((npx + chunk - 1) / chunk), n_frames);
-    static const bool no_fixed = getenv("PM_IMG_NO_FIXED_MASK") != nullptr;  // tuning only
+    static const bool no_fixed = tune_int("PM_IMG_NO_FIXED_MASK", 0) != 0;
     if (mask == kDefaultStackMask && !no_fixed)
         backplanes_img_kernel<false, kDefaultStackMask><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx,
                                                                                    per, mask, po, out);

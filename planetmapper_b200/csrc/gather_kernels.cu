@@ -751,13 +751,13 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
     gather_spline_kernel<KY, KX, MB><<<grid, kGatherBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,    \
                                                                     plane_begin, plane_count, xmap, ymap, n_cells, \
                                                                     flags, out, ppg)
-    static const int v = getenv("PM_CUBIC_VARIANT") ? atoi(getenv("PM_CUBIC_VARIANT")) : -1;  // tuning only
+    static const int v = tune_int("PM_CUBIC_VARIANT", -1);
     // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel
     const bool dense = n_cells >= (int64_t)8 * nx * ny && nx < 16384 && ny < 16384;
     if (ky == 3 && kx == 3 && v != 0 && (dense || v > 0)) {
         // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is heavier here
         // than in the scalar kernel
-        static const int mma_ppg = getenv("PM_MMA_PPG") ? atoi(getenv("PM_MMA_PPG")) : 512;  // tuning only
+        static const int mma_ppg = tune_int("PM_MMA_PPG", 512);
         const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
         // map row length known and regular -> 4 x 8 cell blocks per warp, else 32 consecutive cells
         // (measured on C4: for long rows the 1-D order is ~4 % faster - longer contiguous store

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef PM_TUNING
+#include <cstdlib>
+#endif
 
 #include "../../include/pm_b200.h"
 
@@ -11,6 +14,17 @@ constexpr int kBlock = 128;  // threads per CTA for the FP64 geometry kernels
 
 // kernels launched by this library since load (pm_launch_count)
 void count_launches(int n);
+
+// Tuning knobs exist only in builds made with -DPM_TUNING (tools/tune_*.py); the product build
+// compiles them to their defaults and never reads the environment.
+#ifdef PM_TUNING
+inline int tune_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+#else
+constexpr int tune_int(const char *, int dflt) { return dflt; }
+#endif
 
 cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t mask,
                                   double *out, int sm_count, cudaStream_t st);

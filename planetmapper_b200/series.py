@@ -60,7 +60,7 @@ def _worker_main() -> None:
 
     inp, out = sys.stdin.buffer, sys.stdout.buffer
     sys.stdout = sys.stderr  # stray prints must not corrupt the reply stream
-    provider = None
+    provider, provider_path = None, None
     while True:
         try:
             msg = _recv(inp)
@@ -68,10 +68,9 @@ def _worker_main() -> None:
             return
         try:
             kernel_path, target, observer, ets, disc = msg
-            if provider is None:
-                if kernel_path is not None:
-                    pm.set_kernel_path(kernel_path)
-                provider = pm.get_default_provider()
+            if provider is None or kernel_path != provider_path:   # the cached provider is keyed on its path
+                pm.set_kernel_path(kernel_path)
+                provider, provider_path = pm.get_default_provider(), kernel_path
             _send(out, ('ok', _block(provider, target, observer, ets, disc)))
         except Exception as exc:  # reported to the parent, which raises
             _send(out, ('error', f'{type(exc).__name__}: {exc}'))
@@ -132,13 +131,15 @@ def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: 
     disc = dict(nx=nx, ny=ny, x0=x0, y0=y0, r0=r0, rotation_radians=rotation_radians, alt=alt)
     workers = default_workers() if workers is None else int(workers)
     workers = min(workers, max(1, len(ets) // 16))   # a block under ~16 epochs does not pay for the hand-off
+    if pm.provider_is_custom():   # an in-process provider cannot be rebuilt inside a worker
+        workers = 1
     if provider is not None or workers <= 1:
         return _block(provider if provider is not None else pm.get_default_provider(), target, observer, ets, disc)
     procs = _workers(workers)
     try:
         for w, proc in enumerate(procs):
             block = ets[slice(*shard_range(len(ets), w, workers))]
-            _send(proc.stdin, (pm.get_kernel_path(), str(target), str(observer), block, disc))
+            _send(proc.stdin, (pm._KERNEL_PATH, str(target), str(observer), block, disc))
         replies = [_recv(proc.stdout) for proc in procs]   # every reply is drained before any error is raised
     except BaseException:
         shutdown_pool()   # a dead or half-read worker must not serve the next call

@@ -84,7 +84,7 @@ def test_card_format_round_trip_property():
     values = st.one_of(st.booleans(), st.integers(min_value=-10**15, max_value=10**15),
                        st.floats(allow_nan=False, allow_infinity=False), text)
 
-    @settings(max_examples=400, deadline=None)
+    @settings(max_examples=400, deadline=None, derandomize=True)
     @given(keys, values, st.one_of(st.none(), text.filter(lambda t: t.strip() == t and t != '' and '/' not in t)))
     def check(key, value, comment):
         cards = FS.Header.format_card(key, value, comment)
@@ -101,7 +101,12 @@ def test_card_format_round_trip_property():
                 assert float(v) == pytest.approx(value, rel=1e-11)   # astropy keeps 20 characters: >= 12 digits
         else:
             assert v == value and type(v) is type(value)
-        assert FS.Header.format_card(k, v if not isinstance(value, float) else float(v), c) == cards or isinstance(value, float)
+        if isinstance(value, str):
+            # the card keeps trailing blanks inside the quotes (as astropy does) while parsing strips
+            # them, so the re-format identity holds for the stripped value
+            assert FS.Header.format_card(k, v, c) == FS.Header.format_card(key, value.rstrip(), comment)
+        elif not isinstance(value, float):
+            assert FS.Header.format_card(k, v, c) == cards
 
     check()
 

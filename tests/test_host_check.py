@@ -265,17 +265,16 @@ int main(int argc, char **argv) {
 
 
 @pytest.fixture(scope='module')
-def ld_oracle():
+def ld_oracle(tmp_path_factory):
     import re
 
     if not shutil.which('gcc'):
         pytest.skip('gcc not available')
     root = os.path.dirname(HERE)
-    bdir = os.path.join(HERE, 'host_check', '_build', 'ld')
-    os.makedirs(bdir, exist_ok=True)
+    bdir = str(tmp_path_factory.mktemp('oracle_ld'))   # always rebuilt from the current oracle source
     exe = os.path.join(bdir, 'oracle_ld')
     src_c = os.path.join(root, 'oracle', 'pm_oracle.c')
-    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src_c):
+    if True:
         def ld(text):
             return re.sub(r'\bdouble\b', 'long double', text)
         c = ld(open(src_c).read()).replace('#include <math.h>', '#include <tgmath.h>')
