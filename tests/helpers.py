@@ -151,6 +151,114 @@ OTHER_BODIES = [
 
 
 
+# ---------------------------------------------------------------------------------
+# Triaxial bodies (BASELINE config C5 names Europa: 1562.6 / 1560.3 / 1559.5 km).  The bundled
+# kernels have no SPK segment for 502, so its position comes from an analytic orbit about the
+# Jupiter barycentre (planetmapper_b200/minispice/kepler.py, SURVEY 8(d) C5 option ii); radii and
+# the IAU orientation model are the PCK's.  'triaxial-x' keeps Europa's state and orientation but
+# exaggerates the shape so that every triaxial term (sincpt on (a, b, c), surfnm weights, recpgr
+# against (a, a, c) of a point OFF that spheroid, pgrrec points off the ellipsoid) is far above
+# rounding level.
+# ---------------------------------------------------------------------------------
+class _RadiiOverride:
+    def __init__(self, base, body, radii):
+        self.base, self.body, self.radii = base, int(body), np.asarray(radii, dtype=float)
+
+    def __getattr__(self, item):
+        return getattr(self.base, item)
+
+    def bodvar(self, body, item):
+        if int(body) == self.body and item == 'RADII':
+            return self.radii.copy()
+        return self.base.bodvar(body, item)
+
+
+def triaxial_constants(kind='europa', utc='2004-12-31T00:00:00', observer='EARTH'):
+    import planetmapper_b200 as pm
+    from planetmapper_b200.minispice.kepler import KeplerOrbitProvider
+
+    provider = KeplerOrbitProvider(pm.get_default_provider())
+    if kind == 'triaxial-x':
+        provider = _RadiiOverride(provider, 502, [1562.6, 1420.3, 1260.5])
+    bc = F.build_body_constants(provider, 'Europa', utc, observer)
+    assert len(set(bc.radii)) == 3
+    return bc
+
+
+TRIAXIAL_CASES = [
+    # kind, nx, ny, x0, y0, r0, rotation
+    ('europa', 96, 80, 47.5, 40.0, 33.0, 25.0),
+    ('triaxial-x', 96, 80, 47.5, 40.0, 33.0, 25.0),
+    ('triaxial-x', 64, 64, 20.0, 40.0, 45.0, 250.0),    # disc partly outside the frame
+]
+
+
+# north_star's bars as written, with no conditioning term: angles 1e-9 deg, distances and
+# velocities 1e-12 relative.  raw_plane_stats() reports every compared pixel against them.
+BARE_ANGLE_PLANES = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'PHASE', 'INCIDENCE', 'EMISSION',
+                     'AZIMUTH', 'RA', 'DEC', 'LIMB-LON-GRAPHIC', 'LIMB-LAT-GRAPHIC', 'RING-LON-GRAPHIC']
+BARE_REL_PLANES = ['DISTANCE', 'RADIAL-VELOCITY', 'DOPPLER', 'LIMB-DISTANCE', 'RING-RADIUS', 'RING-DISTANCE']
+EMISSION_BINS = [0.0, 35.0, 60.0, 80.0, 89.0, 90.0]
+
+
+def raw_plane_stats(got, ref, margin, planes=None):
+    """Un-widened statistics of `got` against `ref` (26-plane stacks; absent planes all-NaN): per plane
+    the number of pixels compared, the maximum difference, how many pixels exceed the BARE bar
+    (1e-9 deg / 1e-12 relative) and where they sit in emission angle.  Nothing is asserted here."""
+    grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
+    emi = ref[PID['EMISSION']]
+    out = {'n_px': int(got[0].size), 'n_grazing_excluded': int(grazing.sum())}
+    for name in (planes or BARE_ANGLE_PLANES + BARE_REL_PLANES + ['LOCAL-SOLAR-TIME']):
+        a, b = got[PID[name]], ref[PID[name]]
+        both = np.isfinite(a) & np.isfinite(b) & ~grazing
+        mism = (np.isnan(a) != np.isnan(b))
+        if not both.any() and not mism.any():
+            continue
+        d = angle_diff(a, b) if name in WRAP else np.abs(a - b)
+        if name in BARE_REL_PLANES:
+            with np.errstate(invalid='ignore', divide='ignore'):
+                d = d / np.abs(b)
+            bar, unit = 1e-12, 'relative'
+        elif name == 'LOCAL-SOLAR-TIME':
+            bar, unit = 0.0, 'hours (integer seconds: exact or one second off at a boundary)'
+        else:
+            bar, unit = 1e-9, 'deg'
+        dd = np.where(both, d, 0.0)
+        over = both & (dd > bar)
+        entry = {'unit': unit, 'bare_bar': bar, 'n_compared': int(both.sum()), 'max_diff': float(dd.max()),
+                 'n_over_bare_bar': int(over.sum()), 'frac_over_bare_bar': float(over.sum() / max(1, both.sum())),
+                 'mask_mismatch_outside_grazing': int((mism & ~grazing).sum()),
+                 'mask_mismatch_in_grazing': int((mism & grazing).sum())}
+        if over.any() and np.isfinite(emi[over]).any():
+            hist, _ = np.histogram(emi[over], bins=EMISSION_BINS)
+            entry['over_by_emission_bin'] = {f'{lo:g}-{hi:g}': int(n) for lo, hi, n in
+                                             zip(EMISSION_BINS[:-1], EMISSION_BINS[1:], hist)}
+            entry['min_emission_of_over_deg'] = float(np.nanmin(emi[over]))
+        out[name] = entry
+    return out
+
+
+def write_parity_report(key, stats):
+    """Merges `stats` into gpurun_out/parity_report.json (scratch; the committed copy is
+    profiles/parity_c2_c3.json)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, 'gpurun_out', 'parity_report.json')
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = {}
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                data = json.load(f)
+        except ValueError:
+            data = {}
+    data[key] = stats
+    with open(path, 'w') as f:
+        json.dump(data, f, indent=1)
+
+
 def check_img_planes(got, ref, margin, fr, label, allow_epoch_quantum=False):
     """Shared comparison of 26 image-direction planes (GPU `got` vs oracle `ref`).
     allow_epoch_quantum widens the positional noise term by one epoch quantum (used for

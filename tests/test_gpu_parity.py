@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from helpers import (IMG_CASES, OTHER_BODIES, PID, PLANE_NAMES, WRAP, angle_diff, check_img_planes, check_map_planes,
-                     img_case as _img_case, masks_equal, surface_tolerances)
+                     img_case as _img_case, masks_equal, raw_plane_stats, surface_tolerances, write_parity_report)
 from planetmapper_b200 import frame as F
 
 pytestmark = pytest.mark.gpu
@@ -394,6 +394,10 @@ def test_full_size_2048_vs_oracle(L, oracle, bc_hst):
     got = np.full((len(PLANE_NAMES), sz, sz), np.nan)
     for slot, pid in enumerate(ids):
         ref[pid], got[pid] = ref_k[slot], got_k[slot]
+    # raw, un-widened statistics first (written even if an assertion below fails)
+    stats = raw_plane_stats(got, ref, margin, planes=names)
+    stats['config'] = 'C2: Jupiter / HST 2005-01-01T00:00:00, 2048 x 2048, r0 = 0.9 (n-1)/2, GPU kernels vs CPU oracle'
+    write_parity_report('C2', stats)
     report, n_graz, n_mis = check_img_planes(got, ref, margin, fr, 'C2-2048')
     on = np.isfinite(ref[PID['EMISSION']])
     assert 2.4e6 < on.sum() < 2.6e6
@@ -417,6 +421,9 @@ def test_full_size_saturn_4096_rings_vs_oracle(L, oracle):
     got = np.full((len(PLANE_NAMES), sz, sz), np.nan)
     for slot, pid in enumerate(ids):
         ref[pid], got[pid] = ref_k[slot], got_k[slot]
+    stats = raw_plane_stats(got, ref, margin, planes=[n for n in names if n not in ('KM-X', 'KM-Y')])
+    stats['config'] = 'C3: Saturn / EARTH 2004-12-30T12:00:00, 4096 x 4096, r0 = 800 px, GPU kernels vs CPU oracle'
+    write_parity_report('C3', stats)
     check_img_planes(got, ref, margin, fr, 'C3-4096')
     ring = got[PID['RING-RADIUS']]
     assert np.isfinite(ring).sum() > 1.5e6 and np.nanmax(ring) > 136780   # the A ring is in frame
@@ -494,3 +501,73 @@ def test_full_grid_gather_properties(L, bc_hst):
         # linearity of the whole prepare + gather chain
         lin = 2.5 * out[2][inside] - 0.75 * out[3][inside]
         assert (out[4][inside] - lin).abs().max().item() < 1e-11
+
+
+def test_c4_full_grid_gather_vs_scipy(L, oracle, bc_hst):
+    """C4 at its own geometry - the configuration BENCH times: 64 x 64 planes (the bench's recipe: 1 % NaN
+    pixels, plane 17 all NaN) -> the 0.1 deg grid (3600 x 1800 = 6.48 M cells), gathered in the bench's
+    512-plane chunks (so the cubic DMMA kernel runs its pipelined 1-3-footprint path with plane_begin != 0
+    in the second chunk) and compared with the REAL scipy (RectBivariateSpline.ev through
+    oracle/map_img_oracle.map_cube_fast) on planes at chunk / quad boundaries and the all-NaN plane;
+    the x / y maps themselves against the C oracle on all 6.48 M cells."""
+    import torch
+
+    from oracle import map_img_oracle as MO
+
+    sz, nl, chunk = 64, 520, 512
+    fr = _img_case(bc_hst, sz, sz, 31.5, 31.5, 28.0, 0.0)
+    lo, la = _grid(0.1)
+    assert lo.shape == (1800, 3600)
+    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+    xy = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la), xy_mask)
+    xm, ym = xy[0].cpu().numpy(), xy[1].cpu().numpy()
+    ref_xy, margin = oracle.backplanes_map(fr, lo, la, xy_mask, with_margin=True)
+    grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
+    edge = np.zeros(lo.shape, dtype=bool)   # cells within 1e-9 px of the frame edge may flip (counted)
+    for v, g, n in ((ref_xy[0], xm, sz), (ref_xy[1], ym, sz)):
+        w = np.where(np.isnan(v), g, v)
+        with np.errstate(invalid='ignore'):
+            edge |= (np.abs(w + 0.5) < 1e-9) | (np.abs(w - (n - 0.5)) < 1e-9)
+    mism = (np.isnan(xm) != np.isnan(ref_xy[0])) & ~grazing & ~edge
+    assert not mism.any(), int(mism.sum())
+    ok = np.isfinite(xm) & np.isfinite(ref_xy[0])
+    assert ok.sum() > 2.0e6
+    dx, dy = np.abs(xm - ref_xy[0])[ok].max(), np.abs(ym - ref_xy[1])[ok].max()
+    assert dx <= 1e-9 * sz and dy <= 1e-9 * sz, (dx, dy)     # 64 px span ~0.01 deg of sky: <= 1e-9 relative
+
+    rng = np.random.default_rng(0)
+    cube_h = rng.normal(1.0, 0.1, (nl, sz, sz))
+    cube_h[rng.random((nl, sz, sz)) < 0.01] = np.nan
+    cube_h[17] = np.nan
+    cube = L.to_device(cube_h)
+    check = [0, 3, 4, 17, 255, 256, 511, 512, 519]   # chunk and quad boundaries, the all-NaN plane
+    out = torch.empty((chunk,) + lo.shape, dtype=torch.float64, device='cuda')
+    report = {'cells': int(lo.size), 'visible_cells': int(np.isfinite(xm).sum()), 'planes_checked': check,
+              'xy_map_max_diff_px': [float(dx), float(dy)], 'grazing_cells_excluded': int(grazing.sum()),
+              'edge_cells_excluded': int(edge.sum())}
+    for mode, name in ((L.INTERP_NEAREST, 'nearest'), (L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
+        src = cube if mode == L.INTERP_NEAREST else L.spline_prepare(cube, mode)
+        got = {}
+        for s in range(0, nl, chunk):
+            n = min(chunk, nl - s)
+            L.gather(src, xy[0], xy[1], mode, plane_begin=s, plane_count=n, out=out[:n])
+            for l in check:
+                if s <= l < s + n:
+                    got[l] = out[l - s].cpu().numpy()
+        want = MO.map_cube_fast(cube_h[check], xm, ym, name)
+        worst = 0.0
+        for i, l in enumerate(check):
+            assert np.array_equal(np.isnan(got[l]), np.isnan(want[i])), (name, l)
+            if l == 17:
+                assert np.isnan(got[l]).all()
+                continue
+            fin = np.isfinite(want[i])
+            assert fin.sum() > 1.5e6, (name, l)     # propagate_nan removes the cells touching NaN pixels
+            if mode == L.INTERP_NEAREST:
+                assert np.array_equal(got[l][fin], want[i][fin]), (name, l)
+            else:
+                rel = float(np.max(np.abs(got[l][fin] - want[i][fin]) / np.maximum(np.abs(want[i][fin]), 1.0)))
+                worst = max(worst, rel)
+                assert rel <= 1e-10, f'{name} plane {l}: rel {rel:.3e}'
+        report[name] = {'max_rel_diff_vs_scipy': worst, 'bar': 0.0 if mode == L.INTERP_NEAREST else 1e-10}
+    write_parity_report('C4', report)

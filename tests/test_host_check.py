@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import (IMG_CASES, OTHER_BODIES, PID, angle_diff, check_img_planes, check_map_planes, img_case)
+from helpers import (IMG_CASES, OTHER_BODIES, PID, TRIAXIAL_CASES, angle_diff, check_img_planes, check_map_planes,
+                     img_case, triaxial_constants)
 from planetmapper_b200 import frame as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -142,6 +143,50 @@ def test_device_code_other_bodies_vs_oracle(HC, oracle, target, observer, nx, ny
     check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
 
 
+@pytest.mark.parametrize('kind,nx,ny,x0,y0,r0,rot', TRIAXIAL_CASES)
+def test_device_code_triaxial_vs_oracle(HC, oracle, kind, nx, ny, x0, y0, r0, rot):
+    """Triaxial ellipsoids (Europa, and Europa's state with an exaggerated shape): image planes, map
+    planes and the point transforms of the device code against the oracle."""
+    bc = triaxial_constants(kind)
+    fr = img_case(bc, nx, ny, x0, y0, r0, rot)
+    ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+    got = hc_img(HC, fr, nx, ny)
+    check_img_planes(got, ref, margin, fr, kind, allow_epoch_quantum=True)
+    assert np.isfinite(got[PID['EMISSION']]).sum() > 500
+    lo, la = np.meshgrid(np.arange(2.5, 360, 5.0)[::-1], np.arange(-87.5, 90, 5.0))
+    refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+    gotm = hc_map(HC, fr, lo, la)
+    check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{kind} map')
+    f = np.ascontiguousarray(fr, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    xs, ys = rng.uniform(0, nx - 1, 3000), rng.uniform(0, ny - 1, 3000)
+    rl, rb, rmiss = oracle.xy2lonlat(fr, xs, ys)
+    gl, gb = np.empty_like(xs), np.empty_like(xs)
+    gmiss = ctypes.c_int64(0)
+    assert HC.hc_xy2lonlat(_p(f), _p(xs), _p(ys), ctypes.c_int64(xs.size), _p(gl), _p(gb), ctypes.byref(gmiss)) == 0
+    assert (np.isnan(gl) != np.isnan(rl)).sum() <= 2
+    core = np.isfinite(gl) & np.isfinite(rl) & (np.hypot(xs - x0, ys - y0) < 0.7 * r0 * bc.radii[2] / bc.radii[0])
+    assert core.sum() > 300
+    # conditioning of a 1560 km body 8e8 km away: 2 ulp(|P0|) / r = 9e-9 deg per unit of 1 / cos(emission)
+    # (helpers.surface_tolerances); the selected points have emission < 45 deg
+    p0 = float(np.linalg.norm(F.frame_field(fr, 'P0')))
+    bar = max(1e-9, 4.0 * np.rad2deg(2.0 * np.spacing(p0) / float(np.min(bc.radii))) * 1.5)
+    assert np.max(np.abs(gb[core] - rb[core])) < bar
+    assert np.max(angle_diff(gl[core], rl[core]) * np.cos(np.deg2rad(rb[core]))) < bar
+    lon, lat = rng.uniform(0, 360, 3000), rng.uniform(-90, 90, 3000)
+    for alt, pc in ((0.0, False), (12.5, False), (0.0, True), (-3.0, True)):
+        rx, ry = oracle.lonlat2xy(fr, lon, lat, not_visible_nan=True, alt=alt, planetocentric=pc)
+        gx, gy = np.empty_like(lon), np.empty_like(lon)
+        assert HC.hc_lonlat2xy(_p(f), _p(lon), _p(lat), ctypes.c_int64(lon.size), ctypes.c_double(alt),
+                               ctypes.c_uint32(1 | (4 if pc else 0)), _p(gx), _p(gy)) == 0
+        assert (np.isnan(gx) != np.isnan(rx)).sum() <= 2, (alt, pc)
+        ok = np.isfinite(rx) & np.isfinite(gx)
+        assert ok.sum() > 500 or alt < 0   # points below the surface are always hidden
+        if ok.any():
+            assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-9 * max(nx, ny)
+            assert np.max(np.abs(gy[ok] - ry[ok])) < 1e-9 * max(nx, ny)
+
+
 @pytest.mark.parametrize('target,observer', [('Moon', 'EARTH'), ('Venus', 'EARTH'), ('Jupiter', 'EARTH')])
 def test_device_code_large_disc_limb_vs_oracle(HC, oracle, target, observer):
     """700-pixel discs: dozens of pixels with emission > 89.1 deg take sincpt's grazing-ray branch
@@ -264,29 +309,27 @@ int main(int argc, char **argv) {
 """
 
 
-@pytest.fixture(scope='module')
-def ld_oracle(tmp_path_factory):
+def build_ld_oracle(bdir):
+    """Compiles the oracle with every `double` turned into an 80-bit `long double` into `bdir` and
+    returns run(frame, nx, ny) -> (26, ny, nx) planes (rounded to double at the very end)."""
     import re
 
-    if not shutil.which('gcc'):
-        pytest.skip('gcc not available')
     root = os.path.dirname(HERE)
-    bdir = str(tmp_path_factory.mktemp('oracle_ld'))   # always rebuilt from the current oracle source
     exe = os.path.join(bdir, 'oracle_ld')
     src_c = os.path.join(root, 'oracle', 'pm_oracle.c')
-    if True:
-        def ld(text):
-            return re.sub(r'\bdouble\b', 'long double', text)
-        c = ld(open(src_c).read()).replace('#include <math.h>', '#include <tgmath.h>')
-        c = c.replace('#define PI 3.14159265358979323846264338327950288\n',
-                      '#define PI 3.14159265358979323846264338327950288L\n')
-        h = ld(open(os.path.join(root, 'oracle', 'pm_oracle.h')).read()).replace('"../include/pm_b200.h"', '"pm_b200_ld.h"')
-        open(os.path.join(bdir, 'pm_oracle_ld.c'), 'w').write(c)
-        open(os.path.join(bdir, 'pm_oracle.h'), 'w').write(h)
-        open(os.path.join(bdir, 'pm_b200_ld.h'), 'w').write(ld(open(os.path.join(root, 'include', 'pm_b200.h')).read()))
-        open(os.path.join(bdir, 'drv.c'), 'w').write(LD_DRV)
-        subprocess.run(['gcc', '-O2', '-w', '-o', exe, 'drv.c', 'pm_oracle_ld.c', '-lm'], cwd=bdir, check=True,
-                       capture_output=True)
+
+    def ld(text):
+        return re.sub(r'\bdouble\b', 'long double', text)
+    c = ld(open(src_c).read()).replace('#include <math.h>', '#include <tgmath.h>')
+    c = c.replace('#define PI 3.14159265358979323846264338327950288\n',
+                  '#define PI 3.14159265358979323846264338327950288L\n')
+    h = ld(open(os.path.join(root, 'oracle', 'pm_oracle.h')).read()).replace('"../include/pm_b200.h"', '"pm_b200_ld.h"')
+    open(os.path.join(bdir, 'pm_oracle_ld.c'), 'w').write(c)
+    open(os.path.join(bdir, 'pm_oracle.h'), 'w').write(h)
+    open(os.path.join(bdir, 'pm_b200_ld.h'), 'w').write(ld(open(os.path.join(root, 'include', 'pm_b200.h')).read()))
+    open(os.path.join(bdir, 'drv.c'), 'w').write(LD_DRV)
+    subprocess.run(['gcc', '-O2', '-w', '-fopenmp', '-o', exe, 'drv.c', 'pm_oracle_ld.c', '-lm'], cwd=bdir, check=True,
+                   capture_output=True)
 
     def run(fr, nx, ny):
         fin, fout = os.path.join(bdir, 'frame.bin'), os.path.join(bdir, 'out.bin')
@@ -294,6 +337,13 @@ def ld_oracle(tmp_path_factory):
         subprocess.run([exe, fin, str(nx), str(ny), fout], check=True)
         return np.fromfile(fout).reshape(26, ny, nx)
     return run
+
+
+@pytest.fixture(scope='module')
+def ld_oracle(tmp_path_factory):
+    if not shutil.which('gcc'):
+        pytest.skip('gcc not available')
+    return build_ld_oracle(str(tmp_path_factory.mktemp('oracle_ld')))   # always rebuilt from the current source
 
 
 @pytest.mark.parametrize('target,observer,nx,ny,x0,y0,r0,rot', [('Jupiter', 'EARTH', 100, 100, 49.5, 49.5, 44.55, 0.0),
