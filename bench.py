@@ -572,7 +572,7 @@ def main():
     # ---- kernel path, inputs resident in HBM ---------------------------------------
     W = max(args.warmup, 3)
     for _ in range(W):
-        L.backplanes_img(fd, SZ, SZ, mask, out=out)
+        L.backplanes_img_host(fr, SZ, SZ, mask, out=out[0])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -581,7 +581,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        L.backplanes_img(fd, SZ, SZ, mask, out=out)
+        L.backplanes_img_host(fr, SZ, SZ, mask, out=out[0])   # the 92 frame constants ride in the launch
     e1.record()
     barrier()
     launches = L.launch_count() - launches0

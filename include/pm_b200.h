@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 6
+#define PM_ABI_VERSION 7
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -130,6 +130,13 @@ uint64_t pm_launch_count(void);
  */
 int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny,
                       uint64_t plane_mask, double *out, void *stream);
+/* The same for ONE frame whose constants are in HOST memory (the usual case: the host has just
+ * computed them - BodyXY's constructor and setters, planetmapper/body_xy.py:186-232, :696-961).
+ * The 92 constants and the values derived from them travel with the launch as a kernel parameter,
+ * so the per-pixel code reads them from the constant bank; no host -> device copy is enqueued.
+ * `out` is a DEVICE pointer: [popcount(mask)][ny][nx]. */
+int pm_backplanes_img_host(const PMFrame *frame_host, int nx, int ny, uint64_t plane_mask,
+                           double *out, void *stream);
 
 /*
  * Map-direction backplanes on arbitrary lon/lat cells (degrees, planetographic):

@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
     'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
-    'pm_host_ssb_state', 'pm_host_orientation',
+    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host',
 ]
 
 
@@ -73,6 +73,8 @@ def load_library() -> ctypes.CDLL:
     lib.pm_launch_count.restype = c_u64
     lib.pm_backplanes_img.argtypes = [c_p, c_i, c_i, c_i, c_u64, c_p, c_p]
     lib.pm_backplanes_map.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
+    lib.pm_backplanes_img_host.argtypes = [c_p, c_i, c_i, c_u64, c_p, c_p]
+    lib.pm_backplanes_img_host.restype = c_i
     lib.pm_xy2lonlat.argtypes = [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
     lib.pm_lonlat2xy_alt.argtypes = [c_p, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p]
@@ -111,7 +113,7 @@ def load_library() -> ctypes.CDLL:
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 6:
+    if lib.pm_abi_version() != 7:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -177,6 +179,22 @@ def backplanes_img(frames_dev, nx: int, ny: int, mask: int = ALL_PLANES, out=Non
     rc = lib.pm_backplanes_img(frames_dev.data_ptr(), n_frames, nx, ny, mask, out.data_ptr(),
                                _stream_ptr(torch))
     _check(rc, 'pm_backplanes_img')
+    return out
+
+
+def backplanes_img_host(frame_host, nx: int, ny: int, mask: int = ALL_PLANES, out=None):
+    """One frame whose 92 constants are a HOST float64 array: they ride along with the launch as a
+    kernel parameter (constant bank).  Returns a CUDA tensor (popcount(mask), ny, nx)."""
+    torch = _torch()
+    lib = load_library()
+    fr = np.ascontiguousarray(frame_host, dtype=np.float64).reshape(-1)
+    if fr.size != 92:
+        raise ValueError('frame_host must hold the 92 PMFrame doubles')
+    if out is None:
+        out = torch.empty((popcount(mask), ny, nx), dtype=torch.float64, device='cuda')
+    rc = lib.pm_backplanes_img_host(fr.ctypes.data_as(ctypes.c_void_p), nx, ny, mask, out.data_ptr(),
+                                    _stream_ptr(torch))
+    _check(rc, 'pm_backplanes_img_host')
     return out
 
 

@@ -660,8 +660,8 @@ class BodyXY:
                 # 12-plane surface stack has a specialised kernel; anything else -> all 26), so a
                 # sequence of single-plane getters costs at most three launches
                 new_mask = _SURFACE_STACK if (new_mask & ~_SURFACE_STACK) == 0 else L.ALL_PLANES
-            fd = self._frame_dev(alt).reshape(1, -1)
-            planes = L.backplanes_img(fd, self._nx, self._ny, new_mask)[0]
+            # single frame: the constants ride in the launch (kernel parameter / constant bank)
+            planes = L.backplanes_img_host(self._frame_host(alt), self._nx, self._ny, new_mask)
             entry = (new_mask, planes)
             self._cache[key] = entry   # host copies already handed out stay valid (same values)
         return entry
@@ -701,8 +701,7 @@ class BodyXY:
         if not self._test_if_img_size_valid():
             raise ValueError('nx and ny must be positive to create a backplane image')
         mask = L.mask_from_names(std)
-        fd = self._frame_dev(alt).reshape(1, -1)
-        planes = L.backplanes_img(fd, self._nx, self._ny, mask)[0]
+        planes = L.backplanes_img_host(self._frame_host(alt), self._nx, self._ny, mask)
         order = sorted(set(std), key=lambda n: L.PLANE_ID[n])
         if out is None:
             host = planes.cpu()

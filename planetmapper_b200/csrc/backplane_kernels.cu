@@ -19,6 +19,10 @@
 namespace pm {
 
 constexpr int kPerThread = 4;  // elements per thread and CTA (amortises the frame load)
+#ifndef PM_IMG_PARAM_CTAS
+#define PM_IMG_PARAM_CTAS 4
+#endif
+constexpr int kImgParamCtas = PM_IMG_PARAM_CTAS;  // resident CTAs per SM the single-frame image kernel is compiled for
 
 // plane slot of id k inside the packed output = number of requested planes below k
 __device__ __forceinline__ int slot(uint64_t mask, int k) { return __popcll(mask & (bit(k) - 1ull)); }
@@ -54,15 +58,11 @@ struct PlaneSink {
 // ---------------------------------------------------------------------------------
 // Image direction: all requested backplanes for every pixel of every frame.
 // ---------------------------------------------------------------------------------
+// Pixels idx, idx + 128, ... of this CTA's tile, every requested plane of each
 template <bool kSky, uint64_t kFixedMask>
-__global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame *__restrict__ frames, uint32_t nx,
-                                                                   uint32_t npx, int per_thread, uint64_t mask,
-                                                                   const __grid_constant__ PlaneOffsets po,
-                                                                   double *__restrict__ out_all) {
-    __shared__ FrameD fs;
-    load_frame(fs, frames + blockIdx.y);
-    double *out = out_all + (int64_t)blockIdx.y * __popcll(mask) * npx;
-    uint32_t idx = blockIdx.x * (uint32_t)(kBlock * per_thread) + threadIdx.x;
+__device__ __forceinline__ void img_tile(const FrameD &fs, uint32_t tile, uint32_t nx, uint32_t npx, int per_thread,
+                                         uint64_t mask, const PlaneOffsets &po, double *__restrict__ out) {
+    uint32_t idx = tile * (uint32_t)(kBlock * per_thread) + threadIdx.x;
     uint32_t yi = idx / nx, xi = idx - yi * nx;  // one division per thread, then incremental
 #pragma unroll 1
     for (int r = 0; r < per_thread && idx < npx; r++) {
@@ -75,6 +75,41 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame
             yi++;
         }
     }
+}
+
+// Batched launch (time series): frame blockIdx.y is staged in shared memory by the CTA
+template <bool kSky, uint64_t kFixedMask>
+__global__ void __launch_bounds__(kBlock, 4) backplanes_img_kernel(const PMFrame *__restrict__ frames, uint32_t nx,
+                                                                   uint32_t npx, int per_thread, uint64_t mask,
+                                                                   const __grid_constant__ PlaneOffsets po,
+                                                                   double *__restrict__ out_all) {
+    __shared__ FrameD fs;
+    load_frame(fs, frames + blockIdx.y);
+    img_tile<kSky, kFixedMask>(fs, blockIdx.x, nx, npx, per_thread, mask, po,
+                               out_all + (int64_t)blockIdx.y * __popcll(mask) * npx);
+}
+
+// Single frame: the finished constants (derived on the host with the same exactly rounded
+// arithmetic as load_frame) arrive as a kernel parameter, i.e. in the constant bank - the FP64
+// instructions take them as c[0][offset] operands: no shared-memory loads in the dependency
+// chains, no registers holding constants, no CTA prologue and no barrier.
+//
+// Tiles are handed out from the disc centre outwards (blockIdx.x = 0 is the tile holding the disc
+// centre, then alternately the next tile after / before it): CTAs are dispatched in blockIdx order,
+// an on-disc tile costs ~10x a sky tile, so the expensive tiles all start first and the kernel
+// drains on cheap sky tiles instead of on the last disc rows (longest-processing-time-first).
+__device__ __forceinline__ uint32_t centre_out_tile(uint32_t k, uint32_t n_tiles, uint32_t centre) {
+    const uint32_t lo = centre, hi = n_tiles - 1u - centre;  // tiles before / after the centre tile
+    const uint32_t j = (k + 1u) >> 1;
+    if (j <= min(lo, hi)) return (k & 1u) ? centre + j : centre - j;
+    return lo < hi ? k : n_tiles - 1u - k;  // one side exhausted: the rest in order, moving away
+}
+template <bool kSky, uint64_t kFixedMask>
+__global__ void __launch_bounds__(kBlock, kImgParamCtas) backplanes_img_param_kernel(
+    const __grid_constant__ FrameD fs, uint32_t nx, uint32_t npx, int per_thread, uint32_t centre_tile, uint64_t mask,
+    const __grid_constant__ PlaneOffsets po, double *__restrict__ out) {
+    img_tile<kSky, kFixedMask>(fs, centre_out_tile(blockIdx.x, gridDim.x, centre_tile), nx, npx, per_thread, mask,
+                               po, out);
 }
 
 // ---------------------------------------------------------------------------------
@@ -209,9 +244,9 @@ constexpr uint64_t kDefaultStackMask = kLonLatMask | kCentricMask | kIllumMask |
 
 // Pixels per thread: as many as possible (amortises the per-CTA frame staging) while the
 // grid still has >= 3 waves of resident CTAs for the hardware scheduler to balance.
-static int pick_per_thread(int64_t n, int64_t n_batches, int sm_count) {
+static int pick_per_thread(int64_t n, int64_t n_batches, int sm_count, int ctas_per_sm) {
     const int64_t tiles = ((n + kBlock - 1) / kBlock) * n_batches;
-    const int64_t target = (int64_t)sm_count * 4 * 3;
+    const int64_t target = (int64_t)sm_count * ctas_per_sm * 3;
     int per = 16;
     while (per > 1 && tiles / per < target) per >>= 1;
     return per;
@@ -223,7 +258,7 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
     if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
     const PlaneOffsets po = make_plane_offsets(mask, npx);
     static const int forced = tune_int("PM_IMG_PER_THREAD", 0);
-    const int per = forced > 0 ? forced : pick_per_thread(npx, n_frames, sm_count);
+    const int per = forced > 0 ? forced : pick_per_thread(npx, n_frames, sm_count, 4);
     const int64_t chunk = (int64_t)kBlock * per;
     dim3 grid((unsigned)((npx + chunk - 1) / chunk), n_frames);
     static const bool no_fixed = tune_int("PM_IMG_NO_FIXED_MASK", 0) != 0;
@@ -234,6 +269,39 @@ cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, i
         backplanes_img_kernel<true, 0><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
     else
         backplanes_img_kernel<false, 0><<<grid, kBlock, 0, st>>>(frames, (uint32_t)nx, (uint32_t)npx, per, mask, po, out);
+    count_launches(1);
+    return cudaGetLastError();
+}
+// single frame given on the HOST: constants derived here, passed by value
+cudaError_t launch_backplanes_img_host(const PMFrame *frame_host, int nx, int ny, uint64_t mask, double *out,
+                                       int sm_count, cudaStream_t st) {
+    const int64_t npx = (int64_t)nx * ny;
+    if (npx >= (1ll << 31)) return cudaErrorInvalidValue;
+    FrameD fs;
+    load_frame_host(fs, frame_host);
+    const PlaneOffsets po = make_plane_offsets(mask, npx);
+    static const int forced = tune_int("PM_IMG_PER_THREAD", 0);
+    const int per = forced > 0 ? forced : pick_per_thread(npx, 1, sm_count, kImgParamCtas);
+    const int64_t chunk = (int64_t)kBlock * per;
+    const int64_t n_tiles = (npx + chunk - 1) / chunk;
+    dim3 grid((unsigned)n_tiles, 1);
+    // tile of the disc centre (clamped into the frame); tune: PM_IMG_ORDER=0 keeps the linear order
+    double cy = frame_host->y0 < 0.0 ? 0.0 : (frame_host->y0 > ny - 1.0 ? ny - 1.0 : frame_host->y0);
+    double cx = frame_host->x0 < 0.0 ? 0.0 : (frame_host->x0 > nx - 1.0 ? nx - 1.0 : frame_host->x0);
+    if (!(cy == cy) || !(cx == cx)) cy = cx = 0.0;
+    int64_t ct = ((int64_t)cy * nx + (int64_t)cx) / chunk;
+    static const bool linear = tune_int("PM_IMG_ORDER", 1) == 0;
+    if (linear) ct = 0;
+    const uint32_t centre = (uint32_t)(ct < 0 ? 0 : (ct >= n_tiles ? n_tiles - 1 : ct));
+    if (mask == kDefaultStackMask)
+        backplanes_img_param_kernel<false, kDefaultStackMask><<<grid, kBlock, 0, st>>>(
+            fs, (uint32_t)nx, (uint32_t)npx, per, centre, mask, po, out);
+    else if (mask & kSkyMask)
+        backplanes_img_param_kernel<true, 0><<<grid, kBlock, 0, st>>>(fs, (uint32_t)nx, (uint32_t)npx, per, centre, mask,
+                                                                       po, out);
+    else
+        backplanes_img_param_kernel<false, 0><<<grid, kBlock, 0, st>>>(fs, (uint32_t)nx, (uint32_t)npx, per, centre, mask,
+                                                                        po, out);
     count_launches(1);
     return cudaGetLastError();
 }

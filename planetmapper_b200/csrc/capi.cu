@@ -55,6 +55,15 @@ int pm_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint6
     return check(launch_backplanes_img(frames, n_frames, nx, ny, plane_mask, out, sms, (cudaStream_t)stream));
 }
 
+int pm_backplanes_img_host(const PMFrame *frame_host, int nx, int ny, uint64_t plane_mask, double *out, void *stream) {
+    if (!frame_host || !out || nx <= 0 || ny <= 0) return PM_ERR_BAD_ARG;
+    plane_mask &= PM_ALL_PLANES;
+    if (!plane_mask) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_backplanes_img_host(frame_host, nx, ny, plane_mask, out, sms, (cudaStream_t)stream));
+}
+
 int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat, int64_t n_cells,
                       uint64_t plane_mask, double *out, void *stream) {
     if (!frame || n_cells < 0) return PM_ERR_BAD_ARG;

@@ -86,52 +86,91 @@ struct FrameD {
 };
 
 constexpr int kDeriveItems = 13;
+
+// Exactly rounded IEEE operations for the derived constants.  The derivation runs in two places -
+// in a CTA's prologue (frames read from device memory: batched launches) and on the host
+// (single-frame launches, where the finished FrameD travels as a kernel parameter and the
+// per-pixel code reads it as constant-bank operands) - and both must give the SAME bits, so
+// nothing here may depend on MUFU seeds or on the compiler's choice of FMA contraction.
+PM_HD double ex_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+PM_HD double ex_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+PM_HD double ex_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+PM_HD double ex_sqrt(double a) {
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(a);
+#else
+    return ::sqrt(a);
+#endif
+}
+// a0 b0 + a1 b1 + a2 b2 with a fixed association: (a0 b0 + a1 b1) + a2 b2, every step rounded
+PM_HD double ex_dot3(double a0, double b0, double a1, double b1, double a2, double b2) {
+    return ex_add(ex_add(ex_mul(a0, b0), ex_mul(a1, b1)), ex_mul(a2, b2));
+}
+
 // One independent slice of the derived constants (one thread of a CTA, or a host loop).
-// Uses the MUFU-seeded primitives: this runs in every CTA's prologue while the other
-// warps wait at a barrier, so its latency matters.
 PM_HD void derive_frame_item(FrameD &s, int item) {
     const PMFrame &f = s.f;
     if (item >= 3 && item <= 8) {
         const double *src = item == 3 ? f.P0 : item == 4 ? f.VT : item == 5 ? f.AT : item == 6 ? f.VO : item == 7 ? f.S0 : f.VS;
         double *dst = item == 3 ? s.P0b : item == 4 ? s.VTb : item == 5 ? s.ATb : item == 6 ? s.VOb : item == 7 ? s.S0b : s.VSb;
         for (int r = 0; r < 3; r++)
-            dst[r] = f.R0[3 * r] * src[0] + f.R0[3 * r + 1] * src[1] + f.R0[3 * r + 2] * src[2];
+            dst[r] = ex_dot3(f.R0[3 * r], src[0], f.R0[3 * r + 1], src[1], f.R0[3 * r + 2], src[2]);
     } else if (item >= 9 && item <= 11) {
         const int r = item - 9;  // row r of R0 M^T
         for (int c = 0; c < 3; c++)
-            s.G[3 * r + c] = f.R0[3 * r] * f.M[3 * c] + f.R0[3 * r + 1] * f.M[3 * c + 1] + f.R0[3 * r + 2] * f.M[3 * c + 2];
+            s.G[3 * r + c] = ex_dot3(f.R0[3 * r], f.M[3 * c], f.R0[3 * r + 1], f.M[3 * c + 1], f.R0[3 * r + 2], f.M[3 * c + 2]);
     } else if (item == 12) {
         const double sc = kRpd / 3600.0;
         for (int c = 0; c < 3; c++) {
-            s.As[c] = -(f.A[c] * sc);
-            s.As[3 + c] = f.A[3 + c] * sc;
+            s.As[c] = -ex_mul(f.A[c], sc);
+            s.As[3 + c] = ex_mul(f.A[3 + c], sc);
         }
-        s.inv_kmpa = fast_rcp(f.km_per_arcsec);
+        s.inv_kmpa = ex_div(1.0, f.km_per_arcsec);
     } else if (item == 0) {
-        s.inv_c = fast_rcp(f.clight);
-        const double w2 = f.omega[0] * f.omega[0] + f.omega[1] * f.omega[1] + f.omega[2] * f.omega[2];
-        const double iw = w2 > 0.0 ? fast_rsqrt(w2) : 0.0;
-        s.wn = w2 * iw;
-        s.k[0] = f.omega[0] * iw;
-        s.k[1] = f.omega[1] * iw;
-        s.k[2] = f.omega[2] * iw;
+        s.inv_c = ex_div(1.0, f.clight);
+        const double w2 = ex_dot3(f.omega[0], f.omega[0], f.omega[1], f.omega[1], f.omega[2], f.omega[2]);
+        const double wn = ex_sqrt(w2);
+        s.wn = wn;
+        s.k[0] = wn > 0.0 ? ex_div(f.omega[0], wn) : 0.0;
+        s.k[1] = wn > 0.0 ? ex_div(f.omega[1], wn) : 0.0;
+        s.k[2] = wn > 0.0 ? ex_div(f.omega[2], wn) : 0.0;
     } else if (item == 1) {
         const double a = f.radii[0], b = f.radii[1], c = f.radii[2];
-        const double ia = fast_rcp(a), ib = fast_rcp(b), ic = fast_rcp(c);
-        s.inv_r[0] = ia;
-        s.inv_r[1] = ib;
-        s.inv_r[2] = ic;
+        s.inv_r[0] = ex_div(1.0, a);
+        s.inv_r[1] = ex_div(1.0, b);
+        s.inv_r[2] = ex_div(1.0, c);
         const double m = fmin(a, fmin(b, c));
-        s.nw[0] = (m * ia) * (m * ia);
-        s.nw[1] = (m * ib) * (m * ib);
-        s.nw[2] = (m * ic) * (m * ic);
+        const double ma = ex_div(m, a), mb = ex_div(m, b), mc = ex_div(m, c);
+        s.nw[0] = ex_mul(ma, ma);
+        s.nw[1] = ex_mul(mb, mb);
+        s.nw[2] = ex_mul(mc, mc);
     } else if (item == 2) {
-        const double rp = f.re - f.f * f.re;
+        const double rp = ex_add(f.re, -ex_mul(f.f, f.re));
+        const double re2 = ex_mul(f.re, f.re), rp2 = ex_mul(rp, rp);
+        const double omf = ex_add(1.0, -f.f);
         s.rp = rp;
-        s.e2 = 1.0 - fast_div(rp * rp, f.re * f.re);
-        s.ep2 = fast_div(f.re * f.re, rp * rp) - 1.0;
-        s.omf = 1.0 - f.f;
-        s.inv_omf2 = fast_rcp((1.0 - f.f) * (1.0 - f.f));
+        s.e2 = ex_add(1.0, -ex_div(rp2, re2));
+        s.ep2 = ex_add(ex_div(re2, rp2), -1.0);
+        s.omf = omf;
+        s.inv_omf2 = ex_div(1.0, ex_mul(omf, omf));
         s.biaxial = (f.radii[0] == f.radii[1]) && (f.re == f.radii[0]) && (fabs(rp - f.radii[2]) <= 4e-16 * f.radii[2]);
         s.pad_ = 0;
     }

@@ -28,6 +28,8 @@ constexpr int tune_int(const char *, int dflt) { return dflt; }
 
 cudaError_t launch_backplanes_img(const PMFrame *frames, int n_frames, int nx, int ny, uint64_t mask,
                                   double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_backplanes_img_host(const PMFrame *frame_host, int nx, int ny, uint64_t mask, double *out,
+                                       int sm_count, cudaStream_t st);
 cudaError_t launch_backplanes_map(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
                                   int64_t n, uint64_t mask, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon,
