@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 7
+#define PM_ABI_VERSION 8
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -112,6 +112,15 @@ enum PMPlane {
 #define PM_FLAG_PROPAGATE_NAN 2u   /* map_img(propagate_nan=True)                   */
 #define PM_FLAG_PLANETOCENTRIC 4u   /* lonlat2xy(planetocentric=True) inputs         */
 
+/* coordinate systems of pm_transform (the five systems of Body / BodyXY, planetmapper/body.py:1083-1900,
+ * planetmapper/body_xy.py:385-676; CENTRIC = planetocentric lon / lat as a destination) */
+#define PM_COORD_XY 0
+#define PM_COORD_ANGULAR 1
+#define PM_COORD_KM 2
+#define PM_COORD_RADEC 3
+#define PM_COORD_LONLAT 4
+#define PM_COORD_CENTRIC 5
+
 int pm_abi_version(void);
 const char *pm_error_string(int code);
 /* number of CUDA kernels this library has launched since load (bench evidence) */
@@ -183,6 +192,31 @@ int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int
  * body.py:2131-2150) instead of illumf's `visibl`. */
 int pm_lonlat2xy_alt(const PMFrame *frame, const double *lon, const double *lat, int64_t n,
                      double alt, uint32_t flags, double *x, double *y, void *stream);
+
+/*
+ * Generic vectorised point transform between the coordinate systems above: replaces
+ * SpiceBase._maybe_transform_as_arrays (base.py:718-757) driving the scalar pairs
+ * BodyXY._xy2radec / _radec2xy / _xy2km / _km2xy / _xy2angular / _angular2xy (body_xy.py:409-676) and
+ * Body._lonlat2radec / _radec2lonlat / _lonlat2angular / _angular2lonlat / _lonlat2km / _km2lonlat /
+ * _radec2angular / _angular2radec / _radec2km / _km2radec / _km2angular / _angular2km
+ * (body.py:1083-1900), plus graphic2centric_lonlat (LONLAT -> CENTRIC, body.py:2915-2947) and
+ * centric2graphic_lonlat (LONLAT with PM_FLAG_PLANETOCENTRIC -> LONLAT, :2949-2982).
+ *   a, b / out_a, out_b   first / second coordinate of every point (x, y | arcsec | km | RA, Dec deg |
+ *                         lon, lat deg); non-finite inputs give NaN outputs
+ *   alt                   LONLAT source: altitude of the point (pgrrec).  LONLAT destination: the frame must
+ *                         carry the radii raised by alt (the reference's _AdjustedSurfaceAltitude); alt itself
+ *                         is only used by the planetocentric output conversion
+ *   flags                 PM_FLAG_NOT_VISIBLE_NAN (LONLAT source), PM_FLAG_PLANETOCENTRIC (LONLAT source: the
+ *                         inputs are planetocentric; LONLAT destination: return planetocentric)
+ *   aux13_host            HOST array: the 3 x 3 obsvec -> angular matrix of the ANGULAR system (row major;
+ *                         Body._get_obsvec2angular_matrix for the caller's origin / rotation, body.py:1318-1343)
+ *                         followed by the 2 x 2 km -> angular matrix (body.py:1625-1634); NULL = the frame's own
+ *                         matrix and the inverse of its angular -> km matrix
+ *   n_missed              device int64 (may be NULL): rays that missed the body on the way to lon / lat
+ */
+int pm_transform(const PMFrame *frame, int src, int dst, const double *a, const double *b, int64_t n,
+                 double alt, uint32_t flags, const double *aux13_host, double *out_a, double *out_b,
+                 int64_t *n_missed, void *stream);
 
 /*
  * Inverse map projections, replacing pyproj.Transformer.transform(...,

@@ -96,6 +96,27 @@ def lonlat2xy(frame, lon, lat, not_visible_nan=True, alt=0.0, planetocentric=Fal
     return x, y
 
 
+COORD = {'xy': 0, 'angular': 1, 'km': 2, 'radec': 3, 'lonlat': 4, 'centric': 5}
+
+
+def transform(frame, src, dst, a, b, alt=0.0, not_visible_nan=False, planetocentric=False, aux13=None):
+    """One of the Body / BodyXY point transforms, e.g. transform(fr, 'radec', 'lonlat', ra, dec).
+    Returns (out_a, out_b, n_missed)."""
+    f = _frame(frame)
+    a, b = np.broadcast_arrays(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    oa, ob = np.empty(a.shape), np.empty(a.shape)
+    flags = (1 if not_visible_nan else 0) | (4 if planetocentric else 0)
+    missed = ctypes.c_int64(0)
+    aux = None if aux13 is None else np.ascontiguousarray(aux13, dtype=np.float64)
+    rc = lib().pmo_transform(_p(f), ctypes.c_int(COORD[src]), ctypes.c_int(COORD[dst]), _p(a), _p(b),
+                             ctypes.c_int64(a.size), ctypes.c_double(alt), ctypes.c_uint32(flags),
+                             _p(aux) if aux is not None else None, _p(oa), _p(ob), ctypes.byref(missed))
+    assert rc == 0, rc
+    return oa, ob, missed.value
+
+
 def proj_inverse(kind, a, b, lon0, lat0, lon_sign, xx, yy):
     params = np.array([a, b, lon0, lat0, lon_sign], dtype=np.float64)
     xx = np.ascontiguousarray(xx, dtype=np.float64)

@@ -897,6 +897,157 @@ int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_
     return pmo_lonlat2xy_alt(f, lon, lat, n, 0.0, flags, x, y);
 }
 
+/* ---------- generic point transforms ---------- */
+/* Body._obsvec2angular (body.py:1345-1361) with an explicit obsvec -> angular matrix
+ * (Body._get_obsvec2angular_matrix for any origin_ra / origin_dec / coordinate_rotation) */
+static void obsvec2angular_m(const double M[9], const double ov[3], double *ax, double *ay) {
+    if (!finite3(ov)) {
+        *ax = kNaN; *ay = kNaN;
+        return;
+    }
+    double v[3], r, ra, dec;
+    mxv(M, ov, v);
+    recrad(v, &r, &ra, &dec);
+    double x = pymod(-(ra * DPR), 360.0);
+    if (x > 180.0) x -= 360.0;
+    *ax = x * 3600.0;
+    *ay = (dec * DPR) * 3600.0;
+}
+/* Body._angular2obsvec_norm (body.py:1363-1373) */
+static void angular2obsvec_m(const double M[9], double ax, double ay, double d[3]) {
+    double v[3];
+    radrec(1.0, -((ax / 3600.0) * RPD), (ay / 3600.0) * RPD, v);
+    mtxv(M, v, d);
+}
+/* Body._lonlat2obsvec (body.py:1039-1056); returns 0 when hidden.  lo / la: the planetographic radians the
+ * point was built from, tv the body-fixed point (the middle of pmo_lonlat2xy_alt above) */
+static int lonlat2obsvec(const PMFrame *f, double lon_deg, double lat_deg, double alt, uint32_t flags,
+                         double ov[3], double *lo_out, double *la_out, double tv[3]) {
+    double lo = lon_deg * RPD, la = lat_deg * RPD;
+    if (flags & PM_FLAG_PLANETOCENTRIC) {
+        double sp[3], al;
+        latsrf(f, lo, la, sp);
+        if (alt == 0.0) {
+            recpgr(f, sp, &lo, &la, &al);
+        } else {
+            double re_a = f->re + alt, rp_a = (f->re - f->f * f->re) + alt;
+            recgeo(sp, re_a, (re_a - rp_a) / re_a, &lo, &la, &al);
+            lo = f->lon_sign * lo;
+            if (lo < 0.0) lo += TWOPI;
+        }
+        lo = (lo * DPR) * RPD;
+        la = (la * DPR) * RPD;
+    }
+    *lo_out = lo;
+    *la_out = la;
+    pgrrec(f, lo, la, alt, tv);
+    if (flags & PM_FLAG_NOT_VISIBLE_NAN) {
+        if (alt == 0.0) {
+            PointState s;
+            point_state(f, tv, f->lt0, 1, &s);
+            if (!s.visibl) return 0;
+        } else if (!raycast_visible(f, tv)) {
+            return 0;
+        }
+    }
+    targvec2obsvec(f, tv, ov);
+    return 1;
+}
+
+/* One point between any two of the coordinate systems (include/pm_b200.h PM_COORD_*), every pair through
+ * the observer-frame vector exactly as the reference composes them:
+ *   BodyXY._xy2radec / _radec2xy / _xy2km / _km2xy / _xy2angular / _angular2xy (body_xy.py:409-676),
+ *   Body._lonlat2radec / _radec2lonlat (body.py:1131-1221), _radec2angular / _angular2radec (:1425-1478),
+ *   _angular2lonlat / _lonlat2angular (:1534-1623), _km2radec / _radec2km (:1672-1701),
+ *   _km2lonlat / _lonlat2km (:1752-1830), _km2angular / _angular2km (:1861-1900),
+ *   graphic2centric_lonlat (:2915-2947), centric2graphic_lonlat (:2949-2982).
+ * aux13 = obsvec -> angular matrix (9) + km -> angular matrix (4). Returns 0 for a ray that misses. */
+static int transform_one(const PMFrame *f, const double *aux13, int src, int dst, double a, double b, double alt,
+                         uint32_t flags, double *oa, double *ob) {
+    const double *Mc = aux13, *km2ang = aux13 + 9;
+    *oa = *ob = kNaN;
+    if (!(isfinite(a) && isfinite(b))) return 1;
+    double ov[3];
+    if (src == PM_COORD_LONLAT) {
+        double lo, la, tv[3];
+        uint32_t fl = flags;
+        if (dst == PM_COORD_LONLAT || dst == PM_COORD_CENTRIC) fl &= ~PM_FLAG_NOT_VISIBLE_NAN;
+        int vis = lonlat2obsvec(f, a, b, alt, fl, ov, &lo, &la, tv);
+        if (dst == PM_COORD_LONLAT) {
+            *oa = lo * DPR;
+            *ob = la * DPR;
+            return 1;
+        }
+        if (dst == PM_COORD_CENTRIC) {
+            double r, lc, bc;
+            reclat(tv, &r, &lc, &bc);
+            *oa = lc * DPR;
+            *ob = bc * DPR;
+            return 1;
+        }
+        if (!vis) return 1;
+    } else if (src == PM_COORD_RADEC) {
+        radec_deg2obsvec_norm(a, b, ov);
+    } else if (src == PM_COORD_ANGULAR) {
+        angular2obsvec_m(Mc, a, b, ov);
+    } else if (src == PM_COORD_KM) {
+        angular2obsvec_m(f->M, km2ang[0] * a + km2ang[1] * b, km2ang[2] * a + km2ang[3] * b, ov);
+    } else {
+        xy2obsvec_norm(f, a, b, ov);
+    }
+    if (!finite3(ov)) return 1;
+    if (dst == PM_COORD_RADEC) {
+        double r, ra, dec;
+        recrad(ov, &r, &ra, &dec);
+        *oa = ra * DPR;
+        *ob = dec * DPR;
+    } else if (dst == PM_COORD_ANGULAR) {
+        obsvec2angular_m(Mc, ov, oa, ob);
+    } else if (dst == PM_COORD_KM) {
+        obsvec2km(f, ov, oa, ob);
+    } else if (dst == PM_COORD_XY) {
+        obsvec2xy(f, ov, oa, ob);
+    } else {
+        /* Body._obsvec_norm2lonlat (body.py:1058-1081); f carries the radii raised by alt */
+        double p[3], lt, lo, la, al;
+        if (!sincpt(f, ov, p, &lt, NULL)) return 0;
+        recpgr(f, p, &lo, &la, &al);
+        *oa = lo * DPR;
+        *ob = la * DPR;
+        if ((flags & PM_FLAG_PLANETOCENTRIC) || dst == PM_COORD_CENTRIC) {
+            /* graphic2centric_lonlat(lon, lat, alt=alt) INSIDE the altitude adjustment (body.py:1066-1080) */
+            double tv[3], r, lc, bc;
+            pgrrec(f, (*oa) * RPD, (*ob) * RPD, alt, tv);
+            reclat(tv, &r, &lc, &bc);
+            *oa = lc * DPR;
+            *ob = bc * DPR;
+        }
+    }
+    return 1;
+}
+
+int pmo_transform(const PMFrame *f, int src, int dst, const double *a, const double *b, int64_t n, double alt,
+                  uint32_t flags, const double *aux13, double *out_a, double *out_b, int64_t *n_missed) {
+    if (!f || !a || !b || !out_a || !out_b || n < 0) return PM_ERR_BAD_ARG;
+    double aux[13];
+    if (aux13) {
+        for (int i = 0; i < 13; i++) aux[i] = aux13[i];
+    } else {
+        for (int i = 0; i < 9; i++) aux[i] = f->M[i];
+        double det = f->ang2km[0] * f->ang2km[3] - f->ang2km[1] * f->ang2km[2];
+        aux[9] = f->ang2km[3] / det;
+        aux[10] = -f->ang2km[1] / det;
+        aux[11] = -f->ang2km[2] / det;
+        aux[12] = f->ang2km[0] / det;
+    }
+    int64_t missed = 0;
+#pragma omp parallel for reduction(+ : missed)
+    for (int64_t i = 0; i < n; i++)
+        if (!transform_one(f, aux, src, dst, a[i], b[i], alt, flags, &out_a[i], &out_b[i])) missed++;
+    if (n_missed) *n_missed = missed;
+    return PM_OK;
+}
+
 /* ---------- projections ---------- */
 /* PROJ's spherical orthographic inverse (ortho_s_inverse); x, y in sphere radii.
  * Returns 0 when the point is outside the projection. */

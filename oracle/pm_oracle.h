@@ -22,6 +22,8 @@ int pmo_lonlat2xy(const PMFrame *f, const double *lon, const double *lat, int64_
                   uint32_t flags, double *x, double *y);
 int pmo_lonlat2xy_alt(const PMFrame *f, const double *lon, const double *lat, int64_t n, double alt,
                       uint32_t flags, double *x, double *y);
+int pmo_transform(const PMFrame *f, int src, int dst, const double *a, const double *b, int64_t n, double alt,
+                  uint32_t flags, const double *aux13, double *out_a, double *out_b, int64_t *n_missed);
 int pmo_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                      int64_t n, double *lon, double *lat);
 int pmo_gather_nearest(const double *cube, int n_planes, int ny, int nx,

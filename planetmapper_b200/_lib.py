@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
     'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
-    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host',
+    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host', 'pm_transform',
 ]
 
 
@@ -75,6 +75,8 @@ def load_library() -> ctypes.CDLL:
     lib.pm_backplanes_map.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
     lib.pm_backplanes_img_host.argtypes = [c_p, c_i, c_i, c_u64, c_p, c_p]
     lib.pm_backplanes_img_host.restype = c_i
+    lib.pm_transform.argtypes = [c_p, c_i, c_i, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p, c_p, c_p]
+    lib.pm_transform.restype = c_i
     lib.pm_xy2lonlat.argtypes = [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
     lib.pm_lonlat2xy_alt.argtypes = [c_p, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p]
@@ -113,7 +115,7 @@ def load_library() -> ctypes.CDLL:
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 7:
+    if lib.pm_abi_version() != 8:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -278,6 +280,33 @@ def lonlat2xy(frame_dev, lon_dev, lat_dev, not_visible_nan: bool = True, *, alt:
                               _stream_ptr(torch))
     _check(rc, 'pm_lonlat2xy_alt')
     return x, y
+
+
+COORD = {'xy': 0, 'angular': 1, 'km': 2, 'radec': 3, 'lonlat': 4, 'centric': 5}
+
+
+def transform(frame_dev, src: str, dst: str, a_dev, b_dev, *, alt: float = 0.0, not_visible_nan: bool = False,
+              planetocentric: bool = False, aux13=None):
+    """Points (a, b) of coordinate system ``src`` in system ``dst`` (pm_transform); returns
+    (out_a, out_b, n_missed) as CUDA tensors.  ``aux13``: the obsvec -> angular matrix of the angular system
+    (9 doubles, row major) followed by the km -> angular matrix (4), or None for the frame's defaults."""
+    torch = _torch()
+    lib = load_library()
+    oa = torch.empty_like(a_dev)
+    ob = torch.empty_like(a_dev)
+    missed = torch.zeros(1, dtype=torch.int64, device=a_dev.device)
+    flags = (FLAG_NOT_VISIBLE_NAN if not_visible_nan else 0) | (FLAG_PLANETOCENTRIC if planetocentric else 0)
+    aux = None
+    if aux13 is not None:
+        aux = np.ascontiguousarray(aux13, dtype=np.float64).reshape(-1)
+        if aux.size != 13:
+            raise ValueError('aux13 must hold 9 + 4 doubles')
+    rc = lib.pm_transform(frame_dev.data_ptr(), COORD[src], COORD[dst], a_dev.data_ptr(), b_dev.data_ptr(),
+                          a_dev.numel(), float(alt), flags,
+                          aux.ctypes.data_as(ctypes.c_void_p) if aux is not None else None, oa.data_ptr(),
+                          ob.data_ptr(), missed.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_transform')
+    return oa, ob, missed
 
 
 def proj_inverse(kind: int, a: float, b: float, lon0: float, lat0: float, lon_sign: float,

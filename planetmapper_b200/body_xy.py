@@ -385,6 +385,9 @@ class BodyXY:
                   planetocentric: bool = False):
         """Image pixel coordinates -> planetographic lon/lat (body_xy.py:433-496)."""
         alt = self._check_alt(alt)
+        if planetocentric:
+            # graphic2centric_lonlat runs INSIDE the altitude adjustment (body.py:1066-1080)
+            return self._transform('xy', 'lonlat', x, y, alt=alt, planetocentric=True, not_found_nan=not_found_nan)
         scalar, xa, ya = self._broadcast(x, y)
         fd = self._frame_dev(alt if alt != 0.0 else None)
         lon, lat, missed = L.xy2lonlat(fd, L.to_device(xa), L.to_device(ya))
@@ -393,8 +396,6 @@ class BodyXY:
             finite_in = np.isfinite(xa) & np.isfinite(ya)
             if int(missed.item()) > 0 or np.any(finite_in & np.isnan(lon)):
                 raise NotFoundError('ray does not intercept the target body')
-        if planetocentric:
-            lon, lat = self.graphic2centric_lonlat(lon, lat, alt=alt)
         return self._unbroadcast(scalar, lon, lat)
 
     def lonlat2xy(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
@@ -408,14 +409,135 @@ class BodyXY:
                            alt=alt, planetocentric=planetocentric)
         return self._unbroadcast(scalar, x.cpu().numpy(), y.cpu().numpy())
 
+    # ---- the other coordinate pairs (body.py:1083-1900, body_xy.py:385-676) -----------
+    def _angular_aux(self, origin_ra=None, origin_dec=None, coordinate_rotation: float = 0.0):
+        """Matrices of the angular / km systems for pm_transform (Body._get_obsvec2angular_matrix,
+        body.py:1318-1343, with its defaults, and _get_km2angular_matrix, :1625-1634); None when the
+        frame's own default matrix applies."""
+        if origin_ra is None and origin_dec is None and coordinate_rotation == 0.0:
+            return None
+        ra = self.target_ra if origin_ra is None else float(origin_ra)
+        dec = self.target_dec if origin_dec is None else float(origin_dec)
+        m = F.obsvec2angular_matrix(ra, dec, float(coordinate_rotation))
+        return np.concatenate([m.ravel(), F.km2angular_matrix(self._bc).ravel()])
+
+    def _transform(self, src: str, dst: str, a, b, *, alt: float = 0.0, not_visible_nan: bool = False,
+                   planetocentric: bool = False, not_found_nan: bool = True, angular_kwargs=None):
+        """SpiceBase._maybe_transform_as_arrays (base.py:718-757) around one coordinate pair:
+        broadcast the two inputs, one kernel launch over all points, floats back if both were scalars."""
+        unknown = set(angular_kwargs or ()) - {'origin_ra', 'origin_dec', 'coordinate_rotation'}
+        if unknown:
+            raise TypeError(f'unexpected angular keyword arguments {sorted(unknown)}')
+        alt = float(alt)
+        scalar, aa, bb = self._broadcast(a, b)
+        if not math.isfinite(alt):
+            if dst in ('lonlat', 'centric'):
+                self._check_alt(alt)   # _AdjustedSurfaceAltitude raises (body.py:204-207)
+            # Body._lonlat2targvec_radians: non-finite alt -> NaN (body.py:900-901)
+            return self._unbroadcast(scalar, np.full(aa.shape, np.nan), np.full(aa.shape, np.nan))
+        # a lon / lat destination intersects the ellipsoid raised by alt (_AdjustedSurfaceAltitude)
+        fd = self._frame_dev(alt if (dst in ('lonlat', 'centric') and src != 'lonlat' and alt != 0.0) else None)
+        oa, ob, missed = L.transform(fd, src, dst, L.to_device(aa), L.to_device(bb), alt=alt,
+                                     not_visible_nan=not_visible_nan, planetocentric=planetocentric,
+                                     aux13=self._angular_aux(**(angular_kwargs or {})))
+        if not not_found_nan and int(missed.item()) > 0:
+            raise NotFoundError('ray does not intercept the target body')
+        return self._unbroadcast(scalar, oa.cpu().numpy(), ob.cpu().numpy())
+
+    def xy2radec(self, x, y):
+        """Image pixel coordinates -> RA / Dec (body_xy.py:385-410)."""
+        return self._transform('xy', 'radec', x, y)
+
+    def radec2xy(self, ra, dec):
+        """RA / Dec -> image pixel coordinates (body_xy.py:412-437)."""
+        return self._transform('radec', 'xy', ra, dec)
+
+    def xy2km(self, x, y):
+        """Image pixel coordinates -> km in the target plane (body_xy.py:563-587)."""
+        return self._transform('xy', 'km', x, y)
+
+    def km2xy(self, km_x, km_y):
+        """km in the target plane -> image pixel coordinates (body_xy.py:589-612)."""
+        return self._transform('km', 'xy', km_x, km_y)
+
+    def xy2angular(self, x, y, **angular_kwargs):
+        """Image pixel coordinates -> relative angular coordinates, arcsec (body_xy.py:614-645)."""
+        return self._transform('xy', 'angular', x, y, angular_kwargs=angular_kwargs)
+
+    def angular2xy(self, angular_x, angular_y, **angular_kwargs):
+        """Relative angular coordinates -> image pixel coordinates (body_xy.py:647-676)."""
+        return self._transform('angular', 'xy', angular_x, angular_y, angular_kwargs=angular_kwargs)
+
+    def lonlat2radec(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
+                     planetocentric: bool = False):
+        """Body.lonlat2radec (body.py:1083-1146)."""
+        return self._transform('lonlat', 'radec', lon, lat, alt=alt, not_visible_nan=not_visible_nan,
+                               planetocentric=planetocentric)
+
+    def radec2lonlat(self, ra, dec, *, not_found_nan: bool = True, alt: float = 0.0,
+                     planetocentric: bool = False):
+        """Body.radec2lonlat (body.py:1148-1221)."""
+        return self._transform('radec', 'lonlat', ra, dec, alt=alt, planetocentric=planetocentric,
+                               not_found_nan=not_found_nan)
+
+    def radec2angular(self, ra, dec, *, origin_ra=None, origin_dec=None, coordinate_rotation: float = 0.0):
+        """Body.radec2angular (body.py:1375-1445)."""
+        return self._transform('radec', 'angular', ra, dec, angular_kwargs=dict(
+            origin_ra=origin_ra, origin_dec=origin_dec, coordinate_rotation=coordinate_rotation))
+
+    def angular2radec(self, angular_x, angular_y, **angular_kwargs):
+        """Body.angular2radec (body.py:1447-1478)."""
+        return self._transform('angular', 'radec', angular_x, angular_y, angular_kwargs=angular_kwargs)
+
+    def angular2lonlat(self, angular_x, angular_y, *, not_found_nan: bool = True, alt: float = 0.0,
+                       planetocentric: bool = False, **angular_kwargs):
+        """Body.angular2lonlat (body.py:1480-1549)."""
+        return self._transform('angular', 'lonlat', angular_x, angular_y, alt=alt, planetocentric=planetocentric,
+                               not_found_nan=not_found_nan, angular_kwargs=angular_kwargs)
+
+    def lonlat2angular(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
+                       planetocentric: bool = False, **angular_kwargs):
+        """Body.lonlat2angular (body.py:1551-1623)."""
+        return self._transform('lonlat', 'angular', lon, lat, alt=alt, not_visible_nan=not_visible_nan,
+                               planetocentric=planetocentric, angular_kwargs=angular_kwargs)
+
+    def km2radec(self, km_x, km_y):
+        """Body.km2radec (body.py:1652-1675)."""
+        return self._transform('km', 'radec', km_x, km_y)
+
+    def radec2km(self, ra, dec):
+        """Body.radec2km (body.py:1677-1701)."""
+        return self._transform('radec', 'km', ra, dec)
+
+    def km2lonlat(self, km_x, km_y, *, not_found_nan: bool = True, alt: float = 0.0, planetocentric: bool = False):
+        """Body.km2lonlat (body.py:1703-1766)."""
+        return self._transform('km', 'lonlat', km_x, km_y, alt=alt, planetocentric=planetocentric,
+                               not_found_nan=not_found_nan)
+
+    def lonlat2km(self, lon, lat, *, alt: float = 0.0, not_visible_nan: bool = True,
+                  planetocentric: bool = False):
+        """Body.lonlat2km (body.py:1768-1830)."""
+        return self._transform('lonlat', 'km', lon, lat, alt=alt, not_visible_nan=not_visible_nan,
+                               planetocentric=planetocentric)
+
+    def km2angular(self, km_x, km_y, **angular_kwargs):
+        """Body.km2angular (body.py:1832-1868)."""
+        return self._transform('km', 'angular', km_x, km_y, angular_kwargs=angular_kwargs)
+
+    def angular2km(self, angular_x, angular_y, **angular_kwargs):
+        """Body.angular2km (body.py:1869-1900)."""
+        return self._transform('angular', 'km', angular_x, angular_y, angular_kwargs=angular_kwargs)
+
     def graphic2centric_lonlat(self, lon, lat, *, alt: float = 0.0):
-        """Body.graphic2centric_lonlat (body.py:2915-2947) through the map kernel."""
+        """Body.graphic2centric_lonlat (body.py:2915-2947): reclat of pgrrec(lon, lat, alt)."""
         alt = self._check_alt(alt)
-        scalar, lo, la = self._broadcast(lon, lat)
-        mask = L.mask_from_names(['LON-CENTRIC', 'LAT-CENTRIC'])
-        out = L.backplanes_map(self._frame_dev(alt if alt != 0.0 else None), L.to_device(lo),
-                               L.to_device(la), mask).cpu().numpy()
-        return self._unbroadcast(scalar, out[0], out[1])
+        return self._transform('lonlat', 'centric', lon, lat, alt=alt)
+
+    def centric2graphic_lonlat(self, lon_centric, lat_centric, *, alt: float = 0.0):
+        """Body.centric2graphic_lonlat (body.py:2949-2982): latsrf, then recpgr against the spheroid raised
+        by alt."""
+        alt = self._check_alt(alt)
+        return self._transform('lonlat', 'lonlat', lon_centric, lat_centric, alt=alt, planetocentric=True)
 
     # ---- projections (body_xy.py:2755-3012) -------------------------------------------
     def generate_map_coordinates(self, projection: str = 'rectangular', *,

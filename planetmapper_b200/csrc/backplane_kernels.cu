@@ -189,6 +189,49 @@ __global__ void __launch_bounds__(kBlock, 4) lonlat2xy_kernel(const PMFrame *__r
     }
 }
 
+// Generic point transform (pm_transform): any pair of the xy / angular / km / RA-Dec / lon-lat systems
+__global__ void __launch_bounds__(kBlock, 4) transform_kernel(const PMFrame *__restrict__ frame,
+                                                              const __grid_constant__ TransformAux aux, int use_aux,
+                                                              int src, int dst, const double *__restrict__ a_in,
+                                                              const double *__restrict__ b_in, int64_t n, double alt,
+                                                              uint32_t flags, double *__restrict__ a_out,
+                                                              double *__restrict__ b_out,
+                                                              unsigned long long *__restrict__ n_missed) {
+    __shared__ FrameD fs;
+    __shared__ TransformAux ax;
+    load_frame(fs, frame);
+    if (threadIdx.x < 13) {
+        double v;
+        if (use_aux) {
+            v = threadIdx.x < 9 ? aux.Mc[threadIdx.x] : aux.km2ang[threadIdx.x - 9];
+        } else if (threadIdx.x < 9) {
+            v = fs.f.M[threadIdx.x];
+        } else {  // inverse of the frame's angular -> km matrix
+            const double *m = fs.f.ang2km;
+            const double det = fma(m[0], m[3], -m[1] * m[2]);
+            const int k = threadIdx.x - 9;
+            v = (k == 0 ? m[3] : k == 1 ? -m[1] : k == 2 ? -m[2] : m[0]) / det;
+        }
+        (threadIdx.x < 9 ? ax.Mc[threadIdx.x] : ax.km2ang[threadIdx.x - 9]) = v;
+    }
+    __syncthreads();
+    unsigned long long missed = 0;
+    const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
+#pragma unroll 1
+    for (int r = 0; r < kPerThread; r++) {
+        const int64_t idx = first + r * kBlock;
+        if (idx >= n) break;
+        double oa, ob;
+        if (!point_transform(fs, ax, src, dst, a_in[idx], b_in[idx], alt, flags, oa, ob)) missed++;
+        a_out[idx] = oa;
+        b_out[idx] = ob;
+    }
+    if (n_missed) {
+        for (int o = 16; o > 0; o >>= 1) missed += __shfl_down_sync(0xffffffffu, missed, o);
+        if ((threadIdx.x & 31) == 0 && missed) atomicAdd(n_missed, missed);
+    }
+}
+
 // FP64 FMA throughput probe (roofline denominator for the compute-bound kernels)
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
@@ -324,6 +367,19 @@ cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const doub
                              uint32_t flags, double *x, double *y, int sm_count, cudaStream_t st) {
     (void)sm_count;
     lonlat2xy_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, lon, lat, n, alt, flags, x, y);
+    count_launches(1);
+    return cudaGetLastError();
+}
+cudaError_t launch_transform(const PMFrame *frame, int src, int dst, const double *a, const double *b, int64_t n,
+                             double alt, uint32_t flags, const double *aux13_host, double *out_a, double *out_b,
+                             unsigned long long *n_missed, cudaStream_t st) {
+    TransformAux aux = {};
+    if (aux13_host) {
+        for (int i = 0; i < 9; i++) aux.Mc[i] = aux13_host[i];
+        for (int i = 0; i < 4; i++) aux.km2ang[i] = aux13_host[9 + i];
+    }
+    transform_kernel<<<chunks_for(n), kBlock, 0, st>>>(frame, aux, aux13_host != nullptr, src, dst, a, b, n, alt,
+                                                       flags, out_a, out_b, n_missed);
     count_launches(1);
     return cudaGetLastError();
 }

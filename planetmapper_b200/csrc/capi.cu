@@ -127,6 +127,20 @@ int pm_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int
     return pm_lonlat2xy_alt(frame, lon, lat, n, 0.0, flags, x, y, stream);
 }
 
+int pm_transform(const PMFrame *frame, int src, int dst, const double *a, const double *b, int64_t n, double alt,
+                 uint32_t flags, const double *aux13_host, double *out_a, double *out_b, int64_t *n_missed,
+                 void *stream) {
+    if (!frame || n < 0 || !(alt == alt)) return PM_ERR_BAD_ARG;
+    if (src < PM_COORD_XY || src > PM_COORD_LONLAT || dst < PM_COORD_XY || dst > PM_COORD_CENTRIC) return PM_ERR_BAD_ARG;
+    if ((src == dst && src != PM_COORD_LONLAT) || (dst == PM_COORD_CENTRIC && src == PM_COORD_CENTRIC))
+        return PM_ERR_UNSUPPORTED;
+    if (n == 0) return PM_OK;
+    if (!a || !b || !out_a || !out_b) return PM_ERR_BAD_ARG;
+    if (sm_count() <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_transform(frame, src, dst, a, b, n, alt, flags, aux13_host, out_a, out_b,
+                                  (unsigned long long *)n_missed, (cudaStream_t)stream));
+}
+
 int pm_proj_inverse(int kind, const double *params5_host, const double *xx, const double *yy, int64_t n,
                     double *lon, double *lat, void *stream) {
     if (!params5_host || n < 0) return PM_ERR_BAD_ARG;

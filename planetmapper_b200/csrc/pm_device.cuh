@@ -962,15 +962,17 @@ PM_HD bool xy2lonlat_point(const FrameD &fs, double x, double y, double &lon, do
     return true;
 }
 
-// BodyXY._lonlat2xy (body_xy.py:544-560) -> Body._lonlat2obsvec (body.py:1039-1056).
-// Visibility: alt == 0 via illumf.visibl (body.py:2124-2130); alt != 0 via the ray cast
-// of Body._test_if_targvec_visible (body.py:2131-2150): hidden iff the ray observer ->
-// point meets the surface and the surface is nearer.  planetocentric inputs go through
-// spice.latsrf + recpgr first (Body._centric2graphic_lonlat, body.py:2966-2982).
-PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt, bool not_visible_nan,
-                           bool planetocentric, double &x, double &y) {
-    x = y = NAN;
-    double lo = lon * kRpd, la = lat * kRpd;
+// Body._lonlat2obsvec (body.py:1039-1056): planetographic (or planetocentric) lon / lat in degrees
+// (+ altitude) -> the point as seen from the observer, J2000.  Returns false when the point is
+// hidden (not_visible_nan).  Visibility: alt == 0 via illumf.visibl (body.py:2124-2130); alt != 0
+// via the ray cast of Body._test_if_targvec_visible (body.py:2131-2150): hidden iff the ray
+// observer -> point meets the surface and the surface is nearer.  planetocentric inputs go through
+// spice.latsrf + recpgr first (Body._centric2graphic_lonlat, body.py:2966-2982).  lo / la receive
+// the planetographic coordinates (radians) the point was built from, tv the body-fixed point.
+PM_HD bool lonlat2obsvec_point(const FrameD &fs, double lon, double lat, double alt, bool not_visible_nan,
+                               bool planetocentric, V3 &ov, double &lo, double &la, V3 &tv) {
+    lo = lon * kRpd;
+    la = lat * kRpd;
     if (planetocentric) {
         double sl, cl, sb, cb;
         sincos_full(lo, sl, cl);
@@ -991,7 +993,7 @@ PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt,
         lo = (lo * kDpr) * kRpd;  // Body.targvec2lonlat returns degrees
         la = (la * kDpr) * kRpd;
     }
-    V3 tv = pgrrec0(fs, lo, la);
+    tv = pgrrec0(fs, lo, la);
     if (alt != 0.0) {  // spice.pgrrec with an altitude: along the spheroid normal
         double sl, cl, sb, cb;
         sincos_full(fs.f.lon_sign * lo, sl, cl);
@@ -1006,22 +1008,141 @@ PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt,
             // so that grazing cells agree with the map kernel
             const V3 e = spin_fwd(fs, g.r, -g.X0);
             const V3 n = mul3(tv, fs.nw);
-            if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return;
+            if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return false;
         } else {
             Intercept it;
             if (sincpt(fs, mxv(fs.f.R0, targvec2obsvec(fs, tv)), it)) {
                 PointGeom gi;
                 point_geom(fs, it.p, gi);
-                if (!(g.lt < gi.lt)) return;
+                if (!(g.lt < gi.lt)) return false;
             }
         }
     }
-    const V3 ov = targvec2obsvec(fs, tv);
+    ov = targvec2obsvec(fs, tv);
+    return true;
+}
+
+// BodyXY._lonlat2xy (body_xy.py:544-560)
+PM_HD void lonlat2xy_point(const FrameD &fs, double lon, double lat, double alt, bool not_visible_nan,
+                           bool planetocentric, double &x, double &y) {
+    x = y = NAN;
+    V3 ov, tv;
+    double lo, la;
+    if (!lonlat2obsvec_point(fs, lon, lat, alt, not_visible_nan, planetocentric, ov, lo, la, tv)) return;
     if (!finite3(ov)) return;
     double ax, ay;
     obsvec2angular(fs.f, ov, ax, ay);
     x = fma(fs.f.Ainv[0], ax, fma(fs.f.Ainv[1], ay, fs.f.Ainv[2]));
     y = fma(fs.f.Ainv[3], ax, fma(fs.f.Ainv[4], ay, fs.f.Ainv[5]));
+}
+
+// ---------------------------------------------------------------------------------
+// Generic point transform between the five coordinate systems of Body / BodyXY
+// (SpiceBase._maybe_transform_as_arrays, base.py:718-757, around the scalar pairs
+// Body.lonlat2radec ... Body.angular2km, body.py:1083-1900, and BodyXY.xy2radec ...
+// angular2xy, body_xy.py:385-676).  Every pair goes through the observer-frame vector
+// ("obsvec"), as in the reference.
+// ---------------------------------------------------------------------------------
+struct TransformAux {
+    double Mc[9];      // obsvec -> angular rotation for the ANGULAR system (Body._get_obsvec2angular_matrix
+                       // with the caller's origin_ra / origin_dec / coordinate_rotation; default = frame M)
+    double km2ang[4];  // Body._get_km2angular_matrix (body.py:1625-1634)
+};
+
+// Body._obsvec2angular (body.py:1345-1361) with an explicit matrix, arcsec; ov finite
+PM_HD void obsvec2angular_m(const double *M, V3 ov, double &ax, double &ay) {
+    double ra, dec;
+    recrad_angles(mxv(M, ov), ra, dec);
+    double x = pymod360(-(ra * kDpr));
+    if (x > 180.0) x -= 360.0;
+    ax = x * 3600.0;
+    ay = (dec * kDpr) * 3600.0;
+}
+// Body._angular2obsvec_norm (body.py:1363-1373)
+PM_HD V3 angular2obsvec_m(const double *M, double ax, double ay) {
+    return mtxv(M, radrec1(-((ax * (1.0 / 3600.0)) * kRpd), (ay * (1.0 / 3600.0)) * kRpd));
+}
+
+// Returns false only for a ray that misses the body on the way to lon / lat (counted by the caller).
+PM_HD bool point_transform(const FrameD &fs, const TransformAux &aux, int src, int dst, double a, double b,
+                           double alt, uint32_t flags, double &oa, double &ob) {
+    const PMFrame &f = fs.f;
+    oa = ob = NAN;
+    if (!(fabs(a) < INFINITY) || !(fabs(b) < INFINITY)) return true;
+    const bool pc = (flags & PM_FLAG_PLANETOCENTRIC) != 0;
+    V3 ov;
+    if (src == PM_COORD_LONLAT) {
+        V3 tv;
+        double lo, la;
+        const bool vis = lonlat2obsvec_point(fs, a, b, alt, (flags & PM_FLAG_NOT_VISIBLE_NAN) != 0 &&
+                                                              dst != PM_COORD_LONLAT && dst != PM_COORD_CENTRIC,
+                                             pc, ov, lo, la, tv);
+        if (dst == PM_COORD_LONLAT) {  // Body.centric2graphic_lonlat (body.py:2949-2982) / identity
+            oa = lo * kDpr;
+            ob = la * kDpr;
+            return true;
+        }
+        if (dst == PM_COORD_CENTRIC) {  // Body.graphic2centric_lonlat (body.py:2915-2947): reclat of the point
+            double lc, bc;
+            reclat_angles(tv, lc, bc);
+            oa = lc * kDpr;
+            ob = bc * kDpr;
+            return true;
+        }
+        if (!vis || !finite3(ov)) return true;
+    } else if (src == PM_COORD_RADEC) {
+        ov = radrec1(a * kRpd, b * kRpd);  // Body._radec2obsvec_norm (body.py:964-970)
+    } else if (src == PM_COORD_ANGULAR) {
+        ov = angular2obsvec_m(aux.Mc, a, b);
+    } else if (src == PM_COORD_KM) {  // Body._km2obsvec_norm (body.py:1641-1644)
+        ov = angular2obsvec_m(f.M, fma(aux.km2ang[0], a, aux.km2ang[1] * b), fma(aux.km2ang[2], a, aux.km2ang[3] * b));
+    } else {  // BodyXY._xy2obsvec_norm (body_xy.py:375-377)
+        ov = angular2obsvec_m(f.M, fma(f.A[0], a, fma(f.A[1], b, f.A[2])), fma(f.A[3], a, fma(f.A[4], b, f.A[5])));
+    }
+    if (!finite3(ov)) return true;
+    if (dst == PM_COORD_RADEC) {  // SpiceBase._obsvec2radec (base.py:891-906)
+        double ra, dec;
+        recrad_angles(ov, ra, dec);
+        oa = ra * kDpr;
+        ob = dec * kDpr;
+    } else if (dst == PM_COORD_ANGULAR) {
+        obsvec2angular_m(aux.Mc, ov, oa, ob);
+    } else if (dst == PM_COORD_KM) {  // Body._obsvec2km (body.py:1646-1650)
+        double ax, ay;
+        obsvec2angular_m(f.M, ov, ax, ay);
+        oa = fma(f.ang2km[0], ax, f.ang2km[1] * ay);
+        ob = fma(f.ang2km[2], ax, f.ang2km[3] * ay);
+    } else if (dst == PM_COORD_XY) {  // BodyXY._obsvec2xy (body_xy.py:379-382)
+        double ax, ay;
+        obsvec2angular_m(f.M, ov, ax, ay);
+        oa = fma(f.Ainv[0], ax, fma(f.Ainv[1], ay, f.Ainv[2]));
+        ob = fma(f.Ainv[3], ax, fma(f.Ainv[4], ay, f.Ainv[5]));
+    } else {  // Body._obsvec_norm2lonlat (body.py:1058-1081); the frame carries the radii raised by alt
+        Intercept it;
+        if (!sincpt(fs, mxv(f.R0, ov), it)) return false;
+        double lo, la, al;
+        recpgr(fs, it.p, fs.biaxial != 0, lo, la, al);
+        oa = lo * kDpr;
+        ob = la * kDpr;
+        if (pc || dst == PM_COORD_CENTRIC) {
+            // graphic2centric_lonlat(lon, lat, alt=alt) evaluated INSIDE the altitude adjustment
+            // (body.py:1066-1080): pgrrec(lon, lat, alt) against the already raised spheroid, then reclat
+            lo = oa * kRpd;
+            la = ob * kRpd;
+            V3 tv = pgrrec0(fs, lo, la);
+            if (alt != 0.0) {
+                double sl, cl, sb, cb;
+                sincos_full(f.lon_sign * lo, sl, cl);
+                sincos_full(la, sb, cb);
+                tv = axpy(alt, mk(cb * cl, cb * sl, sb), tv);
+            }
+            double lc, bc;
+            reclat_angles(tv, lc, bc);
+            oa = lc * kDpr;
+            ob = bc * kDpr;
+        }
+    }
+    return true;
 }
 
 }  // namespace pm

@@ -273,6 +273,23 @@ def obsvec2angular(M: np.ndarray, obsvec: np.ndarray) -> tuple[float, float]:
     return x * 3600.0, math.degrees(y) * 3600.0
 
 
+def obsvec2angular_matrix(origin_ra: float, origin_dec: float, coordinate_rotation: float = 0.0) -> np.ndarray:
+    """Body._get_obsvec2angular_matrix (planetmapper/body.py:1318-1343): rotation taking observer-frame
+    vectors to the angular system centred on (origin_ra, origin_dec) [degrees], rotated by
+    ``coordinate_rotation`` degrees."""
+    origin = _radrec(1.0, math.radians(origin_ra), math.radians(origin_dec))
+    _, ra_angle, _ = _recrad(origin)
+    ra_matrix = _rot_axis(ra_angle, 3)
+    _, _, dec_angle = _recrad(ra_matrix @ origin)
+    dec_matrix = _rot_axis(-dec_angle, 2)
+    return _rot_axis(math.radians(coordinate_rotation), 1) @ dec_matrix @ ra_matrix
+
+
+def km2angular_matrix(bc: 'BodyConstants') -> np.ndarray:
+    """Body._get_km2angular_matrix (planetmapper/body.py:1625-1634)."""
+    return (1.0 / bc.km_per_arcsec) * rotation_matrix_radians(np.deg2rad(bc.north_pole_angle))
+
+
 def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
                          et: float | None = None,
                          observer_state: np.ndarray | None = None,
@@ -372,12 +389,7 @@ def build_body_constants(provider, target, utc: str | None, observer='EARTH', *,
     # target RA/Dec & obsvec -> angular matrix (body.py:1318-1343, defaults)
     _, ra, dec = _recrad(P0)
     target_ra, target_dec = math.degrees(ra), math.degrees(dec)
-    origin = _radrec(1.0, math.radians(target_ra), math.radians(target_dec))
-    _, ra_angle, _ = _recrad(origin)
-    ra_matrix = _rot_axis(ra_angle, 3)
-    _, _, dec_angle = _recrad(ra_matrix @ origin)
-    dec_matrix = _rot_axis(-dec_angle, 2)
-    M = _rot_axis(0.0, 1) @ dec_matrix @ ra_matrix
+    M = obsvec2angular_matrix(target_ra, target_dec, 0.0)
 
     target_distance = lt0 * c
     target_diameter_arcsec = float(
@@ -507,9 +519,7 @@ def pack_frame(bc: BodyConstants, *, nx: int, ny: int, x0: float, y0: float,
     put('ring_c', bc.ring_c)
     put('sun_lon_lst', bc.sun_lon_lst)
     put('M', bc.M)
-    s = 1.0 / bc.km_per_arcsec
-    km2ang = s * rotation_matrix_radians(np.deg2rad(bc.north_pole_angle))
-    put('ang2km', np.linalg.inv(km2ang))
+    put('ang2km', np.linalg.inv(km2angular_matrix(bc)))
     put('km_per_arcsec', bc.km_per_arcsec)
     a3 = xy2angular_matrix(bc, x0, y0, r0, rotation_radians)
     a3inv = np.linalg.inv(a3)

@@ -52,9 +52,10 @@ def main():
         bc = F.BodyConstants.from_json_dict(json.load(f))
     fr = img_case(bc, sz, sz, (sz - 1) / 2, (sz - 1) / 2, 0.9 * (sz - 1) / 2, 0.0)
     O.build()
-    if not os.path.exists(T.SO):
+    import conftest
+    if not os.path.exists(conftest.HOST_CHECK_SO):
         raise SystemExit('run `pytest tests/test_host_check.py` once to build the host instantiation')
-    hc = ctypes.CDLL(T.SO)
+    hc = ctypes.CDLL(conftest.HOST_CHECK_SO)
     with tempfile.TemporaryDirectory() as tmp:
         exact = T.build_ld_oracle(tmp)(fr, sz, sz)
     oracle = O.backplanes_img(fr, sz, sz)

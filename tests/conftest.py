@@ -49,3 +49,27 @@ def oracle():
 # disc parameters of the golden FITS files (tests/test_observation.py:1017, :1084)
 GOLDEN_DISC = dict(nx=7, ny=10, x0=2.5, y0=3.1, r0=3.9, rotation_radians=float(np.deg2rad(123.456)))
 GOLDEN_ALT = 34567.8912
+
+
+# Host instantiation of the kernels' per-pixel code (tests/host_check/host_check.cu): TEST INFRASTRUCTURE,
+# never linked into or loaded by the product library
+HOST_CHECK_SRC = os.path.join(ROOT, 'tests', 'host_check', 'host_check.cu')
+HOST_CHECK_SO = os.path.join(ROOT, 'tests', 'host_check', '_build', 'libpm_hostcheck.so')
+
+
+@pytest.fixture(scope='session')
+def HC():
+    import ctypes
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    csrc = os.path.join(ROOT, 'planetmapper_b200', 'csrc')
+    deps = [HOST_CHECK_SRC] + [os.path.join(csrc, f) for f in ('pm_device.cuh', 'pm_math.cuh')]
+    if not os.path.exists(HOST_CHECK_SO) or os.path.getmtime(HOST_CHECK_SO) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(HOST_CHECK_SO), exist_ok=True)
+        subprocess.run([nvcc, '-O2', '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets',
+                        '-o', HOST_CHECK_SO, HOST_CHECK_SRC], check=True, capture_output=True)
+    return ctypes.CDLL(HOST_CHECK_SO)

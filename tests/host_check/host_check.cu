@@ -79,6 +79,21 @@ int hc_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int
     return 0;
 }
 
+// pm_transform's per-point code; aux13 as in include/pm_b200.h (never NULL here)
+int hc_transform(const PMFrame *frame, int src, int dst, const double *a, const double *b, int64_t n, double alt,
+                 uint32_t flags, const double *aux13, double *oa, double *ob, int64_t *missed) {
+    pm::FrameD fs;
+    pm::load_frame_host(fs, frame);
+    pm::TransformAux aux;
+    for (int i = 0; i < 9; i++) aux.Mc[i] = aux13[i];
+    for (int i = 0; i < 4; i++) aux.km2ang[i] = aux13[9 + i];
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++)
+        if (!pm::point_transform(fs, aux, src, dst, a[i], b[i], alt, flags, oa[i], ob[i])) m++;
+    *missed = m;
+    return 0;
+}
+
 // kind as pm_math_probe (include/pm_b200.h)
 int hc_math(int kind, const double *a, const double *b, int64_t n, double *out) {
     for (int64_t i = 0; i < n; i++) {

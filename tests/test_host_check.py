@@ -28,19 +28,6 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-@pytest.fixture(scope='module')
-def HC():
-    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    if not os.path.exists(nvcc):
-        pytest.skip('nvcc not available')
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ('pm_device.cuh', 'pm_math.cuh')]
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
-        os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.run([nvcc, '-O2', '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets',
-                        '-o', SO, SRC], check=True, capture_output=True)
-    return ctypes.CDLL(SO)
-
-
 def hc_img(HC, fr, nx, ny, mask=(1 << 26) - 1):
     out = np.empty((26, ny, nx))
     f = np.ascontiguousarray(fr, dtype=np.float64)
