@@ -8,16 +8,19 @@ bench.py - headline benchmark of the B200-native PlanetMapper hot path.
 Metric (BASELINE.json): full-backplane Mpix/s (FP64) + mapped-cube voxels/s.
 Workload at every N (weak scaling, no data-path collective): each rank computes the
 12-plane default backplane stack of one Jupiter/HST 2048 x 2048 frame per step
-(BASELINE.json configs[1], "C2").  `value` is the whole-job Mpix/s with the frame
-constants resident in HBM; `e2e` is the same metric through the public BodyXY API with
-host buffers (constants H2D + 403 MB of planes D2H per step inside the timed region).
-`mapped_cube` reports configs[3] ("C4": 3000 x 64 x 64 cube -> 0.1 deg grid, 6.48 M
-cells, nearest / linear / cubic) in voxels/s, device-resident and chunked over
-wavelength planes because the 155.5 GB output does not fit next to its own copy.
+(BASELINE.json configs[1], "C2").  `value` is the whole-job Mpix/s of the kernel (CUDA events; the
+92 frame constants ride in the launch as a kernel parameter, nothing else is read); `e2e` is the same
+metric through the drop-in public call - a fresh BodyXY and `get_backplane_img(name)` for each of the
+12 names, host arrays out - with the device -> host copies inside the timed region, next to the raw
+pinned-copy ceiling of the same bytes measured in the same run.
+`mapped_cube` reports configs[3] ("C4": 3000 x 64 x 64 cube -> 0.1 deg grid, 6.48 M cells, nearest /
+linear / cubic) in voxels/s: device-resident (wavelength planes sharded over the ranks, chunked because the
+155.5 GB output does not fit next to its own copy) and end to end through
+`Observation.iter_mapped_data` (double-buffered pinned staging).
 
-The reference (pure Python + spiceypy) cannot be installed here or on the GPU box
-(no spiceypy / CSPICE wheels, no network), so `--impl reference` and `cpu_baseline`
-time the CPU restatement in oracle/ (kind "port") on the box's host cores.
+The reference (pure Python + spiceypy) cannot be installed here or on the GPU box (no spiceypy / CSPICE
+wheels, no network), so `--impl reference` and `cpu_baseline` time the CPU restatement in oracle/
+(kind "port": C + OpenMP for the geometry, the REAL scipy for the map resampling) on the box's host cores.
 """
 import argparse
 import json
@@ -37,6 +40,10 @@ C2_NAMES = ['LON-GRAPHIC', 'LAT-GRAPHIC', 'LON-CENTRIC', 'LAT-CENTRIC', 'INCIDEN
 METRIC = 'full-backplane Mpix/s (FP64) + mapped-cube voxels/s at 1-8 B200 vs host CPU'
 SZ = 2048
 CPU_SAMPLE_SZ = 2048
+# the SAME string in both arms (the driver compares them)
+WORKLOAD = ('C2: Jupiter/HST 2005-01-01T00:00:00, one 2048x2048 frame per GPU per step, 12-plane default backplane '
+            'stack (' + ', '.join(C2_NAMES) + '), disc centred, r0 = 0.9 (n-1)/2')
+C4_NL, C4_SZ, C4_CHUNK = 3000, 64, 512
 
 
 def load_bc():
@@ -161,7 +168,7 @@ def ncu_traffic(key):
     return None if not s else s.get('dram_bytes_per_launch')
 
 
-def cpu_port_mpix(sz, threads=None, repeats=1):
+def cpu_port_mpix(sz, repeats=1):
     """Times the CPU oracle (C port of the reference path) on a sz x sz C2-like frame."""
     from oracle import oracle as O
 
@@ -181,7 +188,104 @@ def cpu_port_mpix(sz, threads=None, repeats=1):
 
 def omp_threads():
     n = os.environ.get('OMP_NUM_THREADS')
-    return int(n) if n else (os.cpu_count() or 1)
+    if n:
+        return int(n)
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_one_core_mpix():
+    """The same port on ONE core: a child process with OMP_NUM_THREADS=1 (the OpenMP runtime reads it at
+    load) on the C2 geometry at 1024 x 1024 (same disc fraction, a quarter of the pixels)."""
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-child', '1024'], env=env,
+                         capture_output=True, text=True, timeout=600)
+    return float(out.stdout.strip().splitlines()[-1])
+
+
+def c4_inputs(n_planes=C4_NL):
+    """C4's synthetic cube and grid: default_rng(0) normal(1, 0.1), 1 % NaN pixels, plane 17 all NaN."""
+    rng = np.random.default_rng(0)
+    cube = rng.normal(1.0, 0.1, (n_planes, C4_SZ, C4_SZ))
+    cube[rng.random((n_planes, C4_SZ, C4_SZ)) < 0.01] = np.nan
+    if n_planes > 17:
+        cube[17] = np.nan
+    lons = np.arange(0.05, 360, 0.1)[::-1]
+    lats = np.arange(-90 + 0.05, 90, 0.1)
+    lo, la = np.meshgrid(lons, lats)
+    return cube, lo, la
+
+
+def c4_frame(bc):
+    from planetmapper_b200 import frame as F
+
+    return F.pack_frame(bc, nx=C4_SZ, ny=C4_SZ, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
+
+
+def cpu_baselines_extra(bc):
+    """CPU rows for the other configs, each on a bounded sample.
+    C4 uses the REAL scipy (RectBivariateSpline.ev etc. arranged as BodyXY.map_img arranges them,
+    oracle/map_img_oracle.py) on the first 8 planes at the full 0.1 deg grid - scipy is single threaded, the
+    reference loops planes serially, cost is linear in planes; the x / y maps (C oracle, all threads) are
+    timed separately because the reference computes them once per cube.  C3 / C5: the C port."""
+    import planetmapper_b200 as pm
+    from oracle import map_img_oracle as MO
+    from oracle import oracle as O
+    from planetmapper_b200 import frame as F
+
+    res = {}
+    n_s = 8
+    cube, lo, la = c4_inputs(24)
+    fr = c4_frame(bc)
+    xy_mask = plane_mask(['PIXEL-X', 'PIXEL-Y'])
+    t0 = time.perf_counter()
+    xy = O.backplanes_map(fr, lo, la, xy_mask)
+    t_xy = time.perf_counter() - t0
+    c4 = {'sample': f'planes 16..{16 + n_s - 1} of the C4 cube (incl. the all-NaN plane 17) at the full 0.1 deg grid '
+                    f'({lo.size} cells), real scipy, 1 core; x / y maps by the C port on {omp_threads()} threads',
+          'xy_map_s': t_xy, 'xy_map_mcells_per_s': lo.size / t_xy / 1e6, 'unit': 'voxels/s', 'cores': 1, 'kind': 'port',
+          'note': 'numpy bookkeeping around the same scipy calls (map_cube_fast, checked equal to the line-by-line '
+                  'form of BodyXY.map_img); the reference itself walks every cell in a Python loop and is slower still'}
+    for interp in ('nearest', 'linear', 'cubic'):
+        t0 = time.perf_counter()
+        MO.map_cube_fast(cube[16:16 + n_s], xy[0], xy[1], interp)
+        dt = time.perf_counter() - t0
+        c4[interp] = {'voxels_per_s': n_s * lo.size / dt, 's_per_plane': dt / n_s,
+                      'whole_cube_s_extrapolated': dt / n_s * C4_NL + t_xy}
+    res['mapped_cube'] = c4
+    # C3: Saturn 4096 x 4096, ring planes + DISTANCE, the full frame
+    bcs = F.build_body_constants(pm.get_default_provider(), 'Saturn', '2004-12-30T12:00:00', 'EARTH')
+    sz = 4096
+    frs = F.pack_frame(bcs, nx=sz, ny=sz, x0=(sz - 1) / 2, y0=(sz - 1) / 2, r0=800.0, rotation_radians=0.0)
+    m3 = plane_mask(['RING-RADIUS', 'RING-LON-GRAPHIC', 'RING-DISTANCE', 'DISTANCE'])
+    t0 = time.perf_counter()
+    O.backplanes_img(frs, sz, sz, m3)
+    dt = time.perf_counter() - t0
+    res['saturn_rings'] = {'img_mpix_per_s': sz * sz / dt / 1e6, 's': dt, 'cores': omp_threads(), 'kind': 'port',
+                           'sample': 'the full C3 frame (4096 x 4096, 3 ring planes + DISTANCE)'}
+    # C5: 4 frames of the Europa series at 1024 x 1024, 12-plane stack (constants + pixels)
+    from planetmapper_b200 import series as S
+
+    prov = pm.get_default_provider()
+    et_end = prov.utc2et('2005-01-01T00:00:00') - 3600.0
+    ets = et_end - 60.0 * np.arange(4)
+    sz = 1024
+    t0 = time.perf_counter()
+    frames = S.build_series_frames('Europa', ets, 'EARTH', nx=sz, ny=sz, x0=(sz - 1) / 2, y0=(sz - 1) / 2, r0=0.45 * sz,
+                                   workers=1, kepler=True)
+    t_host = time.perf_counter() - t0
+    m5 = plane_mask(C2_NAMES)
+    t0 = time.perf_counter()
+    for fr5 in frames:
+        O.backplanes_img(fr5, sz, sz, m5)
+    dt = time.perf_counter() - t0
+    res['time_series'] = {'backplanes_mpix_per_s': len(frames) * sz * sz / dt / 1e6, 'cores': omp_threads(), 'kind': 'port',
+                          'host_constants_ms_per_frame': t_host / len(frames) * 1e3,
+                          'sample': '4 of the 4096 Europa frames (1024 x 1024, 12-plane stack)',
+                          'whole_series_s_extrapolated': dt / len(frames) * 4096}
+    return res
 
 
 def run_reference(args):
@@ -213,8 +317,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'C2: Jupiter/HST 2005-01-01 2048x2048, 12-plane default backplane stack',
-                   'sample': sample},
+        'config': {'workload': WORKLOAD, 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
                          'sample': sample,
                          'note': 'reference (Python + spiceypy/CSPICE) is not installable here; this is the '
@@ -225,15 +328,17 @@ def run_reference(args):
     return 0
 
 
-def bench_mapped_cube(L, torch, bc, rank, world):
-    """C4: 3000 x 64 x 64 cube -> 0.1 deg rectangular grid, device resident, chunked."""
-    from planetmapper_b200 import frame as F
+def bench_mapped_cube(L, torch, pm, bc, rank, world, e2e=True):
+    """C4: 3000 x 64 x 64 cube -> 0.1 deg rectangular grid.  Wavelength planes are sharded over the ranks in
+    plane quads (strong scaling: rank r maps planes lo..hi of the 3000), device resident in chunks of 512
+    planes; then the same shard end to end through Observation.iter_mapped_data (linear)."""
+    from planetmapper_b200.shard import max_over_ranks, shard_range
 
-    sz, nl_total, chunk = 64, 3000, 512
-    fr = F.pack_frame(bc, nx=sz, ny=sz, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
-    lons = np.arange(0.05, 360, 0.1)[::-1]
-    lats = np.arange(-90 + 0.05, 90, 0.1)
-    lo, la = np.meshgrid(lons, lats)
+    sz, nl_total, chunk = C4_SZ, C4_NL, C4_CHUNK
+    q_lo, q_hi = shard_range(nl_total // 4, rank, world)
+    lo_p, hi_p = 4 * q_lo, 4 * q_hi
+    fr = c4_frame(bc)
+    cube_h, lo, la = c4_inputs()
     fd = L.to_device(fr)
     lod, lad = L.to_device(lo), L.to_device(la)
     xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
@@ -245,52 +350,98 @@ def bench_mapped_cube(L, torch, bc, rank, world):
     e1.record()
     torch.cuda.synchronize()
     xy_ms = e0.elapsed_time(e1)
-    rng = np.random.default_rng(0)
-    cube_h = rng.normal(1.0, 0.1, (nl_total, sz, sz))
-    bad = rng.random((nl_total, sz, sz)) < 0.01
-    cube_h[bad] = np.nan
-    cube_h[17] = np.nan
     cube = L.to_device(cube_h)
     n_cells = lo.size
     out = torch.empty((chunk,) + lo.shape, dtype=torch.float64, device='cuda')
     res = {'workload': 'C4: 3000x64x64 cube (1% NaN px, one all-NaN plane) -> 0.1 deg grid '
-                       f'({lo.shape[1]}x{lo.shape[0]} = {n_cells} cells), chunks of {chunk} planes into a reused '
-                       'device buffer (full output 155.5 GB)',
+                       f'({lo.shape[1]}x{lo.shape[0]} = {n_cells} cells), planes sharded over {world} rank(s) '
+                       f'(this rank: {lo_p}..{hi_p}), chunks of {chunk} planes into a reused device buffer '
+                       '(full output 155.5 GB)',
+           'scaling': 'strong', 'planes_this_rank': hi_p - lo_p,
            'xy_map_ms': xy_ms, 'unit': 'voxels/s', 'visible_cell_fraction': float(torch.isfinite(xy[0]).double().mean())}
     peaks, src = measured_peaks()
     for mode, name in ((L.INTERP_NEAREST, 'nearest'), (L.INTERP_LINEAR, 'linear'), (L.INTERP_CUBIC, 'cubic')):
-        def one_pass(timed):
+        def one_pass():
             prep_ms = 0.0
             if mode == L.INTERP_NEAREST:
-                src = cube
+                src_ = cube
             else:
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
-                src = L.spline_prepare(cube, mode)
+                src_ = L.spline_prepare(cube, mode)   # whole cube: 98 MB, 1.5 ms - not worth sharding
                 p1.record()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            for s in range(0, nl_total, chunk):
-                n = min(chunk, nl_total - s)
-                L.gather(src, xy[0], xy[1], mode, plane_begin=s, plane_count=n, out=out[:n])
+            n_launch = 0
+            for s_ in range(lo_p, hi_p, chunk):
+                n = min(chunk, hi_p - s_)
+                L.gather(src_, xy[0], xy[1], mode, plane_begin=s_, plane_count=n, out=out[:n])
+                n_launch += 1
             g1.record()
             torch.cuda.synchronize()
             if mode != L.INTERP_NEAREST:
                 prep_ms = p0.elapsed_time(p1)
-            return g0.elapsed_time(g1), prep_ms
-        one_pass(False)
-        gather_ms, prep_ms = one_pass(True)
-        vox = nl_total * n_cells
-        total_ms = gather_ms + prep_ms
-        alg_bytes = 8.0 * vox + 8.0 * cube.numel() + 16.0 * n_cells * -(-nl_total // chunk)
+            return g0.elapsed_time(g1), prep_ms, n_launch
+        one_pass()
+        gather_ms, prep_ms, n_launch = one_pass()
+        vox_rank = (hi_p - lo_p) * n_cells
+        alg_bytes = 8.0 * vox_rank + 8.0 * (hi_p - lo_p) * sz * sz + 16.0 * n_cells * n_launch
+        total_ms = max_over_ranks(gather_ms + prep_ms, world, device='cuda')
         res[name] = {
-            'voxels_per_s': vox / (total_ms * 1e-3), 'gather_ms': gather_ms, 'prepare_ms': prep_ms,
+            'voxels_per_s': nl_total * n_cells / (total_ms * 1e-3), 'ms_all_ranks': total_ms,
+            'gather_ms': gather_ms, 'prepare_ms': prep_ms, 'launches': n_launch,
             'roofline': {'bound': 'hbm', 'achieved': alg_bytes / (gather_ms * 1e-3) / 1e9,
                          'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                          'frac': alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 'peak_source': src,
                          'traffic': ncu_traffic(f'gather_{name}'),
-                         'algorithmic_bytes_per_voxel': alg_bytes / vox},
+                         'traffic_note': 'ncu dram bytes of ONE launch of this kernel at the bench chunk (512 planes)',
+                         'algorithmic_bytes_per_voxel': alg_bytes / vox_rank},
         }
+    del out
+    if e2e:
+        # end to end: the public streaming call on this rank's planes, host arrays out (pinned double buffer),
+        # D2H inside the timed region; the consumer touches one value per plane
+        obs = pm.Observation(data=cube_h[lo_p:hi_p], constants=bc)
+        obs.set_disc_params(31.5, 31.5, 28.0, 0.0)
+        per = 32
+
+        first_chunk_s = [None]
+
+        def stream():
+            acc, n_planes = 0.0, 0
+            t_start = time.perf_counter()
+            for first, mapped in obs.iter_mapped_data('linear', planes_per_chunk=per, degree_interval=0.1):
+                if first_chunk_s[0] is None:
+                    first_chunk_s[0] = time.perf_counter() - t_start
+                acc += float(np.nansum(mapped[:, 900, 1800]))
+                n_planes += mapped.shape[0]
+            return acc, n_planes
+        # warm: one short pass builds the x / y maps, the spline operand and the pinned buffers
+        warm = pm.Observation(data=cube_h[lo_p:lo_p + 2 * per], constants=bc)
+        warm.set_disc_params(31.5, 31.5, 28.0, 0.0)
+        for _ in warm.iter_mapped_data('linear', planes_per_chunk=per, degree_interval=0.1):
+            pass
+        del warm
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        t0 = time.perf_counter()
+        acc, n_planes = stream()
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device='cuda')
+        nbytes = n_planes * n_cells * 8
+        res['e2e_linear'] = {
+            'api': "Observation(data=cube[lo:hi]).iter_mapped_data('linear', degree_interval=0.1): x / y maps, NaN "
+                   'repair, gather in 32-plane chunks, each chunk to pinned host memory while the next is gathered',
+            'voxels_per_s': nl_total * n_cells / (dt * 1e-3), 'ms_all_ranks': dt, 'planes_this_rank': n_planes,
+            'd2h_bytes_this_rank': int(nbytes), 'd2h_gb_per_s_this_rank': nbytes / (dt * 1e-3) / 1e9,
+            'setup_s_until_first_chunk': first_chunk_s[0],
+            'setup_what': 'lon / lat grid on the host, x / y maps, cube upload, NaN repair, staging buffers, first chunk',
+            'stream_gb_per_s_after_setup': (nbytes * (1 - per / max(n_planes, per))) / max(dt * 1e-3 - first_chunk_s[0], 1e-9) / 1e9,
+            'h2d_bytes_this_rank': int(cube_h[lo_p:hi_p].nbytes), 'checksum': acc}
+        del obs
     if world > 1:
         # result assembly: 64 mapped planes of every rank into one device buffer on rank 0,
         # NCCL point-to-point straight into the destination slices (GPU-to-GPU over NVLink)
@@ -299,12 +450,14 @@ def bench_mapped_cube(L, torch, bc, rank, world):
         from planetmapper_b200.shard import gather_blocks
 
         per = 64
+        blk = torch.empty((per,) + lo.shape, dtype=torch.float64, device='cuda')
+        L.gather(cube, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=lo_p, plane_count=per, out=blk)
         whole = torch.empty((per * world,) + lo.shape, dtype=torch.float64, device='cuda') if rank == 0 else None
         for timed in (False, True):
             dist.barrier()
             torch.cuda.synchronize()
             e0.record()
-            gather_blocks(out[:per], per * world, world, rank, dst=0, out=whole)
+            gather_blocks(blk, per * world, world, rank, dst=0, out=whole)
             e1.record()
             torch.cuda.synchronize()
             dist.barrier()
@@ -312,8 +465,7 @@ def bench_mapped_cube(L, torch, bc, rank, world):
         res['assemble_on_rank0'] = {'planes_per_rank': per, 'bytes_received': nbytes, 'ms': e0.elapsed_time(e1),
                                     'gb_per_s': nbytes / e0.elapsed_time(e1) / 1e6,
                                     'how': 'NCCL send / irecv into slices of one buffer (shard.gather_blocks)'}
-        del whole
-    del out
+        del whole, blk
     return res
 
 
@@ -454,9 +606,11 @@ def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     hour before the fixture epoch, sharded by frame across ranks: the 12-plane stack per frame in
     batched launches (one device buffer reused per batch: the full series would be 412 GB of
     planes) plus a 1 deg rectangular nearest reprojection of one synthetic image per frame.
-    Europa has no ephemeris in the bundled kernels, so the series is Jupiter
-    from EARTH; the kernels only see constants.  The per-frame host constants are extracted by
-    `planetmapper_b200.series` over host processes and reported separately."""
+    Europa has no SPK segment in the bundled kernels, so its position comes from the
+    analytic orbit about the Jupiter barycentre of planetmapper_b200/minispice/kepler.py (SURVEY 8(d) C5
+    option ii) while radii (triaxial: 1562.6 / 1560.3 / 1559.5 km) and the IAU orientation model are the
+    PCK's own.  The per-frame host constants are extracted by `planetmapper_b200.series` over host processes
+    and reported separately."""
     from planetmapper_b200 import frame as F
     from planetmapper_b200.shard import shard_range
 
@@ -470,11 +624,11 @@ def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     disc = dict(nx=sz, ny=sz, x0=(sz - 1) / 2, y0=(sz - 1) / 2, r0=0.45 * sz, rotation_radians=0.0)
     # host constants: one serial sample for the per-frame cost, then the whole shard over host processes
     t0 = time.perf_counter()
-    S.build_series_frames('Jupiter', ets[:16], 'EARTH', workers=1, **disc)
+    S.build_series_frames('Europa', ets[:16], 'EARTH', workers=1, kepler=True, **disc)
     serial_ms_per_frame = (time.perf_counter() - t0) / min(16, len(ets)) * 1e3
-    S.build_series_frames('Jupiter', ets[:16 * S.default_workers()], 'EARTH', **disc)   # starts every worker process
+    S.build_series_frames('Europa', ets[:16 * S.default_workers()], 'EARTH', kepler=True, **disc)   # starts every worker process
     t0 = time.perf_counter()
-    frames = S.build_series_frames('Jupiter', ets, 'EARTH', **disc)
+    frames = S.build_series_frames('Europa', ets, 'EARTH', kepler=True, **disc)
     host_s = time.perf_counter() - t0
     host_workers = S.default_workers()
     S.shutdown_pool()
@@ -510,7 +664,7 @@ def bench_time_series(L, torch, pm, rank, world, n_frames=4096, batch=32):
     reproject()
     e2.record()
     torch.cuda.synchronize()
-    return {'workload': f'C5: {n_frames} Jupiter / EARTH frames of {sz}x{sz}, 60 s apart, 12-plane stack in '
+    return {'workload': f'C5: {n_frames} Europa / EARTH frames (triaxial; analytic orbit, PCK radii and orientation) of {sz}x{sz}, 60 s apart, 12-plane stack in '
                         f'batches of {batch} frames + map_img(img, degree_interval=1) (linear) of one image per frame, batched '
                         f'(series.map_series); frames {lo}..{hi} on this rank',
             'frames_this_rank': hi - lo, 'host_constants_s': host_s, 'host_workers': host_workers,
@@ -526,9 +680,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--skip-cube', action='store_true', help='skip the mapped-cube (C4) section')
-    ap.add_argument('--skip-cpu', action='store_true', help='skip the bounded CPU baseline')
+    ap.add_argument('--skip-cpu', action='store_true', help='skip the bounded CPU baselines')
     ap.add_argument('--skip-extra', action='store_true', help='skip the C3 (Saturn rings) and C5 (time series) sections')
+    ap.add_argument('--cpu-child', type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        print(cpu_port_mpix(args.cpu_child, repeats=2)[0])
+        return 0
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -543,12 +701,15 @@ def main():
 
     import planetmapper_b200 as pm
     from planetmapper_b200 import _lib as L
-    from planetmapper_b200.shard import env_rank_world, max_over_ranks
+    from planetmapper_b200.shard import bind_rank_to_cores, env_rank_world, max_over_ranks
 
     rank, local_rank, world = env_rank_world()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback')
     torch.cuda.set_device(local_rank)
+    # every rank gets its own host cores (and its GPU's NUMA node where the host has more than one) BEFORE it
+    # allocates pinned memory
+    binding = bind_rank_to_cores(local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)), local_rank)
     if world > 1:
         import torch.distributed as dist
 
@@ -566,13 +727,12 @@ def main():
     fr = c2_frame(bc)
     mask = plane_mask(C2_NAMES)
     k = len(C2_NAMES)
-    fd = L.to_device(fr[None])
-    out = torch.empty((1, k, SZ, SZ), dtype=torch.float64, device='cuda')
+    out = torch.empty((k, SZ, SZ), dtype=torch.float64, device='cuda')
 
-    # ---- kernel path, inputs resident in HBM ---------------------------------------
+    # ---- kernel path: the frame constants ride in the launch, planes stay in HBM ----------
     W = max(args.warmup, 3)
     for _ in range(W):
-        L.backplanes_img_host(fr, SZ, SZ, mask, out=out[0])
+        L.backplanes_img_host(fr, SZ, SZ, mask, out=out)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -581,7 +741,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        L.backplanes_img_host(fr, SZ, SZ, mask, out=out[0])   # the 92 frame constants ride in the launch
+        L.backplanes_img_host(fr, SZ, SZ, mask, out=out)
     e1.record()
     barrier()
     launches = L.launch_count() - launches0
@@ -589,90 +749,138 @@ def main():
     ms = max_over_ranks(ms, world, device='cuda')
     value = world * SZ * SZ / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the public API, host buffers ---------------------------
-    pinned = torch.empty((k, SZ, SZ), dtype=torch.float64).pin_memory()
+    # ---- end to end through the public API, host arrays out ---------------------------------
     e2e_steps = max(3, min(args.steps, 10))
+    nbytes = k * SZ * SZ * 8
 
-    def e2e_step():
+    def e2e_dropin():
+        # the reference's own call sequence (body_xy.py:2586-2630): one get_backplane_img per name
         body = pm.BodyXY(constants=bc, nx=SZ, ny=SZ)      # fresh object: empty caches
+        planes = {n: body.get_backplane_img(n) for n in C2_NAMES}
+        return float(planes['EMISSION'][SZ // 2, SZ // 2])
+
+    pinned = torch.empty((k, SZ, SZ), dtype=torch.float64).pin_memory()
+
+    def e2e_batched():
+        body = pm.BodyXY(constants=bc, nx=SZ, ny=SZ)
         planes = body.get_backplane_imgs(C2_NAMES, out=pinned)
         return float(planes['EMISSION'][SZ // 2, SZ // 2])
 
+    def timed_host(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / steps * 1e3
+        return max_over_ranks(t, world, device='cuda')
+
+    e2e_ms = timed_host(e2e_dropin, e2e_steps)
+    e2e_batched_ms = timed_host(e2e_batched, e2e_steps)
+
+    # the ceiling of any end-to-end number: the same bytes, device -> pinned host, all ranks at once
+    def raw_copy():
+        pinned.copy_(out, non_blocking=True)
     for _ in range(2):
-        e2e_step()
+        raw_copy()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        raw_copy()
+    c1.record()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-    e2e_ms = max_over_ranks(e2e_ms, world, device='cuda')
+    d2h_ms = max_over_ranks(c0.elapsed_time(c1) / 5, world, device='cuda')
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * SZ * SZ / (e2e_ms * 1e-3) / 1e6
 
     result = None
     if rank == 0:
-        planes_host = out[0, C2_NAMES.index('EMISSION') if False else 0].cpu().numpy()
+        planes_host = out[0].cpu().numpy()
         # plane 0 of the packed output is LON-GRAPHIC (lowest id); its NaN mask = on-disc mask
         flops, classes = algorithmic_flops_per_frame(planes_host, fr)
         fp64_peak = L.fp64_peak_probe()
+        fp64_peak_3reg = L.fp64_peak_probe(kind=1)
         achieved = flops / (ms * 1e-3) / 1e12
         result = {
             'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'C2: Jupiter/HST 2005-01-01T00:00:00 2048x2048 frame per GPU per step, 12-plane '
-                                   'default backplane stack (' + ', '.join(C2_NAMES) + '), disc centred, r0 = 0.9 (n-1)/2',
+            'config': {'workload': WORKLOAD,
                        'l2': 'each step writes 403 MB of planes (> 126 MB L2); no flush needed',
-                       'frames_per_step_per_gpu': 1, 'parallelism': f'frames sharded, {world} rank(s), no collective'},
+                       'frames_per_step_per_gpu': 1, 'parallelism': f'frames sharded, {world} rank(s), no collective',
+                       'launch': 'pm_backplanes_img_host: the 92 frame constants + derived values are a kernel '
+                                 'parameter (constant bank); no host -> device copy is enqueued',
+                       'host_binding': binding},
             'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': int(fr.nbytes), 'd2h_bytes_per_step': int(k * SZ * SZ * 8),
-                    'api': 'BodyXY(constants=...).get_backplane_imgs(12 names, out=pinned)', 'steps': e2e_steps},
+                    'h2d_bytes_per_step': int(fr.nbytes), 'd2h_bytes_per_step': int(nbytes),
+                    'api': 'drop-in: BodyXY(constants=...) then get_backplane_img(name) for each of the 12 names '
+                           '(2 kernel launches, 12 device -> pinned-host copies, 12 owned float64 arrays returned)',
+                    'steps': e2e_steps,
+                    'batched': {'value': world * SZ * SZ / (e2e_batched_ms * 1e-3) / 1e6, 'ms_per_step': e2e_batched_ms,
+                                'api': 'BodyXY.get_backplane_imgs(12 names, out=pinned): 1 launch, 1 copy'},
+                    'd2h_ceiling': {'ms_per_step': d2h_ms, 'gb_per_s_per_gpu': nbytes / (d2h_ms * 1e-3) / 1e9,
+                                    'gb_per_s_all_gpus': world * nbytes / (d2h_ms * 1e-3) / 1e9,
+                                    'value': world * SZ * SZ / (d2h_ms * 1e-3) / 1e6,
+                                    'what': 'cudaMemcpyAsync of the same 403 MB, device -> pinned host, all ranks '
+                                            'concurrently, max over ranks: no end-to-end number can exceed it'},
+                    'frac_of_d2h_ceiling': d2h_ms / e2e_ms},
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': achieved / fp64_peak, 'traffic': ncu_traffic('backplanes_img_c2'),
-                         'peak_source': 'pm_fp64_peak_probe: 8 independent DFMA chains/thread, full grid, measured '
-                                        'in this run (MEASURED_PEAKS.json has no FP64 entry)',
+                         'peak_source': 'pm_fp64_probe(kind 0): 8 independent DFMA chains/thread with ONE register '
+                                        'operand each, full grid, measured in this run (MEASURED_PEAKS.json has no '
+                                        'FP64 entry)',
+                         'operand_limited': {
+                             'peak_3_register_dfma': fp64_peak_3reg, 'frac': achieved / fp64_peak_3reg,
+                             'what': 'pm_fp64_probe(kind 1): the same probe with three DISTINCT register operands '
+                                     'per DFMA, the form dot / cross / axpy of per-pixel vectors issue.  The '
+                                     'register file needs 3 cycles to deliver their six 32-bit sources, the pipe '
+                                     'issues a DFMA every 2: such code tops out at 2/3 of `peak` '
+                                     '(tools/microbench/fp64_operands.cu, profiles/r2_summary.md)'},
                          'algorithmic_flops_per_launch': flops, 'pixel_classes': classes,
-                         'hbm_bytes_per_launch_algorithmic': int(k * SZ * SZ * 8),
+                         'hbm_bytes_per_launch_algorithmic': int(nbytes),
                          # the same launch seen as an HBM kernel (why the bound is the FP64 pipe, not memory)
-                         'hbm_view': {'bound': 'hbm', 'achieved': k * SZ * SZ * 8 / (ms * 1e-3) / 1e9,
+                         'hbm_view': {'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9,
                                       'peak': measured_peaks()[0]['hbm_gbs'], 'unit': 'GB/s',
-                                      'frac': k * SZ * SZ * 8 / (ms * 1e-3) / 1e9 / measured_peaks()[0]['hbm_gbs']},
-                         'note': 'frac counts flops (FMA = 2) against the DFMA-only peak; a third of the FP64-pipe '
-                                 'instructions are DMUL / DADD / DSETP (1 or 0 flop per issue slot), so the pipe '
-                                 'utilisation ncu reports (ncu.fp64_pipe_util) is the tighter measure of how '
-                                 'close the kernel is to the FP64 pipe',
+                                      'frac': nbytes / (ms * 1e-3) / 1e9 / measured_peaks()[0]['hbm_gbs']},
+                         'note': 'frac counts executed flops (FMA = 2, MUL / ADD = 1) against the one-register-operand '
+                                 'DFMA peak; see operand_limited for what the pipe sustains on this instruction mix',
                          'ncu': ncu_summary('backplanes_img_c2')},
             'clocks': clocks,
         }
     if not args.skip_cube:
-        cube_res = bench_mapped_cube(L, torch, bc, rank, world)
-        if world > 1:
-            for name in ('nearest', 'linear', 'cubic'):
-                t = cube_res[name]['gather_ms'] + cube_res[name]['prepare_ms']
-                t = max_over_ranks(t, world, device='cuda')
-                cube_res[name]['voxels_per_s'] = world * 3000 * 6480000 / (t * 1e-3)
+        cube_res = bench_mapped_cube(L, torch, pm, bc, rank, world)
         if rank == 0:
             result['mapped_cube'] = cube_res
     if not args.skip_extra:
         ts = bench_time_series(L, torch, pm, rank, world)
         t_all = max_over_ranks(ts['backplanes_ms'], world, device='cuda')
+        t_map = max_over_ranks(ts['reprojection_ms'], world, device='cuda')
         if rank == 0:
             ts['backplanes_mpix_per_s_all_ranks'] = 4096 * 1024 * 1024 / t_all / 1e3
+            ts['reprojection_frames_per_s_all_ranks'] = 4096 / t_map * 1e3
+            ts['scaling'] = 'strong'
             result['time_series'] = ts
             result['saturn_rings'] = bench_saturn_rings(L, torch, pm)
             result['save_observation'] = bench_save_observation(L, torch, pm, bc)
             result['point_transforms'] = bench_point_transforms(L, torch, bc)
     if rank == 0:
-        if not args.skip_cpu and world == 1:  # the CPU baseline is an N = 1 measurement
+        if not args.skip_cpu and world == 1:  # the CPU baselines are N = 1 measurements
             mp, dt = cpu_port_mpix(CPU_SAMPLE_SZ, repeats=3)
+            one = cpu_one_core_mpix()
             result['cpu_baseline'] = {
                 'value': mp, 'unit': 'Mpix/s', 'cores': omp_threads(), 'kind': 'port',
                 'sample': f'the full C2 frame ({CPU_SAMPLE_SZ}x{CPU_SAMPLE_SZ}, 12 planes), best of 3 passes '
                           f'({dt:.2f} s wall each on {omp_threads()} OpenMP threads)',
+                'one_core': {'value': one, 'unit': 'Mpix/s', 'cores': 1,
+                             'sample': 'the C2 geometry at 1024 x 1024 (same disc fraction), OMP_NUM_THREADS=1'},
                 'note': 'C restatement in oracle/ (the Python+spiceypy reference is not installable here; '
                         'it is ~3 orders of magnitude slower than this port, SURVEY.md section 6)'}
+            if not args.skip_extra:
+                result['cpu_baseline']['other_configs'] = cpu_baselines_extra(bc)
         os.write(result_fd, (json.dumps(result) + '\n').encode())
     if world > 1:
         import torch.distributed as dist

@@ -290,6 +290,10 @@ int pm_gather_grid_linear(const double *fine, int n_planes, int n_ys, int n_xs, 
  * denominator: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the kernel time in ms through *ms_host (synchronises). */
 int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host);
+/* The same probe for two operand mixes: kind 0 = one register operand per DFMA (pm_fp64_peak_probe, the
+ * datasheet rate), kind 1 = three distinct register operands per DFMA, the form per-pixel vector algebra
+ * issues; the register file feeds that form at 2/3 of the rate (measured: profiles/r2_summary.md). */
+int pm_fp64_probe(int kind, int iters, double *ms_host, double *flops_host);
 
 /*
  * FITS staging for Observation.save_observation (observation.py:1185-1303) and

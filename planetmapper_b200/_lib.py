@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
     'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
-    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host', 'pm_transform',
+    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host', 'pm_transform', 'pm_fp64_probe',
 ]
 
 
@@ -92,6 +92,8 @@ def load_library() -> ctypes.CDLL:
     lib.pm_spline_work_bytes.argtypes = [c_i, c_i, c_i, c_i]
     lib.pm_spline_prepare.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
     lib.pm_fp64_peak_probe.argtypes = [c_i, c_p, c_p]
+    lib.pm_fp64_probe.argtypes = [c_i, c_i, c_p, c_p]
+    lib.pm_fp64_probe.restype = c_i
     lib.pm_math_probe.argtypes = [c_i, c_p, c_p, c_i64, c_p, c_p]
     lib.pm_nan_minmax.argtypes = [c_p, c_i64, c_p, c_p]
     lib.pm_pchip_work_bytes.restype = c_i64
@@ -155,6 +157,84 @@ def to_device(arr, device=None):
         warnings.simplefilter('ignore')
         t = torch.from_numpy(a)
     return t.to(device or 'cuda', non_blocking=False)
+
+
+# ---- device -> host hand-off ---------------------------------------------------------------
+# Results leave the device through PINNED host memory: a pageable destination makes the driver
+# stage every copy through its own bounce buffers (about a third of the PCIe rate) and then the
+# API's `copy=True` would move the bytes a second time.  The arrays handed to the caller are
+# ordinary numpy float64 arrays whose storage is a page-locked block from torch's caching host
+# allocator: the block returns to that cache when the array is garbage collected, so a loop that
+# drops its results reuses the same blocks and never pays for pinning again.  Page-locked memory is
+# a finite resource, so beyond PINNED_BUDGET_BYTES outstanding the copy falls back to pageable memory.
+PINNED_BUDGET_BYTES = int(os.environ.get('PM_B200_PINNED_BUDGET', 16 << 30))
+
+
+def _pinned_outstanding(torch) -> int:
+    try:
+        return int(torch.cuda.host_memory_stats().get('allocated_bytes.current', 0))
+    except Exception:   # older torch: no accounting, no limit
+        return 0
+
+
+def empty_host(shape, torch=None):
+    """A float64 CPU tensor for device results: pinned while the budget allows."""
+    torch = torch or _torch()
+    n = 8
+    for d in shape:
+        n *= int(d)
+    pin = _pinned_outstanding(torch) + n <= PINNED_BUDGET_BYTES
+    return torch.empty(tuple(int(d) for d in shape), dtype=torch.float64, pin_memory=pin)
+
+
+# Staging buffers of the streamed results (Observation.iter_mapped_data): page-locking a gigabyte takes
+# about a second, far longer than filling it over PCIe, so ONE set of buffers is kept between calls.
+_STAGING = {'buffers': None, 'busy': False}
+
+
+class staging_buffers:
+    """Context manager handing out ``n`` pinned float64 CPU tensors of ``shape``: views of the cached set when
+    it is free and large enough, private allocations otherwise (e.g. two streams interleaved)."""
+
+    def __init__(self, shape, n: int = 2):
+        self.shape, self.n = tuple(int(d) for d in shape), n
+        self.owns_cache = False
+
+    def __enter__(self):
+        torch = _torch()
+        numel = 1
+        for d in self.shape:
+            numel *= d
+        st = _STAGING
+        if not st['busy']:
+            bufs = st['buffers']
+            if bufs is None or len(bufs) < self.n or bufs[0].numel() < numel:
+                st['buffers'] = None     # release the smaller set before pinning the larger one
+                bufs = [torch.empty(numel, dtype=torch.float64, pin_memory=True) for _ in range(self.n)]
+                st['buffers'] = bufs
+            st['busy'] = self.owns_cache = True
+            return [b[:numel].view(self.shape) for b in bufs[:self.n]]
+        return [torch.empty(self.shape, dtype=torch.float64, pin_memory=True) for _ in range(self.n)]
+
+    def __exit__(self, *exc):
+        if self.owns_cache:
+            _STAGING['busy'] = False
+
+
+def release_staging() -> None:
+    """Give the cached staging buffers back to the host allocator."""
+    if not _STAGING['busy']:
+        _STAGING['buffers'] = None
+
+
+def to_host(dev, out=None):
+    """Device tensor -> numpy array (a NEW array the caller owns unless ``out``, a CPU tensor, is given).
+    One asynchronous copy on the current stream into pinned memory, then a stream synchronise."""
+    torch = _torch()
+    host = empty_host(dev.shape, torch) if out is None else out
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
 def popcount(mask: int) -> int:
@@ -404,13 +484,15 @@ def gather(src, xmap_dev, ymap_dev, mode: int, *, plane_begin: int = 0, plane_co
     return out
 
 
-def fp64_peak_probe(iters: int = 1 << 15) -> float:
-    """Measured FP64 FMA throughput in TFLOP/s (dependent-chain DFMA microbenchmark)."""
+def fp64_peak_probe(iters: int = 1 << 15, kind: int = 0) -> float:
+    """Measured FP64 FMA throughput in TFLOP/s (8 independent DFMA chains per thread, full grid).
+    kind 0: one register operand per DFMA (the datasheet rate); kind 1: three distinct register
+    operands per DFMA (what per-pixel vector algebra issues)."""
     _torch()
     lib = load_library()
     ms = ctypes.c_double(0.0)
     fl = ctypes.c_double(0.0)
-    _check(lib.pm_fp64_peak_probe(iters, ctypes.byref(ms), ctypes.byref(fl)), 'pm_fp64_peak_probe')
+    _check(lib.pm_fp64_probe(kind, iters, ctypes.byref(ms), ctypes.byref(fl)), 'pm_fp64_probe')
     return fl.value / (ms.value * 1e-3) / 1e12
 
 

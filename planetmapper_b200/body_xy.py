@@ -391,7 +391,7 @@ class BodyXY:
         scalar, xa, ya = self._broadcast(x, y)
         fd = self._frame_dev(alt if alt != 0.0 else None)
         lon, lat, missed = L.xy2lonlat(fd, L.to_device(xa), L.to_device(ya))
-        lon, lat = lon.cpu().numpy(), lat.cpu().numpy()
+        lon, lat = L.to_host(lon), L.to_host(lat)
         if not not_found_nan:
             finite_in = np.isfinite(xa) & np.isfinite(ya)
             if int(missed.item()) > 0 or np.any(finite_in & np.isnan(lon)):
@@ -407,7 +407,7 @@ class BodyXY:
             return self._unbroadcast(scalar, np.full(lo.shape, np.nan), np.full(lo.shape, np.nan))
         x, y = L.lonlat2xy(self._frame_dev(), L.to_device(lo), L.to_device(la), not_visible_nan,
                            alt=alt, planetocentric=planetocentric)
-        return self._unbroadcast(scalar, x.cpu().numpy(), y.cpu().numpy())
+        return self._unbroadcast(scalar, L.to_host(x), L.to_host(y))
 
     # ---- the other coordinate pairs (body.py:1083-1900, body_xy.py:385-676) -----------
     def _angular_aux(self, origin_ra=None, origin_dec=None, coordinate_rotation: float = 0.0):
@@ -442,7 +442,7 @@ class BodyXY:
                                      aux13=self._angular_aux(**(angular_kwargs or {})))
         if not not_found_nan and int(missed.item()) > 0:
             raise NotFoundError('ray does not intercept the target body')
-        return self._unbroadcast(scalar, oa.cpu().numpy(), ob.cpu().numpy())
+        return self._unbroadcast(scalar, L.to_host(oa), L.to_host(ob))
 
     def xy2radec(self, x, y):
         """Image pixel coordinates -> RA / Dec (body_xy.py:385-410)."""
@@ -555,8 +555,7 @@ class BodyXY:
             if self.positive_longitude_direction == 'W':
                 lons = lons[::-1]
             lats = np.arange(-90 + degree_interval / 2, 90, degree_interval)
-            lons, lats = np.meshgrid(lons, lats)
-            lons, lats = lons.astype(float), lats.astype(float)
+            lons, lats = np.meshgrid(lons.astype(float, copy=False), lats.astype(float, copy=False))
             xx, yy = lons, lats
             info = dict(projection=projection, degree_interval=degree_interval)
         elif projection == 'manual':
@@ -589,7 +588,7 @@ class BodyXY:
             xx, yy = np.meshgrid(c, c)
             lo, la = L.proj_inverse(kind, a, b, float(lon), float(lat), lon_sign,
                                     L.to_device(xx), L.to_device(yy))
-            lons, lats = lo.cpu().numpy(), la.cpu().numpy()
+            lons, lats = L.to_host(lo), L.to_host(la)
             info = dict(projection=projection, lon=lon, lat=lat, size=size)
         else:
             # custom proj string (body_xy.py:2970-2980)
@@ -610,10 +609,13 @@ class BodyXY:
             keep = (y_arr >= min(ylim)) & (y_arr <= max(ylim))
             xx, yy, lons, lats = xx[keep, :], yy[keep, :], lons[keep, :], lats[keep, :]
         same = xx is lons
-        lons = np.array(lons, dtype=float)
-        lats = np.array(lats, dtype=float)
-        lons[~np.isfinite(lons)] = np.nan
-        lats[~np.isfinite(lats)] = np.nan
+        # every branch above built fresh arrays; inf -> NaN (body_xy.py:3005-3006) only where there is one
+        lons = np.asarray(lons, dtype=float)
+        lats = np.asarray(lats, dtype=float)
+        if not np.isfinite(lons).all():
+            lons = np.where(np.isfinite(lons), lons, np.nan)
+        if not np.isfinite(lats).all():
+            lats = np.where(np.isfinite(lats), lats, np.nan)
         if same:
             xx, yy = lons, lats
         if alt != 0.0:
@@ -703,7 +705,7 @@ class BodyXY:
         else:
             xi, yi = xi / 2.0, yi / 2.0
         lo, la = L.proj_inverse(kind, a, b, lon0, lat0, self._bc.lon_sign, L.to_device(xi), L.to_device(yi))
-        return lo.cpu().numpy(), la.cpu().numpy(), xx, yy
+        return L.to_host(lo), L.to_host(la), xx, yy
 
     # ---- backplane registry (body_xy.py:2512-2584) -------------------------------------
     @staticmethod
@@ -796,7 +798,7 @@ class BodyXY:
             # get_backplane_img('EMISSION') must not pay for the 26-plane stack)
             have, planes = self.get_backplanes_img_device(1 << pid, alt)
             slot = L.popcount(have & ((1 << pid) - 1))
-            self._cache[key] = _readonly(planes[slot].cpu().numpy())
+            self._cache[key] = _readonly(L.to_host(planes[slot]))
         return self._cache[key]
 
     def get_backplane_img(self, name: str, *, alt: float = 0.0) -> np.ndarray:
@@ -804,6 +806,12 @@ class BodyXY:
         alt = self._check_alt(alt)
         bp = self.get_backplane_or_keyerror(name)
         with _AltitudeScope(self, alt):
+            if self._is_builtin_backplane(bp.name, mapped=False):
+                # the cache is the device-resident plane stack: ONE copy, device -> the (pinned) array the
+                # caller gets, instead of device -> cached host array -> np.array(copy=True)
+                pid = L.PLANE_ID[bp.name]
+                have, planes = self.get_backplanes_img_device(1 << pid, self._alt_adjustment)
+                return L.to_host(planes[L.popcount(have & ((1 << pid) - 1))])
             return np.array(bp.get_img(), copy=True)
 
     def get_backplane_imgs(self, names, *, alt: float = 0.0, out=None) -> dict[str, np.ndarray]:
@@ -826,7 +834,9 @@ class BodyXY:
         planes = L.backplanes_img_host(self._frame_host(alt), self._nx, self._ny, mask)
         order = sorted(set(std), key=lambda n: L.PLANE_ID[n])
         if out is None:
-            host = planes.cpu()
+            host = L.empty_host(planes.shape)
+            host.copy_(planes, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         else:
             host = out[: len(order)]
             host.copy_(planes, non_blocking=True)
@@ -845,16 +855,21 @@ class BodyXY:
             raise TypeError(f'unexpected map keyword arguments {sorted(unknown)}')
         return tuple(sorted((k, _freeze(v)) for k, v in map_kwargs.items()))
 
-    def _get_lonlat_map(self, **map_kwargs) -> np.ndarray:
-        """(n0, n1, 2) lon % 360, lat (body_xy.py:3293-3300); stable cache."""
-        key = ('lonlat_map', self._map_key(map_kwargs))
+    def _get_lonlat_planes(self, **map_kwargs) -> tuple[np.ndarray, np.ndarray]:
+        """lon % 360 and lat of every map cell (body_xy.py:3293-3300) as two contiguous planes - the layout
+        the kernels take; stable cache."""
+        key = ('lonlat_planes', self._map_key(map_kwargs))
         if key not in self._stable_cache:
             lons, lats, *_ = self.generate_map_coordinates(**map_kwargs)
-            lons = lons % 360
-            m = np.stack([lons, lats], axis=-1)
-            m[~np.isfinite(m)] = np.nan
-            self._stable_cache[key] = _readonly(m)
+            if lons.size and not (np.nanmin(lons) >= 0.0 and np.nanmax(lons) < 360.0):
+                lons = lons % 360       # already in [0, 360) for the built-in grids: skip the pass
+            self._stable_cache[key] = (_readonly(np.ascontiguousarray(lons)), _readonly(np.ascontiguousarray(lats)))
         return self._stable_cache[key]
+
+    def _get_lonlat_map(self, **map_kwargs) -> np.ndarray:
+        """(n0, n1, 2) lon % 360, lat, the reference's layout (body_xy.py:3293-3300)."""
+        lons, lats = self._get_lonlat_planes(**map_kwargs)
+        return _readonly(np.stack([lons, lats], axis=-1))
 
     def get_backplanes_map_device(self, mask: int, **map_kwargs):
         """Requested map backplanes as a device tensor (k, n0, n1).  Disc-independent
@@ -876,8 +891,8 @@ class BodyXY:
             entry = cache.get(key)
             if entry is None or (entry[0] & sub) != sub:
                 if lonlat is None:
-                    ll = self._get_lonlat_map(**map_kwargs)
-                    lonlat = (L.to_device(ll[:, :, 0]), L.to_device(ll[:, :, 1]))
+                    lons, lats = self._get_lonlat_planes(**map_kwargs)
+                    lonlat = (L.to_device(lons), L.to_device(lats))
                 want = sub | (entry[0] if entry else 0)
                 if tag == 'map_planes_dev':
                     want = L.ALL_PLANES & ~((1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]))
@@ -900,12 +915,17 @@ class BodyXY:
             tag = 'xy_map_dev' if is_xy else 'map_planes_dev'
             have, planes = self.get_backplanes_map_device(1 << pid, **map_kwargs)[tag]
             slot = L.popcount(have & ((1 << pid) - 1))
-            cache[key] = _readonly(planes[slot].cpu().numpy())
+            cache[key] = _readonly(L.to_host(planes[slot]))
         return cache[key]
 
     def get_backplane_map(self, name: str, **map_kwargs) -> np.ndarray:
         """Copy of a backplane map (body_xy.py:2632-2663)."""
         bp = self.get_backplane_or_keyerror(name)
+        if self._is_builtin_backplane(bp.name, mapped=True):
+            pid = L.PLANE_ID[bp.name]
+            tag = 'xy_map_dev' if pid in _XY_PLANES else 'map_planes_dev'
+            have, planes = self.get_backplanes_map_device(1 << pid, **map_kwargs)[tag]
+            return L.to_host(planes[L.popcount(have & ((1 << pid) - 1))])
         return np.array(bp.get_map(**map_kwargs), copy=True)
 
     # ---- image -> map resampling (body_xy.py:1414-1631) ---------------------------------
@@ -920,7 +940,7 @@ class BodyXY:
                                   smooth_oversample_by=smooth_oversample_by,
                                   smooth_max_oversampled_img_size=smooth_max_oversampled_img_size,
                                   **map_kwargs)
-        res = out.cpu().numpy()
+        res = L.to_host(out)
         return res[0] if np.ndim(img) == 2 else res
 
     def map_img_device(self, img, *, interpolation='linear', spline_smoothing: float = 0,
@@ -928,6 +948,19 @@ class BodyXY:
                        smooth_oversample_by: int = 5, smooth_max_oversampled_img_size: int = 10_000,
                        **map_kwargs):
         """Same as :func:`map_img` but takes/returns device tensors shaped (n, ...)."""
+        src = self._map_source(img, interpolation=interpolation, spline_smoothing=spline_smoothing,
+                               propagate_nan=propagate_nan, warn_nan=warn_nan,
+                               smooth_oversample_by=smooth_oversample_by,
+                               smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs)
+        return src.gather(0, src.n_planes, out=out)
+
+    def _map_source(self, img, *, interpolation='linear', spline_smoothing: float = 0,
+                    propagate_nan: bool = True, warn_nan: bool = False, smooth_oversample_by: int = 5,
+                    smooth_max_oversampled_img_size: int = 10_000, **map_kwargs) -> '_MapSource':
+        """Everything map_img needs ONCE per cube (body_xy.py:1571-1631): the cube on the device, the x / y
+        maps of the requested projection and, for the spline modes, the repaired / prefiltered coefficient
+        planes.  The result maps any range of planes on demand (one gather launch per call), which is how
+        Observation walks a cube whose mapped output is larger than device or host memory."""
         torch = L._torch()
         mode = _interpolation_mode(interpolation, spline_smoothing)
         if isinstance(img, torch.Tensor):
@@ -944,17 +977,35 @@ class BodyXY:
                 f"the body's image size (ny={self._ny}, nx={self._nx})")
         have, xy = self.get_backplanes_map_device(
             (1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]), **map_kwargs)['xy_map_dev']
-        xmap, ymap = xy[0], xy[1]
-        if mode == L.INTERP_NEAREST:
-            return L.gather(cube, xmap, ymap, mode, out=out)
-        if mode == INTERP_SMOOTH:   # body_xy.py:1616-1629
-            return L.map_smooth(cube, xmap, ymap, propagate_nan=propagate_nan,
-                                oversample_by=smooth_oversample_by,
-                                max_oversampled_img_size=smooth_max_oversampled_img_size, out=out)
-        if warn_nan and bool(torch.isfinite(cube).logical_not().any()):
-            print('Warning, image contains NaN values which will be corrected')
-        spline = L.spline_prepare(cube, mode)
-        return L.gather(spline, xmap, ymap, mode, propagate_nan=propagate_nan, out=out)
+        spline = None
+        if mode not in (L.INTERP_NEAREST, INTERP_SMOOTH):
+            if warn_nan and bool(torch.isfinite(cube).logical_not().any()):
+                print('Warning, image contains NaN values which will be corrected')
+            spline = L.spline_prepare(cube, mode)
+        return _MapSource(mode, cube, spline, xy[0], xy[1], propagate_nan, smooth_oversample_by,
+                          smooth_max_oversampled_img_size)
+
+
+class _MapSource:
+    """A cube prepared for mapping onto one x / y map; ``gather(begin, count)`` maps planes
+    [begin, begin + count) (``begin`` a multiple of 4 for the spline modes)."""
+
+    def __init__(self, mode, cube, spline, xmap, ymap, propagate_nan, smooth_oversample_by, smooth_max_size):
+        self.mode, self.cube, self.spline, self.xmap, self.ymap = mode, cube, spline, xmap, ymap
+        self.propagate_nan = propagate_nan
+        self.smooth_oversample_by, self.smooth_max_size = smooth_oversample_by, smooth_max_size
+        self.n_planes = int(cube.shape[0])
+        self.map_shape = tuple(xmap.shape)
+
+    def gather(self, begin: int, count: int, out=None):
+        if self.mode == L.INTERP_NEAREST:
+            return L.gather(self.cube, self.xmap, self.ymap, self.mode, plane_begin=begin, plane_count=count, out=out)
+        if self.mode == INTERP_SMOOTH:   # body_xy.py:1616-1629: planes are independent
+            return L.map_smooth(self.cube[begin:begin + count], self.xmap, self.ymap, propagate_nan=self.propagate_nan,
+                                oversample_by=self.smooth_oversample_by,
+                                max_oversampled_img_size=self.smooth_max_size, out=out)
+        return L.gather(self.spline, self.xmap, self.ymap, self.mode, plane_begin=begin, plane_count=count,
+                        propagate_nan=self.propagate_nan, out=out)
 
 
 INTERP_SMOOTH = -1   # host-side marker: PCHIP oversampling + linear (its own entry points)

@@ -232,16 +232,29 @@ __global__ void __launch_bounds__(kBlock, 4) transform_kernel(const PMFrame *__r
     }
 }
 
-// FP64 FMA throughput probe (roofline denominator for the compute-bound kernels)
-__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
-    double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
-    const double m = 0.999999999, c = 1e-12;
-    for (int i = 0; i < iters; i++) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+// FP64 FMA throughput probes (roofline denominators for the compute-bound kernels): 8 independent
+// DFMA chains per thread on a full grid.
+//   kind 0: a = fma(a, m, c) with m, c kernel constants - ONE register operand per DFMA.  This is the
+//           rate behind the datasheet number (64 FMA / clk / SM).
+//   kind 1: a = fma(a, b, d) with three DISTINCT register operands per DFMA - what vector geometry
+//           (dot / cross / axpy of per-pixel vectors) issues.  The register file delivers the six
+//           32-bit source registers of such an instruction in three cycles, not two, so the pipe
+//           sustains 2/3 of the kind-0 rate (tools/microbench/fp64_operands.cu, profiles/r2_summary.md).
+template <int kKind>
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, const double *in, int iters, double m, double c) {
+    double a[8], b[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = threadIdx.x * 1e-9 + i;
+        b[i] = kKind ? in[(threadIdx.x + 2 * i + 1) & 63] : m;
+        d[i] = kKind ? in[(threadIdx.x + 3 * i + 2) & 63] * 1e-12 : c;
     }
-    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = kKind ? fma(a[i], b[i], d[i]) : fma(a[i], m, c);
+    }
+    double s = a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7];
     if (s == 123.456) out[0] = s;
 }
 
@@ -383,8 +396,12 @@ cudaError_t launch_transform(const PMFrame *frame, int src, int dst, const doubl
     count_launches(1);
     return cudaGetLastError();
 }
-cudaError_t launch_fp64_probe(double *scratch, int iters, int sm_count, cudaStream_t st) {
-    fp64_probe_kernel<<<sm_count * 8, 256, 0, st>>>(scratch, iters);
+cudaError_t launch_fp64_probe(double *scratch, int kind, int iters, int sm_count, cudaStream_t st) {
+    // scratch: >= 65 doubles; [1 .. 64] hold values near 1 (filled by the caller), [0] is the sink
+    if (kind == 0)
+        fp64_probe_kernel<0><<<sm_count * 8, 256, 0, st>>>(scratch, scratch + 1, iters, 0.999999999, 1e-12);
+    else
+        fp64_probe_kernel<1><<<sm_count * 8, 256, 0, st>>>(scratch, scratch + 1, iters, 0.999999999, 1e-12);
     count_launches(1);
     return cudaGetLastError();
 }

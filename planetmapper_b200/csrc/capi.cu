@@ -270,19 +270,22 @@ int pm_math_probe(int kind, const double *a, const double *b, int64_t n, double 
     return check(launch_math_probe(kind, a, b, n, out, (cudaStream_t)stream));
 }
 
-int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host) {
-    if (iters <= 0 || !ms_host || !flops_host) return PM_ERR_BAD_ARG;
+int pm_fp64_probe(int kind, int iters, double *ms_host, double *flops_host) {
+    if (iters <= 0 || !ms_host || !flops_host || kind < 0 || kind > 1) return PM_ERR_BAD_ARG;
     int sms = sm_count();
     if (sms <= 0) return PM_ERR_NO_DEVICE;
     double *scratch = nullptr;
-    if (cudaMalloc(&scratch, 64) != cudaSuccess) return PM_ERR_CUDA;
+    if (cudaMalloc(&scratch, 65 * sizeof(double)) != cudaSuccess) return PM_ERR_CUDA;
+    double init[65];
+    for (int i = 0; i < 65; i++) init[i] = 0.999 + 1e-5 * i;
+    cudaMemcpy(scratch, init, sizeof(init), cudaMemcpyHostToDevice);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    launch_fp64_probe(scratch, iters, sms, 0);  // warm-up
+    launch_fp64_probe(scratch, kind, iters, sms, 0);  // warm-up
     cudaDeviceSynchronize();
     cudaEventRecord(e0, 0);
-    cudaError_t err = launch_fp64_probe(scratch, iters, sms, 0);
+    cudaError_t err = launch_fp64_probe(scratch, kind, iters, sms, 0);
     cudaEventRecord(e1, 0);
     cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -294,6 +297,9 @@ int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host) {
     // 8 independent FMA chains per thread, 2 flop per FMA
     *flops_host = 2.0 * 8.0 * (double)iters * 256.0 * (double)sms * 8.0;
     return check(err);
+}
+int pm_fp64_peak_probe(int iters, double *ms_host, double *flops_host) {
+    return pm_fp64_probe(0, iters, ms_host, flops_host);
 }
 
 }  // extern "C"

@@ -39,7 +39,7 @@ cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const doub
 cudaError_t launch_transform(const PMFrame *frame, int src, int dst, const double *a, const double *b, int64_t n,
                              double alt, uint32_t flags, const double *aux13_host, double *out_a, double *out_b,
                              unsigned long long *n_missed, cudaStream_t st);
-cudaError_t launch_fp64_probe(double *scratch, int iters, int sm_count, cudaStream_t st);
+cudaError_t launch_fp64_probe(double *scratch, int kind, int iters, int sm_count, cudaStream_t st);
 cudaError_t launch_math_probe(int kind, const double *a, const double *b, int64_t n, double *out,
                               cudaStream_t st);
 

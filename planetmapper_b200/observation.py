@@ -75,14 +75,90 @@ class Observation(BodyXY):
         key = ('mapped_data', repr(interpolation), spline_smoothing, propagate_nan, smooth_oversample_by,
                smooth_max_oversampled_img_size, self._map_key(map_kwargs), self._alt_adjustment)
         if key not in self._cache:
-            out = self.map_img_device(self._get_data_device(), interpolation=interpolation,
-                                      spline_smoothing=spline_smoothing,
-                                      propagate_nan=propagate_nan, warn_nan=warn_nan,
-                                      smooth_oversample_by=smooth_oversample_by,
-                                      smooth_max_oversampled_img_size=smooth_max_oversampled_img_size,
-                                      **map_kwargs)
-            self._cache[key] = out.cpu().numpy()
+            # the reference's loop over wavelength planes (observation.py:892-905), in chunks of as many planes
+            # as fit on the device next to their own double buffer
+            src = self._map_source(self._get_data_device(), interpolation=interpolation,
+                                   spline_smoothing=spline_smoothing, propagate_nan=propagate_nan,
+                                   warn_nan=warn_nan, smooth_oversample_by=smooth_oversample_by,
+                                   smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs)
+            host = L.empty_host((src.n_planes,) + src.map_shape)
+            for first, count, _ in self._stream_mapped_chunks(src, None, into=host):
+                pass
+            self._cache[key] = host.numpy()
         return self._cache[key]
+
+    @staticmethod
+    def _planes_per_chunk(src, planes_per_chunk=None, budget_bytes=None) -> int:
+        """Planes per gather launch: the caller's choice, else what fits twice (double buffer) into 40 % of
+        the free device memory; a multiple of 4 (the spline operands are stored as plane quads)."""
+        torch = L._torch()
+        n_cells = 1
+        for d in src.map_shape:
+            n_cells *= int(d)
+        if planes_per_chunk is None:
+            if budget_bytes is None:
+                free, _total = torch.cuda.mem_get_info()
+                budget_bytes = int(0.4 * free)
+            planes_per_chunk = budget_bytes // max(1, 2 * 8 * n_cells)
+        planes_per_chunk = int(min(max(planes_per_chunk, 4), max(src.n_planes, 4)))
+        return max(4, planes_per_chunk // 4 * 4)
+
+    def _stream_mapped_chunks(self, src, planes_per_chunk, into=None, host_buffers=None):
+        """Generator over (first_plane, count, host_view): maps the cube chunk by chunk and moves every chunk
+        to the host while the NEXT chunk is being gathered (two device buffers, a copy stream, events).
+        ``into``: a CPU tensor (n_planes, ...) receiving the whole result (host_view is then its slice);
+        otherwise two pinned staging buffers are cycled and host_view is only valid until the next step."""
+        torch = L._torch()
+        n = src.n_planes
+        if n == 0:
+            return
+        per = self._planes_per_chunk(src, planes_per_chunk)
+        n_buf = 2 if n > per else 1
+        if into is None and host_buffers is None:
+            # the library's cached pinned pair (pinning 1 GB costs ~1 s: never inside the stream)
+            with L.staging_buffers((min(per, n),) + src.map_shape, n_buf) as bufs:
+                yield from self._stream_mapped_chunks(src, per, host_buffers=bufs)
+            return
+        dev = [torch.empty((min(per, n),) + src.map_shape, dtype=torch.float64, device='cuda') for _ in range(n_buf)]
+        compute = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream()
+        gathered = [torch.cuda.Event() for _ in dev]
+        copied = [torch.cuda.Event() for _ in dev]
+        pending = None   # (first, count, host_view, event) of the chunk whose copy is in flight
+        for k, first in enumerate(range(0, n, per)):
+            count = min(per, n - first)
+            b = k % len(dev)
+            if k >= len(dev):
+                compute.wait_event(copied[b])       # the buffer's previous contents have left the device
+            src.gather(first, count, out=dev[b][:count])
+            gathered[b].record(compute)
+            view = into[first:first + count] if into is not None else host_buffers[b][:count]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(gathered[b])
+                view.copy_(dev[b][:count], non_blocking=True)
+                copied[b].record(copy_stream)
+            if pending is not None:
+                pending[3].synchronize()
+                yield pending[:3]
+            pending = (first, count, view, copied[b])
+        pending[3].synchronize()
+        yield pending[:3]
+
+    def iter_mapped_data(self, interpolation='linear', *, planes_per_chunk: int | None = None,
+                         spline_smoothing: float = 0, propagate_nan: bool = True, warn_nan: bool = False,
+                         smooth_oversample_by: int = 5, smooth_max_oversampled_img_size: int = 10_000,
+                         **map_kwargs):
+        """``get_mapped_data`` for cubes whose mapped output does not fit in host memory (BASELINE config C4:
+        3000 x 1800 x 3600 float64 = 155 GB): yields ``(first_plane, mapped)`` with ``mapped`` a float64 array
+        (count,) + map shape holding planes first .. first + count.  The array is a view of a pinned staging
+        buffer that is REUSED two iterations later: consume or copy it before advancing twice.  Chunk k + 1 is
+        gathered while chunk k crosses PCIe."""
+        src = self._map_source(self._get_data_device(), interpolation=interpolation,
+                               spline_smoothing=spline_smoothing, propagate_nan=propagate_nan, warn_nan=warn_nan,
+                               smooth_oversample_by=smooth_oversample_by,
+                               smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs)
+        for first, count, view in self._stream_mapped_chunks(src, planes_per_chunk):
+            yield first, view.numpy()
 
     def get_mapped_data_device(self, interpolation='linear', *, propagate_nan: bool = True,
                                planes: slice | None = None, out=None, **map_kwargs):

@@ -67,13 +67,21 @@ def _worker_main() -> None:
         except EOFError:
             return
         try:
-            kernel_path, target, observer, ets, disc = msg
+            kernel_path, target, observer, ets, disc, kepler = msg
             if provider is None or kernel_path != provider_path:   # the cached provider is keyed on its path
                 pm.set_kernel_path(kernel_path)
                 provider, provider_path = pm.get_default_provider(), kernel_path
-            _send(out, ('ok', _block(provider, target, observer, ets, disc)))
+            _send(out, ('ok', _block(_with_kepler(provider) if kepler else provider, target, observer, ets, disc)))
         except Exception as exc:  # reported to the parent, which raises
             _send(out, ('error', f'{type(exc).__name__}: {exc}'))
+
+
+def _with_kepler(provider):
+    """Analytic orbits for the bodies the kernels do not cover (minispice/kepler.py: BASELINE config C5 names
+    Europa, which has no SPK segment in the bundled kernels)."""
+    from .minispice.kepler import KeplerOrbitProvider
+
+    return provider if isinstance(provider, KeplerOrbitProvider) else KeplerOrbitProvider(provider)
 
 
 _WORKERS: list[subprocess.Popen] = []
@@ -117,13 +125,15 @@ def default_workers() -> int:
 
 def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: float, y0: float,
                         r0: float, rotation_radians: float = 0.0, alt: float = 0.0,
-                        workers: int | None = None, provider=None) -> np.ndarray:
+                        workers: int | None = None, provider=None, kepler: bool = False) -> np.ndarray:
     """PMFrame constants, shape (len(ets), 92), for ``target`` seen from ``observer`` at the
     ephemeris times ``ets`` with one set of disc parameters.
 
     ``workers`` host processes (default: :func:`default_workers`) each take one contiguous
     block of epochs; ``workers <= 1``, a short series, or an explicit in-process ``provider``
-    runs serially in this process.  The result does not depend on ``workers``.
+    runs serially in this process.  The result does not depend on ``workers``.  ``kepler=True`` answers
+    the ephemeris of bodies without SPK coverage from the analytic orbits of ``minispice/kepler.py``
+    (synthetic positions: Europa of BASELINE config C5).
     """
     import planetmapper_b200 as pm
 
@@ -134,12 +144,13 @@ def build_series_frames(target, ets, observer='EARTH', *, nx: int, ny: int, x0: 
     if pm.provider_is_custom():   # an in-process provider cannot be rebuilt inside a worker
         workers = 1
     if provider is not None or workers <= 1:
-        return _block(provider if provider is not None else pm.get_default_provider(), target, observer, ets, disc)
+        prov = provider if provider is not None else pm.get_default_provider()
+        return _block(_with_kepler(prov) if kepler else prov, target, observer, ets, disc)
     procs = _workers(workers)
     try:
         for w, proc in enumerate(procs):
             block = ets[slice(*shard_range(len(ets), w, workers))]
-            _send(proc.stdin, (pm._KERNEL_PATH, str(target), str(observer), block, disc))
+            _send(proc.stdin, (pm._KERNEL_PATH, str(target), str(observer), block, disc, bool(kepler)))
         replies = [_recv(proc.stdout) for proc in procs]   # every reply is drained before any error is raised
     except BaseException:
         shutdown_pool()   # a dead or half-read worker must not serve the next call

@@ -419,3 +419,51 @@ def test_unsupported_options_raise(bc_hst):
     with pytest.raises(pm.ProjStringError):
         # proj strings outside the kernels' subset fail loudly (there is no PROJ fallback)
         b.generate_map_coordinates('+proj=moll +R=1 +axis=wnu +type=crs', projection_x_coords=np.arange(3.0))
+
+
+@pytest.mark.parametrize('interp', ['nearest', 'linear', 'cubic', 'smooth', (1, 3)])
+def test_mapped_data_chunked_streaming_equals_one_launch(obs, interp):
+    """Observation.get_mapped_data walks the cube in wavelength chunks (the reference's plane loop,
+    observation.py:892-905) when the mapped output is larger than device memory: forced here with 4-plane
+    chunks on the 10-plane golden cube.  The streamed iterator (double-buffered pinned staging) and the
+    chunked full result equal the single-launch result bit for bit."""
+    want = obs.map_img(obs.data, interpolation=interp, degree_interval=4)     # one gather launch
+    got = np.full_like(want, -7.0)
+    seen = []
+    for first, chunk in obs.iter_mapped_data(interp, planes_per_chunk=4, degree_interval=4):
+        got[first:first + chunk.shape[0]] = chunk        # consumed before the buffer is reused
+        seen.append((first, chunk.shape[0]))
+    assert seen == [(0, 4), (4, 4), (8, 2)]
+    assert np.array_equal(got, want, equal_nan=True)
+    obs._planes_per_chunk = staticmethod(lambda src, planes_per_chunk=None, budget_bytes=None: 4)
+    whole = obs.get_mapped_data(interp, degree_interval=4)
+    assert whole.shape == want.shape and np.array_equal(whole, want, equal_nan=True)
+    whole[0, 0, 0] = 123.0      # a copy: the cached array is untouched
+    assert not np.array_equal(obs.get_mapped_data(interp, degree_interval=4), whole, equal_nan=True)
+
+
+def test_backplane_getters_return_owned_arrays(body):
+    """get_backplane_img / get_backplane_map hand out NEW writable float64 arrays (copies, body_xy.py:2629,
+    :2663) filled by one device -> host copy; the named getters return read-only cached views."""
+    a = body.get_backplane_img('EMISSION')
+    b = body.get_backplane_img('EMISSION')
+    assert a is not b and a.flags.writeable and a.dtype == np.float64 and a.flags.c_contiguous
+    a[:] = 0.0
+    assert np.array_equal(b, body.get_backplane_img('EMISSION'), equal_nan=True)
+    view = body.get_emission_angle_img()
+    assert not view.flags.writeable and np.array_equal(view, b, equal_nan=True)
+    assert view is body.get_emission_angle_img()
+    m = body.get_backplane_map('EMISSION', degree_interval=10)
+    m2 = body.get_backplane_map('EMISSION', degree_interval=10)
+    assert m is not m2 and m.flags.writeable and np.array_equal(m, m2, equal_nan=True)
+    # single-plane requests cost one plane, a second plane escalates to its group, never the 26-plane stack
+    fresh = type(body)(constants=body._bc, nx=15, ny=10)
+    fresh.get_backplane_img('EMISSION')
+    assert fresh._cache[('img_planes_dev', 0.0)][0] == 1 << 14
+    fresh.get_backplane_img('LON-GRAPHIC')
+    assert bin(fresh._cache[('img_planes_dev', 0.0)][0]).count('1') == 12
+    fresh.get_backplane_img('RA')
+    assert bin(fresh._cache[('img_planes_dev', 0.0)][0]).count('1') == 26
+    # a registered custom backplane still goes through its own getter
+    body.register_backplane('custom', 'a custom plane', lambda: np.ones((10, 15)), lambda **kw: np.ones((3, 3)))
+    assert np.array_equal(body.get_backplane_img('custom'), np.ones((10, 15)))
