@@ -310,7 +310,11 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                             const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int n_planes_padded,
                             int plane_begin, int plane_count, const double *__restrict__ xmap,
                             const double *__restrict__ ymap, int64_t n_cells, int64_t row_len, uint32_t flags,
-                            double *__restrict__ out, int planes_per_group) {
+                            double *__restrict__ out, int planes_per_group, int lead) {
+    // plane_begin is a multiple of 8 here: a plane tile (8 planes) then never straddles a 32-plane NaN word,
+    // which keeps refresh_ok's warp shuffles uniform.  A caller's range starting on an odd quad is launched
+    // from the quad before it with lead = 4: the first `lead` planes are computed but not stored, and `out`
+    // already points `lead` planes before the caller's buffer.
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     // Warp -> cells.  With a known map row length (row_len < n_cells) a warp owns a block of
@@ -391,9 +395,10 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         const int nc = ti == 0 ? ncols[0] : (ti == 1 ? ncols[1] : (ti == 2 ? ncols[2] : ncols[3]));
         const int64_t cell = base0 + ti * tile_step + 2 * pr;
         const bool aligned = ((n_cells & 1) == 0) && (!grid2d || (row_len & 1) == 0);
-        double *d = out + (int64_t)(l0 + (lane >> 4)) * n_cells + cell;
+        const int skip = l0 < lead ? lead - l0 : 0;  // (even) planes of the first tile that belong to the quad before
+        double *d = out + (int64_t)(l0 + skip + (lane >> 4)) * n_cells + cell;
         const int64_t step2 = 2 * n_cells;
-        const int n_it = (l1 - l0 - (lane >> 4) + 1) / 2;  // planes l0 + (lane >> 4), + 2, ... < l1
+        const int n_it = (l1 - l0 - skip - (lane >> 4) + 1) / 2;  // planes l0 + skip + (lane >> 4), + 2, ... < l1
         if (aligned && 2 * pr + 1 < nc) {
 #pragma unroll 4
             for (int it = 0; it < n_it; it++, d += step2)
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                 }
             }
             // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
-            if (l + g < l1) {
+            if (l + g < l1 && l + g >= lead) {
                 const int sh = (gl + g) & 31;
                 auto store_tiles = [&](const int64_t step, const bool all_pairs) {
 #pragma unroll
@@ -638,7 +643,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
             }
         }
         // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
-        if (l + g < l1) {
+        if (l + g < l1 && l + g >= lead) {
             const int sh = (gl + g) & 31;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -758,7 +763,11 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
         // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is heavier here
         // than in the scalar kernel
         static const int mma_ppg = tune_int("PM_MMA_PPG", 512);
-        const int g2 = plane_count < mma_ppg ? (plane_count + 7) / 8 * 8 : mma_ppg;
+        // the kernel wants plane tiles aligned to 8 planes (see its header): a range starting on an odd quad is
+        // launched from the quad before it, whose four planes are computed and dropped
+        const int lead = plane_begin & 7;   // 0 or 4 (plane_begin is a multiple of 4)
+        const int pb = plane_begin - lead, pc = plane_count + lead;
+        const int g2 = pc < mma_ppg ? (pc + 7) / 8 * 8 : mma_ppg;
         // map row length known and regular -> 4 x 8 cell blocks per warp, else 32 consecutive cells
         // (measured on C4: for long rows the 1-D order is ~4 % faster - longer contiguous store
         // runs - so the blocks are only used when a warp's 32 cells would wrap across map rows)
@@ -767,10 +776,11 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
         const int64_t row_len = rows_ok ? cells_per_row : n_cells;
         const int64_t n_warps = rows_ok ? ((n_cells / row_len + 3) / 4) * ((row_len + 7) / 8) : (n_cells + 31) / 32;
         dim3 grid2((unsigned)((n_warps + kCubicBlock / 32 - 1) / (kCubicBlock / 32)),
-                   (unsigned)((plane_count + g2 - 1) / g2));
+                   (unsigned)((pc + g2 - 1) / g2));
         gather_cubic_mma_kernel<<<grid2, kCubicBlock, 0, st>>>(src, nanbits, plane_bits, n_words, ny, nx,
-                                                                (n_planes + 3) / 4 * 4, plane_begin, plane_count, xmap,
-                                                                ymap, n_cells, row_len, flags, out, g2);
+                                                                (n_planes + 3) / 4 * 4, pb, pc, xmap, ymap, n_cells,
+                                                                row_len, flags, out - (int64_t)lead * n_cells, g2,
+                                                                lead);
     } else {
         switch (ky * 4 + kx) {
             case 1 * 4 + 1: PM_SPLINE(2, 2, 5); break;

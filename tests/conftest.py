@@ -15,6 +15,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line('markers', 'timeout: per-test time limit (pytest-timeout; a hung kernel must not hang the run)')
 
 
 @pytest.fixture(scope='session')

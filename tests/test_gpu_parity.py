@@ -586,3 +586,34 @@ def test_c4_full_grid_gather_vs_scipy(L, oracle, bc_hst):
                 assert rel <= 1e-10, f'{name} plane {l}: rel {rel:.3e}'
         report[name] = {'max_rel_diff_vs_scipy': worst, 'bar': 0.0 if mode == L.INTERP_NEAREST else 1e-10}
     write_parity_report('C4', report)
+
+
+@pytest.mark.timeout(300, method='thread')
+def test_dense_cubic_gather_any_quad_aligned_plane_range(L, bc_hst):
+    """The dense-map cubic kernel works on tiles of 8 planes; a range may start on any plane quad (a cube
+    sharded over ranks: 3000 planes / 2 = 1500 = 8 * 187 + 4).  Such a range used to hang the kernel (a plane
+    tile straddling a 32-plane NaN word made a warp shuffle divergent).  Every quad-aligned sub-range, including
+    ones that start 4 planes before a word boundary, equals the same planes of the full launch bit for bit."""
+    import torch
+
+    sz = 64
+    fr = _img_case(bc_hst, sz, sz, 31.5, 31.5, 28.0, 0.0)
+    lo, la = _grid(1.0)     # 64 800 cells >= 8 * 64 * 64: the DMMA kernel
+    xy = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la), L.mask_from_names(['PIXEL-X', 'PIXEL-Y']))
+    rng = np.random.default_rng(5)
+    cube = rng.normal(1.0, 0.1, (80, sz, sz))
+    cube[rng.random(cube.shape) < 0.01] = np.nan
+    cube[29] = np.nan
+    spline = L.spline_prepare(L.to_device(cube), L.INTERP_CUBIC)
+    full = L.gather(spline, xy[0], xy[1], L.INTERP_CUBIC)
+    torch.cuda.synchronize()
+    for begin, count in ((4, 3), (4, 8), (12, 13), (28, 8), (28, 52), (60, 20), (36, 1), (8, 72), (76, 4)):
+        sub = L.gather(spline, xy[0], xy[1], L.INTERP_CUBIC, plane_begin=begin, plane_count=count)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.nan_to_num(sub, nan=-7.0), torch.nan_to_num(full[begin:begin + count], nan=-7.0)), (begin, count)
+    # guard cells around the output are untouched (the kernel is handed a pointer 4 planes before the buffer)
+    buf = torch.full((14,) + tuple(lo.shape), 5.0, dtype=torch.float64, device='cuda')
+    L.gather(spline, xy[0], xy[1], L.INTERP_CUBIC, plane_begin=20, plane_count=6, out=buf[4:10])
+    torch.cuda.synchronize()
+    assert bool((buf[:4] == 5.0).all()) and bool((buf[10:] == 5.0).all())
+    assert torch.equal(torch.nan_to_num(buf[4:10], nan=-7.0), torch.nan_to_num(full[20:26], nan=-7.0))
