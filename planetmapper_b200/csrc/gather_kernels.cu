@@ -291,13 +291,25 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
 // every LDG of the three rotating register sets wrote SB5); waiting for the tile about to be
 // multiplied therefore also waited for the prefetches just issued.
 constexpr int kCubicBlock = 128;   // threads per CTA: 4 CTAs / SM at <= 128 registers, fine-grained tail
-constexpr int kCubicStages = 2;    // stage buffers per warp (power of two): one tile in flight while one is multiplied;
+#ifndef PM_CUBIC_STAGES
+#define PM_CUBIC_STAGES 2
+#endif
+constexpr int kCubicStages = PM_CUBIC_STAGES;    // stage buffers per warp (power of two): one tile in flight while one is multiplied;
                                    // 4 stages measured 2 % slower - the 24 KB they take away from L1 matter more
 constexpr int kCubicFoot = 3;      // distinct 4 x 4 footprints per warp in the pipelined path (48 KB of stages)
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+#ifdef PM_CUBIC_CG
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");   // L2 only
+#else
+    // through L1: ~47 warps per image pixel re-read the same coefficient quads
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -499,53 +511,70 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
 
     // ---- pipelined path: at most three distinct footprints in the warp
     if (simple) {
-        __shared__ double stage[kCubicStages][kCubicFoot][4][kCubicBlock];
+        // A footprint of one plane tile is 8 planes x 4 rows x 4 columns = 1 KB = 64 chunks of 16 bytes in the
+        // plane-quad layout ([quad][y][x][4 planes]: chunk c = ((q * 4 + y) * 4 + x) * 2 + half).  Lane L
+        // copies chunks L (quad 0) and L + 32 (quad 1) with two 16-byte cp.async - a quarter of a kilobyte per
+        // instruction and ONE address per footprint - and reads back the element of its own MMA row / column,
+        // which other lanes copied: __syncwarp() after the wait makes the copies visible inside the warp.
+        __shared__ __align__(16) double stage[kCubicStages][kCubicFoot][kCubicBlock / 32][128];
         const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
         const bool fast_store = full_tiles && pair_ok;
         const int n_it = (l1 - l0 + 7) / 8;
         const int nf = org2 != 0xffffffffu ? 3 : (has1 ? 2 : 1);
-        // Lanes whose plane lies past the padded coefficient array (second quad of the last plane tile)
-        // read the first quad instead and stop advancing: their rows of D are never stored, and the
-        // rows of the product are independent.
-        const int planes_ahead = n_planes_padded - (plane_begin + l0 + g);  // > 0: the lane's first plane exists
-        const double *p0 = pbase + (int64_t)org0 * 4 - (planes_ahead > 0 ? 0 : (int64_t)(g >> 2) * quad_stride);
+        const int warp = threadIdx.x >> 5;
+        // source of this lane's chunk inside a footprint whose top-left coefficient is at `base`:
+        // row (lane >> 3) & 3, column (lane >> 1) & 3, half lane & 1 of quad 0
+        const int64_t chunk_off = (int64_t)((lane >> 3) & 3) * row_stride + ((lane >> 1) & 3) * 4 + (lane & 1) * 2;
+        const double *q0 = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + (int64_t)org0 * 4 + chunk_off;
         // footprints 1 and 2 as element offsets from footprint 0 (they fit 32 bits: nx, ny < 16384)
         const int d1 = nf > 1 ? ((int)org1 - (int)org0) * 4 : 0, d2 = nf > 2 ? ((int)org2 - (int)org0) * 4 : 0;
         const int64_t tile_stride = 2 * quad_stride;
-        double *const my_stage = &stage[0][0][0][threadIdx.x];
-        constexpr int kRow = kCubicBlock, kFoot = 4 * kCubicBlock, kSlot = kCubicFoot * 4 * kCubicBlock;  // doubles
+        // quads of coefficients that exist from this group's first plane on (the last tile may have one)
+        const int quads_ahead = (n_planes_padded - (plane_begin + l0)) >> 2;
+        double *const my_chunk = &stage[0][0][warp][2 * lane];            // + 64 doubles: the quad-1 chunk
+        const double *const my_elem = &stage[0][0][warp][(g >> 2) * 64 + t * 4 + (g & 3)];   // + 16 j: row j
+        constexpr int kFoot = (kCubicBlock / 32) * 128, kSlot = kCubicFoot * kFoot;  // doubles
         int issued = 0;
         auto issue = [&]() {
             if (issued < n_it) {
-                double *dst = my_stage + (issued & (kCubicStages - 1)) * kSlot;
-#pragma unroll
-                for (int j = 0; j < 4; j++) cp_async8(dst + j * kRow, p0 + j * row_stride);
+                double *dst = my_chunk + (issued & (kCubicStages - 1)) * kSlot;
+                // the second quad of the last tile may lie past the array: copy the first one again (its rows of
+                // D are never stored, and the rows of the product are independent)
+                const int64_t second = 2 * issued + 1 < quads_ahead ? quad_stride : 0;
+                cp_async16(dst, q0);
+                cp_async16(dst + 64, q0 + second);
                 if (nf > 1) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) cp_async8(dst + kFoot + j * kRow, p0 + d1 + j * row_stride);
+                    cp_async16(dst + kFoot, q0 + d1);
+                    cp_async16(dst + kFoot + 64, q0 + d1 + second);
                 }
                 if (nf > 2) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) cp_async8(dst + 2 * kFoot + j * kRow, p0 + d2 + j * row_stride);
+                    cp_async16(dst + 2 * kFoot, q0 + d2);
+                    cp_async16(dst + 2 * kFoot + 64, q0 + d2 + second);
                 }
-                if (8 * (issued + 1) < planes_ahead) p0 += tile_stride;
+                if (2 * issued + 2 < quads_ahead) q0 += tile_stride;
             }
             issued++;
             cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
         };
 #pragma unroll
         for (int k = 0; k < kCubicStages - 1; k++) issue();
+        uint32_t clean = 0;   // (uniform) bit b: the 8 planes b*8.. of the current NaN word are good in every cell of the warp
         for (int it = 0; it < n_it; it++) {
             const int l = l0 + 8 * it;
-            const int gl = plane_begin + l;  // global plane of row 0 of this plane tile
+            const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (a multiple of 8)
             issue();
-            const int word = (gl + g) >> 5;
-            if (word != cur_word) {  // changes at most once per 32 planes (per lane: planes gl + g)
+            const int word = gl >> 5;        // the same for the 8 planes of the tile
+            if (word != cur_word) {          // uniform: changes once per 32 planes
                 cur_word = word;
                 refresh_ok(word);
+                uint32_t all = ok[0][0] & ok[0][1] & ok[1][0] & ok[1][1] & ok[2][0] & ok[2][1] & ok[3][0] & ok[3][1];
+                all = __reduce_and_sync(kFull, all);
+                clean = (((all & 0xffu) == 0xffu) ? 1u : 0u) | (((all & 0xff00u) == 0xff00u) ? 2u : 0u) |
+                        (((all & 0xff0000u) == 0xff0000u) ? 4u : 0u) | (((all >> 24) == 0xffu) ? 8u : 0u);
             }
-            cp_async_wait<kCubicStages - 1>();  // the group of plane tile `it` has landed
-            const double *src = my_stage + (it & (kCubicStages - 1)) * kSlot;
+            cp_async_wait<kCubicStages - 1>();  // this lane's chunks of plane tile `it` have landed ...
+            __syncwarp();                       // ... and so have the other lanes'
+            const double *src = my_elem + (it & (kCubicStages - 1)) * kSlot;
             double d[4][2];
 #pragma unroll
             for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
@@ -553,7 +582,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                 // every valid cell reads footprint 0 and invalid cells carry zero weights: no masks
                 double a[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) a[j] = src[j * kRow];
+                for (int j = 0; j < 4; j++) a[j] = src[16 * j];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
 #pragma unroll
@@ -565,7 +594,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                     {
                         double a[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) a[j] = src[f * kFoot + j * kRow];
+                        for (int j = 0; j < 4; j++) a[j] = src[f * kFoot + 16 * j];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (tiles & (1u << (4 * f + i))) {
@@ -580,11 +609,12 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
             // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
             if (l + g < l1 && l + g >= lead) {
                 const int sh = (gl + g) & 31;
-                auto store_tiles = [&](const int64_t step, const bool all_pairs) {
+                const bool tile_clean = (clean >> ((gl >> 3) & 3)) & 1u;   // uniform: no NaN in these 8 planes
+                auto store_tiles = [&](const int64_t step, const bool all_pairs, const bool select) {
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const double o0 = ((ok[i][0] >> sh) & 1u) ? d[i][0] : nan;
-                        const double o1 = ((ok[i][1] >> sh) & 1u) ? d[i][1] : nan;
+                        const double o0 = (!select || ((ok[i][0] >> sh) & 1u)) ? d[i][0] : nan;
+                        const double o1 = (!select || ((ok[i][1] >> sh) & 1u)) ? d[i][1] : nan;
                         double *dst = dst_row + i * step;
                         if (all_pairs || (pair_ok && 2 * t + 1 < ncols[i])) {
                             asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
@@ -595,13 +625,17 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                     }
                 };
                 // the usual case - full tiles of consecutive cells, aligned pairs - is straight-line code
-                // whose tile offsets are immediates of the stores
-                if (fast_store && !grid2d)
-                    store_tiles(8, true);
-                else if (fast_store)
-                    store_tiles(tile_step, true);
-                else
-                    store_tiles(tile_step, false);
+                // whose tile offsets are immediates of the stores; tiles without a NaN skip the selects
+                if (fast_store && !grid2d) {
+                    if (tile_clean)
+                        store_tiles(8, true, false);
+                    else
+                        store_tiles(8, true, true);
+                } else if (fast_store) {
+                    store_tiles(tile_step, true, true);
+                } else {
+                    store_tiles(tile_step, false, true);
+                }
             }
             dst_row += 8 * n_cells;
         }

@@ -338,8 +338,12 @@ def test_api_transforms_on_reference_literals(bc_hst):
     assert _close(ra, body.get_backplane_img('RA'), atol=1e-12) and _close(dec, body.get_backplane_img('DEC'), atol=1e-12)
     kx, ky = body.xy2km(x, y)
     assert _close(kx, body.get_backplane_img('KM-X'), atol=1e-5) and _close(ky, body.get_backplane_img('KM-Y'), atol=1e-5)
+    # the ANGULAR-X / -Y backplanes are the km planes over km_per_arcsec (north up, body_xy.py:3611-3656), not
+    # the RA / Dec aligned system of xy2angular
+    assert _close(kx / body.km_per_arcsec, body.get_backplane_img('ANGULAR-X'), atol=1e-8)
     ax, ay = body.xy2angular(x, y)
-    assert _close(ax, body.get_backplane_img('ANGULAR-X'), atol=1e-8)
+    ra0, dec0 = body.angular2radec(ax, ay)
+    assert _close(ra0, ra, atol=1e-11) and _close(dec0, dec, atol=1e-11)
     for fwd, inv, args in ((body.xy2radec, body.radec2xy, {}), (body.xy2km, body.km2xy, {}),
                            (body.xy2angular, body.angular2xy, dict(coordinate_rotation=12.0, origin_ra=196.0))):
         u, v = fwd(x, y, **args)
