@@ -779,11 +779,14 @@ class BodyXY:
         if entry is None or (entry[0] & mask) != mask:
             have = entry[0] if entry else 0
             new_mask = have | mask
-            if have:
-                # second distinct request: escalate to the whole group the planes belong to (the
-                # 12-plane surface stack has a specialised kernel; anything else -> all 26), so a
-                # sequence of single-plane getters costs at most three launches
-                new_mask = _SURFACE_STACK if (new_mask & ~_SURFACE_STACK) == 0 else L.ALL_PLANES
+            if (new_mask & ~_SURFACE_STACK) == 0:
+                # surface planes share the ray / ellipsoid intercept, which is nearly all of their cost: one
+                # plane or the 12-plane stack (specialised kernel, 0.15 ms for 2048 x 2048) are the same work
+                new_mask = _SURFACE_STACK
+            elif have:
+                # second distinct request outside the surface stack: everything (at most two launches for any
+                # sequence of single-plane getters, and a lone RA / ring plane never pays for the 26-plane stack)
+                new_mask = L.ALL_PLANES
             # single frame: the constants ride in the launch (kernel parameter / constant bank)
             planes = L.backplanes_img_host(self._frame_host(alt), self._nx, self._ny, new_mask)
             entry = (new_mask, planes)
@@ -809,10 +812,51 @@ class BodyXY:
             if self._is_builtin_backplane(bp.name, mapped=False):
                 # the cache is the device-resident plane stack: ONE copy, device -> the (pinned) array the
                 # caller gets, instead of device -> cached host array -> np.array(copy=True)
-                pid = L.PLANE_ID[bp.name]
-                have, planes = self.get_backplanes_img_device(1 << pid, self._alt_adjustment)
-                return L.to_host(planes[L.popcount(have & ((1 << pid) - 1))])
+                return self._img_plane_to_host(L.PLANE_ID[bp.name])
             return np.array(bp.get_img(), copy=True)
+
+    # Planes at least this large are read ahead (below it the per-call overhead is not the copy)
+    _PREFETCH_MIN_BYTES = 4 << 20
+
+    def _img_plane_to_host(self, pid: int) -> np.ndarray:
+        """A new host array holding image plane ``pid``.  The usual caller asks for one backplane after the
+        other (the reference's save_observation loop, observation.py:1275, or user code): on the SECOND distinct
+        plane of a stack the remaining planes of that stack are sent after it, device -> pinned host on a side
+        stream, so their copies run back to back while Python returns to the caller; each read-ahead array is
+        handed to the first request for its plane (ownership moves to the caller), later requests copy again."""
+        torch = L._torch()
+        alt = self._alt_adjustment
+        have, planes = self.get_backplanes_img_device(1 << pid, alt)
+        slot = lambda q: L.popcount(have & ((1 << q) - 1))   # noqa: E731
+        key = ('img_readahead', alt)
+        state = self._cache.get(key)
+        if state is None or state['planes'] is not planes:
+            state = {'planes': planes, 'asked': set(), 'ready': {}, 'stream': None}
+            self._cache[key] = state
+        ready = state['ready'].pop(pid, None)
+        state['asked'].add(pid)
+        if ready is not None:
+            host, event = ready
+            event.synchronize()
+            return host.numpy()
+        out = L.to_host(planes[slot(pid)])
+        if len(state['asked']) == 2 and planes[0].numel() * 8 >= self._PREFETCH_MIN_BYTES:
+            if state['stream'] is None:
+                state['stream'] = torch.cuda.Stream()
+            side = state['stream']
+            side.wait_stream(torch.cuda.current_stream())
+            planes.record_stream(side)     # the stack must outlive the copies even if the cache is cleared meanwhile
+            with torch.cuda.stream(side):
+                for q in range(L.N_PLANES):
+                    if (have >> q) & 1 and q not in state['asked']:
+                        host = L.empty_host(planes[slot(q)].shape, torch)
+                        if not host.is_pinned():
+                            break          # pinned budget exhausted: no read-ahead into pageable memory
+                        host.copy_(planes[slot(q)], non_blocking=True)
+                        event = torch.cuda.Event()
+                        event.record(side)
+                        state['ready'][q] = (host, event)
+        return out
 
     def get_backplane_imgs(self, names, *, alt: float = 0.0, out=None) -> dict[str, np.ndarray]:
         """Several backplane images from ONE kernel launch and ONE device->host copy.

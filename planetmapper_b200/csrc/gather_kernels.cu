@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         for (int it = 0; it < n_it; it++) {
             const int l = l0 + 8 * it;
             const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (a multiple of 8)
+            __syncwarp();                    // every lane has read the stage this issue() overwrites (tile it - 1)
             issue();
             const int word = gl >> 5;        // the same for the 8 planes of the tile
             if (word != cur_word) {          // uniform: changes once per 32 planes

@@ -458,12 +458,29 @@ def test_backplane_getters_return_owned_arrays(body):
     assert m is not m2 and m.flags.writeable and np.array_equal(m, m2, equal_nan=True)
     # single-plane requests cost one plane, a second plane escalates to its group, never the 26-plane stack
     fresh = type(body)(constants=body._bc, nx=15, ny=10)
-    fresh.get_backplane_img('EMISSION')
-    assert fresh._cache[('img_planes_dev', 0.0)][0] == 1 << 14
-    fresh.get_backplane_img('LON-GRAPHIC')
+    fresh.get_backplane_img('EMISSION')       # a surface plane brings its 12-plane stack (same intercept work)
     assert bin(fresh._cache[('img_planes_dev', 0.0)][0]).count('1') == 12
-    fresh.get_backplane_img('RA')
-    assert bin(fresh._cache[('img_planes_dev', 0.0)][0]).count('1') == 26
+    fresh2 = type(body)(constants=body._bc, nx=15, ny=10)
+    fresh2.get_backplane_img('RA')            # a lone sky plane costs one plane ...
+    assert fresh2._cache[('img_planes_dev', 0.0)][0] == 1 << 4
+    fresh2.get_backplane_img('RING-RADIUS')   # ... a second distinct one everything
+    assert bin(fresh2._cache[('img_planes_dev', 0.0)][0]).count('1') == 26
+    # read-ahead (planes >= 4 MB): the second distinct request sends the rest of the stack after it; every array is
+    # handed out once, equals a direct copy, and a repeated request gets a fresh array
+    big = type(body)(constants=body._bc, nx=1024, ny=600)
+    first = {n: big.get_backplane_img(n) for n in ('EMISSION', 'PHASE', 'LON-GRAPHIC', 'DOPPLER')}
+    assert len(big._cache[('img_readahead', 0.0)]['ready']) == 12 - 4
+    have, planes = big.get_backplanes_img_device(1 << 14)
+    for n, arr in first.items():
+        pid = PLANE_NAMES.index(n)
+        direct = planes[bin(have & ((1 << pid) - 1)).count('1')].cpu().numpy()
+        assert arr.flags.writeable and np.array_equal(arr, direct, equal_nan=True), n
+        again = big.get_backplane_img(n)
+        assert again is not arr and np.array_equal(again, arr, equal_nan=True)
+    big.set_x0(500.0)      # a disc parameter change drops planes and read-ahead alike
+    assert ('img_readahead', 0.0) not in big._cache
+    moved = big.get_backplane_img('PHASE')
+    assert not np.array_equal(moved, first['PHASE'], equal_nan=True)
     # a registered custom backplane still goes through its own getter
     body.register_backplane('custom', 'a custom plane', lambda: np.ones((10, 15)), lambda **kw: np.ones((3, 3)))
     assert np.array_equal(body.get_backplane_img('custom'), np.ones((10, 15)))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Short driver for ncu captures: launches each hot kernel a few times at bench shapes.
-   python tools/profile_run.py img|gather|map"""
+"""Short driver for ncu captures: launches each hot kernel a few times at the BENCH's own launch shapes.
+   python tools/profile_run.py img|map|gather|transform"""
 import os
 import sys
 
@@ -12,27 +12,34 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from planetmapper_b200 import _lib as L  # noqa: E402
-from planetmapper_b200 import frame as F  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'img'
 bc = bench.load_bc()
 if what == 'img':
     fr = bench.c2_frame(bc)
-    fd = L.to_device(fr[None])
     mask = L.mask_from_names(bench.C2_NAMES)
-    out = torch.empty((1, 12, bench.SZ, bench.SZ), dtype=torch.float64, device='cuda')
+    out = torch.empty((12, bench.SZ, bench.SZ), dtype=torch.float64, device='cuda')
     for _ in range(4):
-        L.backplanes_img(fd, bench.SZ, bench.SZ, mask, out=out)
-    out26 = torch.empty((1, 26, bench.SZ, bench.SZ), dtype=torch.float64, device='cuda')
+        L.backplanes_img_host(fr, bench.SZ, bench.SZ, mask, out=out)          # the headline launch
+    out26 = torch.empty((26, bench.SZ, bench.SZ), dtype=torch.float64, device='cuda')
     for _ in range(2):
-        L.backplanes_img(fd, bench.SZ, bench.SZ, L.ALL_PLANES, out=out26)
-else:
-    sz = 64
-    fr = F.pack_frame(bc, nx=sz, ny=sz, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)
-    lons = np.arange(0.05, 360, 0.1)[::-1]
-    lats = np.arange(-90 + 0.05, 90, 0.1)
-    lo, la = np.meshgrid(lons, lats)
+        L.backplanes_img_host(fr, bench.SZ, bench.SZ, L.ALL_PLANES, out=out26)
+    fd = L.to_device(np.stack([fr] * 8))
+    outb = torch.empty((8, 12, bench.SZ, bench.SZ), dtype=torch.float64, device='cuda')
+    for _ in range(2):
+        L.backplanes_img(fd, bench.SZ, bench.SZ, mask, out=outb)              # batched (frames in device memory)
+elif what == 'transform':
+    fr = bench.c2_frame(bc)
     fd = L.to_device(fr)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.rand(10_000_000, dtype=torch.float64, device='cuda', generator=g) * bench.SZ
+    y = torch.rand(10_000_000, dtype=torch.float64, device='cuda', generator=g) * bench.SZ
+    for _ in range(2):
+        L.transform(fd, 'xy', 'radec', x, y)
+        L.transform(fd, 'xy', 'lonlat', x, y)
+else:
+    cube_h, lo, la = bench.c4_inputs(1024)
+    fd = L.to_device(bench.c4_frame(bc))
     lod, lad = L.to_device(lo), L.to_device(la)
     for _ in range(2):
         xy = L.backplanes_map(fd, lod, lad, L.mask_from_names(['PIXEL-X', 'PIXEL-Y']))
@@ -40,18 +47,11 @@ else:
         for _ in range(2):
             L.backplanes_map(fd, lod, lad, L.ALL_PLANES)
     else:
-        nl = 256
-        rng = np.random.default_rng(0)
-        cube_h = rng.normal(1.0, 0.1, (nl, sz, sz))
-        cube_h[rng.random(cube_h.shape) < 0.01] = np.nan
         cube = L.to_device(cube_h)
-        out = torch.empty((nl,) + lo.shape, dtype=torch.float64, device='cuda')
-        for mode in (0, 1, 3):
-            if mode:
-                coef = L.spline_prepare(cube, mode)
-            else:
-                coef = cube
-            for _ in range(2):
-                L.gather(coef, xy[0], xy[1], mode, out=out)
+        out = torch.empty((bench.C4_CHUNK,) + lo.shape, dtype=torch.float64, device='cuda')
+        for mode in (L.INTERP_NEAREST, L.INTERP_LINEAR, L.INTERP_CUBIC):
+            src = cube if mode == L.INTERP_NEAREST else L.spline_prepare(cube, mode)
+            for begin in (0, 512):     # one 512-plane chunk per launch, as in bench.py
+                L.gather(src, xy[0], xy[1], mode, plane_begin=begin, plane_count=bench.C4_CHUNK, out=out)
 torch.cuda.synchronize()
 print('done', what)
