@@ -773,7 +773,7 @@ def main():
             fn()
         barrier()
         gc.collect()
-        gc.disable()      # as timeit does: a generation-2 pass over torch's object graph is a 50 ms outlier
+        gc.freeze()       # torch's import graph leaves the collector's view: no 50 ms generation-2 pass mid-loop
         try:
             t0 = time.perf_counter()
             for _ in range(steps):
@@ -781,7 +781,7 @@ def main():
             torch.cuda.synchronize()
             t = (time.perf_counter() - t0) / steps * 1e3
         finally:
-            gc.enable()
+            gc.unfreeze()
         return max_over_ranks(t, world, device='cuda')
 
     e2e_ms = timed_host(e2e_dropin, e2e_steps)
@@ -826,7 +826,7 @@ def main():
                     'h2d_bytes_per_step': int(fr.nbytes), 'd2h_bytes_per_step': int(nbytes),
                     'api': 'drop-in: BodyXY(constants=...) then get_backplane_img(name) for each of the 12 names '
                            '(1 kernel launch, 12 device -> pinned-host copies - the last 10 read ahead on a side '
-                           'stream - 12 owned float64 arrays returned); garbage collector off while timing, like timeit',
+                           'stream - 12 owned float64 arrays returned); gc.freeze() before timing',
                     'steps': e2e_steps,
                     'batched': {'value': world * SZ * SZ / (e2e_batched_ms * 1e-3) / 1e6, 'ms_per_step': e2e_batched_ms,
                                 'api': 'BodyXY.get_backplane_imgs(12 names, out=pinned): 1 launch, 1 copy'},

@@ -748,16 +748,27 @@ class BodyXY:
             return False
         return (bp.get_map is getters[1]) if mapped else (bp.get_img is getters[0])
 
+    # The generated getters live on the instance (and in its `backplanes` registry): they hold the body
+    # through a weak reference, so that a dropped BodyXY - and the device planes and pinned arrays in its
+    # caches - is released at once by reference counting instead of waiting for the cycle collector.
     def _make_img_getter(self, pid: int):
+        import weakref
+
+        ref = weakref.ref(self)
+
         def get_img() -> np.ndarray:
-            return self._get_img_plane(pid)
+            return ref()._get_img_plane(pid)
 
         get_img.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_img'
         return get_img
 
     def _make_map_getter(self, pid: int):
+        import weakref
+
+        ref = weakref.ref(self)
+
         def get_map(**map_kwargs) -> np.ndarray:
-            return self._get_map_plane(pid, **map_kwargs)
+            return ref()._get_map_plane(pid, **map_kwargs)
 
         get_map.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_map'
         return get_map
