@@ -33,6 +33,7 @@ import numpy as np
 
 from . import _lib as L
 from . import frame as F
+from .progress import ProgressMixin, progress_decorator
 
 _PLANE_DESCRIPTIONS = [
     ('LON-GRAPHIC', 'Planetographic longitude, positive {ew} [deg]', 'lon'),
@@ -144,7 +145,7 @@ def _freeze(v: Any):
     return v
 
 
-class BodyXY:
+class BodyXY(ProgressMixin):
     """An astronomical body observed at one epoch with an image pixel grid.
 
     Args mirror ``planetmapper.BodyXY`` (body_xy.py:186-232): ``target``, ``utc``,
@@ -199,6 +200,8 @@ class BodyXY:
         self._r0 = 10.0
         self._rotation_radians = 0.0
         self._alt_adjustment = 0.0
+        self._progress_hook = None
+        self._progress_call_stack = []
         self._cache: dict = {}         # cleared when a disc parameter changes
         self._stable_cache: dict = {}  # never cleared
         self.backplanes: dict[str, Backplane] = {}
@@ -777,6 +780,7 @@ class BodyXY:
     def _test_if_img_size_valid(self) -> bool:
         return (self._nx > 0) and (self._ny > 0)
 
+    @progress_decorator
     def get_backplanes_img_device(self, mask: int = L.ALL_PLANES, alt: float | None = None):
         """All requested image backplanes as ONE device tensor (k, ny, nx), computed by a
         single fused kernel launch and cached per altitude adjustment in ``_cache``
@@ -926,6 +930,7 @@ class BodyXY:
         lons, lats = self._get_lonlat_planes(**map_kwargs)
         return _readonly(np.stack([lons, lats], axis=-1))
 
+    @progress_decorator
     def get_backplanes_map_device(self, mask: int, **map_kwargs):
         """Requested map backplanes as a device tensor (k, n0, n1).  Disc-independent
         planes live in ``_stable_cache`` (never cleared), PIXEL-X / PIXEL-Y (x_map,
@@ -998,6 +1003,7 @@ class BodyXY:
         res = L.to_host(out)
         return res[0] if np.ndim(img) == 2 else res
 
+    @progress_decorator
     def map_img_device(self, img, *, interpolation='linear', spline_smoothing: float = 0,
                        propagate_nan: bool = True, warn_nan: bool = False, out=None,
                        smooth_oversample_by: int = 5, smooth_max_oversampled_img_size: int = 10_000,

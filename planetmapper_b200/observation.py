@@ -23,6 +23,7 @@ import numpy as np
 from . import _lib as L
 from .body_xy import BodyXY
 from .fits_stage import Header, ImageHDU, write_hdus
+from .progress import CLIProgressHook, progress_decorator
 
 _REFERENCE_URL = 'https://github.com/ortk95/planetmapper'
 
@@ -68,6 +69,7 @@ class Observation(BodyXY):
             warn_nan=warn_nan, smooth_oversample_by=smooth_oversample_by,
             smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs), copy=True)
 
+    @progress_decorator
     def _get_mapped_data(self, interpolation, *, spline_smoothing, propagate_nan, warn_nan,
                          smooth_oversample_by=5, smooth_max_oversampled_img_size=10_000,
                          **map_kwargs) -> np.ndarray:
@@ -83,7 +85,7 @@ class Observation(BodyXY):
                                    smooth_max_oversampled_img_size=smooth_max_oversampled_img_size, **map_kwargs)
             host = L.empty_host((src.n_planes,) + src.map_shape)
             for first, count, _ in self._stream_mapped_chunks(src, None, into=host):
-                pass
+                self._update_progress_hook((first + count) / src.n_planes)   # observation.py:903
             self._cache[key] = host.numpy()
         return self._cache[key]
 
@@ -341,6 +343,7 @@ class Observation(BodyXY):
                 'the WIREFRAME HDU is drawn with matplotlib (plotting is out of scope of the '
                 'accelerated path); pass include_wireframe=False')
 
+    @progress_decorator
     def save_observation(self, path, *, backplanes_to_save: Collection[str] | None = None,
                          backplanes_to_skip: Collection[str] = frozenset(), include_wireframe: bool = False,
                          wireframe_kwargs: dict[str, Any] | None = None, show_progress: bool = False,
@@ -348,11 +351,22 @@ class Observation(BodyXY):
         """Save ``data`` + the generated backplanes as a FITS file (observation.py:1185-1303):
         primary HDU = data and header with the PLANMAP metadata, then one float64 image
         extension per backplane.  ``include_wireframe`` defaults to False here."""
-        from .body_xy import _AltitudeScope
-
         self._reject_wireframe(include_wireframe)
         path = os.fspath(path)
         names = self._get_backplane_names_to_save(backplanes_to_save, backplanes_to_skip)
+        own_hook = show_progress and self._get_progress_hook() is None     # observation.py:1250-1254
+        if own_hook:
+            self._set_progress_hook(CLIProgressHook())
+            print_info = False
+        try:
+            self._save_observation(path, names, print_info, alt)
+        finally:
+            if own_hook:
+                self._remove_progress_hook()
+
+    def _save_observation(self, path, names, print_info, alt) -> None:
+        from .body_xy import _AltitudeScope
+
         if print_info:
             print('Saving observation to', path)
         with _AltitudeScope(self, self._check_alt(alt)):
@@ -366,6 +380,7 @@ class Observation(BodyXY):
         if print_info:
             print('File saved')
 
+    @progress_decorator
     def save_mapped_observation(self, path, *, interpolation='linear', propagate_nan: bool = True,
                                 spline_smoothing: float = 0, smooth_oversample_by: int = 5,
                                 smooth_max_oversampled_img_size: int = 10_000, include_backplanes: bool = True,
@@ -379,6 +394,21 @@ class Observation(BodyXY):
         self._reject_wireframe(include_wireframe)
         path = os.fspath(path)
         names = self._get_backplane_names_to_save(backplanes_to_save, backplanes_to_skip)
+        own_hook = show_progress and self._get_progress_hook() is None     # observation.py:1398-1402
+        if own_hook:
+            self._set_progress_hook(CLIProgressHook())
+            print_info = False
+        try:
+            self._save_mapped_observation(path, names, print_info, interpolation, propagate_nan, spline_smoothing,
+                                          smooth_oversample_by, smooth_max_oversampled_img_size, include_backplanes,
+                                          map_kwargs)
+        finally:
+            if own_hook:
+                self._remove_progress_hook()
+
+    def _save_mapped_observation(self, path, names, print_info, interpolation, propagate_nan, spline_smoothing,
+                                 smooth_oversample_by, smooth_max_oversampled_img_size, include_backplanes,
+                                 map_kwargs) -> None:
         if print_info:
             print('Saving map to', path)
             print(' Projecting mapped data...')

@@ -484,3 +484,20 @@ def test_backplane_getters_return_owned_arrays(body):
     # a registered custom backplane still goes through its own getter
     body.register_backplane('custom', 'a custom plane', lambda: np.ones((10, 15)), lambda **kw: np.ones((3, 3)))
     assert np.array_equal(body.get_backplane_img('custom'), np.ones((10, 15)))
+
+
+def test_progress_hook_receives_updates(obs, tmp_path):
+    calls = []
+    obs._set_progress_hook(lambda p, stack: calls.append((float(p), stack[-1] if stack else '')))
+    obs._planes_per_chunk = staticmethod(lambda src, planes_per_chunk=None, budget_bytes=None: 4)
+    obs.get_mapped_data('linear', degree_interval=10)
+    mapped = [p for p, name in calls if name.endswith('_get_mapped_data')]
+    assert mapped[0] == 0 and mapped[-1] == 1 and 0.4 in mapped and 0.8 in mapped    # 4 + 4 + 2 planes of 10
+    calls.clear()
+    obs.save_observation(str(tmp_path / 'nav.fits'), print_info=False)
+    names = {name.split('.')[-1] for _, name in calls}
+    assert {'save_observation', 'get_backplanes_img_device'} <= names
+    obs._remove_progress_hook()
+    calls.clear()
+    obs.get_backplane_img('EMISSION')
+    assert calls == []

@@ -205,3 +205,46 @@ def test_two_process_gloo_sharding(tmp_path):
         bc = F.build_body_constants(prov, 'JUPITER', None, 'EARTH', et=float(et))
         total += float(np.sum(F.pack_frame(bc, nx=64, ny=64, x0=31.5, y0=31.5, r0=28.0, rotation_radians=0.0)))
     assert res['checksum'] == pytest.approx(total, rel=1e-15)
+
+
+def test_progress_hooks_follow_the_reference_protocol():
+    """progress.py:16-41 / base.py:760-781: 0 and 1 around every decorated call, the stack of running
+    qualified names, fractions in between, exceptions from the hook propagate (cancel) and unwind the stack."""
+    from planetmapper_b200.progress import ProgressMixin, progress_decorator
+
+    class Thing(ProgressMixin):
+        def __init__(self):
+            self._progress_hook = None
+            self._progress_call_stack = []
+
+        @progress_decorator
+        def outer(self, n):
+            for k in range(n):
+                self.inner()
+                self._update_progress_hook((k + 1) / n)
+            return n
+
+        @progress_decorator
+        def inner(self):
+            return 1
+
+    calls = []
+    t = Thing()
+    assert t.outer(2) == 2 and calls == []          # no hook: plain call
+    t._set_progress_hook(lambda p, stack: calls.append((p, tuple(stack))))
+    assert t.outer(2) == 2
+    o, i = 'Thing.outer', 'Thing.inner'
+    names = lambda c: tuple(n.split('<locals>.')[-1] for n in c)   # noqa: E731
+    assert [(p, names(s)) for p, s in calls] == [
+        (0, (o,)), (0, (o, i)), (1, (o, i)), (0.5, (o,)), (0, (o, i)), (1, (o, i)), (1.0, (o,)), (1, (o,))]
+    assert t._progress_call_stack == []
+
+    def cancel(p, stack):
+        if len(stack) == 2:
+            raise KeyboardInterrupt('cancelled from the hook')
+    t._set_progress_hook(cancel)
+    with pytest.raises(KeyboardInterrupt):
+        t.outer(3)
+    assert t._progress_call_stack == []
+    t._remove_progress_hook()
+    assert t._get_progress_hook() is None and t.outer(1) == 1
