@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 8
+#define PM_ABI_VERSION 9
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -227,6 +227,11 @@ int pm_transform(const PMFrame *frame, int src, int dst, const double *a, const 
  */
 int pm_proj_inverse(int kind, const double *params5_host, const double *xx,
                     const double *yy, int64_t n, double *lon, double *lat, void *stream);
+/* The forward direction of the same three projections (the default direction of the pyproj.Transformer
+ * generate_map_coordinates returns, body_xy.py:3141-3153): planetographic lon / lat in degrees -> the
+ * projection's own units; points the projection cannot show are NaN. */
+int pm_proj_forward(int kind, const double *params5_host, const double *lon, const double *lat,
+                    int64_t n, double *xx, double *yy, void *stream);
 
 /*
  * Cube -> map resampling: replaces BodyXY._do_nearest_interpolation

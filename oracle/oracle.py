@@ -129,6 +129,18 @@ def proj_inverse(kind, a, b, lon0, lat0, lon_sign, xx, yy):
     return lon, lat
 
 
+def proj_forward(kind, a, b, lon0, lat0, lon_sign, lon, lat):
+    params = np.array([a, b, lon0, lat0, lon_sign], dtype=np.float64)
+    lon = np.ascontiguousarray(lon, dtype=np.float64)
+    lat = np.ascontiguousarray(lat, dtype=np.float64)
+    xx = np.empty(lon.shape)
+    yy = np.empty(lon.shape)
+    rc = lib().pmo_proj_forward(ctypes.c_int(kind), _p(params), _p(lon), _p(lat), ctypes.c_int64(lon.size), _p(xx),
+                                _p(yy))
+    assert rc == 0, rc
+    return xx, yy
+
+
 def gather_nearest(cube, xmap, ymap):
     cube = np.ascontiguousarray(cube, dtype=np.float64)
     if cube.ndim == 2:

@@ -1266,6 +1266,56 @@ static void proj_inverse_one(int kind, double a, double b, double lon0_deg,
     *lat_out = phi * DPR;
 }
 
+/* Forward direction of the same projections (pyproj's default direction; PROJ's published forward
+ * formulas: ellipsoidal ortho e_forward, spherical aeqd / laea s_forward), in the units of the reference's
+ * own strings (body_xy.py:2930-2968: to_meter = a, a pi, 2 a; the ortho's y_0). */
+static void proj_forward_one(int kind, double a, double b, double lon0_deg, double lat0_deg, double lon_sign,
+                             double lon_deg, double lat_deg, double *xx, double *yy) {
+    *xx = *yy = kNaN;
+    if (!(isfinite(lon_deg) && isfinite(lat_deg)) || fabs(lat_deg) > 90.0 + 1e-12) return;
+    double phi0 = lat0_deg * RPD, phi = fmax(-HALFPI, fmin(HALFPI, lat_deg * RPD));
+    double lam = (lon_deg - lon0_deg) * RPD;
+    lam -= TWOPI * floor((lam + PI) / TWOPI);
+    double sinph0 = sin(phi0), cosph0 = cos(phi0), sinphi = sin(phi), cosphi = cos(phi);
+    double sinlam = sin(lam), coslam = cos(lam);
+    double cosc = sinph0 * sinphi + cosph0 * cosphi * coslam;
+    double x, y;
+    if (kind == PM_PROJ_ORTHOGRAPHIC) {
+        if (cosc < -1e-10) return;
+        double es = 1.0 - (b * b) / (a * a);
+        double nu = 1.0 / sqrt(1.0 - es * sinphi * sinphi), nu0 = 1.0 / sqrt(1.0 - es * sinph0 * sinph0);
+        x = nu * cosphi * sinlam;
+        y = nu * (sinphi * cosph0 - cosphi * sinph0 * coslam) + es * (nu0 * sinph0 - nu * sinphi) * cosph0;
+        y += (b / a - 1.0) * sin((lat0_deg * 2.0) * RPD);
+    } else if (kind == PM_PROJ_AZIMUTHAL) {
+        if (cosc <= -1.0 + 1e-14) return;
+        double c = acos(fmax(-1.0, fmin(1.0, cosc)));
+        double k = c < 1e-10 ? 1.0 : c / sin(c);
+        x = k * cosphi * sinlam / PI;
+        y = k * (cosph0 * sinphi - sinph0 * cosphi * coslam) / PI;
+    } else if (kind == PM_PROJ_AZIMUTHAL_EQUAL_AREA) {
+        double d = 1.0 + cosc;
+        if (d <= 1e-10) return;
+        double k = sqrt(2.0 / d);
+        x = k * cosphi * sinlam * 0.5;
+        y = k * (cosph0 * sinphi - sinph0 * cosphi * coslam) * 0.5;
+    } else {
+        return;
+    }
+    *xx = lon_sign < 0.0 ? -x : x;
+    *yy = y;
+}
+
+int pmo_proj_forward(int kind, const double *params5, const double *lon, const double *lat, int64_t n,
+                     double *xx, double *yy) {
+    if (!params5 || !lon || !lat || !xx || !yy || n < 0) return PM_ERR_BAD_ARG;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; i++)
+        proj_forward_one(kind, params5[0], params5[1], params5[2], params5[3], params5[4], lon[i], lat[i], &xx[i],
+                         &yy[i]);
+    return PM_OK;
+}
+
 int pmo_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                      int64_t n, double *lon, double *lat) {
     if (!params5 || !xx || !yy || !lon || !lat || n < 0) return PM_ERR_BAD_ARG;

@@ -26,6 +26,8 @@ int pmo_transform(const PMFrame *f, int src, int dst, const double *a, const dou
                   uint32_t flags, const double *aux13, double *out_a, double *out_b, int64_t *n_missed);
 int pmo_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                      int64_t n, double *lon, double *lat);
+int pmo_proj_forward(int kind, const double *params5, const double *lon, const double *lat, int64_t n,
+                     double *xx, double *yy);
 int pmo_gather_nearest(const double *cube, int n_planes, int ny, int nx,
                        const double *xmap, const double *ymap, int64_t n_cells,
                        double *out);

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import os
 
-from .body_xy import (Backplane, BackplaneNotFoundError, BodyXY, NotFoundError,  # noqa: F401
+from .body_xy import (Backplane, BackplaneNotFoundError, BodyXY, MapTransformer, NotFoundError,  # noqa: F401
                       ProjStringError)
 from .frame import BodyConstants, build_body_constants, pack_frame  # noqa: F401
 from .observation import Observation  # noqa: F401

@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
     'pm_fits_data_unit_bytes', 'pm_fits_stage', 'pm_backplanes_map_batch', 'pm_gather_paired',
-    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host', 'pm_transform', 'pm_fp64_probe',
+    'pm_host_ssb_state', 'pm_host_orientation', 'pm_backplanes_img_host', 'pm_transform', 'pm_fp64_probe', 'pm_proj_forward',
 ]
 
 
@@ -81,6 +81,8 @@ def load_library() -> ctypes.CDLL:
     lib.pm_lonlat2xy.argtypes = [c_p, c_p, c_p, c_i64, c_u32, c_p, c_p, c_p]
     lib.pm_lonlat2xy_alt.argtypes = [c_p, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p]
     lib.pm_proj_inverse.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
+    lib.pm_proj_forward.argtypes = [c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]
+    lib.pm_proj_forward.restype = c_i
     lib.pm_gather.argtypes = [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i64, c_i64, c_i, c_u32,
                               c_p, c_p]
     for fn in ('pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_work_bytes',
@@ -117,7 +119,7 @@ def load_library() -> ctypes.CDLL:
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 8:
+    if lib.pm_abi_version() != 9:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -401,6 +403,18 @@ def proj_inverse(kind: int, a: float, b: float, lon0: float, lat0: float, lon_si
                              _stream_ptr(torch))
     _check(rc, 'pm_proj_inverse')
     return lon, lat
+
+
+def proj_forward(kind: int, a: float, b: float, lon0: float, lat0: float, lon_sign: float, lon_dev, lat_dev):
+    torch = _torch()
+    lib = load_library()
+    params = (ctypes.c_double * 5)(a, b, lon0, lat0, lon_sign)
+    xx = torch.empty_like(lon_dev)
+    yy = torch.empty_like(lon_dev)
+    rc = lib.pm_proj_forward(kind, ctypes.cast(params, ctypes.c_void_p), lon_dev.data_ptr(), lat_dev.data_ptr(),
+                             lon_dev.numel(), xx.data_ptr(), yy.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_proj_forward')
+    return xx, yy
 
 
 class Spline:

@@ -121,6 +121,49 @@ def standardise_utc_to_string(utc) -> str:
     return str(utc)
 
 
+class MapTransformer:
+    """What ``generate_map_coordinates`` returns in the ``transformer`` slot: the reference hands back the
+    ``pyproj.Transformer`` between the body's lon / lat system and the map projection (body_xy.py:3141-3153);
+    this object offers the part of its interface the reference and its users call -
+    ``transform(xx, yy, direction='FORWARD' | 'INVERSE')`` on scalars or arrays - evaluated by the projection
+    kernels (``pm_proj_forward`` / ``pm_proj_inverse``).  FORWARD: planetographic lon / lat (degrees) -> map x / y;
+    INVERSE: map x / y -> lon / lat.  Rectangular and manual maps are their own lon / lat system (identity).
+    Points a projection cannot show come back as inf, like pyproj's."""
+
+    def __init__(self, kind=None, a=1.0, b=1.0, lon0=0.0, lat0=0.0, lon_sign=1.0, to_kernel=None, from_kernel=None,
+                 definition: str = '') -> None:
+        self.kind, self.a, self.b, self.lon0, self.lat0, self.lon_sign = kind, a, b, lon0, lat0, lon_sign
+        self._to_kernel = to_kernel or (lambda x, y: (x, y))
+        self._from_kernel = from_kernel or (lambda x, y: (x, y))
+        self.definition = definition
+
+    def __repr__(self) -> str:
+        return f'<MapTransformer {self.definition or "lon / lat (identity)"}>'
+
+    def transform(self, xx, yy, direction: str = 'FORWARD'):
+        direction = getattr(direction, 'name', str(direction)).upper()
+        if direction not in ('FORWARD', 'INVERSE'):
+            raise ValueError(f'direction must be FORWARD or INVERSE, not {direction!r}')
+        scalar = np.ndim(xx) == 0 and np.ndim(yy) == 0
+        a, b = np.broadcast_arrays(np.asarray(xx, dtype=float), np.asarray(yy, dtype=float))
+        if self.kind is None:
+            u, v = np.array(a), np.array(b)
+        elif direction == 'INVERSE':
+            xi, yi = self._to_kernel(np.ascontiguousarray(a), np.ascontiguousarray(b))
+            lo, la = L.proj_inverse(self.kind, self.a, self.b, self.lon0, self.lat0, self.lon_sign,
+                                    L.to_device(xi), L.to_device(yi))
+            u, v = L.to_host(lo), L.to_host(la)
+        else:
+            x, y = L.proj_forward(self.kind, self.a, self.b, self.lon0, self.lat0, self.lon_sign,
+                                  L.to_device(np.ascontiguousarray(a)), L.to_device(np.ascontiguousarray(b)))
+            u, v = self._from_kernel(L.to_host(x), L.to_host(y))
+        if self.kind is not None:
+            bad = ~(np.isfinite(u) & np.isfinite(v))
+            u = np.where(bad, np.inf, u)
+            v = np.where(bad, np.inf, v)
+        return (float(u.reshape(())), float(v.reshape(()))) if scalar else (u, v)
+
+
 class Backplane(NamedTuple):
     """Registry entry, same fields as the reference's Backplane (body_xy.py:79-107)."""
 
@@ -548,9 +591,11 @@ class BodyXY(ProgressMixin):
                                  size: int = 100, lon_coords=None, lat_coords=None,
                                  projection_x_coords=None, projection_y_coords=None,
                                  xlim=None, ylim=None, alt: float = 0.0):
-        """Returns ``(lons, lats, xx, yy, transformer, info)`` like the reference; the
-        ``transformer`` slot is None (pyproj is not part of the accelerated path)."""
+        """Returns ``(lons, lats, xx, yy, transformer, info)`` like the reference; ``transformer`` is a
+        :class:`MapTransformer` (the ``transform(xx, yy, direction=...)`` part of pyproj's interface on the
+        projection kernels)."""
         info: dict[str, Any]
+        transformer = MapTransformer()     # rectangular / manual: the map is the lon / lat system itself
         a, b = self._bc.r_eq + alt, self._bc.r_polar + alt
         lon_sign = self._bc.lon_sign
         if projection == 'rectangular':
@@ -592,13 +637,15 @@ class BodyXY(ProgressMixin):
             lo, la = L.proj_inverse(kind, a, b, float(lon), float(lat), lon_sign,
                                     L.to_device(xx), L.to_device(yy))
             lons, lats = L.to_host(lo), L.to_host(la)
+            transformer = MapTransformer(kind, a, b, float(lon), float(lat), lon_sign,
+                                         definition=f'{projection} lon_0={lon} lat_0={lat} a={a} b={b}')
             info = dict(projection=projection, lon=lon, lat=lat, size=size)
         else:
             # custom proj string (body_xy.py:2970-2980)
             if projection_x_coords is None:
                 raise ValueError('x coords must be provided')
-            lons, lats, xx, yy = self._custom_proj_map_coords(projection, projection_x_coords,
-                                                             projection_y_coords)
+            lons, lats, xx, yy, transformer = self._custom_proj_map_coords(projection, projection_x_coords,
+                                                                          projection_y_coords)
             info = dict(projection=projection, projection_x_coords=projection_x_coords,
                         projection_y_coords=projection_y_coords)
         info['xlim'] = xlim
@@ -623,7 +670,7 @@ class BodyXY(ProgressMixin):
             xx, yy = lons, lats
         if alt != 0.0:
             info['alt'] = alt
-        return _readonly(lons), _readonly(lats), _readonly(xx), _readonly(yy), None, info
+        return _readonly(lons), _readonly(lats), _readonly(xx), _readonly(yy), transformer, info
 
     def create_proj_string(self, proj: str, **parameters) -> str:
         """Proj string with this body's radii and axis direction filled in
@@ -699,16 +746,21 @@ class BodyXY(ProgressMixin):
         tm = num('to_meter', 1.0)
         # PROJ inverse: internal = (user * to_meter - false origin) / a; then the units the
         # kernels take (the reference's own strings: to_meter = a, a pi and 2 a; y_0 of the ortho)
-        xi = (np.asarray(xx, dtype=float) * tm - num('x_0', 0.0)) / a
-        yi = (np.asarray(yy, dtype=float) * tm - num('y_0', 0.0)) / a
-        if kind == L.PROJ_ORTHOGRAPHIC:
-            yi = yi + (b / a - 1.0) * np.sin(np.radians(lat0 * 2))
-        elif kind == L.PROJ_AZIMUTHAL:
-            xi, yi = xi / np.pi, yi / np.pi
-        else:
-            xi, yi = xi / 2.0, yi / 2.0
+        x_0, y_0 = num('x_0', 0.0), num('y_0', 0.0)
+        y_shift = (b / a - 1.0) * np.sin(np.radians(lat0 * 2)) if kind == L.PROJ_ORTHOGRAPHIC else 0.0
+        unit = {L.PROJ_ORTHOGRAPHIC: 1.0, L.PROJ_AZIMUTHAL: np.pi, L.PROJ_AZIMUTHAL_EQUAL_AREA: 2.0}[kind]
+
+        def to_kernel(x, y):      # the caller's units -> the kernels' (the reference's own strings: to_meter = a, a pi, 2 a)
+            return ((np.asarray(x, dtype=float) * tm - x_0) / a / unit,
+                    ((np.asarray(y, dtype=float) * tm - y_0) / a + y_shift) / unit)
+
+        def from_kernel(x, y):
+            return (x * unit * a + x_0) / tm, ((y * unit - y_shift) * a + y_0) / tm
+
+        transformer = MapTransformer(kind, a, b, lon0, lat0, self._bc.lon_sign, to_kernel, from_kernel, projection)
+        xi, yi = to_kernel(xx, yy)
         lo, la = L.proj_inverse(kind, a, b, lon0, lat0, self._bc.lon_sign, L.to_device(xi), L.to_device(yi))
-        return L.to_host(lo), L.to_host(la), xx, yy
+        return L.to_host(lo), L.to_host(la), xx, yy, transformer
 
     # ---- backplane registry (body_xy.py:2512-2584) -------------------------------------
     @staticmethod

@@ -152,6 +152,17 @@ int pm_proj_inverse(int kind, const double *params5_host, const double *xx, cons
     return check(launch_proj_inverse(kind, params5_host, xx, yy, n, lon, lat, sms, (cudaStream_t)stream));
 }
 
+int pm_proj_forward(int kind, const double *params5_host, const double *lon, const double *lat, int64_t n,
+                    double *xx, double *yy, void *stream) {
+    if (!params5_host || n < 0) return PM_ERR_BAD_ARG;
+    if (kind < PM_PROJ_ORTHOGRAPHIC || kind > PM_PROJ_AZIMUTHAL_EQUAL_AREA) return PM_ERR_UNSUPPORTED;
+    if (n == 0) return PM_OK;
+    if (!xx || !yy || !lon || !lat) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_proj_forward(kind, params5_host, lon, lat, n, xx, yy, sms, (cudaStream_t)stream));
+}
+
 int pm_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes, int ny, int nx,
               int plane_begin, int plane_count, const double *xmap, const double *ymap, int64_t n_cells,
               int64_t cells_per_row, int mode, uint32_t flags, double *out, void *stream) {

@@ -46,6 +46,9 @@ cudaError_t launch_math_probe(int kind, const double *a, const double *b, int64_
 cudaError_t launch_proj_inverse(int kind, const double *params5, const double *xx, const double *yy,
                                 int64_t n, double *lon, double *lat, int sm_count, cudaStream_t st);
 
+cudaError_t launch_proj_forward(int kind, const double *params5, const double *lon, const double *lat, int64_t n,
+                                double *xx, double *yy, int sm_count, cudaStream_t st);
+
 cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint32_t *plane_bits, int n_planes,
                           int ny, int nx, int plane_begin, int plane_count, const double *xmap, const double *ymap,
                           int64_t n_cells, int64_t cells_per_row, int mode, uint32_t flags, double *out, int sm_count,

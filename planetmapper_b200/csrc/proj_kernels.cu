@@ -223,6 +223,63 @@ __device__ __forceinline__ bool proj_inverse_one(int kind, const ProjParams &pp,
     return true;
 }
 
+// Forward direction (pyproj.Transformer.transform(lon, lat), the default direction of the transformer
+// generate_map_coordinates hands back, body_xy.py:3141-3153): planetographic lon / lat (degrees) -> the
+// projection's own units.  Same parameter conventions as the inverse; points the projection cannot show
+// (far side for ortho, antipode for the azimuthal ones) give NaN (pyproj: inf, mapped to NaN by the reference).
+__device__ __forceinline__ bool proj_forward_one(int kind, const ProjParams &pp, double lon_deg, double lat_deg,
+                                                 double &xx, double &yy) {
+    if (!(isfinite(lon_deg) && isfinite(lat_deg)) || fabs(lat_deg) > 90.0 + 1e-12) return false;
+    const double phi0 = pp.lat0_deg * kRpd, phi = fmax(-kHalfPi, fmin(kHalfPi, lat_deg * kRpd));
+    double lam = (lon_deg - pp.lon0_deg) * kRpd;
+    lam -= kTwoPi * floor((lam + kPi) / kTwoPi);   // (-pi, pi]
+    double sinph0, cosph0, sinphi, cosphi, sinlam, coslam;
+    sincos(phi0, &sinph0, &cosph0);
+    sincos(phi, &sinphi, &cosphi);
+    sincos(lam, &sinlam, &coslam);
+    const double cosc = sinph0 * sinphi + cosph0 * cosphi * coslam;   // cosine of the angular distance from the centre
+    double x, y;
+    if (kind == PM_PROJ_ORTHOGRAPHIC) {
+        if (cosc < -1e-10) return false;   // behind the projection plane
+        const double es = 1.0 - (pp.b * pp.b) / (pp.a * pp.a);
+        const double nu = 1.0 / sqrt(1.0 - es * sinphi * sinphi);
+        const double nu0 = 1.0 / sqrt(1.0 - es * sinph0 * sinph0);
+        x = nu * cosphi * sinlam;
+        y = nu * (sinphi * cosph0 - cosphi * sinph0 * coslam) + es * (nu0 * sinph0 - nu * sinphi) * cosph0;
+        y += (pp.b / pp.a - 1.0) * sin((pp.lat0_deg * 2.0) * kRpd);   // +y_0 with +to_meter = a
+    } else if (kind == PM_PROJ_AZIMUTHAL) {
+        if (cosc <= -1.0 + 1e-14) return false;   // the antipode has no image
+        const double c = acos(fmax(-1.0, fmin(1.0, cosc)));
+        const double sinc = sin(c);
+        const double k = c < 1e-10 ? 1.0 : c / sinc;
+        x = k * cosphi * sinlam / kPi;            // +to_meter = a pi
+        y = k * (cosph0 * sinphi - sinph0 * cosphi * coslam) / kPi;
+    } else if (kind == PM_PROJ_AZIMUTHAL_EQUAL_AREA) {
+        const double d = 1.0 + cosc;
+        if (d <= 1e-10) return false;
+        const double k = sqrt(2.0 / d);
+        x = k * cosphi * sinlam * 0.5;            // +to_meter = 2 a
+        y = k * (cosph0 * sinphi - sinph0 * cosphi * coslam) * 0.5;
+    } else {
+        return false;
+    }
+    xx = (pp.lon_sign < 0.0) ? -x : x;   // +axis=wnu
+    yy = y;
+    return true;
+}
+
+__global__ void __launch_bounds__(kBlock) proj_forward_kernel(int kind, ProjParams pp, const double *__restrict__ lon,
+                                                              const double *__restrict__ lat, int64_t n,
+                                                              double *__restrict__ xx, double *__restrict__ yy) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        double x = NAN, y = NAN;
+        if (!proj_forward_one(kind, pp, lon[idx], lat[idx], x, y)) x = y = NAN;
+        xx[idx] = x;
+        yy[idx] = y;
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) proj_inverse_kernel(int kind, ProjParams pp,
                                                               const double *__restrict__ xx,
                                                               const double *__restrict__ yy, int64_t n,
@@ -248,6 +305,18 @@ cudaError_t launch_proj_inverse(int kind, const double *p5, const double *xx, co
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     proj_inverse_kernel<<<(int)blocks, kBlock, 0, st>>>(kind, pp, xx, yy, n, lon, lat);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_proj_forward(int kind, const double *p5, const double *lon, const double *lat, int64_t n,
+                                double *xx, double *yy, int sm_count, cudaStream_t st) {
+    ProjParams pp{p5[0], p5[1], p5[2], p5[3], p5[4]};
+    int64_t blocks = (n + kBlock - 1) / kBlock;
+    int64_t cap = (int64_t)sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    proj_forward_kernel<<<(int)blocks, kBlock, 0, st>>>(kind, pp, lon, lat, n, xx, yy);
     count_launches(1);
     return cudaGetLastError();
 }

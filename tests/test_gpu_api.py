@@ -501,3 +501,38 @@ def test_progress_hook_receives_updates(obs, tmp_path):
     calls.clear()
     obs.get_backplane_img('EMISSION')
     assert calls == []
+
+
+def test_map_transformer_round_trips(body):
+    """generate_map_coordinates' transformer slot: transform(x, y, direction='INVERSE') reproduces the lons / lats
+    it came with, FORWARD maps them back onto the grid (pyproj.Transformer's interface, body_xy.py:3126)."""
+    import planetmapper_b200 as pm
+
+    for kw in (dict(projection='orthographic', lon=30, lat=-20, size=41), dict(projection='azimuthal', lat=90, size=31),
+               dict(projection='azimuthal equal area', lon=-100, lat=45, size=37)):
+        lons, lats, xx, yy, tr, info = body.generate_map_coordinates(**kw)
+        assert isinstance(tr, pm.MapTransformer)
+        lo, la = tr.transform(xx, yy, direction='INVERSE')
+        ok = np.isfinite(lons)
+        assert np.array_equal(np.isfinite(lo), ok) and np.all(np.isinf(lo[~ok]))     # pyproj marks failures with inf
+        assert np.array_equal(lo[ok], lons[ok]) and np.array_equal(la[ok], lats[ok])
+        inside = ok & (np.hypot(xx, yy) < 0.98)
+        fx, fy = tr.transform(lons[inside], lats[inside])
+        assert np.max(np.abs(fx - xx[inside])) < 1e-8 and np.max(np.abs(fy - yy[inside])) < 1e-8
+        x1, y1 = tr.transform(float(lons[inside][0]), float(lats[inside][0]), direction='FORWARD')
+        assert isinstance(x1, float) and abs(x1 - xx[inside][0]) < 1e-8
+    # rectangular / manual maps are their own lon / lat system
+    lons, lats, xx, yy, tr, info = body.generate_map_coordinates(degree_interval=30)
+    u, v = tr.transform(lons, lats, direction='INVERSE')
+    assert np.array_equal(u, lons) and np.array_equal(v, lats)
+    # custom proj string with its own units
+    proj = body.create_proj_string('ortho', lon_0=10, lat_0=20, to_meter=1000.0, x_0=5.0e6, y_0=-2.0e6)
+    c = np.linspace(-60000, 70000, 25)
+    lons, lats, xx, yy, tr, info = body.generate_map_coordinates(proj, projection_x_coords=c + 5000, projection_y_coords=c)
+    ok = np.isfinite(lons)
+    assert ok.sum() > 100
+    fx, fy = tr.transform(lons[ok], lats[ok])
+    core = np.hypot(xx[ok] - 5000, yy[ok] + 2000) < 60000
+    assert np.max(np.abs(fx[core] - xx[ok][core])) < 1e-3 and np.max(np.abs(fy[core] - yy[ok][core])) < 1e-3
+    with pytest.raises(ValueError):
+        tr.transform(0.0, 0.0, direction='sideways')

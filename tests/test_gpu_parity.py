@@ -617,3 +617,21 @@ def test_dense_cubic_gather_any_quad_aligned_plane_range(L, bc_hst):
     torch.cuda.synchronize()
     assert bool((buf[:4] == 5.0).all()) and bool((buf[10:] == 5.0).all())
     assert torch.equal(torch.nan_to_num(buf[4:10], nan=-7.0), torch.nan_to_num(full[20:26], nan=-7.0))
+
+
+@pytest.mark.parametrize('kind,lon0,lat0', [(1, 0, 0), (1, 123.456, -2), (1, 10, 90), (2, 12.345, 42), (2, 0, -90),
+                                            (3, 34, -12), (3, 5, 90)])
+def test_projection_forward_vs_oracle(L, oracle, bc_hst, kind, lon0, lat0):
+    a, b = bc_hst.r_eq, bc_hst.r_polar
+    rng = np.random.default_rng(kind)
+    lon = np.concatenate([rng.uniform(-360, 720, 20000), [np.nan, 0.0, np.inf, lon0 + 180.0]])
+    lat = np.concatenate([rng.uniform(-90, 90, 20000), [0.0, np.nan, 0.0, -lat0]])
+    for sign in (-1.0, 1.0):
+        rx, ry = oracle.proj_forward(kind, a, b, lon0, lat0, sign, lon, lat)
+        gx, gy = L.proj_forward(kind, a, b, lon0, lat0, sign, L.to_device(lon), L.to_device(lat))
+        gx, gy = gx.cpu().numpy(), gy.cpu().numpy()
+        # the visibility threshold of the orthographic projection is a floating-point comparison at the limb
+        assert (np.isnan(gx) != np.isnan(rx)).sum() <= 2
+        ok = np.isfinite(rx) & np.isfinite(gx)
+        assert ok.sum() > 8000
+        assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-12 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-12

@@ -424,3 +424,28 @@ def test_vectorised_map_oracle_equals_loop_oracle():
             want = MO.map_img(cube, x_map, y_map, interp, propagate_nan=prop)
             got = MO.map_cube_fast(cube, x_map, y_map, interp, propagate_nan=prop)
             assert np.array_equal(got, want, equal_nan=True), (interp, prop)
+
+
+@pytest.mark.parametrize('kind,lon0,lat0', [(1, 0, 0), (1, 123.456, -2), (1, -42, -21.3), (1, 10, 90), (2, 0, 0),
+                                            (2, 123.456, 90), (2, 12.345, 42), (3, 0, 0), (3, 34, -12), (3, 5, -90)])
+def test_oracle_projection_forward_inverts_the_pinned_inverse(oracle, bc_hst, kind, lon0, lat0):
+    """The forward projections (the transformer generate_map_coordinates hands back) are the exact inverses
+    of the inverse projections, which the reference's 8-decimal literals pin (test above): every grid node the
+    inverse places on the body maps back onto itself."""
+    a, b = bc_hst.r_eq, bc_hst.r_polar
+    lim = 1.01 * max(1.0, b / a) if kind == 1 else 1.01
+    c = np.linspace(-lim, lim, 101)
+    xx, yy = np.meshgrid(c, c)
+    for sign in (-1.0, 1.0):
+        lon, lat = oracle.proj_inverse(kind, a, b, lon0, lat0, sign, xx, yy)
+        ok = np.isfinite(lon)
+        assert ok.sum() > 3000
+        # the rim of an azimuthal map is the antipode (a single point): keep away from it
+        inside = ok & (np.hypot(xx, yy) < (0.999 if kind != 1 else 2.0))
+        fx, fy = oracle.proj_forward(kind, a, b, lon0, lat0, sign, lon, lat)
+        assert np.all(np.isfinite(fx[inside]))
+        scale = 1e-9 if kind != 1 else 2e-8     # ortho: d(lon, lat)/d(x, y) diverges at the limb, so does the round trip
+        assert np.max(np.abs(fx[inside] - xx[inside])) < scale and np.max(np.abs(fy[inside] - yy[inside])) < scale
+    # the far side has no orthographic image; non-finite input gives NaN
+    fx, fy = oracle.proj_forward(1, a, b, 0.0, 0.0, -1.0, np.array([180.0, np.nan, 10.0]), np.array([0.0, 0.0, np.inf]))
+    assert np.isnan(fx).all() and np.isnan(fy).all()
