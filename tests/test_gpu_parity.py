@@ -634,4 +634,10 @@ def test_projection_forward_vs_oracle(L, oracle, bc_hst, kind, lon0, lat0):
         assert (np.isnan(gx) != np.isnan(rx)).sum() <= 2
         ok = np.isfinite(rx) & np.isfinite(gx)
         assert ok.sum() > 8000
-        assert np.max(np.abs(gx[ok] - rx[ok])) < 1e-12 and np.max(np.abs(gy[ok] - ry[ok])) < 1e-12
+        # towards the antipode the azimuthal scale c / sin(c) amplifies the last bits of acos / sin: compare
+        # at 1e-12 away from it and relative to that scale near it
+        with np.errstate(invalid='ignore'):
+            cosc = (np.sin(np.deg2rad(lat0)) * np.sin(np.deg2rad(lat))
+                    + np.cos(np.deg2rad(lat0)) * np.cos(np.deg2rad(lat)) * np.cos(np.deg2rad(lon - lon0)))
+        tol = 1e-12 / np.maximum(1.0 + cosc, 1e-6) if kind != 1 else np.full(lon.shape, 1e-12)
+        assert np.all(np.abs(gx[ok] - rx[ok]) <= tol[ok]) and np.all(np.abs(gy[ok] - ry[ok]) <= tol[ok])
