@@ -115,10 +115,13 @@ atexit.register(shutdown_pool)
 def default_workers() -> int:
     """Host processes to use: the cores this process may run on, shared between the ranks
     of a torchrun job (LOCAL_WORLD_SIZE)."""
+    total = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
-        cores = os.cpu_count() or 1
+        cores = total
+    if cores < total:   # this rank already owns a slice of the host (shard.bind_rank_to_cores, taskset, cgroups)
+        return max(1, cores)
     ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
     return max(1, cores // ranks)
 

@@ -248,3 +248,29 @@ def test_progress_hooks_follow_the_reference_protocol():
     assert t._progress_call_stack == []
     t._remove_progress_hook()
     assert t._get_progress_hook() is None and t.outer(1) == 1
+
+
+def test_interpolation_modes_and_the_smoothing_refusal():
+    """map_img's `interpolation` argument (body_xy.py:1592-1631) as the kernels see it.  FITPACK smoothing
+    splines (spline_smoothing > 0, body_xy.py:1673-1680) are NOT accelerated: the reference's own tests call
+    their values scipy-version dependent (tests/test_observation.py:1163-1169), so there is nothing to hold
+    parity against and the call is refused loudly instead of approximated."""
+    from planetmapper_b200 import _lib as L
+    from planetmapper_b200.body_xy import INTERP_SMOOTH, _interpolation_mode
+
+    assert _interpolation_mode('nearest', 0) == L.INTERP_NEAREST
+    assert _interpolation_mode('linear', 0) == _interpolation_mode(1, 0) == _interpolation_mode((1, 1), 0) == L.INTERP_LINEAR
+    assert _interpolation_mode('quadratic', 0) == _interpolation_mode(2, 0) == L.INTERP_QUADRATIC
+    assert _interpolation_mode('cubic', 0) == _interpolation_mode(3, 0) == _interpolation_mode((3, 3), 0) == L.INTERP_CUBIC
+    assert _interpolation_mode((1, 3), 0) == L.INTERP_MIXED | (1 << 4) | 3
+    assert _interpolation_mode('smooth', 0) == INTERP_SMOOTH
+    assert _interpolation_mode('nearest', 0.5) == L.INTERP_NEAREST and _interpolation_mode('smooth', 2) == INTERP_SMOOTH
+    for interp in ('linear', 'quadratic', 'cubic', 1, 3, (2, 3)):
+        with pytest.raises(NotImplementedError, match='smoothing'):
+            _interpolation_mode(interp, 0.5)
+    for interp in (4, 5, (1, 5), (0, 2)):
+        with pytest.raises(NotImplementedError):
+            _interpolation_mode(interp, 0)
+    for interp in ('<<<test>>>', (1, 2, 3), None, True):
+        with pytest.raises(ValueError):
+            _interpolation_mode(interp, 0)
