@@ -840,6 +840,7 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
 struct PlaneStats {
     long long n_nan;
     long long n_bad;
+    long long n_iso;   // bad pixels whose nine (edge-clamped) neighbours are all bad: the only ones the median fills
 };
 
 // Planes of a cube are small (C4: 64 x 64) and many, planes of a time series are large (C5:
@@ -942,7 +943,7 @@ __global__ void __launch_bounds__(256) median_kernel(const double *__restrict__ 
                                                      double *__restrict__ median) {
     const int l = blockIdx.x;
     const long long n_bad = stats[l].n_bad;
-    if (n_bad == 0) return;  // nothing to repair (uniform for the CTA)
+    if (stats[l].n_iso == 0) return;  // no pixel takes the median (uniform for the CTA)
     const long long m = plane_px - n_bad;
     double med = 0.0;  // np.all(bad) -> 0.0 (body_xy.py:1890-1891)
     if (m > 0) {
@@ -983,7 +984,7 @@ __global__ void select_init_kernel(const PlaneStats *__restrict__ stats, int n_p
     st.k[0] = st.k[1] = 0;
     st.n_sel = 0;
     const long long n_bad = stats[l].n_bad, m = plane_px - n_bad;
-    if (n_bad > 0) {
+    if (stats[l].n_iso > 0) {   // the median is only ever written into isolated bad pixels: skip it otherwise
         if (m <= 0) {
             median[l] = 0.0;  // np.all(bad) -> 0.0 (body_xy.py:1890-1891)
         } else if (m & 1) {
@@ -1083,44 +1084,68 @@ __global__ void __launch_bounds__(128) select_pick_kernel(SelectState *__restric
     }
 }
 
-// pass 3: replace bad pixels (body_xy.py:1893-1903)
+// pass 2: replace bad pixels that have a good neighbour by the 3 x 3 nan-mean (body_xy.py:1893-1903) and
+// COUNT the others (all nine edge-clamped neighbours bad): only those take np.nanmedian of the plane
+// (`cleaned[bad] = median` is overwritten everywhere else), so the median - six passes over the batch for
+// megapixel planes - is computed only for planes that have such a pixel (pass 3) and written by pass 4.
+__device__ __forceinline__ bool all_neighbours_bad(const double *__restrict__ img, int i, int j, int ny, int nx) {
+    // uniform_filter(bad, size=3) on a bool array is True only when all nine
+    // reflected neighbours are bad; reflect == clamp for size 3
+    bool all_bad = true;
+    for (int di = -1; di <= 1; di++)
+        for (int dj = -1; dj <= 1; dj++) {
+            int ii = min(max(i + di, 0), ny - 1), jj = min(max(j + dj, 0), nx - 1);
+            all_bad = all_bad && !isfinite(img[(int64_t)ii * nx + jj]);
+        }
+    return all_bad;
+}
 __global__ void __launch_bounds__(256) repair_kernel(const double *__restrict__ cube, int n_planes, int ny,
-                                                     int nx, const PlaneStats *__restrict__ stats,
-                                                     const double *__restrict__ median,
+                                                     int nx, PlaneStats *__restrict__ stats,
                                                      double *__restrict__ coef) {
     // blockIdx.y = plane; rows are walked with 32-bit arithmetic (no 64-bit division per pixel)
     const int l = blockIdx.y;
     if (stats[l].n_bad == 0) return;
     const int64_t plane_px = (int64_t)ny * nx;
+    const double *img = cube + (int64_t)l * plane_px;
+    unsigned long long n_iso = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < plane_px; r += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t idx = (int64_t)l * plane_px + r;
-        const double *img = cube + (int64_t)l * plane_px;
         if (isfinite(img[r])) continue;
         const int i = (int)(r / nx), j = (int)(r - (int64_t)i * nx);   // bad pixels only
-        // uniform_filter(bad, size=3) on a bool array is True only when all nine
-        // reflected neighbours are bad; reflect == clamp for size 3
-        bool all_bad = true;
-        for (int di = -1; di <= 1; di++)
-            for (int dj = -1; dj <= 1; dj++) {
-                int ii = min(max(i + di, 0), ny - 1), jj = min(max(j + dj, 0), nx - 1);
-                all_bad = all_bad && !isfinite(img[(int64_t)ii * nx + jj]);
-            }
-        double v = median[l];
-        if (!all_bad) {
-            // np.nanmean over the window clipped at the image edge, inf treated as NaN
-            double sum = 0.0;
-            int cnt = 0;
-            for (int ii = max(i - 1, 0); ii <= min(i + 1, ny - 1); ii++)
-                for (int jj = max(j - 1, 0); jj <= min(j + 1, nx - 1); jj++) {
-                    double w = img[(int64_t)ii * nx + jj];
-                    if (isfinite(w)) {
-                        sum += w;
-                        cnt++;
-                    }
-                }
-            v = sum / (double)cnt;
+        if (all_neighbours_bad(img, i, j, ny, nx)) {
+            n_iso++;
+            continue;
         }
-        coef[idx] = v;
+        // np.nanmean over the window clipped at the image edge, inf treated as NaN
+        double sum = 0.0;
+        int cnt = 0;
+        for (int ii = max(i - 1, 0); ii <= min(i + 1, ny - 1); ii++)
+            for (int jj = max(j - 1, 0); jj <= min(j + 1, nx - 1); jj++) {
+                double w = img[(int64_t)ii * nx + jj];
+                if (isfinite(w)) {
+                    sum += w;
+                    cnt++;
+                }
+            }
+        coef[(int64_t)l * plane_px + r] = sum / (double)cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) n_iso += __shfl_down_sync(0xffffffffu, n_iso, o);
+    if ((threadIdx.x & 31) == 0 && n_iso)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&stats[l].n_iso), n_iso);
+}
+// pass 4: the isolated bad pixels take the plane's median
+__global__ void __launch_bounds__(256) fill_isolated_kernel(const double *__restrict__ cube, int ny, int nx,
+                                                            const PlaneStats *__restrict__ stats,
+                                                            const double *__restrict__ median,
+                                                            double *__restrict__ coef) {
+    const int l = blockIdx.y;
+    if (stats[l].n_iso == 0) return;
+    const int64_t plane_px = (int64_t)ny * nx;
+    const double *img = cube + (int64_t)l * plane_px;
+    const double med = median[l];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < plane_px; r += (int64_t)gridDim.x * blockDim.x) {
+        if (isfinite(img[r])) continue;
+        const int i = (int)(r / nx), j = (int)(r - (int64_t)i * nx);
+        if (all_neighbours_bad(img, i, j, ny, nx)) coef[(int64_t)l * plane_px + r] = med;
     }
 }
 
@@ -1295,6 +1320,9 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
     classify_kernel<<<dim3(n_planes, chunks), 256, 0, st>>>(cube, plane_px, coef, stats);
     plane_flags_kernel<<<(n_planes + 255) / 256, 256, 0, st>>>(stats, n_planes, plane_px, plane_skip);
     count_launches(1);
+    const int rblocks = (int)std::max<int64_t>(
+        1, std::min<int64_t>((plane_px + 255) / 256, ((int64_t)sm_count * 16 + n_planes - 1) / n_planes));
+    repair_kernel<<<dim3(rblocks, n_planes), 256, 0, st>>>(cube, n_planes, ny, nx, stats, coef);
     if (chunks == 1) {
         median_kernel<<<n_planes, 256, 0, st>>>(cube, plane_px, stats, median);
     } else {
@@ -1310,10 +1338,8 @@ cudaError_t launch_spline_prepare(const double *cube, int n_planes, int ny, int 
         }
         count_launches(2 * kSelPasses);
     }
-    const int rblocks = (int)std::max<int64_t>(
-        1, std::min<int64_t>((plane_px + 255) / 256, ((int64_t)sm_count * 16 + n_planes - 1) / n_planes));
-    repair_kernel<<<dim3(rblocks, n_planes), 256, 0, st>>>(cube, n_planes, ny, nx, stats, median, coef);
-    count_launches(3);
+    fill_isolated_kernel<<<dim3(rblocks, n_planes), 256, 0, st>>>(cube, ny, nx, stats, median, coef);
+    count_launches(4);
     int deg_y = degree, deg_x = degree;  // rows (image y) / columns (image x)
     if (degree & PM_INTERP_MIXED) {
         deg_y = (degree >> 4) & 0xF;
