@@ -350,7 +350,7 @@ def bench_mapped_cube(L, torch, pm, bc, rank, world, e2e=True):
     e1.record()
     torch.cuda.synchronize()
     xy_ms = e0.elapsed_time(e1)
-    cube = L.to_device(cube_h)
+    cube = L.to_device(cube_h[lo_p:hi_p])     # this rank's planes only: NaN repair / spline fit shard with the gather
     n_cells = lo.size
     out = torch.empty((chunk,) + lo.shape, dtype=torch.float64, device='cuda')
     res = {'workload': 'C4: 3000x64x64 cube (1% NaN px, one all-NaN plane) -> 0.1 deg grid '
@@ -368,13 +368,13 @@ def bench_mapped_cube(L, torch, pm, bc, rank, world, e2e=True):
             else:
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
-                src_ = L.spline_prepare(cube, mode)   # whole cube: 98 MB, 1.5 ms - not worth sharding
+                src_ = L.spline_prepare(cube, mode)
                 p1.record()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             n_launch = 0
-            for s_ in range(lo_p, hi_p, chunk):
-                n = min(chunk, hi_p - s_)
+            for s_ in range(0, hi_p - lo_p, chunk):
+                n = min(chunk, hi_p - lo_p - s_)
                 L.gather(src_, xy[0], xy[1], mode, plane_begin=s_, plane_count=n, out=out[:n])
                 n_launch += 1
             g1.record()
@@ -451,7 +451,7 @@ def bench_mapped_cube(L, torch, pm, bc, rank, world, e2e=True):
 
         per = 64
         blk = torch.empty((per,) + lo.shape, dtype=torch.float64, device='cuda')
-        L.gather(cube, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=lo_p, plane_count=per, out=blk)
+        L.gather(cube, xy[0], xy[1], L.INTERP_NEAREST, plane_begin=0, plane_count=per, out=blk)
         whole = torch.empty((per * world,) + lo.shape, dtype=torch.float64, device='cuda') if rank == 0 else None
         for timed in (False, True):
             dist.barrier()
