@@ -27,7 +27,7 @@ extern "C" {
 #define PM_ERR_UNSUPPORTED (-3)
 #define PM_ERR_NO_DEVICE (-4)
 
-#define PM_ABI_VERSION 9
+#define PM_ABI_VERSION 10
 
 /*
  * Per-frame constants, computed once per frame on the host from SPICE
@@ -158,6 +158,12 @@ int pm_backplanes_img_host(const PMFrame *frame_host, int nx, int ny, uint64_t p
  */
 int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat,
                       int64_t n_cells, uint64_t plane_mask, double *out, void *stream);
+/* The same for ONE frame whose constants are in HOST memory (see pm_backplanes_img_host): this is what
+ * BodyXY.get_backplane_map and the x / y map of BodyXY.map_img (body_xy.py:1414, :3482) launch.  `lon`,
+ * `lat`, `out` are DEVICE pointers.  With plane_mask = PIXEL-X | PIXEL-Y the kernel is the instantiation
+ * that computes only what x_map / y_map need (illumf's emission angle for the visibility test). */
+int pm_backplanes_map_host(const PMFrame *frame_host, const double *lon, const double *lat,
+                           int64_t n_cells, uint64_t plane_mask, double *out, void *stream);
 
 /*
  * Time series (BASELINE config C5: a fresh BodyXY per epoch, then map_img of that epoch's image,

@@ -38,7 +38,7 @@ PLANE_ID = {n: i for i, n in enumerate(PLANE_NAMES)}
 # every symbol include/pm_b200.h declares
 EXPORTED_SYMBOLS = [
     'pm_abi_version', 'pm_error_string', 'pm_launch_count', 'pm_backplanes_img',
-    'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt', 'pm_proj_inverse', 'pm_gather',
+    'pm_backplanes_map', 'pm_backplanes_map_host', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt', 'pm_proj_inverse', 'pm_gather',
     'pm_spline_coef_bytes', 'pm_spline_nanbits_bytes', 'pm_spline_planebits_bytes',
     'pm_spline_work_bytes', 'pm_spline_prepare', 'pm_fp64_peak_probe', 'pm_math_probe',
     'pm_nan_minmax', 'pm_pchip_work_bytes', 'pm_pchip_resample', 'pm_gather_grid_linear',
@@ -73,6 +73,7 @@ def load_library() -> ctypes.CDLL:
     lib.pm_launch_count.restype = c_u64
     lib.pm_backplanes_img.argtypes = [c_p, c_i, c_i, c_i, c_u64, c_p, c_p]
     lib.pm_backplanes_map.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
+    lib.pm_backplanes_map_host.argtypes = [c_p, c_p, c_p, c_i64, c_u64, c_p, c_p]
     lib.pm_backplanes_img_host.argtypes = [c_p, c_i, c_i, c_u64, c_p, c_p]
     lib.pm_backplanes_img_host.restype = c_i
     lib.pm_transform.argtypes = [c_p, c_i, c_i, c_p, c_p, c_i64, ctypes.c_double, c_u32, c_p, c_p, c_p, c_p, c_p]
@@ -115,11 +116,12 @@ def load_library() -> ctypes.CDLL:
     lib.pm_host_ssb_state.restype = c_i
     lib.pm_host_orientation.argtypes = [c_p, ctypes.c_double, c_p, c_p]
     lib.pm_host_orientation.restype = c_i
-    for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_xy2lonlat', 'pm_lonlat2xy', 'pm_lonlat2xy_alt',
+    for fn in ('pm_backplanes_img', 'pm_backplanes_map', 'pm_backplanes_map_host', 'pm_xy2lonlat', 'pm_lonlat2xy',
+               'pm_lonlat2xy_alt',
                'pm_proj_inverse', 'pm_gather', 'pm_spline_prepare', 'pm_fp64_peak_probe',
                'pm_math_probe', 'pm_nan_minmax', 'pm_pchip_resample', 'pm_gather_grid_linear'):
         getattr(lib, fn).restype = c_i
-    if lib.pm_abi_version() != 9:
+    if lib.pm_abi_version() != 10:
         raise PMLibraryError('libpm_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -292,6 +294,23 @@ def backplanes_map(frame_dev, lon_dev, lat_dev, mask: int = ALL_PLANES, out=None
     rc = lib.pm_backplanes_map(frame_dev.data_ptr(), lon_dev.data_ptr(), lat_dev.data_ptr(), n,
                                mask, out.data_ptr(), _stream_ptr(torch))
     _check(rc, 'pm_backplanes_map')
+    return out
+
+
+def backplanes_map_host(frame_host, lon_dev, lat_dev, mask: int = ALL_PLANES, out=None):
+    """pm_backplanes_map for one frame whose 92 constants are a HOST float64 array (kernel-parameter
+    frame, no upload).  Returns a CUDA tensor (popcount(mask),) + lon_dev.shape."""
+    torch = _torch()
+    lib = load_library()
+    fr = np.ascontiguousarray(frame_host, dtype=np.float64).reshape(-1)
+    if fr.size != 92:
+        raise ValueError('frame_host must hold the 92 PMFrame doubles')
+    assert lon_dev.is_cuda and lat_dev.is_cuda and lon_dev.is_contiguous() and lat_dev.is_contiguous()
+    if out is None:
+        out = torch.empty((popcount(mask),) + tuple(lon_dev.shape), dtype=torch.float64, device=lon_dev.device)
+    rc = lib.pm_backplanes_map_host(fr.ctypes.data_as(ctypes.c_void_p), lon_dev.data_ptr(), lat_dev.data_ptr(),
+                                    lon_dev.numel(), mask, out.data_ptr(), _stream_ptr(torch))
+    _check(rc, 'pm_backplanes_map_host')
     return out
 
 

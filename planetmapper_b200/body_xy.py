@@ -1010,8 +1010,7 @@ class BodyXY(ProgressMixin):
                     want = L.ALL_PLANES & ~((1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1]))
                 else:
                     want = (1 << _XY_PLANES[0]) | (1 << _XY_PLANES[1])
-                fd = self._frame_dev(alt)
-                planes = L.backplanes_map(fd, lonlat[0], lonlat[1], want)
+                planes = L.backplanes_map_host(self._frame_host(alt), lonlat[0], lonlat[1], want)
                 entry = (want, planes)
                 cache[key] = entry
             out[tag] = entry

@@ -115,6 +115,24 @@ __global__ void __launch_bounds__(kBlock, kImgParamCtas) backplanes_img_param_ke
 // ---------------------------------------------------------------------------------
 // Map direction
 // ---------------------------------------------------------------------------------
+// x_map / y_map of BodyXY.map_img (body_xy.py:3482): the plane set of every reprojection
+constexpr uint64_t kXYMapMask = bit(PM_PIXEL_X) | bit(PM_PIXEL_Y);
+
+template <uint64_t kFixedMask>
+__device__ __forceinline__ void map_tile(const FrameD &fs, const double *__restrict__ lon_in,
+                                         const double *__restrict__ lat_in, int64_t n, uint64_t mask,
+                                         const PlaneOffsets &po, double *__restrict__ out) {
+    const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
+#pragma unroll 1
+    for (int r = 0; r < kPerThread; r++) {
+        const int64_t idx = first + r * kBlock;
+        if (idx >= n) break;
+        PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
+        map_cell<kFixedMask>(fs, __ldg(lon_in + idx), __ldg(lat_in + idx), mask, sink);
+    }
+}
+
+template <uint64_t kFixedMask>
 __global__ void __launch_bounds__(kBlock, 4) backplanes_map_kernel(const PMFrame *__restrict__ frame,
                                                                    const double *__restrict__ lon_in,
                                                                    const double *__restrict__ lat_in,
@@ -125,15 +143,18 @@ __global__ void __launch_bounds__(kBlock, 4) backplanes_map_kernel(const PMFrame
     // blockIdx.y = frame of a series sharing the lon / lat grid (pm_backplanes_map_batch); each
     // frame's planes follow the previous frame's: po.frame_stride doubles apart
     load_frame(fs, frame + blockIdx.y);
-    out += (int64_t)blockIdx.y * po.frame_stride;
-    const int64_t first = (int64_t)blockIdx.x * (kBlock * kPerThread) + threadIdx.x;
-#pragma unroll 1
-    for (int r = 0; r < kPerThread; r++) {
-        const int64_t idx = first + r * kBlock;
-        if (idx >= n) break;
-        PlaneSink sink{reinterpret_cast<char *>(out + idx), po};
-        map_cell(fs, __ldg(lon_in + idx), __ldg(lat_in + idx), mask, sink);
-    }
+    map_tile<kFixedMask>(fs, lon_in, lat_in, n, mask, po, out + (int64_t)blockIdx.y * po.frame_stride);
+}
+
+// Single frame given on the host: constants in the kernel's parameter space, like the image kernel
+template <uint64_t kFixedMask>
+__global__ void __launch_bounds__(kBlock, 4) backplanes_map_param_kernel(const __grid_constant__ FrameD fs,
+                                                                         const double *__restrict__ lon_in,
+                                                                         const double *__restrict__ lat_in,
+                                                                         int64_t n, uint64_t mask,
+                                                                         const __grid_constant__ PlaneOffsets po,
+                                                                         double *__restrict__ out) {
+    map_tile<kFixedMask>(fs, lon_in, lat_in, n, mask, po, out);
 }
 
 // BodyXY._xy2lonlat (body_xy.py:482-496) -> Body._obsvec_norm2lonlat (body.py:1058-1081)
@@ -365,7 +386,24 @@ cudaError_t launch_backplanes_map(const PMFrame *frames, int n_frames, const dou
                                   int64_t n, uint64_t mask, double *out, int sm_count, cudaStream_t st) {
     (void)sm_count;
     const dim3 grid(chunks_for(n), (unsigned)n_frames);
-    backplanes_map_kernel<<<grid, kBlock, 0, st>>>(frames, lon, lat, n, mask, make_plane_offsets(mask, n), out);
+    const PlaneOffsets po = make_plane_offsets(mask, n);
+    if (mask == kXYMapMask)
+        backplanes_map_kernel<kXYMapMask><<<grid, kBlock, 0, st>>>(frames, lon, lat, n, mask, po, out);
+    else
+        backplanes_map_kernel<0><<<grid, kBlock, 0, st>>>(frames, lon, lat, n, mask, po, out);
+    count_launches(1);
+    return cudaGetLastError();
+}
+cudaError_t launch_backplanes_map_host(const PMFrame *frame_host, const double *lon, const double *lat, int64_t n,
+                                       uint64_t mask, double *out, int sm_count, cudaStream_t st) {
+    (void)sm_count;
+    FrameD fs;
+    load_frame_host(fs, frame_host);
+    const PlaneOffsets po = make_plane_offsets(mask, n);
+    if (mask == kXYMapMask)
+        backplanes_map_param_kernel<kXYMapMask><<<chunks_for(n), kBlock, 0, st>>>(fs, lon, lat, n, mask, po, out);
+    else
+        backplanes_map_param_kernel<0><<<chunks_for(n), kBlock, 0, st>>>(fs, lon, lat, n, mask, po, out);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -76,6 +76,19 @@ int pm_backplanes_map(const PMFrame *frame, const double *lon, const double *lat
     return check(launch_backplanes_map(frame, 1, lon, lat, n_cells, plane_mask, out, sms, (cudaStream_t)stream));
 }
 
+int pm_backplanes_map_host(const PMFrame *frame_host, const double *lon, const double *lat, int64_t n_cells,
+                           uint64_t plane_mask, double *out, void *stream) {
+    if (!frame_host || n_cells < 0) return PM_ERR_BAD_ARG;
+    plane_mask &= PM_ALL_PLANES;
+    if (!plane_mask) return PM_ERR_BAD_ARG;
+    if (n_cells == 0) return PM_OK;
+    if (!lon || !lat || !out) return PM_ERR_BAD_ARG;
+    int sms = sm_count();
+    if (sms <= 0) return PM_ERR_NO_DEVICE;
+    return check(launch_backplanes_map_host(frame_host, lon, lat, n_cells, plane_mask, out, sms,
+                                            (cudaStream_t)stream));
+}
+
 int pm_backplanes_map_batch(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
                             int64_t n_cells, uint64_t plane_mask, double *out, void *stream) {
     if (!frames || n_frames <= 0 || n_frames > 65535 || n_cells < 0) return PM_ERR_BAD_ARG;

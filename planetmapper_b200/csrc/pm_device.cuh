@@ -846,8 +846,11 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
 // inverse mapping cell -> image xy with the reference's visibility test.
 // Replaces the loops listed at pm_backplanes_map in include/pm_b200.h.
 // ---------------------------------------------------------------------------------
-template <class Sink>
-PM_HD void map_cell(const FrameD &fs, double lon_deg, double lat_deg, uint64_t mask, Sink &out) {
+// kFixedMask != 0 fixes the plane set at compile time (the x / y map of map_img needs only the
+// emission angle of illumf: phase, incidence and the state are then dead code).
+template <uint64_t kFixedMask = 0, class Sink>
+PM_HD void map_cell(const FrameD &fs, double lon_deg, double lat_deg, uint64_t mask_in, Sink &out) {
+    const uint64_t mask = kFixedMask ? kFixedMask : mask_in;
     const PMFrame &f = fs.f;
     const double nan = NAN;
     // BodyXY._get_lonlat_map (body_xy.py:3293-3300)

@@ -32,6 +32,8 @@ cudaError_t launch_backplanes_img_host(const PMFrame *frame_host, int nx, int ny
                                        int sm_count, cudaStream_t st);
 cudaError_t launch_backplanes_map(const PMFrame *frames, int n_frames, const double *lon, const double *lat,
                                   int64_t n, uint64_t mask, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_backplanes_map_host(const PMFrame *frame_host, const double *lon, const double *lat, int64_t n,
+                                       uint64_t mask, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_xy2lonlat(const PMFrame *frame, const double *x, const double *y, int64_t n, double *lon,
                              double *lat, unsigned long long *n_missed, int sm_count, cudaStream_t st);
 cudaError_t launch_lonlat2xy(const PMFrame *frame, const double *lon, const double *lat, int64_t n, double alt,

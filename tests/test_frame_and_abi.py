@@ -45,7 +45,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = L.load_library()
     for sym in sorted(declared):
         assert hasattr(lib, sym), f'{sym} not exported by libpm_b200.so'
-    assert lib.pm_abi_version() == 9
+    assert lib.pm_abi_version() == 10
     assert lib.pm_error_string(-1) == b'bad argument'
     # argument validation happens before any device work
     assert lib.pm_backplanes_img(None, 1, 4, 4, 1, None, None) == -1

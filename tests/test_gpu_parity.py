@@ -133,6 +133,31 @@ def _grid(step):
     return np.meshgrid(lons, lats)
 
 
+def test_map_host_frame_and_xy_instantiation_equal_the_general_kernel(L, bc_hst):
+    """pm_backplanes_map_host (kernel-parameter frame) equals pm_backplanes_map bit for bit, and the x / y map
+    instantiation (plane set fixed at compile time, phase / incidence / state never computed) gives the same
+    x_map / y_map bits as the general kernel asked for more planes; the batched launch too.  (The general kernel is the one compared with the oracle below.)"""
+    nx, ny = 200, 160
+    fr = _img_case(bc_hst, nx, ny, 101.3, 77.9, 61.0, 33.0)
+    lo, la = _grid(0.75)
+    lo = lo.copy()
+    lo[0, 0] = np.nan
+    la[1, 1] = np.inf
+    lo[2, 2] = -725.0
+    lod, lad, frd = L.to_device(lo), L.to_device(la), L.to_device(fr)
+    xy = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
+    wide = L.mask_from_names(['PIXEL-X', 'PIXEL-Y', 'RA', 'EMISSION', 'DOPPLER'])
+    ref_all = L.backplanes_map(frd, lod, lad).cpu().numpy()
+    assert np.array_equal(L.backplanes_map_host(fr, lod, lad).cpu().numpy(), ref_all, equal_nan=True)
+    ref_xy = ref_all[[L.PLANE_ID['PIXEL-X'], L.PLANE_ID['PIXEL-Y']]]
+    assert np.isfinite(ref_xy).sum() > 10000
+    for got in (L.backplanes_map(frd, lod, lad, xy), L.backplanes_map_host(fr, lod, lad, xy),
+                L.backplanes_map_batch(L.to_device(np.stack([fr, fr])), lod, lad, xy)[1]):
+        assert np.array_equal(got.cpu().numpy(), ref_xy, equal_nan=True)
+    w = L.backplanes_map_host(fr, lod, lad, wide).cpu().numpy()
+    ids = sorted(L.PLANE_ID[n] for n in ('PIXEL-X', 'PIXEL-Y', 'RA', 'EMISSION', 'DOPPLER'))
+    assert np.array_equal(w, ref_all[ids], equal_nan=True)
+
 @pytest.mark.parametrize('case', ['golden-7x10', 'rot-200x160', 'golden-7x10-alt'])
 def test_map_backplanes_vs_oracle(L, oracle, bc_hst, case):
     nx, ny, x0, y0, r0, rot, alt = IMG_CASES[case]

@@ -39,12 +39,16 @@ elif what == 'transform':
         L.transform(fd, 'xy', 'lonlat', x, y)
 else:
     cube_h, lo, la = bench.c4_inputs(1024)
-    fd = L.to_device(bench.c4_frame(bc))
+    fr4 = bench.c4_frame(bc)
+    fd = L.to_device(fr4)
     lod, lad = L.to_device(lo), L.to_device(la)
+    xy_mask = L.mask_from_names(['PIXEL-X', 'PIXEL-Y'])
     for _ in range(2):
-        xy = L.backplanes_map(fd, lod, lad, L.mask_from_names(['PIXEL-X', 'PIXEL-Y']))
+        xy = L.backplanes_map_host(fr4, lod, lad, xy_mask)                    # what map_img launches
     if what == 'map':
         for _ in range(2):
+            L.backplanes_map_host(fr4, lod, lad, L.ALL_PLANES)
+            L.backplanes_map(fd, lod, lad, xy_mask)                           # frame staged in shared memory
             L.backplanes_map(fd, lod, lad, L.ALL_PLANES)
     else:
         cube = L.to_device(cube_h)
