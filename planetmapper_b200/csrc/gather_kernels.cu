@@ -16,6 +16,8 @@
 #include "pm_device.cuh"
 #include "pm_kernels.h"
 
+#include <type_traits>
+
 #include <cstdlib>
 #include <map>
 #include <utility>
@@ -291,12 +293,10 @@ __device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, doub
 // every LDG of the three rotating register sets wrote SB5); waiting for the tile about to be
 // multiplied therefore also waited for the prefetches just issued.
 constexpr int kCubicBlock = 128;   // threads per CTA: 4 CTAs / SM at <= 128 registers, fine-grained tail
-#ifndef PM_CUBIC_STAGES
-#define PM_CUBIC_STAGES 2
+#ifndef PM_CUBIC_SLOTS
+#define PM_CUBIC_SLOTS 6
 #endif
-constexpr int kCubicStages = PM_CUBIC_STAGES;    // stage buffers per warp (power of two): one tile in flight while one is multiplied;
-                                   // 4 stages measured 2 % slower - the 24 KB they take away from L1 matter more
-constexpr int kCubicFoot = 3;      // distinct 4 x 4 footprints per warp in the pipelined path (48 KB of stages)
+constexpr int kCubicSlots = PM_CUBIC_SLOTS;  // 1 KB footprint slots per warp: 6 = 24 KB per CTA, 96 KB per SM at four CTAs
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -317,7 +317,10 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(kCubicBlock, 4)
+#ifndef PM_CUBIC_CTAS
+#define PM_CUBIC_CTAS 4
+#endif
+__global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
     gather_cubic_mma_kernel(const double *__restrict__ coefq, const uint32_t *__restrict__ nanbits,
                             const uint32_t *__restrict__ plane_bits, int n_words, int ny, int nx, int n_planes_padded,
                             int plane_begin, int plane_count, const double *__restrict__ xmap,
@@ -516,7 +519,12 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         // copies chunks L (quad 0) and L + 32 (quad 1) with two 16-byte cp.async - a quarter of a kilobyte per
         // instruction and ONE address per footprint - and reads back the element of its own MMA row / column,
         // which other lanes copied: __syncwarp() after the wait makes the copies visible inside the warp.
-        __shared__ __align__(16) double stage[kCubicStages][kCubicFoot][kCubicBlock / 32][128];
+        //
+        // Each warp owns kCubicSlots footprint slots of 1 KB, used as a ring of DEPTH = kCubicSlots / NF plane
+        // tiles for a warp with NF distinct footprints: the common single-footprint warp keeps five tiles in
+        // flight behind the one being multiplied (an L2 round trip under a full store stream is ~4 tile times),
+        // a three-footprint warp one.
+        __shared__ __align__(16) double stage[kCubicBlock / 32][kCubicSlots][128];
         const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
         const bool fast_store = full_tiles && pair_ok;
         const int n_it = (l1 - l0 + 7) / 8;
@@ -531,71 +539,101 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
         const int64_t tile_stride = 2 * quad_stride;
         // quads of coefficients that exist from this group's first plane on (the last tile may have one)
         const int quads_ahead = (n_planes_padded - (plane_begin + l0)) >> 2;
-        double *const my_chunk = &stage[0][0][warp][2 * lane];            // + 64 doubles: the quad-1 chunk
-        const double *const my_elem = &stage[0][0][warp][(g >> 2) * 64 + t * 4 + (g & 3)];   // + 16 j: row j
-        constexpr int kFoot = (kCubicBlock / 32) * 128, kSlot = kCubicFoot * kFoot;  // doubles
-        int issued = 0;
-        auto issue = [&]() {
-            if (issued < n_it) {
-                double *dst = my_chunk + (issued & (kCubicStages - 1)) * kSlot;
-                // the second quad of the last tile may lie past the array: copy the first one again (its rows of
-                // D are never stored, and the rows of the product are independent)
-                const int64_t second = 2 * issued + 1 < quads_ahead ? quad_stride : 0;
-                cp_async16(dst, q0);
-                cp_async16(dst + 64, q0 + second);
-                if (nf > 1) {
-                    cp_async16(dst + kFoot, q0 + d1);
-                    cp_async16(dst + kFoot + 64, q0 + d1 + second);
-                }
-                if (nf > 2) {
-                    cp_async16(dst + 2 * kFoot, q0 + d2);
-                    cp_async16(dst + 2 * kFoot + 64, q0 + d2 + second);
-                }
-                if (2 * issued + 2 < quads_ahead) q0 += tile_stride;
-            }
-            issued++;
-            cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
-        };
-#pragma unroll
-        for (int k = 0; k < kCubicStages - 1; k++) issue();
+        double *const my_chunk = &stage[warp][0][2 * lane];            // + 64 doubles: the quad-1 chunk
+        const double *const my_elem = &stage[warp][0][(g >> 2) * 64 + t * 4 + (g & 3)];   // + 16 j: row j
         uint32_t clean = 0;   // (uniform) bit b: the 8 planes b*8.. of the current NaN word are good in every cell of the warp
-        for (int it = 0; it < n_it; it++) {
-            const int l = l0 + 8 * it;
-            const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (a multiple of 8)
-            __syncwarp();                    // every lane has read the stage this issue() overwrites (tile it - 1)
-            issue();
-            const int word = gl >> 5;        // the same for the 8 planes of the tile
-            if (word != cur_word) {          // uniform: changes once per 32 planes
-                cur_word = word;
-                refresh_ok(word);
-                uint32_t all = ok[0][0] & ok[0][1] & ok[1][0] & ok[1][1] & ok[2][0] & ok[2][1] & ok[3][0] & ok[3][1];
-                all = __reduce_and_sync(kFull, all);
-                clean = (((all & 0xffu) == 0xffu) ? 1u : 0u) | (((all & 0xff00u) == 0xff00u) ? 2u : 0u) |
-                        (((all & 0xff0000u) == 0xff0000u) ? 4u : 0u) | (((all >> 24) == 0xffu) ? 8u : 0u);
+
+        // refresh_ok split in two so that the loads run one 32-plane word ahead of their use
+        uint32_t nw[4], nskip = 0;
+        auto fetch_ok = [&](int word) {
+            word = min(word, n_words - 1);
+            nskip = __ldg(plane_bits + word);
+            const bool consult = propagate && __ldg(plane_bits + n_words + word);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                nw[i] = (consult && pixel[i] != 0xffffffffu) ? __ldg(nanbits + (int64_t)pixel[i] * n_words + word) : 0u;
+        };
+        auto apply_ok = [&]() {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t w = nw[i];
+                w |= __shfl_xor_sync(kFull, w, 4);
+                w |= __shfl_xor_sync(kFull, w, 8);
+                const uint32_t good = pixel[i] != 0xffffffffu ? ~(w | nskip) : 0u;
+                const uint32_t other = __shfl_xor_sync(kFull, good, 16);
+                ok[i][0] = (g >> 2) ? other : good;
+                ok[i][1] = (g >> 2) ? good : other;
             }
-            cp_async_wait<kCubicStages - 1>();  // this lane's chunks of plane tile `it` have landed ...
-            __syncwarp();                       // ... and so have the other lanes'
-            const double *src = my_elem + (it & (kCubicStages - 1)) * kSlot;
-            double d[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
-            if (nf == 1) {
-                // every valid cell reads footprint 0 and invalid cells carry zero weights: no masks
-                double a[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) a[j] = src[16 * j];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) dmma8x8x4(d[i][0], d[i][1], a[j], bw[i][j]);
+        };
+        auto pipeline = [&](auto nf_tag) {
+            constexpr int NF = decltype(nf_tag)::value;
+            constexpr int DEPTH = kCubicSlots / NF;   // plane tiles in the ring
+            constexpr int kTile = NF * 128;           // doubles per ring entry
+            int issued = 0, issue_slot = 0;
+            auto issue = [&]() {
+                if (issued < n_it) {
+                    double *dst = my_chunk + issue_slot * kTile;
+                    // the second quad of the last tile may lie past the array: copy the first one again (its rows
+                    // of D are never stored, and the rows of the product are independent)
+                    const int64_t second = 2 * issued + 1 < quads_ahead ? quad_stride : 0;
+                    cp_async16(dst, q0);
+                    cp_async16(dst + 64, q0 + second);
+                    if (NF > 1) {
+                        cp_async16(dst + 128, q0 + d1);
+                        cp_async16(dst + 128 + 64, q0 + d1 + second);
+                    }
+                    if (NF > 2) {
+                        cp_async16(dst + 256, q0 + d2);
+                        cp_async16(dst + 256 + 64, q0 + d2 + second);
+                    }
+                    if (2 * issued + 2 < quads_ahead) q0 += tile_stride;
                 }
-            } else {
+                issued++;
+                issue_slot = issue_slot + 1 == DEPTH ? 0 : issue_slot + 1;
+                cp_async_commit();  // one group per plane tile, empty past the end: uniform accounting
+            };
+#pragma unroll
+            for (int k = 0; k < DEPTH - 1; k++) issue();
+            fetch_ok((plane_begin + l0) >> 5);
+            int use_slot = 0;
+            for (int it = 0; it < n_it; it++) {
+                const int l = l0 + 8 * it;
+                const int gl = plane_begin + l;  // global plane of row 0 of this plane tile (a multiple of 8)
+                __syncwarp();                    // every lane has read the ring entry this issue() overwrites (tile it - 1)
+                issue();
+                const int word = gl >> 5;        // the same for the 8 planes of the tile
+                if (word != cur_word) {          // uniform: changes once per 32 planes
+                    cur_word = word;
+                    apply_ok();                  // the words fetched four tiles ago ...
+                    fetch_ok(word + 1);          // ... and the next ones, consumed four tiles from now
+                    uint32_t all = ok[0][0] & ok[0][1] & ok[1][0] & ok[1][1] & ok[2][0] & ok[2][1] & ok[3][0] & ok[3][1];
+                    all = __reduce_and_sync(kFull, all);
+                    clean = (((all & 0xffu) == 0xffu) ? 1u : 0u) | (((all & 0xff00u) == 0xff00u) ? 2u : 0u) |
+                            (((all & 0xff0000u) == 0xff0000u) ? 4u : 0u) | (((all >> 24) == 0xffu) ? 8u : 0u);
+                }
+                cp_async_wait<DEPTH - 1>();  // this lane's chunks of plane tile `it` have landed ...
+                __syncwarp();                // ... and so have the other lanes'
+                const double *src = my_elem + use_slot * kTile;
+                use_slot = use_slot + 1 == DEPTH ? 0 : use_slot + 1;
+                double d[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[i][0] = d[i][1] = 0.0;
+                if (NF == 1) {
+                    // every valid cell reads footprint 0 and invalid cells carry zero weights: no masks
+                    double a[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) a[j] = src[16 * j];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) dmma8x8x4(d[i][0], d[i][1], a[j], bw[i][j]);
+                    }
+                } else {
 #pragma unroll 1
-                for (int f = 0; f < nf; f++) {   // rolled: the footprint only enters through bit positions
-                    {
+                    for (int f = 0; f < NF; f++) {   // rolled: the footprint only enters through bit positions
                         double a[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) a[j] = src[f * kFoot + 16 * j];
+                        for (int j = 0; j < 4; j++) a[j] = src[f * 128 + 16 * j];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (tiles & (1u << (4 * f + i))) {
@@ -606,40 +644,46 @@ __global__ void __launch_bounds__(kCubicBlock, 4)
                         }
                     }
                 }
-            }
-            // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
-            if (l + g < l1 && l + g >= lead) {
-                const int sh = (gl + g) & 31;
-                const bool tile_clean = (clean >> ((gl >> 3) & 3)) & 1u;   // uniform: no NaN in these 8 planes
-                auto store_tiles = [&](const int64_t step, const bool all_pairs, const bool select) {
+                // ---- store: lane holds plane gl + g, cells 2t, 2t + 1 of every tile
+                if (l + g < l1 && l + g >= lead) {
+                    const int sh = (gl + g) & 31;
+                    const bool tile_clean = (clean >> ((gl >> 3) & 3)) & 1u;   // uniform: no NaN in these 8 planes
+                    auto store_tiles = [&](const int64_t step, const bool all_pairs, const bool select) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const double o0 = (!select || ((ok[i][0] >> sh) & 1u)) ? d[i][0] : nan;
-                        const double o1 = (!select || ((ok[i][1] >> sh) & 1u)) ? d[i][1] : nan;
-                        double *dst = dst_row + i * step;
-                        if (all_pairs || (pair_ok && 2 * t + 1 < ncols[i])) {
-                            asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
-                        } else {
-                            if (2 * t < ncols[i]) __stcs(dst, o0);
-                            if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
+                        for (int i = 0; i < 4; i++) {
+                            const double o0 = (!select || ((ok[i][0] >> sh) & 1u)) ? d[i][0] : nan;
+                            const double o1 = (!select || ((ok[i][1] >> sh) & 1u)) ? d[i][1] : nan;
+                            double *dst = dst_row + i * step;
+                            if (all_pairs || (pair_ok && 2 * t + 1 < ncols[i])) {
+                                asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(o0), "d"(o1) : "memory");
+                            } else {
+                                if (2 * t < ncols[i]) __stcs(dst, o0);
+                                if (2 * t + 1 < ncols[i]) __stcs(dst + 1, o1);
+                            }
                         }
+                    };
+                    // the usual case - full tiles of consecutive cells, aligned pairs - is straight-line code
+                    // whose tile offsets are immediates of the stores; tiles without a NaN skip the selects
+                    if (fast_store && !grid2d) {
+                        if (tile_clean)
+                            store_tiles(8, true, false);
+                        else
+                            store_tiles(8, true, true);
+                    } else if (fast_store) {
+                        store_tiles(tile_step, true, true);
+                    } else {
+                        store_tiles(tile_step, false, true);
                     }
-                };
-                // the usual case - full tiles of consecutive cells, aligned pairs - is straight-line code
-                // whose tile offsets are immediates of the stores; tiles without a NaN skip the selects
-                if (fast_store && !grid2d) {
-                    if (tile_clean)
-                        store_tiles(8, true, false);
-                    else
-                        store_tiles(8, true, true);
-                } else if (fast_store) {
-                    store_tiles(tile_step, true, true);
-                } else {
-                    store_tiles(tile_step, false, true);
                 }
+                dst_row += 8 * n_cells;
             }
-            dst_row += 8 * n_cells;
-        }
+        };
+        if (nf == 1)
+            pipeline(std::integral_constant<int, 1>{});
+        else if (nf == 2)
+            pipeline(std::integral_constant<int, 2>{});
+        else
+            pipeline(std::integral_constant<int, 3>{});
         return;
     }
 
