@@ -278,7 +278,7 @@ PM_HD double vsep(V3 a, V3 b) { return fast_atan2_ypos(norm(cross(a, b)), dot(a,
 // spice.surfpt (inside sincpt, body.py:1010): nearest ray / ellipsoid intersection,
 // perpendicular-projection form.  o, u in the body frame.  `margin2` receives
 // |p_perp|^2 (scaled space): < 1 hit, > 1 miss.
-PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr) {
+PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, double *half = nullptr) {
     // scaled space (unit sphere); the direction x is deliberately NOT normalised: the
     // three dot products are independent and a single reciprocal serves both the
     // projection and the half-chord
@@ -295,7 +295,9 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr) {
     if (ym2 > 1.0) {
         if (pm2 > 1.0) return false;
         if (yx > 0.0) return false;
-        q = axpy(-fast_sqrt_lite((1.0 - pm2) * ixx), x, pp);
+        const double h = fast_sqrt_lite((1.0 - pm2) * ixx);  // half-chord in units of |x|: p = (pp - h x) r
+        if (half) *half = h;
+        q = axpy(-h, x, pp);
     } else if (ym2 == 1.0) {
         q = y;
     } else {
@@ -359,14 +361,16 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
     V3 p1, p2;
     const V3 o1 = -ld3(fs.P0b);
-    if (!surfpt(fs, o1, u0, p1)) return false;
+    double h1 = 0.0, h2 = 0.0;
+    if (!surfpt(fs, o1, u0, p1, nullptr, &h1)) return false;
     const double lt1 = norm(p1 - o1) * fs.inv_c;
 
     const double dt1 = (f.et - lt1) - f.t_ref;
     const Rot r1 = make_rot(fs, dt1);
     const V3 o2 = spin_fwd(fs, r1, -target_pos_b(fs, dt1));
+    const V3 u2 = spin_fwd(fs, r1, u0);
     double cos2;
-    if (!surfpt(fs, o2, spin_fwd(fs, r1, u0), p2, &cos2)) return false;
+    if (!surfpt(fs, o2, u2, p2, &cos2, &h2)) return false;
     const double lt2 = norm(p2 - o2) * fs.inv_c;
 
     // epochs as CSPICE forms them: et - lt rounded to a double (granularity ulp(et) ~ 3e-8 s,
@@ -375,7 +379,19 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     double dt = (f.et - lt2) - f.t_ref;
     V3 p;
     if (fabs(dt1) > 1.0e-6 && cos2 > kGrazingCos2) {
-        p = axpy(fast_div_lite(dt - dt1, dt1), p2 - p1, p2);
+        // The epochs e_0 = t_ref, e_1, e_2 of CSPICE's loop contract geometrically (ratio lam = (e_2 - e_1) /
+        // (e_1 - e_0)); its fixed point is e_1 + (e_1 - e_0) lam / (1 - lam).  The body-fixed intercept is moved
+        // there along the secant through passes 1 and 2 - except for its one non-smooth ingredient, the
+        // half-chord h = sqrt(q): q (a smooth, nearly linear function of the epoch) is extrapolated and the
+        // root taken again, which removes the secant's 1 / cos^3(emission) curvature error (it matters for an
+        // observer a few radii away, where |P0| rounding no longer hides it).
+        const double lam = fast_div_lite(dt - dt1, dt1 - (dt - dt1));
+        const double q2 = h2 * h2;
+        const double h3 = fast_sqrt_lite(fmax(fma(lam, q2 - h1 * h1, q2), 0.0));
+        p = axpy(lam, p2 - p1, p2);
+        p = axpy(fma(lam, h2 - h1, h2) - h3, u2, p);
+        dt = fma(lam, dt1, dt1) + f.t_ref;  // the converged epoch, rounded as et - lt is
+        dt -= f.t_ref;
     } else {
         double dt_c = dt;  // address-taken copies: keep dt and p themselves in registers
         V3 p_c;

@@ -26,6 +26,10 @@ ORBITS = {
     502: (5, 671_100.0, 0.0094, 3.551181, 345.4, 88.97),    # Europa
     503: (5, 1_070_400.0, 0.0013, 7.154553, 324.8, 192.4),  # Ganymede
     504: (5, 1_882_700.0, 0.0074, 16.689017, 87.4, 52.6),   # Callisto
+    # Amalthea: an OBSERVER 2.5 Jupiter radii from the centre (the reference's close-range mapping test,
+    # tests/test_body_xy.py:2592-2608; its jup120 kernel holds 505 as an SPK type 17 segment, which the
+    # bundled reader does not evaluate)
+    505: (5, 181_365.8, 0.0032, 0.498179, 185.2, 155.9),
 }
 
 

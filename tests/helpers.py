@@ -185,6 +185,14 @@ def triaxial_constants(kind='europa', utc='2004-12-31T00:00:00', observer='EARTH
     return bc
 
 
+def close_observer_constants(utc='2005-01-01T03:00:00'):
+    """Jupiter from Amalthea (synthetic two-body orbit, minispice/kepler.py): observer 2.5 radii out."""
+    import planetmapper_b200 as pm
+    from planetmapper_b200.minispice.kepler import KeplerOrbitProvider
+
+    return F.build_body_constants(KeplerOrbitProvider(pm.get_default_provider()), 'Jupiter', utc, 'AMALTHEA')
+
+
 TRIAXIAL_CASES = [
     # kind, nx, ny, x0, y0, r0, rotation
     ('europa', 96, 80, 47.5, 40.0, 33.0, 25.0),

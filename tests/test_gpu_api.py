@@ -537,3 +537,40 @@ def test_map_transformer_round_trips(body):
     assert np.max(np.abs(fx[core] - xx[ok][core])) < 1e-6 and np.max(np.abs(fy[core] - yy[ok][core])) < 1e-6
     with pytest.raises(ValueError):
         tr.transform(0.0, 0.0, direction='sideways')
+
+
+def test_mapping_visible_areas_close_observer(oracle):
+    """The reference's test_mapping_visible_areas (tests/test_body_xy.py:2592-2608): Jupiter seen from
+    Amalthea, 2.5 radii from the centre.  The visible part of a map is exactly where the emission angle
+    is <= 90 deg, for the RA map and for a mapped image alike.  (Amalthea's state comes from the synthetic
+    orbit of minispice/kepler.py: the reference kernel holds it as an SPK type 17 segment.)  The image and
+    map planes of the same frame are then compared with the oracle."""
+    import planetmapper_b200 as pm
+    from helpers import PID, check_img_planes, check_map_planes
+    from planetmapper_b200.minispice.kepler import KeplerOrbitProvider
+
+    body = pm.BodyXY('Jupiter', observer='amalthea', utc='2005-01-01T03:00:00', sz=10,
+                     provider=KeplerOrbitProvider(pm.get_default_provider()))
+    body.set_disc_params(5, 5, 3, 0)
+    assert 2.0 < body.target_distance / body.r_eq < 3.0
+    map_kwargs = dict(degree_interval=15)
+    emission_map = body.get_backplane_map('EMISSION', **map_kwargs)
+    ra_map = body.get_backplane_map('RA', **map_kwargs)
+    map_img = body.map_img(np.ones((10, 10)), **map_kwargs)
+    assert np.all(np.isfinite(ra_map[emission_map <= 90]))
+    assert np.all(~np.isfinite(ra_map[emission_map > 90]))
+    assert np.all(np.isfinite(map_img[emission_map <= 90]))
+    assert np.all(~np.isfinite(map_img[emission_map > 90]))
+    assert 0.15 < np.isfinite(ra_map).mean() < 0.35
+
+    body.set_img_size(120, 90)
+    body.set_disc_params(61.0, 40.5, 55.0, 200.0)
+    fr = body._frame_host()
+    ref, margin = oracle.backplanes_img(fr, 120, 90, with_margin=True)
+    got = np.stack([body.get_backplane_img(n) for n in PLANE_NAMES])
+    check_img_planes(got, ref, margin, fr, 'jupiter/amalthea', allow_epoch_quantum=True)
+    lons, lats = body.generate_map_coordinates(degree_interval=5)[:2]
+    refm, marginm = oracle.backplanes_map(fr, lons, lats, with_margin=True)
+    gotm = np.stack([body.get_backplane_map(n, degree_interval=5) for n in PLANE_NAMES])
+    check_map_planes(gotm, refm, marginm, fr, 120, 90, 'jupiter/amalthea map')
+    assert np.isfinite(got[PID['EMISSION']]).sum() > 3000

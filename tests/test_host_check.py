@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from helpers import (IMG_CASES, OTHER_BODIES, PID, TRIAXIAL_CASES, angle_diff, check_img_planes, check_map_planes,
-                     img_case, triaxial_constants)
+                     close_observer_constants, img_case, triaxial_constants)
 from planetmapper_b200 import frame as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -128,6 +128,27 @@ def test_device_code_other_bodies_vs_oracle(HC, oracle, target, observer, nx, ny
     refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
     gotm = hc_map(HC, fr, lo, la)
     check_map_planes(gotm, refm, marginm, fr, nx, ny, f'{target}/{observer} map')
+
+
+@pytest.mark.parametrize('nx,ny,x0,y0,r0,rot', [(10, 10, 5.0, 5.0, 3.0, 0.0), (120, 90, 61.0, 40.5, 55.0, 200.0)])
+def test_device_code_close_observer_vs_oracle(HC, oracle, nx, ny, x0, y0, r0, rot):
+    """Jupiter seen from Amalthea's distance (2.5 radii from the centre: the horizon is 67 deg from the
+    sub-observer point, limb rays graze at large emission angles everywhere) - the geometry of the
+    reference's test_mapping_visible_areas (tests/test_body_xy.py:2592-2608), on a synthetic orbit."""
+    bc = close_observer_constants()
+    assert 2.0 < bc.target_distance / max(bc.radii) < 3.0
+    fr = img_case(bc, nx, ny, x0, y0, r0, rot)
+    ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+    got = hc_img(HC, fr, nx, ny)
+    check_img_planes(got, ref, margin, fr, 'jupiter/amalthea', allow_epoch_quantum=True)
+    lo, la = np.meshgrid(np.arange(7.5, 360, 15.0)[::-1], np.arange(-82.5, 90, 15.0))
+    refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+    gotm = hc_map(HC, fr, lo, la)
+    check_map_planes(gotm, refm, marginm, fr, nx, ny, 'jupiter/amalthea map')
+    # visible part of the map <=> emission angle <= 90 deg <=> RA is defined (:2600-2605)
+    emi, ra = gotm[PID['EMISSION']], gotm[PID['RA']]
+    assert np.all(np.isfinite(ra[emi <= 90])) and not np.any(np.isfinite(ra[emi > 90]))
+    assert 0.15 < np.isfinite(ra).mean() < 0.35     # a cap of 67 deg radius is 30 % of the sphere
 
 
 @pytest.mark.parametrize('kind,nx,ny,x0,y0,r0,rot', TRIAXIAL_CASES)
@@ -356,8 +377,10 @@ def test_device_code_vs_extended_precision(HC, oracle, ld_oracle, target, observ
         e_dev = np.abs(got[k][sel] - exact[k][sel])
         e_orc = np.abs(ref[k][sel] - exact[k][sel])
         report[name] = (float(e_dev.max()), float(e_orc.max()))
-        # the kernels' formulation is no further from the extended-precision result than the oracle
-        assert np.sqrt(np.mean(e_dev ** 2)) <= 1.5 * np.sqrt(np.mean(e_orc ** 2)) + 1e-15, (name, report[name])
+        # the kernels' formulation is no further from the extended-precision result than the oracle (up to a
+        # thousandth of north_star's bar: below that both are rounding noise of the last FP64 operations)
+        floor = 1e-15 if name in ('DISTANCE', 'RADIAL-VELOCITY') else 1e-12
+        assert np.sqrt(np.mean(e_dev ** 2)) <= 1.5 * np.sqrt(np.mean(e_orc ** 2)) + floor, (name, report[name])
     # and both sit within ~one epoch quantum of relative motion of it (the FP64 noise floor of the path)
     assert report['DISTANCE'][0] <= 2.5 * quantum + 8 * np.spacing(float(np.linalg.norm(F.frame_field(fr, 'P0'))))
     ang_floor = np.rad2deg(2.5 * quantum / r_min) / np.cos(np.deg2rad(70.0)) ** 2 + 1e-10
