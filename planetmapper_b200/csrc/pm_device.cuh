@@ -278,7 +278,7 @@ PM_HD double vsep(V3 a, V3 b) { return fast_atan2_ypos(norm(cross(a, b)), dot(a,
 // spice.surfpt (inside sincpt, body.py:1010): nearest ray / ellipsoid intersection,
 // perpendicular-projection form.  o, u in the body frame.  `margin2` receives
 // |p_perp|^2 (scaled space): < 1 hit, > 1 miss.
-PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, double *half = nullptr) {
+PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, V3 *foot = nullptr) {
     // scaled space (unit sphere); the direction x is deliberately NOT normalised: the
     // three dot products are independent and a single reciprocal serves both the
     // projection and the half-chord
@@ -295,9 +295,8 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, d
     if (ym2 > 1.0) {
         if (pm2 > 1.0) return false;
         if (yx > 0.0) return false;
-        const double h = fast_sqrt_lite((1.0 - pm2) * ixx);  // half-chord in units of |x|: p = (pp - h x) r
-        if (half) *half = h;
-        q = axpy(-h, x, pp);
+        if (foot) *foot = pp;  // p = (pp - h x) r with the half-chord h = sqrt((1 - |pp|^2) / |x|^2)
+        q = axpy(-fast_sqrt_lite((1.0 - pm2) * ixx), x, pp);
     } else if (ym2 == 1.0) {
         q = y;
     } else {
@@ -311,16 +310,19 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, d
 // epoch t_ref + dt unless stated.
 struct Intercept {
     V3 p;        // surface point (body-fixed)
-    V3 E;        // observer -> point
-    V3 Pb;       // observer -> target centre, body frame at t_ref (no spin)
+    V3 u;        // unit ray observer -> point in the body frame at the intercept epoch: the line of sight
+                 // itself (exact), not (p - o) / L, which carries p's error magnified by r / L for a near observer
     Rot r;       // spin over dt
     double dt;   // intercept epoch - t_ref
-    double L;    // |E| (km)
+    double L;    // observer -> point range (km)
     double lt;   // L / c
 };
 
-// cos^2 (scaled-space emission) below which sincpt iterates to convergence: emission > ~89.1 deg
-constexpr double kGrazingCos2 = 2.5e-4;
+// cos^2 (scaled-space emission) below which sincpt iterates to convergence: emission > ~86.9 deg.
+// Above it the fixed-point step's own error (the light time is not linear in the epoch:
+// V^3 de^2 / (2 r c^2 cos^4 e) km) stays below the target motion in one epoch quantum ulp(et) ~ 3e-8 s
+// (V ulp(et) / cos e), which is the resolution of CSPICE's own result.
+constexpr double kGrazingCos2 = 3.0e-3;
 
 // Slow path of sincpt for grazing rays and for frames whose first two passes coincide in
 // epoch: CSPICE's loop as written - full intercepts until the FP64 epoch et - lt stops
@@ -359,10 +361,9 @@ PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p) 
 //   are not converged, so those pixels run CSPICE's loop as written (until et - lt is stable).
 PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
-    V3 p1, p2;
+    V3 p1, p2, pp1, pp2;
     const V3 o1 = -ld3(fs.P0b);
-    double h1 = 0.0, h2 = 0.0;
-    if (!surfpt(fs, o1, u0, p1, nullptr, &h1)) return false;
+    if (!surfpt(fs, o1, u0, p1, nullptr, &pp1)) return false;
     const double lt1 = norm(p1 - o1) * fs.inv_c;
 
     const double dt1 = (f.et - lt1) - f.t_ref;
@@ -370,27 +371,29 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const V3 o2 = spin_fwd(fs, r1, -target_pos_b(fs, dt1));
     const V3 u2 = spin_fwd(fs, r1, u0);
     double cos2;
-    if (!surfpt(fs, o2, u2, p2, &cos2, &h2)) return false;
+    if (!surfpt(fs, o2, u2, p2, &cos2, &pp2)) return false;
     const double lt2 = norm(p2 - o2) * fs.inv_c;
 
     // epochs as CSPICE forms them: et - lt rounded to a double (granularity ulp(et) ~ 3e-8 s,
-    // i.e. ~1e-6 km of target motion), so the secant runs between the QUANTISED epoch offsets
-    // dt1 (pass 2) and dt (pass 3); their difference is exact
+    // i.e. ~1e-6 km of target motion)
     double dt = (f.et - lt2) - f.t_ref;
     V3 p;
     if (fabs(dt1) > 1.0e-6 && cos2 > kGrazingCos2) {
-        // The epochs e_0 = t_ref, e_1, e_2 of CSPICE's loop contract geometrically (ratio lam = (e_2 - e_1) /
-        // (e_1 - e_0)); its fixed point is e_1 + (e_1 - e_0) lam / (1 - lam).  The body-fixed intercept is moved
-        // there along the secant through passes 1 and 2 - except for its one non-smooth ingredient, the
-        // half-chord h = sqrt(q): q (a smooth, nearly linear function of the epoch) is extrapolated and the
-        // root taken again, which removes the secant's 1 / cos^3(emission) curvature error (it matters for an
-        // observer a few radii away, where |P0| rounding no longer hides it).
+        // The epochs e_0 = t_ref, e_1, e_2 of CSPICE's loop contract geometrically (ratio (e_2 - e_1) /
+        // (e_1 - e_0)); the loop's fixed point is e_1 + lam (e_1 - e_0), lam = (e_2 - e_1) / (e_1 - e_2 + e_1 - e_0).
+        // The intercept there comes from the two solves without a third one: the foot pp of the
+        // perpendicular from the centre to the ray and the ray direction x (scaled space) are smooth in the
+        // epoch and are moved along their secants; the half-chord h = sqrt((1 - |pp|^2) / |x|^2) - the one
+        // ingredient that is NOT smooth towards the limb - is then formed exactly from them.  (Moving the
+        // intercept itself along its secant leaves an error ~ 1 / cos^3(emission): invisible under the
+        // |P0| rounding of a distant observer, 1.6e-7 deg at 88 deg emission from 2.5 radii.)
         const double lam = fast_div_lite(dt - dt1, dt1 - (dt - dt1));
-        const double q2 = h2 * h2;
-        const double h3 = fast_sqrt_lite(fmax(fma(lam, q2 - h1 * h1, q2), 0.0));
-        p = axpy(lam, p2 - p1, p2);
-        p = axpy(fma(lam, h2 - h1, h2) - h3, u2, p);
-        dt = fma(lam, dt1, dt1) + f.t_ref;  // the converged epoch, rounded as et - lt is
+        const V3 pps = axpy(lam, pp2 - pp1, pp2);
+        const V3 us = axpy(lam, u2 - u0, u2);
+        const V3 xs = mul3(us, fs.inv_r);
+        const double hs = fast_sqrt_lite(fmax(1.0 - dot(pps, pps), 0.0) * fast_rcp(dot(xs, xs)));
+        p = axpy(-hs, us, mul3(pps, fs.f.radii));
+        dt = fma(lam, dt1, dt1) + f.t_ref;  // the fixed point, rounded as et - lt is
         dt -= f.t_ref;
     } else {
         double dt_c = dt;  // address-taken copies: keep dt and p themselves in registers
@@ -400,12 +403,10 @@ PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
         p = p_c;
     }
     const Rot r = make_rot(fs, dt);
-    const V3 Pb = target_pos_b(fs, dt);
-    const V3 E = p - spin_fwd(fs, r, -Pb);
-    const double L = norm(E);
+    const V3 u = spin_fwd(fs, r, u0);
+    const double L = dot(p - spin_fwd(fs, r, -target_pos_b(fs, dt)), u);  // |p - o| up to the square of p's offset from the ray
     it.p = p;
-    it.E = E;
-    it.Pb = Pb;
+    it.u = u;
     it.r = r;
     it.dt = dt;
     it.L = L;
@@ -779,7 +780,8 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
     // BodyXY._get_targvec_img (body_xy.py:3197-3225) incl. the early-out circle
     bool on_disc = false;
     Intercept it;
-    if (try_disc) on_disc = sincpt(fs, mxv(fs.G, v), it);
+    const V3 u0 = mxv(fs.G, v);  // unit ray, body frame at t_ref
+    if (try_disc) on_disc = sincpt(fs, u0, it);
 
     double v_dist = nan;
     if (on_disc) {
@@ -812,7 +814,7 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
             const V3 p0 = spin_bwd_c(fs, it.r, p, kxp);
             if (mask & kIllumMask) {  // _get_illumination_gie_img (body_xy.py:3661-3665)
                 Illum il;
-                illum_at(fs, p, p0, -it.E, it.r, it.dt, (mask & bit(PM_AZIMUTH)) != 0, il);
+                illum_at(fs, p, p0, -it.u, it.r, it.dt, (mask & bit(PM_AZIMUTH)) != 0, il);
                 if (mask & bit(PM_PHASE)) out.put(PM_PHASE, il.phase * kDpr);
                 if (mask & bit(PM_INCIDENCE)) out.put(PM_INCIDENCE, il.incdnc * kDpr);
                 if (mask & bit(PM_EMISSION)) out.put(PM_EMISSION, il.emissn * kDpr);
@@ -821,12 +823,11 @@ PM_HD void image_pixel(const FrameD &fs, double x, double y, uint64_t mask_in, S
             v_dist = it.lt * f.clight;  // get_distance_img (body_xy.py:3870-3880)
             if (mask & bit(PM_DISTANCE)) out.put(PM_DISTANCE, v_dist);
             if (mask & (bit(PM_RADIAL_VELOCITY) | bit(PM_DOPPLER))) {
-                // get_radial_velocity_img (body_xy.py:3898-3913): project on the line of sight
-                const double iL = fast_rcp(it.L);
+                // get_radial_velocity_img (body_xy.py:3898-3913): project on the line of sight - the pixel's
+                // own ray (u0 in the frame of t_ref, it.u at the intercept epoch)
                 const V3 vt = axpy(it.dt, ld3(fs.ATb), ld3(fs.VTb));
-                const V3 X0 = it.Pb + p0;
-                const double a = fma(fs.wn, dot(kxp, it.E), dot(vt, X0)) * iL;
-                const double b = dot(ld3(fs.VOb), X0) * iL;
+                const double a = fma(fs.wn, dot(kxp, it.u), dot(vt, u0));
+                const double b = dot(ld3(fs.VOb), u0);
                 const double rv = radial_velocity(fs, a, b);
                 if (mask & bit(PM_RADIAL_VELOCITY)) out.put(PM_RADIAL_VELOCITY, rv);
                 if (mask & bit(PM_DOPPLER)) out.put(PM_DOPPLER, doppler_factor(fs, rv));

@@ -193,6 +193,74 @@ def close_observer_constants(utc='2005-01-01T03:00:00'):
     return F.build_body_constants(KeplerOrbitProvider(pm.get_default_provider()), 'Jupiter', utc, 'AMALTHEA')
 
 
+def random_geometry(seed):
+    """A random frame for the referee tests: target among six bodies (oblate, spherical, triaxial, retrograde,
+    fast and slow rotators), observer anywhere between 1.3 and 1e5 body radii in a random direction with a
+    random velocity of up to ~50 km/s relative to the target, random disc position / size / rotation.
+    Returns (frame, nx, ny, label)."""
+    import planetmapper_b200 as pm
+    from planetmapper_b200.minispice.kepler import KeplerOrbitProvider
+
+    prov = KeplerOrbitProvider(pm.get_default_provider())
+    rng = np.random.default_rng(seed)
+    target = ['Jupiter', 'Saturn', 'Moon', 'Europa', 'Mars', 'Venus'][rng.integers(6)]
+    utc = '2004-12-%02dT%02d:00:00' % (rng.integers(27, 31), rng.integers(0, 24))
+    et = prov.utc2et(utc)
+    tid = prov.bods2c(target)
+    tstate = prov.ssb_state(tid, et)
+    rmax = float(max(prov.bodvar(tid, 'RADII')))
+    dist = rmax * 10 ** rng.uniform(np.log10(1.3), 5)
+    n = rng.normal(size=3)
+    n /= np.linalg.norm(n)
+    v = rng.normal(size=3) * rng.uniform(0, 30)
+    obs = np.concatenate([tstate[:3] + dist * n, tstate[3:] + v])
+    bc = F.build_body_constants(prov, target, utc, 'EARTH', observer_state=obs)
+    nx, ny = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+    r0 = rng.uniform(0.2, 0.9) * min(nx, ny)
+    x0, y0 = rng.uniform(0.2, 0.8) * nx, rng.uniform(0.2, 0.8) * ny
+    rot = rng.uniform(0, 360)
+    return (img_case(bc, nx, ny, x0, y0, r0, rot), nx, ny,
+            f'seed {seed}: {target} D/r={dist / rmax:.3g} {nx}x{ny} r0={r0:.1f} rot={rot:.0f}')
+
+
+def referee_ratios(got, ref, exact, margin):
+    """For every continuous plane: how far `got` (kernel code) and `ref` (FP64 oracle) each sit from `exact`
+    (the oracle in 80-bit arithmetic), as (max ratio, rms ratio) of got-vs-exact over ref-vs-exact.  The
+    denominators are floored at north_star's bare bars (1e-9 deg, 1e-12 relative; a tenth of them for the
+    rms): below those both are inside the bar and the ratio says nothing."""
+    grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
+    out = {}
+    for name in PLANE_NAMES:
+        if name in ('LOCAL-SOLAR-TIME', 'PIXEL-X', 'PIXEL-Y'):
+            continue
+        k = PID[name]
+        both = np.isfinite(got[k]) & np.isfinite(ref[k]) & np.isfinite(exact[k]) & ~grazing
+        if not both.any():
+            continue
+        diff = angle_diff if name in WRAP else (lambda a, b: np.abs(a - b))
+        de, oe = diff(got[k], exact[k])[both], diff(ref[k], exact[k])[both]
+        floor = 1e-9 if name in BARE_ANGLE_PLANES else 1e-12 * float(np.abs(exact[k][both]).max())
+        out[name] = (float(de.max() / max(oe.max(), floor)),
+                     float(np.sqrt(np.mean(de ** 2)) / max(np.sqrt(np.mean(oe ** 2)), 0.1 * floor)),
+                     float(de.max()), float(oe.max()))
+    return out
+
+
+def assert_referee(got, ref, exact, margin, label):
+    """The kernel code is as close to the extended-precision result as the FP64 oracle is: rms within 3x,
+    worst pixel within 10x (a maximum over a few thousand pixels of two independent rounding-noise fields;
+    200 random geometries give <= 3.3x, LIMB-LON 8.3x), NaN masks identical outside grazing pixels."""
+    grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
+    for name in PLANE_NAMES:
+        ok, n_bad, _ = masks_equal(got[PID[name]], ref[PID[name]], exclude=grazing)
+        assert ok, f'{label} {name}: {n_bad} NaN-mask mismatches outside grazing pixels'
+    rr = referee_ratios(got, ref, exact, margin)
+    for name, (r_max, r_rms, d_max, o_max) in rr.items():
+        assert r_rms <= 3.0 and r_max <= 10.0, (f'{label} {name}: kernel-vs-exact / oracle-vs-exact = {r_max:.2f} (max), '
+                                                f'{r_rms:.2f} (rms); max errors {d_max:.3e} / {o_max:.3e}')
+    return rr
+
+
 TRIAXIAL_CASES = [
     # kind, nx, ny, x0, y0, r0, rotation
     ('europa', 96, 80, 47.5, 40.0, 33.0, 25.0),
@@ -309,9 +377,13 @@ def check_img_planes(got, ref, margin, fr, label, allow_epoch_quantum=False):
         elif name in ('PIXEL-X', 'PIXEL-Y'):
             assert np.array_equal(a[both], b[both])
         elif name in ('KM-X', 'KM-Y'):
-            assert np.max(d[both]) <= 1e-5, f'{label} {name}: {np.max(d[both]):.3e} km'
+            # 1e-5 km at the named configs; 1e-12 relative for wide fields, and never below the RA / Dec
+            # round trip in degrees the reference goes through (ulp(360 deg) of sky at the target's distance)
+            t = max(1e-5, 1e-12 * float(np.max(np.abs(b[both]))), 4.0 * np.deg2rad(np.spacing(360.0)) * p0)
+            assert np.max(d[both]) <= t, f'{label} {name}: {np.max(d[both]):.3e} km'
         elif name in ('ANGULAR-X', 'ANGULAR-Y'):
-            assert np.max(d[both]) <= 1e-8, f'{label} {name}: {np.max(d[both]):.3e} arcsec'
+            t = max(1e-8, 1e-12 * float(np.max(np.abs(b[both]))))
+            assert np.max(d[both]) <= t, f'{label} {name}: {np.max(d[both]):.3e} arcsec'
         elif name in ('RING-DISTANCE', 'RING-RADIUS'):
             assert np.max(d[both]) <= 1e-12 * p0 * 50, f'{label} {name}: {np.max(d[both]):.3e} km'
         elif name == 'RING-LON-GRAPHIC':

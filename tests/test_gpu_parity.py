@@ -666,3 +666,31 @@ def test_projection_forward_vs_oracle(L, oracle, bc_hst, kind, lon0, lat0):
                     + np.cos(np.deg2rad(lat0)) * np.cos(np.deg2rad(lat)) * np.cos(np.deg2rad(lon - lon0)))
         tol = 1e-12 / np.maximum(1.0 + cosc, 1e-6) if kind != 1 else np.full(lon.shape, 1e-12)
         assert np.all(np.abs(gx[ok] - rx[ok]) <= tol[ok]) and np.all(np.abs(gy[ok] - ry[ok]) <= tol[ok])
+
+
+@pytest.fixture(scope='module')
+def ld_oracle(tmp_path_factory):
+    import shutil
+
+    from test_host_check import build_ld_oracle
+
+    if not shutil.which('gcc'):
+        pytest.skip('gcc not available')
+    return build_ld_oracle(str(tmp_path_factory.mktemp('oracle_ld')))
+
+
+@pytest.mark.parametrize('block', range(3))
+def test_random_geometries_vs_extended_precision(L, oracle, ld_oracle, block):
+    """The referee of tests/test_host_check.py::test_device_code_random_geometries_vs_extended_precision on
+    the GPU itself: observers from 1.3 to 1e5 radii, six bodies, image and map direction - in every plane
+    the kernels are as close to the 80-bit evaluation of the reference algorithm as the FP64 oracle is."""
+    from helpers import assert_referee, random_geometry
+
+    for seed in range(16 * block, 16 * block + 16):
+        fr, nx, ny, label = random_geometry(seed)
+        ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+        assert_referee(L.backplanes_img_host(fr, nx, ny).cpu().numpy(), ref, ld_oracle(fr, nx, ny), margin, label)
+        lo, la = np.meshgrid(np.arange(3.5, 360, 7.0)[::-1], np.arange(-87.5, 90, 5.0))
+        refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+        gotm = L.backplanes_map_host(fr, L.to_device(lo), L.to_device(la)).cpu().numpy()
+        assert_referee(gotm, refm, ld_oracle(fr, nx, ny, (lo, la)), marginm, label + ' map')

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from helpers import (IMG_CASES, OTHER_BODIES, PID, TRIAXIAL_CASES, angle_diff, check_img_planes, check_map_planes,
-                     close_observer_constants, img_case, triaxial_constants)
+                     assert_referee, close_observer_constants, img_case, random_geometry, triaxial_constants)
 from planetmapper_b200 import frame as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -295,6 +295,8 @@ LD_DRV = r"""
 #include <stdint.h>
 #include "pm_b200_ld.h"
 int pmo_backplanes_img(const PMFrame *f, int nx, int ny, uint64_t mask, long double *out, long double *margin);
+int pmo_backplanes_map(const PMFrame *f, const long double *lon, const long double *lat, int64_t n, uint64_t mask,
+                       long double *out, long double *margin);
 int main(int argc, char **argv) {
     double fd[PM_FRAME_NDOUBLES];
     FILE *fp = fopen(argv[1], "rb");
@@ -306,7 +308,15 @@ int main(int argc, char **argv) {
     int nx = atoi(argv[2]), ny = atoi(argv[3]);
     size_t n = (size_t)nx * ny;
     long double *out = malloc(sizeof(long double) * 26 * n), *m = malloc(sizeof(long double) * n);
-    if (pmo_backplanes_img(&f, nx, ny, (1ull << 26) - 1, out, m)) return 2;
+    if (argc > 5) {   /* map direction: argv[5] holds n longitudes then n latitudes (doubles, degrees) */
+        double *ll = malloc(16 * n);
+        long double *lo = malloc(sizeof(long double) * n), *la = malloc(sizeof(long double) * n);
+        fp = fopen(argv[5], "rb");
+        if (!fp || fread(ll, 8, 2 * n, fp) != 2 * n) return 3;
+        fclose(fp);
+        for (size_t i = 0; i < n; i++) { lo[i] = ll[i]; la[i] = ll[n + i]; }
+        if (pmo_backplanes_map(&f, lo, la, (int64_t)n, (1ull << 26) - 1, out, m)) return 2;
+    } else if (pmo_backplanes_img(&f, nx, ny, (1ull << 26) - 1, out, m)) return 2;
     double *o = malloc(8 * 26 * n);
     for (size_t i = 0; i < 26 * n; i++) o[i] = (double)out[i];
     fp = fopen(argv[4], "wb");
@@ -339,11 +349,18 @@ def build_ld_oracle(bdir):
     subprocess.run(['gcc', '-O2', '-w', '-fopenmp', '-o', exe, 'drv.c', 'pm_oracle_ld.c', '-lm'], cwd=bdir, check=True,
                    capture_output=True)
 
-    def run(fr, nx, ny):
+    def run(fr, nx, ny, lonlat=None):
+        """Image planes of an nx x ny frame, or (lonlat = (lon, lat) arrays) the map planes on those cells."""
         fin, fout = os.path.join(bdir, 'frame.bin'), os.path.join(bdir, 'out.bin')
         np.ascontiguousarray(fr, dtype=np.float64).tofile(fin)
-        subprocess.run([exe, fin, str(nx), str(ny), fout], check=True)
-        return np.fromfile(fout).reshape(26, ny, nx)
+        if lonlat is None:
+            subprocess.run([exe, fin, str(nx), str(ny), fout], check=True)
+            return np.fromfile(fout).reshape(26, ny, nx)
+        lo, la = (np.ascontiguousarray(a, dtype=np.float64) for a in lonlat)
+        fll = os.path.join(bdir, 'lonlat.bin')
+        np.concatenate([lo.ravel(), la.ravel()]).tofile(fll)
+        subprocess.run([exe, fin, str(lo.size), '1', fout, fll], check=True)
+        return np.fromfile(fout).reshape((26,) + lo.shape)
     return run
 
 
@@ -386,3 +403,18 @@ def test_device_code_vs_extended_precision(HC, oracle, ld_oracle, target, observ
     ang_floor = np.rad2deg(2.5 * quantum / r_min) / np.cos(np.deg2rad(70.0)) ** 2 + 1e-10
     assert report['LAT-GRAPHIC'][0] <= ang_floor and report['EMISSION'][0] <= ang_floor
     print(target, {k: (f'{a:.2e}', f'{b:.2e}') for k, (a, b) in report.items()}, 'quantum km', quantum)
+
+
+@pytest.mark.parametrize('block', range(6))
+def test_device_code_random_geometries_vs_extended_precision(HC, oracle, ld_oracle, block):
+    """Referee on random geometries far outside BASELINE.json's configs (observers from 1.3 to 1e5 radii,
+    fields of view up to ~100 deg, six bodies): in every plane the kernels' per-pixel code is as close to
+    the 80-bit evaluation of the reference algorithm as the FP64 oracle is.  This is the test that caught
+    the secant error of the first intercept formulation for near observers."""
+    for seed in range(16 * block, 16 * block + 16):
+        fr, nx, ny, label = random_geometry(seed)
+        ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+        assert_referee(hc_img(HC, fr, nx, ny), ref, ld_oracle(fr, nx, ny), margin, label)
+        lo, la = np.meshgrid(np.arange(3.5, 360, 7.0)[::-1], np.arange(-87.5, 90, 5.0))
+        refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
+        assert_referee(hc_map(HC, fr, lo, la), refm, ld_oracle(fr, nx, ny, (lo, la)), marginm, label + ' map')
