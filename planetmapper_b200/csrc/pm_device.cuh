@@ -276,9 +276,15 @@ PM_HD V3 radrec1(double ra, double dec) {
 PM_HD double vsep(V3 a, V3 b) { return fast_atan2_ypos(norm(cross(a, b)), dot(a, b)); }
 
 // spice.surfpt (inside sincpt, body.py:1010): nearest ray / ellipsoid intersection,
-// perpendicular-projection form.  o, u in the body frame.  `margin2` receives
-// |p_perp|^2 (scaled space): < 1 hit, > 1 miss.
-PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, V3 *foot = nullptr) {
+// perpendicular-projection form.  o, u in the body frame; p = o + t u.
+struct RayHit {
+    V3 pp;        // foot of the perpendicular from the centre to the ray, scaled (unit-sphere) space
+    double ixx;   // 1 / |x|^2, x = u / radii
+    double a;     // ray parameter of that foot: pp = y + a x (for a unit u: km from the observer)
+    double t;     // ray parameter of the intercept, t = a - h with the half-chord h = sqrt((1 - |pp|^2) ixx)
+    double cos2;  // 1 - |pp|^2: squared half-chord in the unit-sphere space, -> 0 at tangency
+};
+PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, RayHit &hit) {
     // scaled space (unit sphere); the direction x is deliberately NOT normalised: the
     // three dot products are independent and a single reciprocal serves both the
     // projection and the half-chord
@@ -287,22 +293,26 @@ PM_HD bool surfpt(const FrameD &fs, V3 o, V3 u, V3 &p, double *cos2 = nullptr, V
     const double xx = dot(x, x), yx = dot(y, x), ym2 = dot(y, y);
     if (!(xx > 0.0)) return false;
     const double ixx = fast_rcp(xx);
-    const V3 pp = axpy(-(yx * ixx), x, y);  // component of y perpendicular to the ray
+    const double a = -(yx * ixx);
+    const V3 pp = axpy(a, x, y);  // component of y perpendicular to the ray
     const double pm2 = dot(pp, pp);
     if (!(pm2 < INFINITY)) return false;
-    if (cos2) *cos2 = 1.0 - pm2;  // squared half-chord in the unit-sphere space: -> 0 at tangency
-    V3 q;
+    hit.pp = pp;
+    hit.ixx = ixx;
+    hit.a = a;
+    hit.cos2 = 1.0 - pm2;
+    double h;
     if (ym2 > 1.0) {
         if (pm2 > 1.0) return false;
         if (yx > 0.0) return false;
-        if (foot) *foot = pp;  // p = (pp - h x) r with the half-chord h = sqrt((1 - |pp|^2) / |x|^2)
-        q = axpy(-fast_sqrt_lite((1.0 - pm2) * ixx), x, pp);
+        h = -fast_sqrt_lite((1.0 - pm2) * ixx);
     } else if (ym2 == 1.0) {
-        q = y;
+        h = -a;  // the origin itself
     } else {
-        q = axpy(fast_sqrt_lite(fmax(0.0, 1.0 - pm2) * ixx), x, pp);
+        h = fast_sqrt_lite(fmax(0.0, 1.0 - pm2) * ixx);
     }
-    p = mul3(q, fs.f.radii);
+    hit.t = a + h;
+    p = mul3(axpy(h, x, pp), fs.f.radii);
     return true;
 }
 
@@ -322,20 +332,25 @@ struct Intercept {
 // Above it the fixed-point step's own error (the light time is not linear in the epoch:
 // V^3 de^2 / (2 r c^2 cos^4 e) km) stays below the target motion in one epoch quantum ulp(et) ~ 3e-8 s
 // (V ulp(et) / cos e), which is the resolution of CSPICE's own result.
-constexpr double kGrazingCos2 = 3.0e-3;
+#ifndef PM_GRAZING_COS2
+#define PM_GRAZING_COS2 3.0e-3
+#endif
+constexpr double kGrazingCos2 = PM_GRAZING_COS2;
 
 // Slow path of sincpt for grazing rays and for frames whose first two passes coincide in
 // epoch: CSPICE's loop as written - full intercepts until the FP64 epoch et - lt stops
 // changing (at most 10 passes in total).  dt (in: epoch offset of the next pass) and p come
 // back for the converged pass.  Kept out of line so the common path keeps its registers.
-PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p) {
+PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p, double &range) {
     const PMFrame &f = fs.f;
     for (int it = 0; it < 8; it++) {
         const Rot r = make_rot(fs, dt);
         const V3 o = spin_fwd(fs, r, -target_pos_b(fs, dt));
-        if (!surfpt(fs, o, spin_fwd(fs, r, u0), p)) return false;
+        RayHit hit;
+        if (!surfpt(fs, o, spin_fwd(fs, r, u0), p, hit)) return false;
+        range = hit.t;
         const double t = dt + f.t_ref;
-        const double t_new = f.et - norm(p - o) * fs.inv_c;
+        const double t_new = f.et - hit.t * fs.inv_c;  // u0 is a unit vector: the ray parameter is the range
         if (!(fabs(t_new - t) > 1.0e-17 * fabs(t_new))) break;
         dt = t_new - f.t_ref;
     }
@@ -343,7 +358,8 @@ PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p) 
 }
 
 // spice.sincpt(..., 'CN', ..., d) (body.py:1008-1020): intercept with the light time
-// iterated on the intercept point.  u0: ray direction in the body frame at t_ref.
+// iterated on the intercept point.  u0: UNIT ray direction in the body frame at t_ref (ray parameters
+// are used as ranges).
 //
 // CSPICE iterates  epoch e_{i+1} = et - lt(e_i)  from e_0 = et - lt0 = t_ref until the
 // light time stops changing; the contraction factor is v_surface / c ~ 4e-5, so that is
@@ -361,53 +377,51 @@ PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p) 
 //   are not converged, so those pixels run CSPICE's loop as written (until et - lt is stable).
 PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
-    V3 p1, p2, pp1, pp2;
-    const V3 o1 = -ld3(fs.P0b);
-    if (!surfpt(fs, o1, u0, p1, nullptr, &pp1)) return false;
-    const double lt1 = norm(p1 - o1) * fs.inv_c;
+    V3 p1, p2;
+    RayHit h1, h2;
+    if (!surfpt(fs, -ld3(fs.P0b), u0, p1, h1)) return false;
+    const double lt1 = h1.t * fs.inv_c;  // u0 is a unit vector: the ray parameter is the range
 
     const double dt1 = (f.et - lt1) - f.t_ref;
     const Rot r1 = make_rot(fs, dt1);
-    const V3 o2 = spin_fwd(fs, r1, -target_pos_b(fs, dt1));
-    const V3 u2 = spin_fwd(fs, r1, u0);
-    double cos2;
-    if (!surfpt(fs, o2, u2, p2, &cos2, &pp2)) return false;
-    const double lt2 = norm(p2 - o2) * fs.inv_c;
+    if (!surfpt(fs, spin_fwd(fs, r1, -target_pos_b(fs, dt1)), spin_fwd(fs, r1, u0), p2, h2)) return false;
+    const double lt2 = h2.t * fs.inv_c;
 
     // epochs as CSPICE forms them: et - lt rounded to a double (granularity ulp(et) ~ 3e-8 s,
     // i.e. ~1e-6 km of target motion)
     double dt = (f.et - lt2) - f.t_ref;
     V3 p;
-    if (fabs(dt1) > 1.0e-6 && cos2 > kGrazingCos2) {
+    double L;
+    if (fabs(dt1) > 1.0e-6 && h2.cos2 > kGrazingCos2) {
         // The epochs e_0 = t_ref, e_1, e_2 of CSPICE's loop contract geometrically (ratio (e_2 - e_1) /
         // (e_1 - e_0)); the loop's fixed point is e_1 + lam (e_1 - e_0), lam = (e_2 - e_1) / (e_1 - e_2 + e_1 - e_0).
         // The intercept there comes from the two solves without a third one: the foot pp of the
-        // perpendicular from the centre to the ray and the ray direction x (scaled space) are smooth in the
-        // epoch and are moved along their secants; the half-chord h = sqrt((1 - |pp|^2) / |x|^2) - the one
-        // ingredient that is NOT smooth towards the limb - is then formed exactly from them.  (Moving the
-        // intercept itself along its secant leaves an error ~ 1 / cos^3(emission): invisible under the
-        // |P0| rounding of a distant observer, 1.6e-7 deg at 88 deg emission from 2.5 radii.)
+        // perpendicular from the centre to the ray, its ray parameter a (an inertial quantity: linear in
+        // the epoch up to the target's acceleration) and 1 / |x|^2 are smooth in the epoch and are moved along
+        // their secants, the ray direction is spun to the new epoch exactly, and the half-chord
+        // h = sqrt((1 - |pp|^2) / |x|^2) - the one ingredient that is NOT smooth towards the limb - is formed
+        // from them.  (Moving the intercept itself along its secant leaves an error ~ 1 / cos^3(emission):
+        // invisible under the |P0| rounding of a distant observer, 1.6e-7 deg at 88 deg emission from 2.5 radii.)
         const double lam = fast_div_lite(dt - dt1, dt1 - (dt - dt1));
-        const V3 pps = axpy(lam, pp2 - pp1, pp2);
-        const V3 us = axpy(lam, u2 - u0, u2);
-        const V3 xs = mul3(us, fs.inv_r);
-        const double hs = fast_sqrt_lite(fmax(1.0 - dot(pps, pps), 0.0) * fast_rcp(dot(xs, xs)));
-        p = axpy(-hs, us, mul3(pps, fs.f.radii));
         dt = fma(lam, dt1, dt1) + f.t_ref;  // the fixed point, rounded as et - lt is
         dt -= f.t_ref;
+        const V3 pps = axpy(lam, h2.pp - h1.pp, h2.pp);
+        const double hs = fast_sqrt_lite(fmax(1.0 - dot(pps, pps), 0.0) * fma(lam, h2.ixx - h1.ixx, h2.ixx));
+        L = fma(lam, h2.a - h1.a, h2.a) - hs;
+        it.r = make_rot(fs, dt);
+        it.u = spin_fwd(fs, it.r, u0);
+        p = axpy(-hs, it.u, mul3(pps, fs.f.radii));
     } else {
-        double dt_c = dt;  // address-taken copies: keep dt and p themselves in registers
+        double dt_c = dt, L_c;  // address-taken copies: keep dt and p themselves in registers
         V3 p_c;
-        if (!sincpt_converge(fs, u0, dt_c, p_c)) return false;
+        if (!sincpt_converge(fs, u0, dt_c, p_c, L_c)) return false;
         dt = dt_c;
         p = p_c;
+        L = L_c;
+        it.r = make_rot(fs, dt);
+        it.u = spin_fwd(fs, it.r, u0);
     }
-    const Rot r = make_rot(fs, dt);
-    const V3 u = spin_fwd(fs, r, u0);
-    const double L = dot(p - spin_fwd(fs, r, -target_pos_b(fs, dt)), u);  // |p - o| up to the square of p's offset from the ray
     it.p = p;
-    it.u = u;
-    it.r = r;
     it.dt = dt;
     it.L = L;
     it.lt = L * fs.inv_c;
@@ -1031,7 +1045,8 @@ PM_HD bool lonlat2obsvec_point(const FrameD &fs, double lon, double lat, double 
             if (!(fast_atan2_ypos(norm(cross(n, e)), dot(n, e)) < kHalfPi)) return false;
         } else {
             Intercept it;
-            if (sincpt(fs, mxv(fs.f.R0, targvec2obsvec(fs, tv)), it)) {
+            const V3 dir = mxv(fs.f.R0, targvec2obsvec(fs, tv));
+            if (sincpt(fs, fast_rsqrt(dot(dir, dir)) * dir, it)) {
                 PointGeom gi;
                 point_geom(fs, it.p, gi);
                 if (!(g.lt < gi.lt)) return false;
@@ -1139,7 +1154,8 @@ PM_HD bool point_transform(const FrameD &fs, const TransformAux &aux, int src, i
         ob = fma(f.Ainv[3], ax, fma(f.Ainv[4], ay, f.Ainv[5]));
     } else {  // Body._obsvec_norm2lonlat (body.py:1058-1081); the frame carries the radii raised by alt
         Intercept it;
-        if (!sincpt(fs, mxv(f.R0, ov), it)) return false;
+        const V3 dir = mxv(f.R0, ov);
+        if (!sincpt(fs, fast_rsqrt(dot(dir, dir)) * dir, it)) return false;
         double lo, la, al;
         recpgr(fs, it.p, fs.biaxial != 0, lo, la, al);
         oa = lo * kDpr;
