@@ -11,7 +11,11 @@ constexpr int kChains = 8;
 template <int kKind>
 __global__ void __launch_bounds__(256) probe(double *out, const double *in, int iters, double m, double c) {
     double a[kChains], b[kChains], d[kChains];
+    unsigned x[kChains];   // kinds 8 - 10: independent non-FP64 work issued between the DFMAs
+    float fl[kChains];
     for (int i = 0; i < kChains; i++) {
+        x[i] = threadIdx.x * 2654435761u + i;
+        fl[i] = (float)(threadIdx.x + i);
         a[i] = in[(threadIdx.x + i) & 255];
         b[i] = in[(threadIdx.x + 2 * i + 1) & 255] * 1e-3 + 0.999;
         d[i] = in[(threadIdx.x + 3 * i + 2) & 255] * 1e-9;
@@ -27,6 +31,11 @@ __global__ void __launch_bounds__(256) probe(double *out, const double *in, int 
             if (kKind == 4) a[i] = a[i] * b[i];                  // DMUL 2 regs
             if (kKind == 5) a[i] = a[i] + d[i];                  // DADD 2 regs
             if (kKind == 6) a[i] = fma(b[0], d[0], a[i]);        // 3 regs, two shared by all chains (.reuse)
+            if (kKind == 8 || kKind == 9 || kKind == 10 || kKind == 11) a[i] = fma(a[i], b[i], c);   // 2 regs
+            if (kKind == 8 || kKind == 9) x[i] = x[i] * 1664525u + 1013904223u;                        // + 1 IMAD
+            if (kKind == 9) x[i] ^= x[i] >> 7;                                                       // + SHF / LOP3
+            if (kKind == 10) fl[i] = fmaf(fl[i], 0.999f, 0.25f);                                     // + 1 FFMA
+            if (kKind == 11) { fl[i] = fmaf(fl[i], 0.999f, 0.25f); x[i] = x[i] * 1664525u + 1013904223u; x[i] ^= x[i] >> 7; }
             if (kKind == 7) {                                    // blend ~ kernel mix: 58% DFMA(3 reg) 29% DMUL 13% DADD
                 a[i] = fma(a[i], b[i], d[i]);
                 if ((i & 1) == 0) a[i] = a[i] * b[(i + 1) % kChains];
@@ -35,7 +44,7 @@ __global__ void __launch_bounds__(256) probe(double *out, const double *in, int 
         }
     }
     double s = 0;
-    for (int i = 0; i < kChains; i++) s += a[i];
+    for (int i = 0; i < kChains; i++) s += a[i] + (double)x[i] + (double)fl[i];
     if (s == 123.456) out[0] = s;
 }
 
@@ -74,5 +83,10 @@ int main() {
     run<4>("DMUL a = a*b (2 regs)", 8, out, in, sms);
     run<5>("DADD a = a+d (2 regs)", 8, out, in, sms);
     run<7>("blend 8 DFMA(3 reg) + 4 DMUL + 2 DADD", 14, out, in, sms);
+    // does a non-FP64 instruction issued between two DFMAs cost FP64 throughput?  (DFMA count only)
+    run<8>("DFMA (2 regs) + 1 IMAD each: DFMA rate", 8, out, in, sms);
+    run<9>("DFMA (2 regs) + IMAD + SHF + LOP3 each: DFMA rate", 8, out, in, sms);
+    run<10>("DFMA (2 regs) + 1 FFMA each: DFMA rate", 8, out, in, sms);
+    run<11>("DFMA (2 regs) + FFMA + IMAD + SHF + LOP3 each: DFMA rate", 8, out, in, sms);
     return 0;
 }
