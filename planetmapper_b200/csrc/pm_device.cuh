@@ -362,19 +362,16 @@ PM_HD_NOINLINE bool sincpt_converge(const FrameD &fs, V3 u0, double &dt, V3 &p, 
 // are used as ranges).
 //
 // CSPICE iterates  epoch e_{i+1} = et - lt(e_i)  from e_0 = et - lt0 = t_ref until the
-// light time stops changing; the contraction factor is v_surface / c ~ 4e-5, so that is
-// three intercepts: at e_0, e_1 and e_2.  Here
+// light time stops changing; the epochs contract geometrically with ratio V_lateral tan(emission) / c
+// (4e-5 at the disc centre, 5e-3 at 89 deg).  Here
 //   pass 1 (e_0): dt = 0, the spin is the identity (exactly CSPICE's first pass);
 //   pass 2 (e_1): full intercept;
-//   pass 3 (e_2): e_2 - e_1 ~ 1e-5 s, so instead of a third ray / ellipsoid solve the
-//     body-fixed intercept is moved along the secant through passes 1 and 2,
-//     p(e_2) = p2 + (p2 - p1) (e_2 - e_1) / (e_1 - e_0); the neglected curvature term is
-//     ~ V^2 r kappa / (2 c^2 cos(emission)) ~ 1e-8 km / cos(emission), an order below
-//     ulp(|P0|) with the same limb scaling as the intercept's own conditioning.  The
-//     observer position, the range and the light time are evaluated exactly at e_2.
-//   Grazing rays (cos^2 of the scaled-space emission <= 1e-3, i.e. emission > ~88 deg) are the
-//   exception: there d(lt)/d(epoch) = V_lateral tan(emission) / c reaches ~0.1 and three passes
-//   are not converged, so those pixels run CSPICE's loop as written (until et - lt is stable).
+//   then the fixed point e* of the loop is taken from the ratio of the two steps, and the intercept at
+//   e* is assembled from quantities of the two solves that ARE smooth in the epoch (see below) - no
+//   third ray / ellipsoid solve.  The ranges are the ray parameters themselves (u0 is a unit vector).
+//   Grazing rays (cos^2 of the scaled-space emission <= kGrazingCos2, i.e. emission > ~86.9 deg) are the
+//   exception: there the light time is too far from linear in the epoch for the two-point fixed point,
+//   so those pixels run CSPICE's loop as written (until et - lt is stable).
 PM_HD bool sincpt(const FrameD &fs, V3 u0, Intercept &it) {
     const PMFrame &f = fs.f;
     V3 p1, p2;
