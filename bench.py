@@ -855,7 +855,11 @@ def main():
                                       'peak': measured_peaks()[0]['hbm_gbs'], 'unit': 'GB/s',
                                       'frac': nbytes / (ms * 1e-3) / 1e9 / measured_peaks()[0]['hbm_gbs']},
                          'note': 'frac counts executed flops (FMA = 2, MUL / ADD = 1) against the one-register-operand '
-                                 'DFMA peak; see operand_limited for what the pipe sustains on this instruction mix',
+                                 'DFMA peak; see operand_limited for what the pipe sustains on three-register DFMAs.  The kernel '
+                                 'is ISSUE bound: an FP64 instruction holds the issue port 2 (3) cycles and the non-FP64 '
+                                 'instructions (45 % of the stream: selects, constant loads, moves, addresses) are not hidden '
+                                 'behind it (tools/microbench/fp64_operands.cu, DESIGN.md 3.4): 138 - 160 M of the 168 M '
+                                 'sub-partition cycles of a launch are issue cycles',
                          'ncu': ncu_summary('backplanes_img_c2')},
             'clocks': clocks,
         }
