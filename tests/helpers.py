@@ -219,8 +219,10 @@ def random_geometry(seed):
     r0 = rng.uniform(0.2, 0.9) * min(nx, ny)
     x0, y0 = rng.uniform(0.2, 0.8) * nx, rng.uniform(0.2, 0.8) * ny
     rot = rng.uniform(0, 360)
-    return (img_case(bc, nx, ny, x0, y0, r0, rot), nx, ny,
-            f'seed {seed}: {target} D/r={dist / rmax:.3g} {nx}x{ny} r0={r0:.1f} rot={rot:.0f}')
+    # every fourth geometry on an altitude-adjusted surface (get_backplane_img(..., alt=...), body_xy.py:2586)
+    alt = float(rng.uniform(-0.01, 0.05) * rmax) if seed % 4 == 3 else 0.0
+    return (img_case(bc, nx, ny, x0, y0, r0, rot, alt), nx, ny,
+            f'seed {seed}: {target} D/r={dist / rmax:.3g} {nx}x{ny} r0={r0:.1f} rot={rot:.0f} alt={alt:.0f}')
 
 
 def referee_ratios(got, ref, exact, margin):
