@@ -225,16 +225,17 @@ def random_geometry(seed):
             f'seed {seed}: {target} D/r={dist / rmax:.3g} {nx}x{ny} r0={r0:.1f} rot={rot:.0f} alt={alt:.0f}')
 
 
-def referee_ratios(got, ref, exact, margin):
+def referee_ratios(got, ref, exact, margin, xy_floor=None):
     """For every continuous plane: how far `got` (kernel code) and `ref` (FP64 oracle) each sit from `exact`
     (the oracle in 80-bit arithmetic), as (max ratio, rms ratio) of got-vs-exact over ref-vs-exact.  The
     denominators are floored at north_star's bare bars (1e-9 deg, 1e-12 relative; a tenth of them for the
-    rms): below those both are inside the bar and the ratio says nothing."""
+    rms): below those both are inside the bar and the ratio says nothing.  xy_floor (pixels) switches the
+    PIXEL-X / PIXEL-Y planes on - the x / y maps of the map direction - with that floor."""
     grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
     out = {}
     for name in PLANE_NAMES:
-        if name in ('LOCAL-SOLAR-TIME', 'PIXEL-X', 'PIXEL-Y'):
-            continue
+        if name == 'LOCAL-SOLAR-TIME' or (name in ('PIXEL-X', 'PIXEL-Y') and xy_floor is None):
+            continue   # integer seconds; pixel indices in the image direction
         k = PID[name]
         both = np.isfinite(got[k]) & np.isfinite(ref[k]) & np.isfinite(exact[k]) & ~grazing
         if not both.any():
@@ -242,13 +243,15 @@ def referee_ratios(got, ref, exact, margin):
         diff = angle_diff if name in WRAP else (lambda a, b: np.abs(a - b))
         de, oe = diff(got[k], exact[k])[both], diff(ref[k], exact[k])[both]
         floor = 1e-9 if name in BARE_ANGLE_PLANES else 1e-12 * float(np.abs(exact[k][both]).max())
+        if name in ('PIXEL-X', 'PIXEL-Y'):
+            floor = xy_floor   # x_map / y_map of the map direction, pixels
         out[name] = (float(de.max() / max(oe.max(), floor)),
                      float(np.sqrt(np.mean(de ** 2)) / max(np.sqrt(np.mean(oe ** 2)), 0.1 * floor)),
                      float(de.max()), float(oe.max()))
     return out
 
 
-def assert_referee(got, ref, exact, margin, label):
+def assert_referee(got, ref, exact, margin, label, xy_floor=None):
     """The kernel code is as close to the extended-precision result as the FP64 oracle is: rms within 3x,
     worst pixel within 10x (a maximum over a few thousand pixels of two independent rounding-noise fields;
     200 random geometries give <= 3.3x, LIMB-LON 8.3x), NaN masks identical outside grazing pixels."""
@@ -256,7 +259,7 @@ def assert_referee(got, ref, exact, margin, label):
     for name in PLANE_NAMES:
         ok, n_bad, _ = masks_equal(got[PID[name]], ref[PID[name]], exclude=grazing)
         assert ok, f'{label} {name}: {n_bad} NaN-mask mismatches outside grazing pixels'
-    rr = referee_ratios(got, ref, exact, margin)
+    rr = referee_ratios(got, ref, exact, margin, xy_floor)
     for name, (r_max, r_rms, d_max, o_max) in rr.items():
         assert r_rms <= 3.0 and r_max <= 10.0, (f'{label} {name}: kernel-vs-exact / oracle-vs-exact = {r_max:.2f} (max), '
                                                 f'{r_rms:.2f} (rms); max errors {d_max:.3e} / {o_max:.3e}')
