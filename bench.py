@@ -149,8 +149,35 @@ def algorithmic_flops_per_frame(planes_host, frame):
     n_out = int((~in_circle).sum())
     c = fpp['c2_12plane']
     flops = n_on * c['on_disc'] + n_miss * c['in_circle_miss'] + n_out * c['outside_circle']
+    det = fpp.get('detail', {})
+    counts = {'on_disc': n_on, 'in_circle_miss': n_miss, 'outside_circle': n_out}
+    warp_inst = {k: sum(counts[c_] * det[c_][k] for c_ in counts) for k in ('warp_inst', 'fp64_pipe_inst')} if det else None
     return flops, {'on_disc_px': n_on, 'in_circle_miss_px': n_miss, 'outside_px': n_out,
-                   'flops_per_px': c, 'flop_definition': fpp['flop_definition']}
+                   'flops_per_px': c, 'flop_definition': fpp['flop_definition'], 'warp_instructions': warp_inst}
+
+
+# share of the FP64 instructions of the C2 kernel that are DFMAs with three distinct register sources
+# (static property of the build: ncu source page of profiles/, 12.94 M of 51.85 M warp instructions)
+THREE_REGISTER_DFMA_SHARE = 0.25
+
+
+def issue_model(classes, ms, clocks, sms):
+    """Issue cycles of one launch by the rules measured with tools/microbench/fp64_operands.cu (an FP64
+    instruction holds the sub-partition's issue port 2 cycles, 3 with three register sources; every other
+    instruction costs 0.5 ... 1 cycle) over the sub-partition cycles the launch took."""
+    wi = classes.get('warp_instructions')
+    mhz = (clocks or {}).get('sm_mhz')
+    if not wi or not mhz:
+        return None
+    fp64, other = wi['fp64_pipe_inst'], wi['warp_inst'] - wi['fp64_pipe_inst']
+    fp64_cycles = fp64 * (2.0 + THREE_REGISTER_DFMA_SHARE)
+    elapsed = ms * 1e-3 * mhz * 1e6 * sms * 4
+    return {'fp64_warp_inst': fp64, 'other_warp_inst': other, 'three_register_dfma_share': THREE_REGISTER_DFMA_SHARE,
+            'issue_cycles_fp64': fp64_cycles, 'issue_cycles_total_lo_hi': [fp64_cycles + 0.5 * other, fp64_cycles + other],
+            'elapsed_subpartition_cycles': elapsed,
+            'frac_lo_hi': [(fp64_cycles + 0.5 * other) / elapsed, (fp64_cycles + other) / elapsed],
+            'what': 'warp instructions = per-class counts of profiles/flops_per_pixel.json x the pixels of each class; '
+                    'cycles per instruction from profiles/r2_fp64_operands.log (DESIGN.md 3.4)'}
 
 
 def ncu_summary(key):
@@ -848,6 +875,7 @@ def main():
                                      'register file needs 3 cycles to deliver their six 32-bit sources, the pipe '
                                      'issues a DFMA every 2: such code tops out at 2/3 of `peak` '
                                      '(tools/microbench/fp64_operands.cu, profiles/r2_summary.md)'},
+                         'issue_model': issue_model(classes, ms, clocks, torch.cuda.get_device_properties(0).multi_processor_count),
                          'algorithmic_flops_per_launch': flops, 'pixel_classes': classes,
                          'hbm_bytes_per_launch_algorithmic': int(nbytes),
                          # the same launch seen as an HBM kernel (why the bound is the FP64 pipe, not memory)
