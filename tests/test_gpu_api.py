@@ -574,3 +574,22 @@ def test_mapping_visible_areas_close_observer(oracle):
     gotm = np.stack([body.get_backplane_map(n, degree_interval=5) for n in PLANE_NAMES])
     check_map_planes(gotm, refm, marginm, fr, 120, 90, 'jupiter/amalthea map')
     assert np.isfinite(got[PID['EMISSION']]).sum() > 3000
+
+
+def test_optimize_speed_flag(bc_hst, oracle):
+    """BodyXY(optimize_speed=False) (body_xy.py:186-232, :3200-3217) runs the intercept for every pixel; with the
+    reference's cut-off radius the results are identical to the default, and the header of a saved observation
+    records the setting (observation.py:1330)."""
+    import planetmapper_b200 as pm
+    from helpers import PID, check_img_planes
+
+    planes = {}
+    for opt in (True, False):
+        body = pm.BodyXY(constants=bc_hst, nx=64, ny=48, optimize_speed=opt)
+        body.set_disc_params(30.0, 22.0, 18.0, 17.0)
+        fr = body._frame_host()
+        ref, margin = oracle.backplanes_img(fr, 64, 48, with_margin=True)
+        planes[opt] = np.stack([body.get_backplane_img(n) for n in PLANE_NAMES])
+        check_img_planes(planes[opt], ref, margin, fr, f'optimize_speed={opt}')
+    assert np.array_equal(planes[True], planes[False], equal_nan=True)
+    assert np.isfinite(planes[True][PID['EMISSION']]).sum() > 900

@@ -419,3 +419,27 @@ def test_device_code_random_geometries_vs_extended_precision(HC, oracle, ld_orac
         refm, marginm = oracle.backplanes_map(fr, lo, la, with_margin=True)
         assert_referee(hc_map(HC, fr, lo, la), refm, ld_oracle(fr, nx, ny, (lo, la)), marginm, label + ' map',
                        xy_floor=1e-9 * max(nx, ny))   # 1e-9 of the frame, the bar of check_map_planes
+
+
+def test_device_code_early_out_circle_flag(HC, oracle, bc_hst):
+    """BodyXY(optimize_speed=...) (body_xy.py:3200-3217): pixels further than 1.05 r_max + 1 from the disc centre
+    skip the intercept.  With the reference's radius the flag cannot change a result; with the cut-off radius
+    shrunk INTO the disc (frame field r_cut2) the flag decides which pixels exist - the oracle and the kernel
+    code must agree on both settings."""
+    nx, ny = 64, 48
+    frames = {}
+    for opt in (True, False):
+        fr = F.pack_frame(bc_hst, nx=nx, ny=ny, x0=30.0, y0=22.0, r0=18.0, rotation_radians=0.3, optimize_speed=opt)
+        frames[opt] = fr
+        ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+        check_img_planes(hc_img(HC, fr, nx, ny), ref, margin, fr, f'optimize_speed={opt}')
+    a, b = hc_img(HC, frames[True], nx, ny), hc_img(HC, frames[False], nx, ny)
+    assert np.array_equal(a, b, equal_nan=True)
+    for opt in (True, False):
+        fr = frames[opt].copy()
+        F.frame_field(fr, 'r_cut2')[0] = 10.0 ** 2          # a view into the frame: cut the disc at 10 px
+        ref, margin = oracle.backplanes_img(fr, nx, ny, with_margin=True)
+        got = hc_img(HC, fr, nx, ny)
+        check_img_planes(got, ref, margin, fr, f'cut disc, optimize_speed={opt}')
+        n_on = int(np.isfinite(got[PID['EMISSION']]).sum())
+        assert (250 < n_on < 330) if opt else (n_on > 900), (opt, n_on)
