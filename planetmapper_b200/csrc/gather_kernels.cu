@@ -836,8 +836,10 @@ cudaError_t launch_gather(const double *src, const uint32_t *nanbits, const uint
                                                                     plane_begin, plane_count, xmap, ymap, n_cells, \
                                                                     flags, out, ppg)
     static const int v = tune_int("PM_CUBIC_VARIANT", -1);
-    // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel
-    const bool dense = n_cells >= (int64_t)8 * nx * ny && nx < 16384 && ny < 16384;
+    // dense maps (many cells per image pixel share a footprint): warp-tiled DMMA kernel.  Measured crossover
+    // with the one-cell-per-thread kernel (tools/probe_density.py): ~16 map cells per image pixel - at 15.8 the
+    // scalar kernel is 10 % faster, at 63 the DMMA kernel 1.5x, at 400 (BASELINE C4) 2x
+    const bool dense = n_cells >= (int64_t)20 * nx * ny && nx < 16384 && ny < 16384;
     if (ky == 3 && kx == 3 && v != 0 && (dense || v > 0)) {
         // larger plane groups: the per-warp setup (map loads, weights, footprint classes) is heavier here
         // than in the scalar kernel

@@ -623,7 +623,7 @@ def test_dense_cubic_gather_any_quad_aligned_plane_range(L, bc_hst):
 
     sz = 64
     fr = _img_case(bc_hst, sz, sz, 31.5, 31.5, 28.0, 0.0)
-    lo, la = _grid(1.0)     # 64 800 cells >= 8 * 64 * 64: the DMMA kernel
+    lo, la = _grid(0.75)    # 115 200 cells >= 20 * 64 * 64: the DMMA kernel
     xy = L.backplanes_map(L.to_device(fr), L.to_device(lo), L.to_device(la), L.mask_from_names(['PIXEL-X', 'PIXEL-Y']))
     rng = np.random.default_rng(5)
     cube = rng.normal(1.0, 0.1, (80, sz, sz))
