@@ -188,6 +188,34 @@ def _freeze(v: Any):
     return v
 
 
+# The generated getters live on the instance (and in its `backplanes` registry): they hold the body
+# through a weak reference, so that a dropped BodyXY - and the device planes and pinned arrays in its
+# caches - is released at once by reference counting instead of waiting for the cycle collector.
+def _img_getter(ref, pid: int, stem: str):
+    def get_img() -> np.ndarray:
+        return ref()._get_img_plane(pid)
+
+    get_img.__name__ = f'get_{stem}_img'
+    return get_img
+
+
+def _map_getter(ref, pid: int, stem: str):
+    def get_map(**map_kwargs) -> np.ndarray:
+        return ref()._get_map_plane(pid, **map_kwargs)
+
+    get_map.__name__ = f'get_{stem}_map'
+    return get_map
+
+
+_DESCRIPTION_CACHE: dict = {}
+
+
+def _default_descriptions(ew: str) -> list:
+    if ew not in _DESCRIPTION_CACHE:
+        _DESCRIPTION_CACHE[ew] = [desc.format(ew=ew) for _, desc, _ in _PLANE_DESCRIPTIONS]
+    return _DESCRIPTION_CACHE[ew]
+
+
 class BodyXY(ProgressMixin):
     """An astronomical body observed at one epoch with an image pixel grid.
 
@@ -786,14 +814,21 @@ class BodyXY(ProgressMixin):
         return '\n'.join(f'{bp.name}: {bp.description}' for bp in self.backplanes.values())
 
     def _register_default_backplanes(self) -> None:
+        # one pass over the 26 defaults (body_xy.py:4198-4356); this runs in every constructor, i.e. inside every
+        # end-to-end step, so it avoids per-plane method calls: 52 closures over ONE weak reference
+        import weakref
+
         ew = self.positive_longitude_direction  # body_xy.py:4201-4203
-        for pid, (name, desc, stem) in enumerate(_PLANE_DESCRIPTIONS):
-            get_img = self._make_img_getter(pid)
-            get_map = self._make_map_getter(pid)
-            setattr(self, f'get_{stem}_img', get_img)
-            setattr(self, f'get_{stem}_map', get_map)
-            self.register_backplane(name, desc.format(ew=ew), get_img, get_map)
-            self._builtin_getters[name] = (get_img, get_map)
+        descriptions = _default_descriptions(ew)
+        ref = weakref.ref(self)
+        attrs, backplanes, builtin = self.__dict__, self.backplanes, self._builtin_getters
+        for pid, (name, _, stem) in enumerate(_PLANE_DESCRIPTIONS):
+            get_img = _img_getter(ref, pid, stem)
+            get_map = _map_getter(ref, pid, stem)
+            attrs[f'get_{stem}_img'] = get_img
+            attrs[f'get_{stem}_map'] = get_map
+            backplanes[name] = Backplane(name, descriptions[pid], get_img, get_map)
+            builtin[name] = (get_img, get_map)
 
     def _is_builtin_backplane(self, name: str, mapped: bool) -> bool:
         """True while ``backplanes[name]`` is still the kernel-backed default getter."""
@@ -802,31 +837,6 @@ class BodyXY(ProgressMixin):
         if getters is None or bp is None:
             return False
         return (bp.get_map is getters[1]) if mapped else (bp.get_img is getters[0])
-
-    # The generated getters live on the instance (and in its `backplanes` registry): they hold the body
-    # through a weak reference, so that a dropped BodyXY - and the device planes and pinned arrays in its
-    # caches - is released at once by reference counting instead of waiting for the cycle collector.
-    def _make_img_getter(self, pid: int):
-        import weakref
-
-        ref = weakref.ref(self)
-
-        def get_img() -> np.ndarray:
-            return ref()._get_img_plane(pid)
-
-        get_img.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_img'
-        return get_img
-
-    def _make_map_getter(self, pid: int):
-        import weakref
-
-        ref = weakref.ref(self)
-
-        def get_map(**map_kwargs) -> np.ndarray:
-            return ref()._get_map_plane(pid, **map_kwargs)
-
-        get_map.__name__ = f'get_{_PLANE_DESCRIPTIONS[pid][2]}_map'
-        return get_map
 
     # ---- image-direction backplanes ----------------------------------------------------
     def _test_if_img_size_valid(self) -> bool:
@@ -884,46 +894,64 @@ class BodyXY(ProgressMixin):
 
     # Planes at least this large are read ahead (below it the per-call overhead is not the copy)
     _PREFETCH_MIN_BYTES = 4 << 20
+    # Planes kept in flight ahead of the caller: enough to bridge Python's return to the caller and its next
+    # request (a copy of a 2048 x 2048 plane takes 0.6 ms), few enough that a caller who wanted ONE plane has
+    # paid for two small background copies, not for the whole stack
+    _PREFETCH_WINDOW = 2
 
     def _img_plane_to_host(self, pid: int) -> np.ndarray:
         """A new host array holding image plane ``pid``.  The usual caller asks for one backplane after the
-        other (the reference's save_observation loop, observation.py:1275, or user code): on the SECOND distinct
-        plane of a stack the remaining planes of that stack are sent after it, device -> pinned host on a side
-        stream, so their copies run back to back while Python returns to the caller; each read-ahead array is
-        handed to the first request for its plane (ownership moves to the caller), later requests copy again."""
+        other (the reference's save_observation loop, observation.py:1275, or user code), so the copy engine is
+        kept busy across the calls: the requested plane is copied device -> pinned host on a side stream and,
+        BEFORE waiting for it, the next ``_PREFETCH_WINDOW`` planes of the stack nobody has asked for yet are
+        queued behind it.  Each read-ahead array is handed to the first request for its plane (ownership moves
+        to the caller); later requests copy again."""
         torch = L._torch()
         alt = self._alt_adjustment
         have, planes = self.get_backplanes_img_device(1 << pid, alt)
         slot = lambda q: L.popcount(have & ((1 << q) - 1))   # noqa: E731
+        if planes[0].numel() * 8 < self._PREFETCH_MIN_BYTES:
+            return L.to_host(planes[slot(pid)])
         key = ('img_readahead', alt)
         state = self._cache.get(key)
         if state is None or state['planes'] is not planes:
-            state = {'planes': planes, 'asked': set(), 'ready': {}, 'stream': None}
-            self._cache[key] = state
-        ready = state['ready'].pop(pid, None)
-        state['asked'].add(pid)
-        if ready is not None:
-            host, event = ready
-            event.synchronize()
-            return host.numpy()
-        out = L.to_host(planes[slot(pid)])
-        if len(state['asked']) == 2 and planes[0].numel() * 8 >= self._PREFETCH_MIN_BYTES:
-            if state['stream'] is None:
-                state['stream'] = torch.cuda.Stream()
-            side = state['stream']
-            side.wait_stream(torch.cuda.current_stream())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())    # the kernel that fills `planes`
             planes.record_stream(side)     # the stack must outlive the copies even if the cache is cleared meanwhile
-            with torch.cuda.stream(side):
+            state = {'planes': planes, 'asked': set(), 'ready': {}, 'stream': side}
+            self._cache[key] = state
+        side = state['stream']
+
+        def enqueue(q):
+            host = L.empty_host(planes[slot(q)].shape, torch)
+            if not host.is_pinned():
+                return None            # pinned budget exhausted: no asynchronous copy into pageable memory
+            host.copy_(planes[slot(q)], non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(side)
+            return host, event
+
+        mine = state['ready'].pop(pid, None)
+        state['asked'].add(pid)
+        with torch.cuda.stream(side):
+            if mine is None:
+                mine = enqueue(pid)
+            if mine is not None:
+                ahead = len(state['ready'])
                 for q in range(L.N_PLANES):
-                    if (have >> q) & 1 and q not in state['asked']:
-                        host = L.empty_host(planes[slot(q)].shape, torch)
-                        if not host.is_pinned():
-                            break          # pinned budget exhausted: no read-ahead into pageable memory
-                        host.copy_(planes[slot(q)], non_blocking=True)
-                        event = torch.cuda.Event()
-                        event.record(side)
-                        state['ready'][q] = (host, event)
-        return out
+                    if ahead >= self._PREFETCH_WINDOW:
+                        break
+                    if (have >> q) & 1 and q not in state['asked'] and q not in state['ready']:
+                        nxt = enqueue(q)
+                        if nxt is None:
+                            break
+                        state['ready'][q] = nxt
+                        ahead += 1
+        if mine is None:
+            return L.to_host(planes[slot(pid)])
+        host, event = mine
+        event.synchronize()
+        return host.numpy()
 
     def get_backplane_imgs(self, names, *, alt: float = 0.0, out=None) -> dict[str, np.ndarray]:
         """Several backplane images from ONE kernel launch and ONE device->host copy.

@@ -212,6 +212,8 @@ class BodyConstants:
     def to_json_dict(self) -> dict:
         out = {}
         for k, v in self.__dict__.items():
+            if k.startswith('_'):
+                continue   # per-instance caches (_packed_constants)
             if isinstance(v, np.ndarray):
                 out[k] = [float.hex(float(x)) for x in v.ravel()]
             elif isinstance(v, float):
@@ -475,15 +477,14 @@ def xy2angular_matrix(bc: BodyConstants, x0: float, y0: float, r0: float,
     return m3
 
 
-def pack_frame(bc: BodyConstants, *, nx: int, ny: int, x0: float, y0: float,
-               r0: float, rotation_radians: float, alt: float = 0.0,
-               optimize_speed: bool = True) -> np.ndarray:
-    """Pack BodyConstants + disc parameters into the flat PMFrame double array.
-
-    ``alt`` reproduces _AdjustedSurfaceAltitude (planetmapper/body.py:172-229): the
-    radii handed to the per-pixel code grow by alt; nothing computed at construction
-    (sub-point, ring plane, plate scale) changes.
-    """
+def _pack_constants(bc: BodyConstants, alt: float) -> np.ndarray:
+    """The disc-independent part of the PMFrame array (everything but A, Ainv, nx, ny, x0, y0, r_cut2,
+    optimize_speed).  Cached on the BodyConstants instance per altitude: a BodyXY whose disc parameters
+    change (or many BodyXY sharing one set of constants) re-packs only the disc fields."""
+    cache = bc.__dict__.setdefault('_packed_constants', {})
+    buf = cache.get(alt)
+    if buf is not None:
+        return buf
     buf = np.zeros(PMFRAME_NDOUBLES, dtype=np.float64)
 
     def put(name, value):
@@ -521,18 +522,38 @@ def pack_frame(bc: BodyConstants, *, nx: int, ny: int, x0: float, y0: float,
     put('M', bc.M)
     put('ang2km', np.linalg.inv(km2angular_matrix(bc)))
     put('km_per_arcsec', bc.km_per_arcsec)
+    put('r_eq', re)
+    buf.setflags(write=False)
+    if len(cache) < 64:   # altitudes are user input: do not grow without bound
+        cache[alt] = buf
+    return buf
+
+
+def pack_frame(bc: BodyConstants, *, nx: int, ny: int, x0: float, y0: float,
+               r0: float, rotation_radians: float, alt: float = 0.0,
+               optimize_speed: bool = True) -> np.ndarray:
+    """Pack BodyConstants + disc parameters into the flat PMFrame double array.
+
+    ``alt`` reproduces _AdjustedSurfaceAltitude (planetmapper/body.py:172-229): the
+    radii handed to the per-pixel code grow by alt; nothing computed at construction
+    (sub-point, ring plane, plate scale) changes.
+    """
+    buf = _pack_constants(bc, float(alt)).copy()
+    off = PMFRAME_OFFSETS
     a3 = xy2angular_matrix(bc, x0, y0, r0, rotation_radians)
     a3inv = np.linalg.inv(a3)
-    put('A', a3[:2, :])
-    put('Ainv', a3inv[:2, :])
-    put('nx', nx)
-    put('ny', ny)
-    put('x0', x0)
-    put('y0', y0)
-    r_cut = (r0 * float(max(radii)) / re) * 1.05 + 1  # body_xy.py:3190-3202
-    put('r_cut2', r_cut**2)
-    put('optimize_speed', 1.0 if optimize_speed else 0.0)
-    put('r_eq', re)
+    o = off['A'][0]
+    buf[o : o + 6] = a3[:2, :].ravel()
+    o = off['Ainv'][0]
+    buf[o : o + 6] = a3inv[:2, :].ravel()
+    buf[off['nx'][0]] = nx
+    buf[off['ny'][0]] = ny
+    buf[off['x0'][0]] = x0
+    buf[off['y0'][0]] = y0
+    radii = buf[off['radii'][0] : off['radii'][0] + 3]
+    r_cut = (r0 * float(max(radii)) / float(radii[0])) * 1.05 + 1  # body_xy.py:3190-3202
+    buf[off['r_cut2'][0]] = r_cut**2
+    buf[off['optimize_speed'][0]] = 1.0 if optimize_speed else 0.0
     return buf
 
 

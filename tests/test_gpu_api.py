@@ -465,11 +465,15 @@ def test_backplane_getters_return_owned_arrays(body):
     assert fresh2._cache[('img_planes_dev', 0.0)][0] == 1 << 4
     fresh2.get_backplane_img('RING-RADIUS')   # ... a second distinct one everything
     assert bin(fresh2._cache[('img_planes_dev', 0.0)][0]).count('1') == 26
-    # read-ahead (planes >= 4 MB): the second distinct request sends the rest of the stack after it; every array is
-    # handed out once, equals a direct copy, and a repeated request gets a fresh array
+    # read-ahead (planes >= 4 MB): every request leaves the next two planes nobody asked for in flight behind its
+    # own copy; every array is handed out once, equals a direct copy, and a repeated request gets a fresh array
     big = type(body)(constants=body._bc, nx=1024, ny=600)
-    first = {n: big.get_backplane_img(n) for n in ('EMISSION', 'PHASE', 'LON-GRAPHIC', 'DOPPLER')}
-    assert len(big._cache[('img_readahead', 0.0)]['ready']) == 12 - 4
+    one = big.get_backplane_img('EMISSION')
+    state = big._cache[('img_readahead', 0.0)]
+    assert sorted(state['ready']) == [PLANE_NAMES.index('LON-GRAPHIC'), PLANE_NAMES.index('LAT-GRAPHIC')]
+    first = {n: big.get_backplane_img(n) for n in ('PHASE', 'LON-GRAPHIC', 'DOPPLER')}
+    first['EMISSION'] = one
+    assert len(state['ready']) == big._PREFETCH_WINDOW and not set(state['ready']) & state['asked']
     have, planes = big.get_backplanes_img_device(1 << 14)
     for n, arr in first.items():
         pid = PLANE_NAMES.index(n)
