@@ -434,13 +434,13 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
     const bool pair_ok = ((n_cells & 1) == 0) && (!grid2d || (row_len & 1) == 0);
 
     // ---- distinct footprints of the warp (plane independent).  32 consecutive cells of a dense map
-    // cover one to three image pixels along the row: up to three footprints are kept for the
-    // pipelined path; more (a map coarser than the launcher's density rule expects) take the
+    // cover one to three image pixels along the row (four at a corner of 2 x 2 pixels): up to four footprints
+    // are kept for the pipelined path; more (a map coarser than the launcher's density rule expects) take the
     // general path at the end.
-    uint32_t org0 = 0xffffffffu, org1 = 0xffffffffu, org2 = 0xffffffffu;
+    uint32_t org0 = 0xffffffffu, org1 = 0xffffffffu, org2 = 0xffffffffu, org3 = 0xffffffffu;
     uint32_t mine = 0;     // bit 4 f + i: this lane's cell of tile i reads footprint f
     uint32_t tiles = 0;    // (uniform) bit 4 f + i: tile i has cells of footprint f;
-                           // bit 12 + i: every valid cell of tile i reads ONE footprint (no masking needed)
+                           // bit 16 + i: every valid cell of tile i reads ONE footprint (no masking needed)
     bool simple = true;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
             const uint32_t members = __shfl_sync(kFull, cls[i], leader);
             const uint32_t org = __shfl_sync(kFull, origin[i], leader);
             const uint32_t me = (members >> lane) & 1u;
-            if (members == valid_mask[i]) tiles |= 1u << (12 + i);
+            if (members == valid_mask[i]) tiles |= 1u << (16 + i);
             if (org0 == 0xffffffffu || org == org0) {
                 org0 = org;
                 mine |= me << i;
@@ -463,6 +463,10 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
                 org2 = org;
                 mine |= me << (8 + i);
                 tiles |= 1u << (8 + i);
+            } else if (org3 == 0xffffffffu || org == org3) {   // the corner of 2 x 2 image pixels
+                org3 = org;
+                mine |= me << (12 + i);
+                tiles |= 1u << (12 + i);
             } else {
                 simple = false;
             }
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
         }
     };
 
-    // ---- pipelined path: at most three distinct footprints in the warp
+    // ---- pipelined path: at most four distinct footprints in the warp
     if (simple) {
         // A footprint of one plane tile is 8 planes x 4 rows x 4 columns = 1 KB = 64 chunks of 16 bytes in the
         // plane-quad layout ([quad][y][x][4 planes]: chunk c = ((q * 4 + y) * 4 + x) * 2 + half).  Lane L
@@ -523,12 +527,12 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
         // Each warp owns kCubicSlots footprint slots of 1 KB, used as a ring of DEPTH = kCubicSlots / NF plane
         // tiles for a warp with NF distinct footprints: the common single-footprint warp keeps five tiles in
         // flight behind the one being multiplied (an L2 round trip under a full store stream is ~4 tile times),
-        // a three-footprint warp one.
+        // a three-footprint warp one, a four-footprint warp (a corner of 2 x 2 image pixels) none.
         __shared__ __align__(16) double stage[kCubicBlock / 32][kCubicSlots][128];
         const bool full_tiles = ncols[0] == 8 && ncols[1] == 8 && ncols[2] == 8 && ncols[3] == 8;
         const bool fast_store = full_tiles && pair_ok;
         const int n_it = (l1 - l0 + 7) / 8;
-        const int nf = org2 != 0xffffffffu ? 3 : (has1 ? 2 : 1);
+        const int nf = org3 != 0xffffffffu ? 4 : (org2 != 0xffffffffu ? 3 : (has1 ? 2 : 1));
         const int warp = threadIdx.x >> 5;
         // source of this lane's chunk inside a footprint whose top-left coefficient is at `base`:
         // row (lane >> 3) & 3, column (lane >> 1) & 3, half lane & 1 of quad 0
@@ -536,6 +540,7 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
         const double *q0 = coefq + (int64_t)((plane_begin + l0) >> 2) * quad_stride + (int64_t)org0 * 4 + chunk_off;
         // footprints 1 and 2 as element offsets from footprint 0 (they fit 32 bits: nx, ny < 16384)
         const int d1 = nf > 1 ? ((int)org1 - (int)org0) * 4 : 0, d2 = nf > 2 ? ((int)org2 - (int)org0) * 4 : 0;
+        const int d3 = nf > 3 ? ((int)org3 - (int)org0) * 4 : 0;
         const int64_t tile_stride = 2 * quad_stride;
         // quads of coefficients that exist from this group's first plane on (the last tile may have one)
         const int quads_ahead = (n_planes_padded - (plane_begin + l0)) >> 2;
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
         auto pipeline = [&](auto nf_tag) {
             constexpr int NF = decltype(nf_tag)::value;
             constexpr int DEPTH = kCubicSlots / NF;   // plane tiles in the ring
+            static_assert(DEPTH >= 1, "a ring entry must hold every footprint of a plane tile");
             constexpr int kTile = NF * 128;           // doubles per ring entry
             int issued = 0, issue_slot = 0;
             auto issue = [&]() {
@@ -585,6 +591,10 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
                     if (NF > 2) {
                         cp_async16(dst + 256, q0 + d2);
                         cp_async16(dst + 256 + 64, q0 + d2 + second);
+                    }
+                    if (NF > 3) {
+                        cp_async16(dst + 384, q0 + d3);
+                        cp_async16(dst + 384 + 64, q0 + d3 + second);
                     }
                     if (2 * issued + 2 < quads_ahead) q0 += tile_stride;
                 }
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (tiles & (1u << (4 * f + i))) {
-                                const bool keep = (tiles & (1u << (12 + i))) || ((mine >> (4 * f + i)) & 1u);
+                                const bool keep = (tiles & (1u << (16 + i))) || ((mine >> (4 * f + i)) & 1u);
 #pragma unroll
                                 for (int j = 0; j < 4; j++) dmma8x8x4(d[i][0], d[i][1], a[j], keep ? bw[i][j] : 0.0);
                             }
@@ -682,8 +692,10 @@ __global__ void __launch_bounds__(kCubicBlock, PM_CUBIC_CTAS)
             pipeline(std::integral_constant<int, 1>{});
         else if (nf == 2)
             pipeline(std::integral_constant<int, 2>{});
-        else
+        else if (nf == 3)
             pipeline(std::integral_constant<int, 3>{});
+        else
+            pipeline(std::integral_constant<int, 4>{});   // one ring entry: no tile in flight, but the same staged loads
         return;
     }
 
