@@ -254,15 +254,22 @@ def referee_ratios(got, ref, exact, margin, xy_floor=None):
 def assert_referee(got, ref, exact, margin, label, xy_floor=None):
     """The kernel code is as close to the extended-precision result as the FP64 oracle is: rms within 3x,
     worst pixel within 10x (a maximum over a few thousand pixels of two independent rounding-noise fields;
-    200 random geometries give <= 3.3x, LIMB-LON 8.3x), NaN masks identical outside grazing pixels."""
+    420 random geometries give <= 7.8x and <= 2.9x rms outside the two limb-angle planes, see below), NaN masks
+    identical outside grazing pixels."""
     grazing = np.where(np.isnan(margin), False, np.abs(margin) < 1e-9)
     for name in PLANE_NAMES:
         ok, n_bad, _ = masks_equal(got[PID[name]], ref[PID[name]], exclude=grazing)
         assert ok, f'{label} {name}: {n_bad} NaN-mask mismatches outside grazing pixels'
     rr = referee_ratios(got, ref, exact, margin, xy_floor)
     for name, (r_max, r_rms, d_max, o_max) in rr.items():
-        assert r_rms <= 3.0 and r_max <= 10.0, (f'{label} {name}: kernel-vs-exact / oracle-vs-exact = {r_max:.2f} (max), '
-                                                f'{r_rms:.2f} (rms); max errors {d_max:.3e} / {o_max:.3e}')
+        # LIMB-LON / LIMB-LAT: the limb point is the radial projection of the ray's closest approach to the body
+        # centre, a difference of two |P0|-sized vectors - a ray through the centre has no defined limb point at
+        # all, and the worst pixel of a frame is whichever ray passes nearest to it (324 further geometries: up to
+        # 13x in the maximum, 4.9x rms, with both errors below 5e-8 deg)
+        lim_max, lim_rms = (30.0, 6.0) if name in ('LIMB-LON-GRAPHIC', 'LIMB-LAT-GRAPHIC') else (10.0, 3.0)
+        assert r_rms <= lim_rms and r_max <= lim_max, (
+            f'{label} {name}: kernel-vs-exact / oracle-vs-exact = {r_max:.2f} (max), {r_rms:.2f} (rms); '
+            f'max errors {d_max:.3e} / {o_max:.3e}')
     return rr
 
 
